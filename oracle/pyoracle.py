@@ -1,0 +1,337 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+ctypes binding of oracle/liboracle.so (the CPU restatement) and, when present, of
+oracle/_ref/libsl2ref.so (the reference's own improc sources compiled unmodified).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module; nothing under scenelib2_b200/ does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "liboracle.so")
+_REF = os.path.join(_HERE, "_ref", "libsl2ref.so")
+
+u8p = C.POINTER(C.c_uint8)
+i32p = C.POINTER(C.c_int32)
+f64p = C.POINTER(C.c_double)
+
+
+class OrcConfig(C.Structure):
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32),
+        ("fku", C.c_double), ("fkv", C.c_double), ("u0", C.c_double), ("v0", C.c_double),
+        ("kd1", C.c_double), ("sd", C.c_double),
+        ("delta_t", C.c_double),
+        ("number_of_features_to_select", C.c_int32),
+        ("boxsize", C.c_int32),
+        ("search_override", C.c_double * 3),
+        ("minimum_attempted_measurements_of_feature", C.c_int32),
+        ("successful_match_fraction", C.c_double),
+    ]
+
+
+def build(force=False):
+    """Compile liboracle.so (and _ref when /root/reference exists).  Building is not using."""
+    if force or not os.path.exists(_LIB) or (
+            os.path.isdir("/root/reference/scenelib2/improc") and not os.path.exists(_REF)):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+def _u8(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a, _p(a, u8p)
+
+
+def _f64(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, _p(a, f64p)
+
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB)
+        L.orc_correlate2_warning.restype = C.c_double
+        L.orc_slam_create.restype = C.c_void_p
+        L.orc_slam_run.restype = C.c_double
+        for name in ("orc_slam_destroy", "orc_slam_add_feature", "orc_slam_set_state",
+                     "orc_slam_get_state", "orc_slam_step", "orc_slam_predict",
+                     "orc_slam_update", "orc_slam_normalise", "orc_slam_finish",
+                     "orc_slam_get_features"):
+            getattr(L, name).restype = None
+        _lib = L
+    return _lib
+
+
+def ref():
+    """The reference's own improc code (None when the prebuilt .so is absent)."""
+    global _ref
+    if _ref is None and os.path.exists(_REF):
+        R = C.CDLL(_REF)
+        R.ref_correlate2_warning.restype = C.c_double
+        _ref = R
+    return _ref
+
+
+def make_config(width=320, height=240, fku=195.0, fkv=195.0, u0=162.0, v0=125.0, kd1=9e-6, sd=1.0,
+                delta_t=0.033333333, n_select=10, boxsize=11, search_override=(0.0, 0.0, 0.0),
+                min_attempts=10, match_fraction=0.5):
+    c = OrcConfig()
+    c.width, c.height = width, height
+    c.fku, c.fkv, c.u0, c.v0, c.kd1, c.sd = fku, fkv, u0, v0, kd1, sd
+    c.delta_t = delta_t
+    c.number_of_features_to_select = n_select
+    c.boxsize = boxsize
+    for i in range(3):
+        c.search_override[i] = search_override[i]
+    c.minimum_attempted_measurements_of_feature = min_attempts
+    c.successful_match_fraction = match_fraction
+    return c
+
+
+# ---- primitives -------------------------------------------------------------------------------
+def correlate2_warning(patch, image, x1, y1, use_ref=False):
+    """A1.  patch (B,B) u8, image (H,W) u8 -> (corr, sd_patch, sd_image)."""
+    patch, pp = _u8(patch)
+    image, ip = _u8(image)
+    sd0, sd1 = C.c_double(), C.c_double()
+    if use_ref:
+        r = ref().ref_correlate2_warning(pp, patch.shape[1], patch.shape[0], patch.shape[1],
+                                         patch.shape[0], ip, image.shape[1], image.shape[0],
+                                         int(x1), int(y1), C.byref(sd0), C.byref(sd1))
+    else:
+        r = lib().orc_correlate2_warning(pp, patch.shape[1], patch.shape[1], patch.shape[0], ip,
+                                         image.shape[1], int(x1), int(y1), C.byref(sd0),
+                                         C.byref(sd1))
+    return r, sd0.value, sd1.value
+
+
+def elliptical_search(image, patches, centres, puinv3):
+    """A2 batched.  patches (n,B,B), centres (n,2), puinv3 (n,3) -> u,v (int32), found (u8), best."""
+    image, ip = _u8(image)
+    patches, pp = _u8(patches)
+    centres, cp = _f64(centres)
+    puinv3, qp = _f64(puinv3)
+    n, B = patches.shape[0], patches.shape[1]
+    u = np.zeros(n, np.int32)
+    v = np.zeros(n, np.int32)
+    found = np.zeros(n, np.uint8)
+    best = np.zeros(n, np.float64)
+    lib().orc_elliptical_search_batch(ip, image.shape[1], image.shape[0], pp, B, n, cp, qp,
+                                      _p(u, i32p), _p(v, i32p), _p(found, u8p), _p(best, f64p))
+    return u, v, found, best
+
+
+def search_box(width, height, B, centre, puinv3):
+    centre, cp = _f64(centre)
+    puinv3, qp = _f64(puinv3)
+    box = np.zeros(6, np.int32)
+    lib().orc_search_box(width, height, B, cp, qp, _p(box, i32p))
+    return box
+
+
+def score_map(image, patch, centre, puinv3):
+    """Scores of one feature over its clamped bounding box, urel-major."""
+    image, ip = _u8(image)
+    patch, pp = _u8(patch)
+    centre, cp = _f64(centre)
+    puinv3, qp = _f64(puinv3)
+    B = patch.shape[0]
+    box = search_box(image.shape[1], image.shape[0], B, centre, puinv3)
+    nu, nv = max(0, box[1] - box[0] + 1), max(0, box[3] - box[2] + 1)
+    corr = np.zeros((nu, nv), np.float64)
+    sd = np.zeros((nu, nv), np.float64)
+    inside = np.zeros((nu, nv), np.uint8)
+    if nu and nv:
+        lib().orc_score_map(ip, image.shape[1], image.shape[0], pp, B, cp, qp, _p(corr, f64p),
+                            _p(sd, f64p), _p(inside, u8p))
+    return box, corr, sd, inside
+
+
+def puinv_from_S(S):
+    S, sp = _f64(np.asarray(S, np.float64).reshape(2, 2).T)  # col-major
+    out = np.zeros(3)
+    lib().orc_puinv_from_S(sp, _p(out, f64p))
+    return out
+
+
+def smoe_search(image, patch, puinv3, centres, use_ref=False):
+    """A11.  K ellipses sharing one template."""
+    image, ip = _u8(image)
+    patch, pp = _u8(patch)
+    puinv3, qp = _f64(puinv3)
+    centres, cp = _f64(centres)
+    K = puinv3.shape[0]
+    ru = np.zeros(K, np.int32)
+    rv = np.zeros(K, np.int32)
+    rf = np.zeros(K, np.uint8)
+    best = np.zeros(K, np.float64)
+    if use_ref:
+        ref().ref_smoe_search(ip, image.shape[1], image.shape[0], pp, patch.shape[0], K, qp, cp,
+                              _p(ru, i32p), _p(rv, i32p), _p(rf, u8p))
+    else:
+        lib().orc_smoe_search(ip, image.shape[1], image.shape[0], pp, patch.shape[0], K, qp, cp,
+                              _p(ru, i32p), _p(rv, i32p), _p(rf, u8p), _p(best, f64p))
+    return ru, rv, rf, best
+
+
+def motion(xv, dt, u=(0.0, 0.0, 0.0)):
+    """A5.  -> fv (13), F (13,13), Q (13,13) as numpy (row/col = math indices)."""
+    xv, xp = _f64(xv)
+    uu, up = _f64(u)
+    fv = np.zeros(13)
+    F = np.zeros((13, 13), order="F")
+    Q = np.zeros((13, 13), order="F")
+    lib().orc_motion(xp, up, C.c_double(dt), _p(fv, f64p), _p(F, f64p), _p(Q, f64p))
+    return fv, F, Q
+
+
+def dxvnorm_by_dxv(xv):
+    xv, xp = _f64(xv)
+    J = np.zeros((13, 13), order="F")
+    lib().orc_dxvnorm_by_dxv(xp, _p(J, f64p))
+    return J
+
+
+def _colmajor(a):
+    a = np.asfortranarray(np.asarray(a, np.float64))
+    return a, _p(a, f64p)
+
+
+def predict_feature(cam8, xv, y, Pxx, Pxy, Pyy):
+    cam8, cp = _f64(cam8)
+    xv, xp = _f64(xv)
+    y, yp = _f64(y)
+    Pxx, a = _colmajor(Pxx)
+    Pxy, b = _colmajor(Pxy)
+    Pyy, c = _colmajor(Pyy)
+    h = np.zeros(2)
+    dxv = np.zeros((2, 13), order="F")
+    dy = np.zeros((2, 3), order="F")
+    R = np.zeros((2, 2), order="F")
+    S = np.zeros((2, 2), order="F")
+    lib().orc_predict_feature(cp, xp, yp, a, b, c, _p(h, f64p), _p(dxv, f64p), _p(dy, f64p),
+                              _p(R, f64p), _p(S, f64p))
+    return h, dxv, dy, R, S
+
+
+def visibility_test(cam8, xp, y, xp_org, h):
+    cam8, cp = _f64(cam8)
+    xp, a = _f64(xp)
+    y, b = _f64(y)
+    xp_org, c = _f64(xp_org)
+    h, d = _f64(h)
+    return lib().orc_visibility_test(cp, a, b, c, d)
+
+
+def kalman_update_dense(x, P, H, R, nu):
+    """A6 dense, as written in kalman.cpp:100-115.  Returns (x_new, P_new)."""
+    x = np.array(x, np.float64)
+    P = np.array(P, np.float64, order="F")
+    H, hp = _colmajor(H)
+    R, rp = _colmajor(R)
+    nu, np_ = _f64(nu)
+    lib().orc_kalman_update_dense(x.size, nu.size, _p(x, f64p), _p(P, f64p), hp, rp, np_)
+    return x, P
+
+
+class Slam:
+    """Whole-step oracle (monoslam.cpp:108-180, tracking only)."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.h = C.c_void_p(lib().orc_slam_create(C.byref(cfg)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_slam_destroy(self.h)
+            self.h = None
+
+    def add_feature(self, y, xp_org, patch):
+        y, a = _f64(y)
+        xp_org, b = _f64(xp_org)
+        patch, c = _u8(patch)
+        lib().orc_slam_add_feature(self.h, a, b, c)
+
+    @property
+    def num_features(self):
+        return lib().orc_slam_num_features(self.h)
+
+    @property
+    def n(self):
+        return lib().orc_slam_state_size(self.h)
+
+    def set_state(self, x, P):
+        x, a = _f64(x)
+        P, b = _colmajor(P)
+        lib().orc_slam_set_state(self.h, a, b)
+
+    def get_state(self):
+        n = self.n
+        x = np.zeros(n)
+        P = np.zeros((n, n), order="F")
+        lib().orc_slam_get_state(self.h, _p(x, f64p), _p(P, f64p))
+        return x, P
+
+    def step(self, frame):
+        frame, fp = _u8(frame)
+        lib().orc_slam_step(self.h, fp)
+
+    def predict(self):
+        lib().orc_slam_predict(self.h)
+
+    def select(self):
+        return lib().orc_slam_select(self.h)
+
+    def measure(self, frame):
+        frame, fp = _u8(frame)
+        return lib().orc_slam_measure(self.h, fp)
+
+    def update(self):
+        lib().orc_slam_update(self.h)
+
+    def normalise(self):
+        lib().orc_slam_normalise(self.h)
+
+    def finish(self):
+        lib().orc_slam_finish(self.h)
+
+    def features(self):
+        nf = self.num_features
+        out = dict(label=np.zeros(nf, np.int32), h=np.zeros((nf, 2)), z=np.zeros((nf, 2)),
+                   S=np.zeros((nf, 4)), flags=np.zeros(nf, np.uint8),
+                   attempted=np.zeros(nf, np.int32), successful=np.zeros(nf, np.int32),
+                   select_rank=np.zeros(nf, np.int32))
+        lib().orc_slam_get_features(self.h, _p(out["label"], i32p), _p(out["h"], f64p),
+                                    _p(out["z"], f64p), _p(out["S"], f64p), _p(out["flags"], u8p),
+                                    _p(out["attempted"], i32p), _p(out["successful"], i32p),
+                                    _p(out["select_rank"], i32p))
+        return out
+
+
+def run_slams(slams, frames, nsteps, nthreads):
+    """Step every Slam nsteps times over its own frame ring; returns wall seconds."""
+    n = len(slams)
+    handles = (C.c_void_p * n)(*[s.h for s in slams])
+    keep = [np.ascontiguousarray(f, np.uint8) for f in frames]
+    ptrs = (u8p * n)(*[_p(f, u8p) for f in keep])
+    nframes = keep[0].shape[0]
+    return lib().orc_slam_run(handles, n, ptrs, nframes, nsteps, nthreads)
+
+
+def hardware_threads():
+    return lib().orc_hardware_threads()

@@ -1,0 +1,84 @@
+"""Pins the oracle's patch-correlation restatement (A1, A11, and through A11 the A2 loop) to the
+REFERENCE's own source: golden vectors under tests/golden/ were produced by
+oracle/_ref/libsl2ref.so = /root/reference/scenelib2/improc/{improc,search_multiple_overlapping_
+ellipses}.cpp compiled unmodified (see tests/golden/make_golden.py).  Bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_a1_matches_reference_golden(oracle):
+    k = np.load(os.path.join(G, "a1_ref_kat.npz"))
+    assert len(k["B"]) == 48
+    for B, patch, image, xy, out in zip(k["B"], k["patch"], k["image"], k["xy"], k["out"]):
+        c, s0, s1 = oracle.correlate2_warning(patch[:B, :B], image, xy[0], xy[1])
+        # bit-exact, NaN-safe
+        assert np.array([c, s0, s1]).tobytes() == out.tobytes()
+    # the degenerate branches (improc.cpp:117-125) are present in the vectors
+    assert (k["out"][:, 1] == 0).any() and (k["out"][:, 2] == 0).any()
+    assert ((k["out"][:, 1] == 0) & (k["out"][:, 2] == 0) & (k["out"][:, 0] == 0)).any()
+
+
+def test_a11_matches_reference_golden(oracle):
+    k = np.load(os.path.join(G, "a11_ref_kat.npz"))
+    ru, rv, rf, _ = oracle.smoe_search(k["image"], k["patch"], k["puinv3"], k["centres"])
+    assert (ru == k["res_u"]).all() and (rv == k["res_v"]).all() and (rf == k["res_flag"]).all()
+    assert rf.any() and not rf.all()
+
+
+def test_a1_live_reference_random(oracle, refimpl):
+    rng = np.random.default_rng(7)
+    for B in (11, 15, 9):
+        img = rng.integers(0, 256, (40, 50), dtype=np.uint8)
+        for _ in range(200):
+            patch = rng.integers(0, 256, (B, B), dtype=np.uint8)
+            x1, y1 = int(rng.integers(0, 50 - B)), int(rng.integers(0, 40 - B))
+            a = oracle.correlate2_warning(patch, img, x1, y1)
+            b = oracle.correlate2_warning(patch, img, x1, y1, use_ref=True)
+            assert np.array(a).tobytes() == np.array(b).tobytes()
+
+
+def test_a11_live_reference_random(oracle, refimpl):
+    from scenelib2_b200 import synth
+    rng = np.random.default_rng(11)
+    img = synth.make_texture(rng, 96, 128)
+    img[20:50, 30:70] = 90
+    for B in (11, 15):
+        patch = img[60:60 + B, 80:80 + B].copy()
+        K = 20
+        centres = np.column_stack([rng.uniform(0, 128, K), rng.uniform(0, 96, K)])
+        centres[:4] = [[80 + B // 2 + 0.4, 60 + B // 2 + 0.6]] * 4
+        sx, sy = rng.uniform(1.5, 6, K), rng.uniform(1.5, 6, K)
+        rho = rng.uniform(-0.8, 0.8, K)
+        pu = []
+        for a, b, r in zip(sx, sy, rho):
+            Si = np.linalg.inv(np.array([[a * a, r * a * b], [r * a * b, b * b]]))
+            pu.append([Si[0, 0], Si[0, 1], Si[1, 1]])
+        pu = np.array(pu)
+        a = oracle.smoe_search(img, patch, pu, centres)
+        b = oracle.smoe_search(img, patch, pu, centres, use_ref=True)
+        for x, y in zip(a[:3], b[:3]):
+            assert (x == y).all()
+
+
+def test_a2_equals_a11_where_they_coincide(oracle):
+    """A2 (monoslam.cpp:401-477) and A11 share the scan; with integer+0.0 centres (rounding ==
+    truncation), image sigma >= 10 everywhere and one ellipse they must agree exactly."""
+    from scenelib2_b200 import synth
+    rng = np.random.default_rng(5)
+    img = synth.make_texture(rng, 100, 140)
+    B = 11
+    for _ in range(10):
+        cx, cy = int(rng.integers(10, 130)), int(rng.integers(10, 90))
+        patch = img[cy - 5:cy + 6, cx - 5:cx + 6].copy()
+        c = np.array([[cx + int(rng.integers(-4, 5)), cy + int(rng.integers(-4, 5))]], float)
+        a, b, r = rng.uniform(2, 7), rng.uniform(2, 7), rng.uniform(-0.7, 0.7)
+        Si = np.linalg.inv(np.array([[a * a, r * a * b], [r * a * b, b * b]]))
+        pu = np.array([[Si[0, 0], Si[0, 1], Si[1, 1]]])
+        u, v, f, best = oracle.elliptical_search(img, patch[None], c, pu)
+        ru, rv, rf, rbest = oracle.smoe_search(img, patch, pu, c)
+        assert (u[0], v[0], f[0]) == (ru[0], rv[0], rf[0])
+        assert best[0] == rbest[0]
