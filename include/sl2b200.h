@@ -1,0 +1,156 @@
+/* sl2b200.h — C ABI of libsl2b200.so: the B200-native (sm_100a) implementation of the
+ * SceneLib2 per-frame EKF-MonoSLAM hot path.
+ *
+ * The reference (hanmekim/SceneLib2) has no plugin / FFI seam; the boundary is the set of C++
+ * member functions on the hot path.  Each entry point below names the reference interface it
+ * replaces (paths relative to /root/reference/scenelib2/).  The C++ host shim under
+ * scenelib2_b200/host/ keeps the MonoSLAM / Kalman / Feature class surface on top of this ABI
+ * (INTEGRATION.md shows the binding a maintainer would add).
+ *
+ * Conventions
+ *   - return 0 on success, negative on error; sl2_last_error() gives the message.
+ *   - all pointers are caller-owned HOST memory unless the name ends in _dev.
+ *   - matrices are column-major FP64 (Eigen's default); images are row-major u8.
+ *   - one context per GPU; calls on one context are serialised by the caller; work is queued
+ *     on the context's CUDA stream and functions that return data synchronise that stream.
+ *   - a context holds `num_streams` independent camera streams (one EKF + one frame each);
+ *     stream_id selects one of them.  Batched entry points (sl2_step*) advance all of them.
+ *   - NO CPU fallback: every function fails with SL2_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef SL2B200_H
+#define SL2B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SL2_OK 0
+#define SL2_ERR_ARG (-1)
+#define SL2_ERR_CUDA (-2)
+#define SL2_ERR_STATE (-3)
+
+#define SL2_MAX_FEATURES 128 /* per stream; state dimension n = 13 + 3 * features <= 397 */
+
+typedef struct sl2_ctx sl2_ctx;
+
+typedef struct sl2_config {
+  int32_t device;      /* CUDA device ordinal */
+  int32_t num_streams; /* independent camera streams resident in this context (>= 1) */
+  int32_t frame_slots; /* frames kept in HBM per stream (ring, >= 1) */
+  int32_t width, height;
+  int32_t boxsize;      /* BOXSIZE: 11 (MonoSLAM::kBoxSize_, monoslam.cpp:48) or 15 */
+  int32_t max_features; /* capacity per stream, <= SL2_MAX_FEATURES */
+  int32_t number_of_features_to_select; /* params.number_of_features_to_select (cfg:60) */
+  int32_t search_tile_radius; /* search half-extent served by ONE TMA window tile (default 20);
+                                 larger ellipses are searched in several tiles */
+  double fku, fkv, u0, v0, kd1, sd; /* Camera::SetCameraParameters (camera.cpp:58-82) */
+  double delta_t;                   /* params.delta_t (cfg:59) */
+  double search_override[3];        /* benchmark only: fixed (P00,P01,P11); P00 <= 0 = use S_i */
+  int32_t minimum_attempted_measurements_of_feature; /* monoslam.cpp:1875 (10) */
+  double successful_match_fraction;                  /* monoslam.cpp:1876 (0.5) */
+  void *cuda_stream; /* optional cudaStream_t to run on (e.g. torch's current stream); NULL = own */
+} sl2_config;
+
+/* fills *cfg with the reference's defaults (data/SceneLib2.cfg:24-31,59-61; monoslam.cpp:47-49) */
+void sl2_default_config(sl2_config *cfg);
+
+int sl2_create(const sl2_config *cfg, sl2_ctx **out);
+void sl2_destroy(sl2_ctx *ctx);
+const char *sl2_last_error(const sl2_ctx *ctx); /* ctx may be NULL: error of the last failed create */
+int sl2_sync(sl2_ctx *ctx);
+/* library self-description: "sl2b200 <version> sm_100a" */
+const char *sl2_version(void);
+
+/* ---- frames (replaces the cv::Mat `frame` argument of MonoSLAM::GoOneStep, monoslam.cpp:108) */
+/* one stream, one slot; `stride` = bytes between image rows */
+int sl2_set_frame(sl2_ctx *ctx, int32_t stream_id, int32_t slot, const uint8_t *gray, size_t stride);
+/* all streams of a slot at once: gray is [num_streams][height][width] contiguous (pinned memory
+ * makes the copy asynchronous) */
+int sl2_set_frames(sl2_ctx *ctx, int32_t slot, const uint8_t *gray);
+/* device-resident producer: copy device -> device, same layout as sl2_set_frames */
+int sl2_set_frames_dev(sl2_ctx *ctx, int32_t slot, const uint8_t *gray_dev);
+
+/* ---- map and state (Feature::y_/xp_org_/patch_, feature.cpp:108-149; MonoSLAM::xv_/Pxx_ and the
+ *      per-feature Pxy_/Pyy_/matrix_block_list_ blocks held as ONE dense P, layout of
+ *      construct_total_covariance, monoslam.cpp:518-546) */
+int sl2_set_features(sl2_ctx *ctx, int32_t stream_id, int32_t n, const double *y /* n x 3 */,
+                     const double *xp_org /* n x 7 */, const uint8_t *patches /* n x B x B */);
+int sl2_num_features(sl2_ctx *ctx, int32_t stream_id);
+int sl2_state_size(sl2_ctx *ctx, int32_t stream_id); /* 13 + 3 * features */
+int sl2_set_state(sl2_ctx *ctx, int32_t stream_id, const double *x, const double *P);
+int sl2_get_state(sl2_ctx *ctx, int32_t stream_id, double *x, double *P);
+/* MonoSLAM::delete_feature (monoslam.cpp:770-812): drop feature `index` and its rows/cols of P */
+int sl2_delete_feature(sl2_ctx *ctx, int32_t stream_id, int32_t index);
+
+/* ---- patch search --------------------------------------------------------------------------- */
+/* MonoSLAM::elliptical_search (monoslam.cpp:401-477) o correlate2_warning (improc/improc.cpp:
+ * 55-134), batched over n features of one stream.  feat_index[i] selects the stored template;
+ * centre = h_i, PuInv3 = (P00,P01,P11) of Sinv (monoslam.cpp:371-378).  u/v are the patch-centre
+ * pixel of the best match (unchanged, = -1, when nothing was accepted), found = corrmax <= 0.40,
+ * best = final corrmax (1e6 when nothing was accepted).  Outputs may be NULL. */
+int sl2_patch_search(sl2_ctx *ctx, int32_t stream_id, int32_t slot, int32_t n,
+                     const int32_t *feat_index, const double *centre /* n x 2 */,
+                     const double *PuInv3 /* n x 3 */, int32_t *u, int32_t *v, uint8_t *found,
+                     double *best);
+/* per-candidate scores of ONE feature over its clamped search box (urel-major, vrel-minor), for
+ * bit-level parity of correlate2_warning: box6 = (urelstart, urelfinish, vrelstart, vrelfinish,
+ * ucentre, vcentre); corr/sd_image/inside have (urelfinish-urelstart+1)*(vrelfinish-vrelstart+1)
+ * entries (capacity given by cap); candidates outside the ellipse carry corr = NaN. */
+int sl2_score_map(sl2_ctx *ctx, int32_t stream_id, int32_t slot, int32_t feat_index,
+                  const double *centre, const double *PuInv3, int32_t *box6, double *corr,
+                  double *sd_image, uint8_t *inside, size_t cap);
+/* SearchMultipleOverlappingEllipses::search (improc/search_multiple_overlapping_ellipses.cpp:
+ * 106-196): K ellipses sharing the template of feat_index. */
+int sl2_smoe_search(sl2_ctx *ctx, int32_t stream_id, int32_t slot, int32_t feat_index, int32_t K,
+                    const double *PuInv3 /* K x 3 */, const double *centres /* K x 2 */,
+                    int32_t *res_u, int32_t *res_v, uint8_t *res_flag);
+
+/* ---- EKF ------------------------------------------------------------------------------------ */
+/* Kalman::KalmanFilterPredict (kalman.cpp:50-69) incl. MotionModel::func_fv_and_dfv_by_dxv and
+ * func_Q (motion_model.cpp:84-217) evaluated on the device.  u3 = control accelerations (zero in
+ * GoOneStep, monoslam.cpp:114-115); NULL = zero. */
+int sl2_ekf_predict(sl2_ctx *ctx, int32_t stream_id, const double *u3);
+/* MonoSLAM::auto_select_n_features (monoslam.cpp:187-254): per-feature prediction (h, dh/dxv,
+ * dh/dy, R, S: monoslam.cpp:289-308), visibility (full_feature_model.cpp:103-170) and selection.
+ * Returns the number of visible features (>= 0) or a negative error. */
+int sl2_predict_measurements(sl2_ctx *ctx, int32_t stream_id);
+/* MonoSLAM::make_measurements (monoslam.cpp:336-359) for the features selected by
+ * sl2_predict_measurements; returns the number of successful measurements. */
+int sl2_make_measurements(sl2_ctx *ctx, int32_t stream_id, int32_t slot);
+/* Kalman::KalmanFilterUpdate (kalman.cpp:72-119) with host-supplied measurement rows, in the
+ * order of construct_total_measurement_stuff (monoslam.cpp:548-572): row pair k belongs to
+ * feature feat_index[k]; H_xv is (2k_meas) x 13 row-major, H_y (2k_meas) x 3 row-major,
+ * R k_meas x (2x2 col-major), nu 2k_meas.  m = 2 * k_meas. */
+int sl2_ekf_update(sl2_ctx *ctx, int32_t stream_id, int32_t m, const int32_t *feat_index,
+                   const double *H_xv, const double *H_y, const double *R, const double *nu);
+/* same, using the device-resident predictions/measurements of the two calls above */
+int sl2_ekf_update_measured(sl2_ctx *ctx, int32_t stream_id);
+/* MonoSLAM::normalise_state (monoslam.cpp:616-637) + the symmetrisation of GoOneStep
+ * (monoslam.cpp:143-150).  sl2_ekf_update* already include both; exposed for the shim. */
+int sl2_normalise_state(sl2_ctx *ctx, int32_t stream_id);
+
+/* ---- fused step: MonoSLAM::GoOneStep (monoslam.cpp:108-180), tracking only, for ALL streams of
+ *      the context: predict -> select -> measure -> update -> normalise -> cull -> symmetrise.
+ *      Everything stays on the device; no host round trip inside the frame. */
+int sl2_step(sl2_ctx *ctx, int32_t slot);
+/* end-to-end form: host frames in ([num_streams][height][width]), camera states out
+ * (xv_out: [num_streams][13], may be NULL).  Copies run on the context's stream. */
+int sl2_step_host(sl2_ctx *ctx, int32_t slot, const uint8_t *gray, double *xv_out);
+
+/* ---- read-back of per-feature results (Feature::h_/z_/S_/flags/counters, feature.h:96-140) */
+int sl2_get_features(sl2_ctx *ctx, int32_t stream_id, double *h /* n x 2 */, double *z /* n x 2 */,
+                     double *S /* n x 4 col-major */, uint8_t *flags /* bit0 selected, bit1 successful */,
+                     int32_t *attempted, int32_t *successful, int32_t *select_rank);
+/* device-time of the kernels of the last sl2_step (ms): [0] predict+select, [1] patch search,
+ * [2] EKF update, [3] cull.  Valid after sl2_enable_timing(ctx, 1). */
+int sl2_enable_timing(sl2_ctx *ctx, int32_t on);
+int sl2_last_step_times(sl2_ctx *ctx, float *ms4);
+/* kernels launched by this context since creation */
+int64_t sl2_launch_count(const sl2_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SL2B200_H */

@@ -1,0 +1,33 @@
+"""In-tree build of libsl2b200.so (sm_100a only).  nvcc cross-compiles without a GPU."""
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SOURCES = ["csrc/api.cu", "csrc/search.cu", "csrc/ekf.cu"]
+HEADERS = ["csrc/sl2_common.cuh", "../include/sl2b200.h"]
+LIB = os.path.join(HERE, "libsl2b200.so")
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(HERE, f)) > t for f in SOURCES + HEADERS)
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA source for sm_100a into scenelib2_b200/libsl2b200.so."""
+    if not force and not _stale():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+           "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "-o", LIB] + SOURCES
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+    subprocess.check_call(cmd, cwd=HERE)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

@@ -1,0 +1,706 @@
+// api.cu — context management and the extern "C" surface declared in include/sl2b200.h.
+// Host side only orchestrates: every arithmetic step of the hot path runs in the sm_100a
+// kernels of search.cu / ekf.cu.  There is deliberately no CPU fallback.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sl2b200.h"
+#include "sl2_common.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+};
+
+}  // namespace
+
+struct sl2_ctx {
+  sl2_config cfg;
+  Sl2Dev d;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  CUtensorMap tmap;
+  std::string err;
+  std::vector<void *> allocs;
+  // staging
+  uint8_t *stg_dev = nullptr;   // device scratch for staged API calls
+  size_t stg_bytes = 0;
+  uint8_t *stg_host = nullptr;  // pinned
+  int64_t launches = 0;
+  bool timing = false;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  float last_ms[4] = {0, 0, 0, 0};
+};
+
+namespace {
+
+int fail(sl2_ctx *c, int code, const std::string &msg) {
+  if (c) c->err = msg;
+  else g_create_error = msg;
+  return code;
+}
+
+#define CU_TRY(c, expr)                                                              \
+  do {                                                                               \
+    cudaError_t e__ = (expr);                                                        \
+    if (e__ != cudaSuccess)                                                          \
+      return fail((c), SL2_ERR_CUDA,                                                 \
+                  std::string(#expr) + ": " + cudaGetErrorString(e__));             \
+  } while (0)
+
+template <typename T>
+cudaError_t dev_alloc(sl2_ctx *c, T **p, size_t count, bool zero = true) {
+  void *q = nullptr;
+  cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 256);
+  if (e != cudaSuccess) return e;
+  c->allocs.push_back(q);
+  if (zero) {
+    e = cudaMemsetAsync(q, 0, count * sizeof(T) + 256, c->stream);
+    if (e != cudaSuccess) return e;
+  }
+  *p = static_cast<T *>(q);
+  return cudaSuccess;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                    const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                    const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_tensor_map(sl2_ctx *c) {
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CU_TRY(c, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess)
+    return fail(c, SL2_ERR_CUDA, "cuTensorMapEncodeTiled not available in this driver");
+  const Sl2Dev &d = c->d;
+  cuuint64_t dims[3] = {(cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.slots * d.B};
+  cuuint64_t strides[2] = {(cuuint64_t)d.pitch, (cuuint64_t)d.pitch * d.H};
+  cuuint32_t box[3] = {(cuuint32_t)d.tile_w, (cuuint32_t)d.tile_h, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = ((PFN_encodeTiled)fn)(&c->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, d.frames, dims,
+                                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char b[96];
+    snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    return fail(c, SL2_ERR_CUDA, b);
+  }
+  return SL2_OK;
+}
+
+bool bad_stream(sl2_ctx *c, int s) { return !c || s < 0 || s >= c->cfg.num_streams; }
+bool bad_slot(sl2_ctx *c, int s) { return s < 0 || s >= c->cfg.frame_slots; }
+
+int stage_reserve(sl2_ctx *c, size_t bytes) {
+  if (bytes <= c->stg_bytes) return SL2_OK;
+  if (c->stg_dev) {
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->stg_dev);
+    cudaFreeHost(c->stg_host);
+    c->stg_dev = nullptr;
+    c->stg_host = nullptr;
+  }
+  bytes = (bytes + 4095) & ~(size_t)4095;
+  CU_TRY(c, cudaMalloc((void **)&c->stg_dev, bytes));
+  CU_TRY(c, cudaMallocHost((void **)&c->stg_host, bytes));
+  c->stg_bytes = bytes;
+  return SL2_OK;
+}
+
+int device_nfeat(sl2_ctx *c, int s, int *out) {
+  CU_TRY(c, cudaMemcpyAsync(out, c->d.nfeat + s, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return SL2_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *sl2_version(void) { return "sl2b200 0.1.0 sm_100a"; }
+
+void sl2_default_config(sl2_config *cfg) {
+  memset(cfg, 0, sizeof *cfg);
+  cfg->device = 0;
+  cfg->num_streams = 1;
+  cfg->frame_slots = 1;
+  cfg->width = 320;   // data/SceneLib2.cfg:24-31
+  cfg->height = 240;
+  cfg->boxsize = 11;  // monoslam.cpp:48
+  cfg->max_features = 100;
+  cfg->number_of_features_to_select = 10;  // cfg:60
+  cfg->search_tile_radius = 20;
+  cfg->fku = 195;
+  cfg->fkv = 195;
+  cfg->u0 = 162;
+  cfg->v0 = 125;
+  cfg->kd1 = 9e-06;
+  cfg->sd = 1;
+  cfg->delta_t = 0.033333333;  // cfg:59
+  cfg->minimum_attempted_measurements_of_feature = 10;  // monoslam.cpp:1875
+  cfg->successful_match_fraction = 0.5;                 // monoslam.cpp:1876
+  cfg->cuda_stream = nullptr;
+}
+
+const char *sl2_last_error(const sl2_ctx *ctx) {
+  return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+int sl2_create(const sl2_config *cfg, sl2_ctx **out) {
+  if (!cfg || !out) return fail(nullptr, SL2_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (cfg->num_streams < 1 || cfg->frame_slots < 1 || cfg->width < 16 || cfg->height < 16 ||
+      cfg->max_features < 1 || cfg->max_features > SL2_MAX_FEATURES)
+    return fail(nullptr, SL2_ERR_ARG, "bad sizes in sl2_config");
+  if (cfg->boxsize != 11 && cfg->boxsize != 15)
+    return fail(nullptr, SL2_ERR_ARG, "boxsize must be 11 or 15");
+  if (cfg->width < cfg->boxsize || cfg->height < cfg->boxsize)
+    return fail(nullptr, SL2_ERR_ARG, "frame smaller than the patch");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, SL2_ERR_CUDA,
+                std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                    " (libsl2b200 has no CPU fallback)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, SL2_ERR_ARG, "bad device ordinal");
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, cfg->device);
+  if (e != cudaSuccess) return fail(nullptr, SL2_ERR_CUDA, cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, SL2_ERR_CUDA, "libsl2b200 is built for sm_100a (B200) only");
+  e = cudaSetDevice(cfg->device);
+  if (e != cudaSuccess) return fail(nullptr, SL2_ERR_CUDA, cudaGetErrorString(e));
+
+  sl2_ctx *c = new sl2_ctx();
+  c->cfg = *cfg;
+  if (cfg->cuda_stream) {
+    c->stream = static_cast<cudaStream_t>(cfg->cuda_stream);
+  } else {
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      delete c;
+      return fail(nullptr, SL2_ERR_CUDA, cudaGetErrorString(e));
+    }
+    c->own_stream = true;
+  }
+  Sl2Dev &d = c->d;
+  memset(&d, 0, sizeof d);
+  d.B = cfg->num_streams;
+  d.Nmax = cfg->max_features;
+  d.W = cfg->width;
+  d.H = cfg->height;
+  d.pitch = (cfg->width + 15) & ~15;
+  d.slots = cfg->frame_slots;
+  d.box = cfg->boxsize;
+  d.ld = ((SL2_NXV + 3 * d.Nmax) + 7) & ~7;
+  d.mmax = 2 * d.Nmax;
+  d.ldg = ((d.mmax + SL2_NXV + 3 * d.Nmax + 1) + 7) & ~7;
+  d.n_select = cfg->number_of_features_to_select;
+  const int radius = cfg->search_tile_radius > 0 ? cfg->search_tile_radius : 20;
+  d.tile_h = 2 * radius + d.box;
+  if (d.tile_h > 255) d.tile_h = 255;
+  d.tile_w = (2 * radius + d.box + 15) & ~15;
+  if (d.tile_w > 256) d.tile_w = 256;
+  d.min_attempts = cfg->minimum_attempted_measurements_of_feature;
+  d.match_fraction = cfg->successful_match_fraction;
+  d.cam[0] = cfg->width;
+  d.cam[1] = cfg->height;
+  d.cam[2] = cfg->fku;
+  d.cam[3] = cfg->fkv;
+  d.cam[4] = cfg->u0;
+  d.cam[5] = cfg->v0;
+  d.cam[6] = cfg->kd1;
+  d.cam[7] = cfg->sd;
+  d.dt = cfg->delta_t;
+  for (int i = 0; i < 3; ++i) d.ovr[i] = cfg->search_override[i];
+
+  const size_t B = d.B, N = d.Nmax;
+  bool ok = true;
+#define ALLOC(ptr, count) ok = ok && (dev_alloc(c, &(ptr), (count)) == cudaSuccess)
+  ALLOC(d.frames, (size_t)d.slots * B * d.H * d.pitch);
+  ALLOC(d.patches, B * N * d.box * 16);
+  ALLOC(d.x, B * d.ld);
+  ALLOC(d.P, B * d.ld * d.ld);
+  ALLOC(d.G, B * d.mmax * d.ldg);
+  ALLOC(d.nfeat, B);
+  ALLOC(d.xp_org, B * N * 7);
+  ALLOC(d.attempted, B * N);
+  ALLOC(d.successful, B * N);
+  ALLOC(d.h, B * N * 2);
+  ALLOC(d.S, B * N * 4);
+  ALLOC(d.Rvar, B * N);
+  ALLOC(d.dh_dxp, B * N * 14);
+  ALLOC(d.dh_dy, B * N * 6);
+  ALLOC(d.sel_rank, B * N);
+  ALLOC(d.z_uv, B * N * 2);
+  ALLOC(d.found, B * N);
+  ALLOC(d.best, B * N);
+  ALLOC(d.job_feat, B * N);
+  ALLOC(d.job_centre, B * N * 2);
+  ALLOC(d.job_puinv, B * N * 3);
+  ALLOC(d.nsel, B);
+  ALLOC(d.nvisible, B);
+  ALLOC(d.nmeas, B);
+#undef ALLOC
+  if (!ok) {
+    const std::string m = std::string("cudaMalloc failed: ") + cudaGetErrorString(cudaGetLastError());
+    sl2_destroy(c);
+    return fail(nullptr, SL2_ERR_CUDA, m);
+  }
+  int rc = make_tensor_map(c);
+  if (rc == SL2_OK) rc = stage_reserve(c, 1 << 20);
+  if (rc == SL2_OK) {
+    for (int i = 0; i < 5 && rc == SL2_OK; ++i)
+      if (cudaEventCreate(&c->ev[i]) != cudaSuccess) rc = SL2_ERR_CUDA;
+  }
+  if (rc == SL2_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = SL2_ERR_CUDA;
+  if (rc != SL2_OK) {
+    g_create_error = c->err.empty() ? "context initialisation failed" : c->err;
+    sl2_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return SL2_OK;
+}
+
+void sl2_destroy(sl2_ctx *c) {
+  if (!c) return;
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (void *p : c->allocs) cudaFree(p);
+  if (c->stg_dev) cudaFree(c->stg_dev);
+  if (c->stg_host) cudaFreeHost(c->stg_host);
+  for (auto &e : c->ev)
+    if (e) cudaEventDestroy(e);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int sl2_sync(sl2_ctx *c) {
+  if (!c) return SL2_ERR_ARG;
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return SL2_OK;
+}
+
+int64_t sl2_launch_count(const sl2_ctx *c) { return c ? c->launches : 0; }
+
+// ---- frames -----------------------------------------------------------------------------------
+int sl2_set_frame(sl2_ctx *c, int32_t s, int32_t slot, const uint8_t *gray, size_t stride) {
+  if (bad_stream(c, s) || bad_slot(c, slot) || !gray) return fail(c, SL2_ERR_ARG, "sl2_set_frame: bad argument");
+  const Sl2Dev &d = c->d;
+  uint8_t *dst = d.frames + ((size_t)slot * d.B + s) * d.H * d.pitch;
+  CU_TRY(c, cudaMemcpy2DAsync(dst, d.pitch, gray, stride, d.W, d.H, cudaMemcpyHostToDevice, c->stream));
+  return SL2_OK;
+}
+
+static int set_frames_any(sl2_ctx *c, int32_t slot, const uint8_t *gray, cudaMemcpyKind kind) {
+  if (!c || bad_slot(c, slot) || !gray) return fail(c, SL2_ERR_ARG, "sl2_set_frames: bad argument");
+  const Sl2Dev &d = c->d;
+  uint8_t *dst = d.frames + (size_t)slot * d.B * d.H * d.pitch;
+  if (d.pitch == d.W) {
+    CU_TRY(c, cudaMemcpyAsync(dst, gray, (size_t)d.B * d.H * d.W, kind, c->stream));
+  } else {
+    CU_TRY(c, cudaMemcpy2DAsync(dst, d.pitch, gray, d.W, d.W, (size_t)d.B * d.H, kind, c->stream));
+  }
+  return SL2_OK;
+}
+int sl2_set_frames(sl2_ctx *c, int32_t slot, const uint8_t *gray) {
+  return set_frames_any(c, slot, gray, cudaMemcpyHostToDevice);
+}
+int sl2_set_frames_dev(sl2_ctx *c, int32_t slot, const uint8_t *gray_dev) {
+  return set_frames_any(c, slot, gray_dev, cudaMemcpyDeviceToDevice);
+}
+
+// ---- map / state ------------------------------------------------------------------------------
+int sl2_set_features(sl2_ctx *c, int32_t s, int32_t n, const double *y, const double *xp_org,
+                     const uint8_t *patches) {
+  if (bad_stream(c, s) || n < 0 || n > c->cfg.max_features || (n && (!y || !xp_org || !patches)))
+    return fail(c, SL2_ERR_ARG, "sl2_set_features: bad argument");
+  const Sl2Dev &d = c->d;
+  const int box = d.box;
+  const size_t pb = (size_t)n * box * 16, yb = (size_t)n * 3 * 8, xb = (size_t)n * 7 * 8;
+  int rc = stage_reserve(c, pb + yb + xb + 64);
+  if (rc) return rc;
+  CU_TRY(c, cudaStreamSynchronize(c->stream));  // staging buffer reuse
+  uint8_t *hp = c->stg_host;
+  memset(hp, 0, pb);
+  for (int i = 0; i < n; ++i)
+    for (int r = 0; r < box; ++r)
+      memcpy(hp + ((size_t)i * box + r) * 16, patches + ((size_t)i * box + r) * box, box);
+  memcpy(hp + pb, y, yb);
+  memcpy(hp + pb + yb, xp_org, xb);
+  int nn = n;
+  memcpy(hp + pb + yb + xb, &nn, sizeof(int));
+  const size_t fb = (size_t)s * d.Nmax;
+  if (n) {
+    CU_TRY(c, cudaMemcpyAsync(d.patches + fb * box * 16, hp, pb, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(d.x + (size_t)s * d.ld + SL2_NXV, hp + pb, yb, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(d.xp_org + fb * 7, hp + pb + yb, xb, cudaMemcpyHostToDevice, c->stream));
+  }
+  CU_TRY(c, cudaMemcpyAsync(d.nfeat + s, hp + pb + yb + xb, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaMemsetAsync(d.attempted + fb, 0, sizeof(int) * d.Nmax, c->stream));
+  CU_TRY(c, cudaMemsetAsync(d.successful + fb, 0, sizeof(int) * d.Nmax, c->stream));
+  CU_TRY(c, cudaMemsetAsync(d.sel_rank + fb, 0xff, sizeof(int) * d.Nmax, c->stream));
+  CU_TRY(c, cudaMemsetAsync(d.found + fb, 0, d.Nmax, c->stream));
+  CU_TRY(c, cudaMemsetAsync(d.job_feat + fb, 0xff, sizeof(int) * d.Nmax, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return SL2_OK;
+}
+
+int sl2_num_features(sl2_ctx *c, int32_t s) {
+  if (bad_stream(c, s)) return fail(c, SL2_ERR_ARG, "bad stream");
+  int n = 0;
+  int rc = device_nfeat(c, s, &n);
+  return rc ? rc : n;
+}
+
+int sl2_state_size(sl2_ctx *c, int32_t s) {
+  const int n = sl2_num_features(c, s);
+  return n < 0 ? n : SL2_NXV + 3 * n;
+}
+
+int sl2_set_state(sl2_ctx *c, int32_t s, const double *x, const double *P) {
+  if (bad_stream(c, s) || !x || !P) return fail(c, SL2_ERR_ARG, "sl2_set_state: bad argument");
+  const int n = sl2_state_size(c, s);
+  if (n < 0) return n;
+  const Sl2Dev &d = c->d;
+  CU_TRY(c, cudaMemcpyAsync(d.x + (size_t)s * d.ld, x, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaMemcpy2DAsync(d.P + (size_t)s * d.ld * d.ld, sizeof(double) * d.ld, P,
+                              sizeof(double) * n, sizeof(double) * n, n, cudaMemcpyHostToDevice,
+                              c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return SL2_OK;
+}
+
+int sl2_get_state(sl2_ctx *c, int32_t s, double *x, double *P) {
+  if (bad_stream(c, s)) return fail(c, SL2_ERR_ARG, "sl2_get_state: bad argument");
+  const int n = sl2_state_size(c, s);
+  if (n < 0) return n;
+  const Sl2Dev &d = c->d;
+  if (x)
+    CU_TRY(c, cudaMemcpyAsync(x, d.x + (size_t)s * d.ld, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+  if (P)
+    CU_TRY(c, cudaMemcpy2DAsync(P, sizeof(double) * n, d.P + (size_t)s * d.ld * d.ld,
+                                sizeof(double) * d.ld, sizeof(double) * n, n,
+                                cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return SL2_OK;
+}
+
+int sl2_delete_feature(sl2_ctx *c, int32_t s, int32_t index) {
+  if (bad_stream(c, s)) return fail(c, SL2_ERR_ARG, "bad stream");
+  const int n = sl2_num_features(c, s);
+  if (n < 0) return n;
+  if (index < 0 || index >= n) return fail(c, SL2_ERR_ARG, "sl2_delete_feature: bad index");
+  CU_TRY(c, sl2_launch_cull(c->d, s, 1, index, c->stream));
+  ++c->launches;
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return SL2_OK;
+}
+
+// ---- patch search -----------------------------------------------------------------------------
+static int search_staged(sl2_ctx *c, int32_t s, int32_t slot, int32_t n, const int32_t *feat_index,
+                         int32_t single_feat, const double *centre, const double *PuInv3,
+                         int32_t *u, int32_t *v, uint8_t *found, double *best, int smoe) {
+  if (bad_stream(c, s) || bad_slot(c, slot) || n < 0 || !centre || !PuInv3)
+    return fail(c, SL2_ERR_ARG, "patch search: bad argument");
+  if (n == 0) return SL2_OK;
+  int nf = 0;
+  int rc = device_nfeat(c, s, &nf);
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i) {
+    const int f = feat_index ? feat_index[i] : single_feat;
+    if (f < 0 || f >= nf) return fail(c, SL2_ERR_ARG, "patch search: feature index out of range");
+  }
+  // staging layout: centre(2n) puinv(3n) best(n) | feat(n) uv(2n) | found(n)
+  const size_t o_c = 0, o_p = o_c + 16 * (size_t)n, o_b = o_p + 24 * (size_t)n,
+               o_f = o_b + 8 * (size_t)n, o_uv = o_f + 4 * (size_t)n, o_fd = o_uv + 8 * (size_t)n,
+               total = o_fd + n + 64;
+  rc = stage_reserve(c, total);
+  if (rc) return rc;
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  uint8_t *hp = c->stg_host;
+  memcpy(hp + o_c, centre, 16 * (size_t)n);
+  memcpy(hp + o_p, PuInv3, 24 * (size_t)n);
+  int *hf = reinterpret_cast<int *>(hp + o_f);
+  for (int i = 0; i < n; ++i) hf[i] = feat_index ? feat_index[i] : single_feat;
+  CU_TRY(c, cudaMemcpyAsync(c->stg_dev, hp, o_uv, cudaMemcpyHostToDevice, c->stream));
+  SearchLaunch L = {};
+  L.job_centre = reinterpret_cast<const double *>(c->stg_dev + o_c);
+  L.job_puinv = reinterpret_cast<const double *>(c->stg_dev + o_p);
+  L.job_feat = reinterpret_cast<const int *>(c->stg_dev + o_f);
+  L.jobs_per_stream = n;
+  L.stream_lo = s;
+  L.stream_cnt = 1;
+  L.slot = slot;
+  L.out_uv = reinterpret_cast<int *>(c->stg_dev + o_uv);
+  L.out_found = c->stg_dev + o_fd;
+  L.out_best = reinterpret_cast<double *>(c->stg_dev + o_b);
+  L.scatter_to_features = 0;
+  L.smoe_mode = smoe;
+  CU_TRY(c, sl2_launch_search(c->d, c->tmap, L, c->stream));
+  ++c->launches;
+  CU_TRY(c, cudaMemcpyAsync(hp + o_b, c->stg_dev + o_b, total - 64 - o_b, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  const int *huv = reinterpret_cast<const int *>(hp + o_uv);
+  const double *hb = reinterpret_cast<const double *>(hp + o_b);
+  for (int i = 0; i < n; ++i) {
+    if (u) u[i] = huv[2 * i];
+    if (v) v[i] = huv[2 * i + 1];
+    if (found) found[i] = hp[o_fd + i];
+    if (best) best[i] = hb[i];
+  }
+  return SL2_OK;
+}
+
+int sl2_patch_search(sl2_ctx *c, int32_t s, int32_t slot, int32_t n, const int32_t *feat_index,
+                     const double *centre, const double *PuInv3, int32_t *u, int32_t *v,
+                     uint8_t *found, double *best) {
+  if (n > 0 && !feat_index) return fail(c, SL2_ERR_ARG, "sl2_patch_search: feat_index is null");
+  return search_staged(c, s, slot, n, feat_index, 0, centre, PuInv3, u, v, found, best, 0);
+}
+
+int sl2_smoe_search(sl2_ctx *c, int32_t s, int32_t slot, int32_t feat_index, int32_t K,
+                    const double *PuInv3, const double *centres, int32_t *res_u, int32_t *res_v,
+                    uint8_t *res_flag) {
+  return search_staged(c, s, slot, K, nullptr, feat_index, centres, PuInv3, res_u, res_v, res_flag,
+                       nullptr, 1);
+}
+
+int sl2_score_map(sl2_ctx *c, int32_t s, int32_t slot, int32_t feat, const double *centre,
+                  const double *PuInv3, int32_t *box6, double *corr, double *sd_image,
+                  uint8_t *inside, size_t cap) {
+  if (bad_stream(c, s) || bad_slot(c, slot) || !centre || !PuInv3 || !box6)
+    return fail(c, SL2_ERR_ARG, "sl2_score_map: bad argument");
+  int nf = 0;
+  int rc = device_nfeat(c, s, &nf);
+  if (rc) return rc;
+  if (feat < 0 || feat >= nf) return fail(c, SL2_ERR_ARG, "sl2_score_map: bad feature index");
+  // staging: centre(2) puinv(3) feat(int, 8 B slot) box(6 int -> 32 B) corr(cap) sd(cap) inside(cap)
+  const size_t o_box = 48, o_corr = 80, o_sd = o_corr + 8 * cap, o_in = o_sd + 8 * cap,
+               total = o_in + cap + 64;
+  rc = stage_reserve(c, total);
+  if (rc) return rc;
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  uint8_t *hp = c->stg_host;
+  memcpy(hp, centre, 16);
+  memcpy(hp + 16, PuInv3, 24);
+  int f = feat;
+  memcpy(hp + 40, &f, sizeof(int));
+  CU_TRY(c, cudaMemcpyAsync(c->stg_dev, hp, 48, cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaMemsetAsync(c->stg_dev + o_box, 0xff, total - o_box, c->stream));  // NaN / 0xff fill
+  CU_TRY(c, sl2_launch_score_map(c->d, c->tmap, s, slot, feat,
+                                 reinterpret_cast<const double *>(c->stg_dev),
+                                 reinterpret_cast<int *>(c->stg_dev + o_box),
+                                 reinterpret_cast<double *>(c->stg_dev + o_corr),
+                                 reinterpret_cast<double *>(c->stg_dev + o_sd), c->stg_dev + o_in,
+                                 (int)cap, c->stream));
+  ++c->launches;
+  CU_TRY(c, cudaMemcpyAsync(hp + o_box, c->stg_dev + o_box, total - 64 - o_box, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  memcpy(box6, hp + o_box, 24);
+  if (corr) memcpy(corr, hp + o_corr, 8 * cap);
+  if (sd_image) memcpy(sd_image, hp + o_sd, 8 * cap);
+  if (inside) memcpy(inside, hp + o_in, cap);
+  return SL2_OK;
+}
+
+// ---- EKF ----------------------------------------------------------------------------------------
+int sl2_ekf_predict(sl2_ctx *c, int32_t s, const double *u3) {
+  if (bad_stream(c, s)) return fail(c, SL2_ERR_ARG, "bad stream");
+  const double *u_dev = nullptr;
+  if (u3) {
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    memcpy(c->stg_host, u3, 24);
+    CU_TRY(c, cudaMemcpyAsync(c->stg_dev, c->stg_host, 24, cudaMemcpyHostToDevice, c->stream));
+    u_dev = reinterpret_cast<const double *>(c->stg_dev);
+  }
+  CU_TRY(c, sl2_launch_predict(c->d, s, 1, u_dev, 1, 0, c->stream));
+  ++c->launches;
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return SL2_OK;
+}
+
+int sl2_predict_measurements(sl2_ctx *c, int32_t s) {
+  if (bad_stream(c, s)) return fail(c, SL2_ERR_ARG, "bad stream");
+  CU_TRY(c, sl2_launch_predict(c->d, s, 1, nullptr, 0, 1, c->stream));
+  ++c->launches;
+  int nv = 0;
+  CU_TRY(c, cudaMemcpyAsync(&nv, c->d.nvisible + s, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return nv;
+}
+
+int sl2_make_measurements(sl2_ctx *c, int32_t s, int32_t slot) {
+  if (bad_stream(c, s) || bad_slot(c, slot)) return fail(c, SL2_ERR_ARG, "bad stream/slot");
+  const Sl2Dev &d = c->d;
+  const size_t fb = (size_t)s * d.Nmax;
+  SearchLaunch L = {};
+  L.job_feat = d.job_feat + fb;
+  L.job_centre = d.job_centre + fb * 2;
+  L.job_puinv = d.job_puinv + fb * 3;
+  L.jobs_per_stream = d.Nmax;
+  L.stream_lo = s;
+  L.stream_cnt = 1;
+  L.slot = slot;
+  L.scatter_to_features = 1;
+  CU_TRY(c, sl2_launch_search(d, c->tmap, L, c->stream));
+  ++c->launches;
+  std::vector<uint8_t> f(d.Nmax);
+  CU_TRY(c, cudaMemcpyAsync(f.data(), d.found + fb, d.Nmax, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  int cnt = 0;
+  for (uint8_t b : f) cnt += b ? 1 : 0;
+  return cnt;
+}
+
+int sl2_ekf_update(sl2_ctx *c, int32_t s, int32_t m, const int32_t *feat_index, const double *H_xv,
+                   const double *H_y, const double *R, const double *nu) {
+  if (bad_stream(c, s) || m < 0 || (m & 1) || m > 2 * c->cfg.max_features)
+    return fail(c, SL2_ERR_ARG, "sl2_ekf_update: bad m");
+  if (m == 0) return SL2_OK;
+  if (!feat_index || !H_xv || !H_y || !R || !nu) return fail(c, SL2_ERR_ARG, "sl2_ekf_update: null argument");
+  const int K = m / 2;
+  int nf = 0;
+  int rc = device_nfeat(c, s, &nf);
+  if (rc) return rc;
+  for (int k = 0; k < K; ++k)
+    if (feat_index[k] < 0 || feat_index[k] >= nf) return fail(c, SL2_ERR_ARG, "sl2_ekf_update: bad feature index");
+  const size_t o_hx = 0, o_hy = o_hx + 8 * 26 * (size_t)K, o_r = o_hy + 8 * 6 * (size_t)K,
+               o_nu = o_r + 8 * 4 * (size_t)K, o_f = o_nu + 8 * 2 * (size_t)K,
+               total = o_f + 4 * (size_t)K + 64;
+  rc = stage_reserve(c, total);
+  if (rc) return rc;
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  uint8_t *hp = c->stg_host;
+  memcpy(hp + o_hx, H_xv, 8 * 26 * (size_t)K);
+  memcpy(hp + o_hy, H_y, 8 * 6 * (size_t)K);
+  memcpy(hp + o_r, R, 8 * 4 * (size_t)K);
+  memcpy(hp + o_nu, nu, 8 * 2 * (size_t)K);
+  memcpy(hp + o_f, feat_index, 4 * (size_t)K);
+  CU_TRY(c, cudaMemcpyAsync(c->stg_dev, hp, total - 64, cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, sl2_launch_update(c->d, s, 1, m, reinterpret_cast<const int *>(c->stg_dev + o_f),
+                              reinterpret_cast<const double *>(c->stg_dev + o_hx),
+                              reinterpret_cast<const double *>(c->stg_dev + o_hy),
+                              reinterpret_cast<const double *>(c->stg_dev + o_r),
+                              reinterpret_cast<const double *>(c->stg_dev + o_nu), 0, c->stream));
+  ++c->launches;
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return SL2_OK;
+}
+
+int sl2_ekf_update_measured(sl2_ctx *c, int32_t s) {
+  if (bad_stream(c, s)) return fail(c, SL2_ERR_ARG, "bad stream");
+  CU_TRY(c, sl2_launch_update(c->d, s, 1, -1, nullptr, nullptr, nullptr, nullptr, nullptr, 0, c->stream));
+  ++c->launches;
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return SL2_OK;
+}
+
+int sl2_normalise_state(sl2_ctx *c, int32_t s) {
+  if (bad_stream(c, s)) return fail(c, SL2_ERR_ARG, "bad stream");
+  CU_TRY(c, sl2_launch_update(c->d, s, 1, -1, nullptr, nullptr, nullptr, nullptr, nullptr, 1, c->stream));
+  ++c->launches;
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return SL2_OK;
+}
+
+// ---- fused step ---------------------------------------------------------------------------------
+static int step_enqueue(sl2_ctx *c, int32_t slot) {
+  const Sl2Dev &d = c->d;
+  const bool t = c->timing;
+  if (t) CU_TRY(c, cudaEventRecord(c->ev[0], c->stream));
+  CU_TRY(c, sl2_launch_predict(d, 0, d.B, nullptr, 1, 1, c->stream));
+  if (t) CU_TRY(c, cudaEventRecord(c->ev[1], c->stream));
+  SearchLaunch L = {};
+  L.job_feat = d.job_feat;
+  L.job_centre = d.job_centre;
+  L.job_puinv = d.job_puinv;
+  L.jobs_per_stream = d.Nmax;
+  L.stream_lo = 0;
+  L.stream_cnt = d.B;
+  L.slot = slot;
+  L.scatter_to_features = 1;
+  CU_TRY(c, sl2_launch_search(d, c->tmap, L, c->stream));
+  if (t) CU_TRY(c, cudaEventRecord(c->ev[2], c->stream));
+  CU_TRY(c, sl2_launch_update(d, 0, d.B, -1, nullptr, nullptr, nullptr, nullptr, nullptr, 0, c->stream));
+  if (t) CU_TRY(c, cudaEventRecord(c->ev[3], c->stream));
+  CU_TRY(c, sl2_launch_cull(d, 0, d.B, -1, c->stream));
+  if (t) CU_TRY(c, cudaEventRecord(c->ev[4], c->stream));
+  c->launches += 4;
+  return SL2_OK;
+}
+
+int sl2_step(sl2_ctx *c, int32_t slot) {
+  if (!c || bad_slot(c, slot)) return fail(c, SL2_ERR_ARG, "sl2_step: bad slot");
+  return step_enqueue(c, slot);
+}
+
+int sl2_step_host(sl2_ctx *c, int32_t slot, const uint8_t *gray, double *xv_out) {
+  if (!c || bad_slot(c, slot) || !gray) return fail(c, SL2_ERR_ARG, "sl2_step_host: bad argument");
+  int rc = sl2_set_frames(c, slot, gray);
+  if (rc) return rc;
+  rc = step_enqueue(c, slot);
+  if (rc) return rc;
+  const Sl2Dev &d = c->d;
+  if (xv_out)
+    CU_TRY(c, cudaMemcpy2DAsync(xv_out, sizeof(double) * SL2_NXV, d.x, sizeof(double) * d.ld,
+                                sizeof(double) * SL2_NXV, d.B, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return SL2_OK;
+}
+
+int sl2_enable_timing(sl2_ctx *c, int32_t on) {
+  if (!c) return SL2_ERR_ARG;
+  c->timing = on != 0;
+  return SL2_OK;
+}
+
+int sl2_last_step_times(sl2_ctx *c, float *ms4) {
+  if (!c || !ms4) return SL2_ERR_ARG;
+  if (!c->timing) return fail(c, SL2_ERR_STATE, "timing not enabled");
+  CU_TRY(c, cudaEventSynchronize(c->ev[4]));
+  for (int i = 0; i < 4; ++i) CU_TRY(c, cudaEventElapsedTime(&ms4[i], c->ev[i], c->ev[i + 1]));
+  return SL2_OK;
+}
+
+// ---- read-back ----------------------------------------------------------------------------------
+int sl2_get_features(sl2_ctx *c, int32_t s, double *h, double *z, double *S, uint8_t *flags,
+                     int32_t *attempted, int32_t *successful, int32_t *select_rank) {
+  if (bad_stream(c, s)) return fail(c, SL2_ERR_ARG, "bad stream");
+  const Sl2Dev &d = c->d;
+  const int N = d.Nmax;
+  const size_t fb = (size_t)s * N;
+  int nf = 0;
+  std::vector<double> hh(2 * N), SS(4 * N);
+  std::vector<int> zz(2 * N), rk(N), at(N), su(N);
+  std::vector<uint8_t> fd(N);
+  CU_TRY(c, cudaMemcpyAsync(&nf, d.nfeat + s, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(hh.data(), d.h + fb * 2, 16 * (size_t)N, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(SS.data(), d.S + fb * 4, 32 * (size_t)N, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(zz.data(), d.z_uv + fb * 2, 8 * (size_t)N, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(rk.data(), d.sel_rank + fb, 4 * (size_t)N, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(at.data(), d.attempted + fb, 4 * (size_t)N, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(su.data(), d.successful + fb, 4 * (size_t)N, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(fd.data(), d.found + fb, N, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < nf; ++i) {
+    if (h) { h[2 * i] = hh[2 * i]; h[2 * i + 1] = hh[2 * i + 1]; }
+    if (z) { z[2 * i] = (double)zz[2 * i]; z[2 * i + 1] = (double)zz[2 * i + 1]; }
+    if (S) for (int k = 0; k < 4; ++k) S[4 * i + k] = SS[4 * i + k];
+    if (flags) flags[i] = (uint8_t)((rk[i] >= 0 ? 1 : 0) | (fd[i] ? 2 : 0));
+    if (attempted) attempted[i] = at[i];
+    if (successful) successful[i] = su[i];
+    if (select_rank) select_rank[i] = rk[i];
+  }
+  return nf;
+}
+
+}  // extern "C"

@@ -1,0 +1,1027 @@
+// ekf.cu — EKF predict / measurement prediction + selection / update / cull on sm_100a.
+//
+// Replaces, per camera stream (one CTA per stream, all streams of a context in one launch):
+//   Kalman::KalmanFilterPredict            kalman.cpp:50-69   (+ motion_model.cpp:84-217)
+//   MonoSLAM::auto_select_n_features       monoslam.cpp:187-254 (+ :289-308,
+//                                          full_feature_model.cpp:67-195, camera.cpp:90-300)
+//   Kalman::KalmanFilterUpdate             kalman.cpp:72-119  (+ gather/scatter monoslam.cpp:501-614)
+//   MonoSLAM::normalise_state + symmetrise monoslam.cpp:616-637, 143-150
+//   MonoSLAM::delete_bad_features          monoslam.cpp:644-703, 770-812
+//
+// State layout in HBM: ONE dense column-major P (ld x ld) per stream in the order of
+// construct_total_covariance (monoslam.cpp:518-546): [xv(13) | y_0 | y_1 | ...], with both
+// triangles kept bit-consistent (the reference rebuilds the lower triangle from the upper blocks
+// on every gather, so P is exactly block-symmetric whenever it is read).
+//
+// Update algorithm (mathematically the reference's K = P H^T S^-1, P -= K S K^T):
+//   G = [ S | H P | nu ]  (m x (m+n+1), row-major scratch),  S = H P H^T + R
+//   left-looking blocked Cholesky by row panels of SL2_NB rows applied to the whole of G
+//   => G = [ U | Y | w ] with U^T U = S, Y = U^-T H P, w = U^-T nu
+//   x += Y^T w ;  P -= Y^T Y  (upper 64x64 tiles computed, mirrored to the lower triangle)
+// H is structurally sparse (13 + 3 non-zero columns per row) and is never formed.
+// Small bit-critical prologue math (everything that decides WHICH pixels are searched: S_i,
+// Sinv, h_i) uses never-fused __d*_rn ops in the oracle's evaluation order; the dense O(n^2 m)
+// parts use ordinary FP64 FMAs (tolerance 1e-5 relative, north star).
+#include "sl2_common.cuh"
+
+namespace {
+
+// never-fused FP64 scalar with natural operator syntax
+struct rd {
+  double v;
+  __device__ __forceinline__ rd() : v(0.0) {}
+  __device__ __forceinline__ rd(double x) : v(x) {}
+};
+__device__ __forceinline__ rd operator+(rd a, rd b) { return rd(__dadd_rn(a.v, b.v)); }
+__device__ __forceinline__ rd operator-(rd a, rd b) { return rd(__dsub_rn(a.v, b.v)); }
+__device__ __forceinline__ rd operator*(rd a, rd b) { return rd(__dmul_rn(a.v, b.v)); }
+__device__ __forceinline__ rd operator/(rd a, rd b) { return rd(__ddiv_rn(a.v, b.v)); }
+__device__ __forceinline__ rd operator-(rd a) { return rd(-a.v); }
+__device__ __forceinline__ rd rsqrt_(rd a) { return rd(__dsqrt_rn(a.v)); }
+
+struct Quat {
+  rd w, x, y, z;
+};
+
+__device__ Quat quat_mul(const Quat &a, const Quat &b) {
+  Quat q;
+  q.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+  q.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+  q.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
+  q.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
+  return q;
+}
+
+__device__ Quat quat_inverse(const Quat &q) {
+  const rd n2 = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z;
+  Quat r;
+  if (n2.v > 0.0) {
+    r.w = q.w / n2;
+    r.x = (-q.x) / n2;
+    r.y = (-q.y) / n2;
+    r.z = (-q.z) / n2;
+  }
+  return r;
+}
+
+__device__ void quat_to_R(const Quat &q, rd R[3][3]) {
+  const rd two(2.0), one(1.0);
+  const rd tx = two * q.x, ty = two * q.y, tz = two * q.z;
+  const rd twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+  const rd txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+  const rd tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+  R[0][0] = one - (tyy + tzz);
+  R[0][1] = txy - twz;
+  R[0][2] = txz + twy;
+  R[1][0] = txy + twz;
+  R[1][1] = one - (txx + tzz);
+  R[1][2] = tyz - twx;
+  R[2][0] = txz - twy;
+  R[2][1] = tyz + twx;
+  R[2][2] = one - (txx + tyy);
+}
+
+// ---------------------------------------------------------------------------------------------
+// motion model on one thread: fv, F (13x13 col-major), G (13x6 col-major) -- motion_model.cpp
+// ---------------------------------------------------------------------------------------------
+__device__ void dqomegadt_by_domega(const rd om[3], rd dt, rd m[4][3]) {
+  const rd omega = rsqrt_(om[0] * om[0] + om[1] * om[1] + om[2] * om[2]);
+  const rd two(2.0), one(1.0);
+  const double sn = sin((omega * dt / two).v), cs = cos((omega * dt / two).v);
+  const rd s(sn), c(cs);
+  // motion_model.cpp:318-349
+  auto dq0 = [&](rd a) { return ((-dt) / two) * (a / omega) * s; };
+  auto dqA_A = [&](rd a) {
+    return (dt / two) * a * a / (omega * omega) * c +
+           (one / omega) * (one - a * a / (omega * omega)) * s;
+  };
+  auto dqA_B = [&](rd a, rd b) {
+    return (a * b / (omega * omega)) * ((dt / two) * c - (one / omega) * s);
+  };
+  m[0][0] = dq0(om[0]);
+  m[0][1] = dq0(om[1]);
+  m[0][2] = dq0(om[2]);
+  m[1][0] = dqA_A(om[0]);
+  m[1][1] = dqA_B(om[0], om[1]);
+  m[1][2] = dqA_B(om[0], om[2]);
+  m[2][0] = dqA_B(om[1], om[0]);
+  m[2][1] = dqA_A(om[1]);
+  m[2][2] = dqA_B(om[1], om[2]);
+  m[3][0] = dqA_B(om[2], om[0]);
+  m[3][1] = dqA_B(om[2], om[1]);
+  m[3][2] = dqA_A(om[2]);
+}
+
+__device__ void dq3_by_dq1(const Quat &q, rd m[4][4]) {  // math_util.cpp:82-97
+  const rd x = q.x, y = q.y, z = q.z, w = q.w;
+  const rd v[16] = {w, -x, -y, -z, x, w, -z, y, y, z, w, -x, z, -y, x, w};
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) m[i][j] = v[i * 4 + j];
+}
+__device__ void dq3_by_dq2(const Quat &q, rd m[4][4]) {  // math_util.cpp:99-114
+  const rd x = q.x, y = q.y, z = q.z, w = q.w;
+  const rd v[16] = {w, -x, -y, -z, x, w, z, -y, y, -z, w, x, z, y, -x, w};
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) m[i][j] = v[i * 4 + j];
+}
+
+// F and Gn are shared-memory col-major arrays (13x13, 13x6); fv 13.
+__device__ void motion_model(const double *xv, const double *u3, double dt_, double *fv, double *F,
+                             double *Gn) {
+  const rd dt(dt_);
+  const Quat qold = {rd(xv[3]), rd(xv[4]), rd(xv[5]), rd(xv[6])};
+  const rd om[3] = {rd(xv[10]), rd(xv[11]), rd(xv[12])};
+  // QuaternionFromAngularVelocity(omega * dt), math_util.cpp:61-80
+  const rd av[3] = {om[0] * dt, om[1] * dt, om[2] * dt};
+  const rd angle = rsqrt_(av[0] * av[0] + av[1] * av[1] + av[2] * av[2]);
+  Quat qwt;
+  if (angle.v > 0.0) {
+    const rd sn(sin((angle / rd(2.0)).v)), cs(cos((angle / rd(2.0)).v));
+    const rd s = sn / angle;
+    qwt.x = s * av[0];
+    qwt.y = s * av[1];
+    qwt.z = s * av[2];
+    qwt.w = cs;
+  } else {
+    qwt.w = rd(1.0);
+  }
+  const Quat qnew = quat_mul(qold, qwt);
+  for (int i = 0; i < 3; ++i) fv[i] = (rd(xv[i]) + rd(xv[7 + i]) * dt).v;
+  fv[3] = qnew.w.v;
+  fv[4] = qnew.x.v;
+  fv[5] = qnew.y.v;
+  fv[6] = qnew.z.v;
+  for (int i = 0; i < 3; ++i) fv[7 + i] = (rd(xv[7 + i]) + rd(u3 ? u3[i] : 0.0) * dt).v;
+  for (int i = 0; i < 3; ++i) fv[10 + i] = om[i].v;
+
+  for (int i = 0; i < 169; ++i) F[i] = 0.0;
+  for (int i = 0; i < 13; ++i) F[i + 13 * i] = 1.0;
+  for (int i = 0; i < 3; ++i) F[i + 13 * (7 + i)] = (rd(1.0) * dt).v;
+  rd m44[4][4], m43[4][3], t44[4][4];
+  dq3_by_dq2(qwt, m44);
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) F[(3 + i) + 13 * (3 + j)] = m44[i][j].v;
+  dq3_by_dq1(qold, t44);
+  dqomegadt_by_domega(om, dt, m43);
+  for (int i = 0; i < 78; ++i) Gn[i] = 0.0;
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 3; ++j) {
+      rd sacc(0.0);
+      for (int k = 0; k < 4; ++k) sacc = sacc + t44[i][k] * m43[k][j];
+      F[(3 + i) + 13 * (10 + j)] = sacc.v;
+      Gn[(3 + i) + 13 * (3 + j)] = sacc.v;  // same product in func_Q (motion_model.cpp:202-213)
+    }
+  for (int i = 0; i < 3; ++i) {
+    Gn[(7 + i) + 13 * i] = 1.0;
+    Gn[(10 + i) + 13 * (3 + i)] = 1.0;
+    Gn[i + 13 * i] = (rd(1.0) * dt).v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-feature measurement prediction (one thread per feature)
+// ---------------------------------------------------------------------------------------------
+struct FeatPred {
+  rd h[2];
+  rd dxp[2][7];
+  rd dy[2][3];
+  rd var;
+  rd S[2][2];
+};
+
+__device__ void zeroedyi(const rd yi[3], const double *xp, rd z[3], rd dz_dxp[3][7], rd RRW[3][3]) {
+  const rd d[3] = {yi[0] - rd(xp[0]), yi[1] - rd(xp[1]), yi[2] - rd(xp[2])};
+  const Quat q = {rd(xp[3]), rd(xp[4]), rd(xp[5]), rd(xp[6])};
+  const Quat qi = quat_inverse(q);
+  quat_to_R(qi, RRW);
+  for (int i = 0; i < 3; ++i) {
+    rd s(0.0);
+    for (int k = 0; k < 3; ++k) s = s + RRW[i][k] * d[k];
+    z[i] = s;
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) dz_dxp[i][j] = RRW[i][j] * rd(-1.0);
+  // feature_model.cpp:187-238 applied to (qRW, d); then * dqbar_by_dq = diag(1,-1,-1,-1)
+  const rd two(2.0);
+  const rd w2 = two * qi.w, x2 = two * qi.x, y2 = two * qi.y, z2 = two * qi.z;
+  const rd m0[9] = {w2, -z2, y2, z2, w2, -x2, -y2, x2, w2};
+  const rd mx[9] = {x2, y2, z2, y2, -x2, -w2, z2, w2, -x2};
+  const rd my[9] = {-y2, x2, w2, x2, y2, z2, -w2, z2, -y2};
+  const rd mz[9] = {-z2, -w2, x2, w2, -z2, y2, x2, y2, z2};
+  for (int i = 0; i < 3; ++i) {
+    rd s0(0.0), s1(0.0), s2(0.0), s3(0.0);
+    for (int k = 0; k < 3; ++k) {
+      s0 = s0 + m0[i * 3 + k] * d[k];
+      s1 = s1 + mx[i * 3 + k] * d[k];
+      s2 = s2 + my[i * 3 + k] * d[k];
+      s3 = s3 + mz[i * 3 + k] * d[k];
+    }
+    dz_dxp[i][3] = s0;
+    dz_dxp[i][4] = -s1;
+    dz_dxp[i][5] = -s2;
+    dz_dxp[i][6] = -s3;
+  }
+}
+
+// Pxx: shared 13x13 col-major; Pcol: global pointer to P(0, pos) (column-major, ld)
+__device__ void predict_feature(const double *cam, const double *xv, const rd yi[3],
+                                const double *Pxx, const double *Pcol, int ld, int pos,
+                                FeatPred &o) {
+  rd z[3], dz_dxp[3][7], RRW[3][3];
+  zeroedyi(yi, xv, z, dz_dxp, RRW);
+  const rd fku(cam[2]), fkv(cam[3]), u0(cam[4]), v0(cam[5]), kd1(cam[6]), sd(cam[7]);
+  const rd one(1.0), two(2.0);
+  // Camera::Project, camera.cpp:90-114
+  const rd uc = (-fku) * z[0] / z[2];
+  const rd vc = (-fkv) * z[1] / z[2];
+  const rd radius2 = uc * uc + vc * vc;
+  const rd factor = rsqrt_(one + two * kd1 * radius2);
+  o.h[0] = uc / factor + u0;
+  o.h[1] = vc / factor + v0;
+  // Camera::ProjectionJacobian, camera.cpp:183-215
+  const rd fku_yz = fku / z[2], fkv_yz = fkv / z[2];
+  rd du[2][3];
+  du[0][0] = -fku_yz;
+  du[0][1] = rd(0.0);
+  du[0][2] = fku_yz * z[0] / z[2];
+  du[1][0] = rd(0.0);
+  du[1][1] = -fkv_yz;
+  du[1][2] = fkv_yz * z[1] / z[2];
+  rd dh[2][2];
+  dh[0][0] = uc * uc;
+  dh[0][1] = uc * vc;
+  dh[1][0] = vc * uc;
+  dh[1][1] = vc * vc;
+  const rd r2 = dh[0][0] + dh[1][1];
+  const rd distor = one + two * kd1 * r2;
+  const rd distor1_2 = rsqrt_(distor);
+  const rd distor3_2 = distor1_2 * distor;
+  const rd scale = rd(-2.0) * kd1 / distor3_2;
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j) dh[i][j] = dh[i][j] * scale;
+  dh[0][0] = dh[0][0] + (one / distor1_2);
+  dh[1][1] = dh[1][1] + (one / distor1_2);
+  rd dhid[2][3];
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 3; ++j) {
+      rd s(0.0);
+      for (int k = 0; k < 2; ++k) s = s + dh[i][k] * du[k][j];
+      dhid[i][j] = s;
+    }
+  for (int i = 0; i < 2; ++i) {
+    for (int j = 0; j < 7; ++j) {
+      rd s(0.0);
+      for (int k = 0; k < 3; ++k) s = s + dhid[i][k] * dz_dxp[k][j];
+      o.dxp[i][j] = s;
+    }
+    for (int j = 0; j < 3; ++j) {
+      rd s(0.0);
+      for (int k = 0; k < 3; ++k) s = s + dhid[i][k] * RRW[k][j];
+      o.dy[i][j] = s;
+    }
+  }
+  // Camera::MeasurementNoise, camera.cpp:282-300
+  const rd dx = o.h[0] - u0, dyv = o.h[1] - v0;
+  const rd distance = rsqrt_(dx * dx + dyv * dyv);
+  const rd max_distance = rsqrt_(u0 * u0 + v0 * v0);
+  const rd ratio = distance / max_distance;
+  const rd sd_use = sd * (one + ratio);
+  o.var = one * (sd_use * sd_use);
+  // FeatureModel::func_Si, feature_model.cpp:99-116.  dh_by_dxv = [dh_by_dxp | 0(2x6)]
+  // (motion_model.cpp:224-235), so terms with k >= 7 are exact zeros and are skipped.
+  rd A[2][7], Bm[2][3], Cm[2][3];
+  for (int r = 0; r < 2; ++r) {
+    for (int j = 0; j < 7; ++j) {
+      rd s(0.0);
+      for (int k = 0; k < 7; ++k) s = s + o.dxp[r][k] * rd(Pxx[k + 13 * j]);
+      A[r][j] = s;
+    }
+    for (int j = 0; j < 3; ++j) {
+      rd s(0.0);
+      for (int k = 0; k < 7; ++k) s = s + o.dxp[r][k] * rd(Pcol[k + (size_t)ld * j]);
+      Bm[r][j] = s;
+      rd t(0.0);
+      for (int k = 0; k < 3; ++k) t = t + o.dy[r][k] * rd(Pcol[(pos + k) + (size_t)ld * j]);
+      Cm[r][j] = t;
+    }
+  }
+  for (int r = 0; r < 2; ++r)
+    for (int c = 0; c < 2; ++c) {
+      rd s1(0.0), t1(0.0), t1t(0.0), s4(0.0);
+      for (int k = 0; k < 7; ++k) s1 = s1 + A[r][k] * o.dxp[c][k];
+      for (int k = 0; k < 3; ++k) t1 = t1 + Bm[r][k] * o.dy[c][k];
+      for (int k = 0; k < 3; ++k) t1t = t1t + Bm[c][k] * o.dy[r][k];
+      for (int k = 0; k < 3; ++k) s4 = s4 + Cm[r][k] * o.dy[c][k];
+      rd S = rd(0.0) + s1;
+      S = S + t1;
+      S = S + t1t;
+      S = S + s4;
+      S = S + (r == c ? o.var : rd(0.0));
+      o.S[r][c] = S;
+    }
+}
+
+__device__ int visibility_test(const double *cam, const double *xp, const rd yi[3],
+                               const double *xp_orig, const rd h[2]) {
+  int cant = 0;
+  const double bound = 20.0;  // kImageSearchBoundary_, full_feature_model.cpp:51
+  if (h[0].v < 0.0 + bound || h[0].v > (double)((int)cam[0] - 1 - bound)) cant |= 1;
+  if (h[1].v < 0.0 + bound || h[1].v > (double)((int)cam[1] - 1 - bound)) cant |= 2;
+  rd z[3], t[3][7], R1[3][3], RWR[3][3];
+  zeroedyi(yi, xp, z, t, R1);
+  if (z[2].v <= 0) cant |= 16;
+  rd a[3], b[3];
+  quat_to_R(Quat{rd(xp[3]), rd(xp[4]), rd(xp[5]), rd(xp[6])}, RWR);
+  for (int i = 0; i < 3; ++i) {
+    rd s(0.0);
+    for (int k = 0; k < 3; ++k) s = s + RWR[i][k] * z[k];
+    a[i] = s;
+  }
+  zeroedyi(yi, xp_orig, z, t, R1);
+  quat_to_R(Quat{rd(xp_orig[3]), rd(xp_orig[4]), rd(xp_orig[5]), rd(xp_orig[6])}, RWR);
+  for (int i = 0; i < 3; ++i) {
+    rd s(0.0);
+    for (int k = 0; k < 3; ++k) s = s + RWR[i][k] * z[k];
+    b[i] = s;
+  }
+  const rd ma = rsqrt_(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+  const rd mb = rsqrt_(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]);
+  const rd ratio = ma / mb;
+  if (ratio.v > 2.0 || ratio.v < (1.0 / 2.0)) cant |= 4;
+  const rd dot = a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+  double angle = acos((dot / (ma * mb)).v);
+  angle = (angle >= 0.0 ? angle : -angle);
+  if (angle > 3.14159265358979323846 * 45.0 / 180.0) cant |= 8;
+  return cant;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel 1: predict (kalman.cpp:50-69) + measurement prediction / selection (monoslam.cpp:187-254)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) predict_kernel(const Sl2Dev d, int stream_lo,
+                                                      const double *u3, int do_predict,
+                                                      int do_measure) {
+  const int s = stream_lo + blockIdx.x;
+  const int tid = threadIdx.x;
+  const int nf = d.nfeat[s];
+  const int n = SL2_NXV + 3 * nf;
+  const int ld = d.ld;
+  double *P = d.P + (size_t)s * ld * ld;
+  double *x = d.x + (size_t)s * ld;
+
+  __shared__ double F[169], Gn[78], Pxx[169], TT[169], Qm[169], xv[13], fv[13];
+  __shared__ double score[SL2_MAX_FEAT_SMEM];
+  __shared__ int vis[SL2_MAX_FEAT_SMEM];
+  __shared__ int s_nvis, s_r0;
+
+  if (tid < 13) xv[tid] = x[tid];
+  if (tid < 169) Pxx[tid] = P[(tid % 13) + (size_t)ld * (tid / 13)];
+  __syncthreads();
+
+  if (do_predict) {
+    if (tid == 0) motion_model(xv, u3, d.dt, fv, F, Gn);
+    __syncthreads();
+    // Q = (G * Pnn) * G^T, Pnn = diag(lin x3, ang x3)   (motion_model.cpp:157-216)
+    // TT = F * Pxx
+    if (tid < 169) {
+      const int i = tid % 13, j = tid / 13;
+      const rd dt(d.dt);
+      const rd lin = rd(4.0) * rd(4.0) * dt * dt, ang = rd(6.0) * rd(6.0) * dt * dt;
+      rd q(0.0), t(0.0);
+      for (int k = 0; k < 6; ++k) {
+        const rd gp = rd(0.0) + rd(Gn[i + 13 * k]) * (k < 3 ? lin : ang);  // (G*Pnn)(i,k)
+        q = q + gp * rd(Gn[j + 13 * k]);
+      }
+      for (int k = 0; k < 13; ++k) t = t + rd(F[i + 13 * k]) * rd(Pxx[k + 13 * j]);
+      Qm[tid] = q.v;
+      TT[tid] = t.v;
+    }
+    __syncthreads();
+    // Pxx = TT * F^T + Q
+    if (tid < 169) {
+      const int i = tid % 13, j = tid / 13;
+      rd a(0.0);
+      for (int k = 0; k < 13; ++k) a = a + rd(TT[i + 13 * k]) * rd(F[j + 13 * k]);
+      const double v = (a + rd(Qm[tid])).v;
+      Pxx[tid] = v;  // own element only: no hazard with TT/F readers
+      P[i + (size_t)ld * j] = v;
+    }
+    // Pxy_i = F * Pxy_i  (one thread per column of the 13 x 3N panel), mirrored below the diagonal
+    for (int c = SL2_NXV + tid; c < n; c += blockDim.x) {
+      double col[13], out[13];
+      for (int k = 0; k < 13; ++k) col[k] = P[k + (size_t)ld * c];
+      for (int i = 0; i < 13; ++i) {
+        rd a(0.0);
+        for (int k = 0; k < 13; ++k) a = a + rd(F[i + 13 * k]) * rd(col[k]);
+        out[i] = a.v;
+      }
+      for (int i = 0; i < 13; ++i) {
+        P[i + (size_t)ld * c] = out[i];
+        P[c + (size_t)ld * i] = out[i];
+      }
+    }
+    if (tid < 13) {
+      x[tid] = fv[tid];
+      xv[tid] = fv[tid];
+    }
+    __syncthreads();
+  }
+  if (!do_measure) return;
+
+  // ---- per-feature prediction, visibility, score ---------------------------------------------
+  const size_t fb = (size_t)s * d.Nmax;
+  for (int i0 = 0; i0 < d.Nmax; i0 += blockDim.x) {
+    const int i = i0 + tid;
+    if (i < d.Nmax) {
+      vis[i] = 0;
+      score[i] = 0.0;
+      d.sel_rank[fb + i] = -1;
+      d.found[fb + i] = 0;
+      d.job_feat[fb + i] = -1;
+    }
+    if (i < nf) {
+      const int pos = SL2_NXV + 3 * i;
+      const rd yi[3] = {rd(x[pos]), rd(x[pos + 1]), rd(x[pos + 2])};
+      FeatPred fp;
+      predict_feature(d.cam, xv, yi, Pxx, P + (size_t)ld * pos, ld, pos, fp);
+      d.h[(fb + i) * 2 + 0] = fp.h[0].v;
+      d.h[(fb + i) * 2 + 1] = fp.h[1].v;
+      for (int r = 0; r < 2; ++r) {
+        for (int j = 0; j < 7; ++j) d.dh_dxp[(fb + i) * 14 + r * 7 + j] = fp.dxp[r][j].v;
+        for (int j = 0; j < 3; ++j) d.dh_dy[(fb + i) * 6 + r * 3 + j] = fp.dy[r][j].v;
+      }
+      d.Rvar[fb + i] = fp.var.v;
+      d.S[(fb + i) * 4 + 0] = fp.S[0][0].v;
+      d.S[(fb + i) * 4 + 1] = fp.S[1][0].v;
+      d.S[(fb + i) * 4 + 2] = fp.S[0][1].v;
+      d.S[(fb + i) * 4 + 3] = fp.S[1][1].v;
+      const int cant = visibility_test(d.cam, xv, yi, d.xp_org + (fb + i) * 7, fp.h);
+      vis[i] = (cant == 0);
+      score[i] = (fp.S[0][0] + fp.S[1][1]).v;  // trace, full_feature_model.cpp:172-176
+    }
+  }
+  __syncthreads();
+  // ---- insertion sort of monoslam.cpp:211-230 as a rank: strictly larger scores first, ties in
+  //      feature order; selection stops at the first zero score or after n_select (:241-249)
+  if (tid == 0) {
+    s_nvis = 0;
+    s_r0 = 1 << 30;
+  }
+  __syncthreads();
+  for (int i = tid; i < nf; i += blockDim.x) {
+    if (vis[i]) {
+      int rank = 0;
+      const double si = score[i];
+      for (int j = 0; j < nf; ++j)
+        if (vis[j] && (score[j] > si || (j < i && !(si > score[j])))) ++rank;
+      d.sel_rank[fb + i] = rank;  // provisional: rank among visible
+      atomicAdd(&s_nvis, 1);
+      if (si == 0.0) atomicMin(&s_r0, rank);
+    }
+  }
+  __syncthreads();
+  const int nsel = min(min(d.n_select, s_r0), s_nvis);
+  for (int i = tid; i < nf; i += blockDim.x) {
+    int rank = d.sel_rank[fb + i];
+    if (rank >= nsel) rank = -1;
+    d.sel_rank[fb + i] = rank;
+    if (rank >= 0) {
+      d.job_feat[fb + rank] = i;
+      d.job_centre[(fb + rank) * 2 + 0] = d.h[(fb + i) * 2 + 0];
+      d.job_centre[(fb + rank) * 2 + 1] = d.h[(fb + i) * 2 + 1];
+      double p00, p01, p11;
+      if (d.ovr[0] > 0.0) {
+        p00 = d.ovr[0];
+        p01 = d.ovr[1];
+        p11 = d.ovr[2];
+      } else {
+        // monoslam.cpp:371-374: LLT, inverse of L, Sinv = Linv^T Linv (closed form, see oracle)
+        const rd s00(d.S[(fb + i) * 4 + 0]), s10(d.S[(fb + i) * 4 + 1]), s11(d.S[(fb + i) * 4 + 3]);
+        const rd l00 = rsqrt_(s00);
+        const rd l10 = s10 / l00;
+        const rd l11 = rsqrt_(s11 - l10 * l10);
+        const rd x00 = rd(1.0) / l00;
+        const rd x10 = (rd(0.0) - l10 * x00) / l11;
+        const rd x11 = rd(1.0) / l11;
+        p00 = (x00 * x00 + x10 * x10).v;
+        p01 = (x10 * x11).v;
+        p11 = (x11 * x11).v;
+      }
+      d.job_puinv[(fb + rank) * 3 + 0] = p00;
+      d.job_puinv[(fb + rank) * 3 + 1] = p01;
+      d.job_puinv[(fb + rank) * 3 + 2] = p11;
+    }
+  }
+  if (tid == 0) {
+    d.nsel[s] = nsel;
+    d.nvisible[s] = s_nvis;
+    d.nmeas[s] = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel 2: EKF update (kalman.cpp:72-119) + normalise (monoslam.cpp:616-637) + bookkeeping
+// ---------------------------------------------------------------------------------------------
+struct UpdSmem {
+  // carved from dynamic shared memory; sizes depend on Nmax
+  double *Hx;    // [K][2][13]
+  double *Hy;    // [K][2][3]
+  double *Rv;    // [K]
+  double *wv;    // [mmax]  nu, later w = U^-T nu
+  int *mfeat;    // [K]
+  double *mult;  // [mmax][NB] multipliers of the current panel
+  double *ublk;  // [NB][NB]
+  double *invd;  // [NB]
+  double *tile;  // phase 4: max(2*KC*64, 64*65) doubles
+};
+
+constexpr int UPD_THREADS = 256;
+constexpr int UPD_KC = 16;
+
+__device__ __forceinline__ UpdSmem carve(uint8_t *base, int Nmax) {
+  UpdSmem u;
+  const int K = Nmax, mmax = 2 * Nmax;
+  double *p = reinterpret_cast<double *>(base);
+  u.Hx = p;  p += (size_t)K * 26;
+  u.Hy = p;  p += (size_t)K * 6;
+  u.Rv = p;  p += K;
+  u.wv = p;  p += mmax;
+  u.mult = p;  p += (size_t)mmax * SL2_NB;
+  u.ublk = p;  p += SL2_NB * SL2_NB;
+  u.invd = p;  p += SL2_NB;
+  u.tile = p;  p += 64 * 65;
+  u.mfeat = reinterpret_cast<int *>(p);
+  return u;
+}
+
+__global__ void __launch_bounds__(UPD_THREADS) update_kernel(
+    const Sl2Dev d, int stream_lo, int staged_m, const int *st_feat, const double *st_Hxv,
+    const double *st_Hy, const double *st_R, const double *st_nu, int only_normalise) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const UpdSmem sm = carve(smem_raw, d.Nmax);
+  const int s = stream_lo + blockIdx.x;
+  const int tid = threadIdx.x;
+  const int nf = d.nfeat[s];
+  const int n = SL2_NXV + 3 * nf;
+  const int ld = d.ld, ldg = d.ldg;
+  double *P = d.P + (size_t)s * ld * ld;
+  double *x = d.x + (size_t)s * ld;
+  double *G = d.G + (size_t)s * d.mmax * ldg;
+  const size_t fb = (size_t)s * d.Nmax;
+  __shared__ int s_m;
+
+  // ---- phase 0: measurement list in selected order, successful only (monoslam.cpp:556-571) ---
+  if (tid == 0) {
+    int k = 0;
+    if (only_normalise) {
+      k = 0;
+    } else if (staged_m >= 0) {
+      k = staged_m / 2;
+    } else {
+      const int nsel = d.nsel[s];
+      for (int r = 0; r < nsel; ++r) {
+        const int i = d.job_feat[fb + r];
+        if (i >= 0 && d.found[fb + i]) sm.mfeat[k++] = i;
+      }
+      d.nmeas[s] = k;
+    }
+    s_m = 2 * k;
+  }
+  __syncthreads();
+  const int m = s_m;
+  const int K = m / 2;
+  if (m > 0) {
+    if (staged_m >= 0) {
+      for (int k = tid; k < K; k += UPD_THREADS) {
+        sm.mfeat[k] = st_feat[k];
+        sm.Rv[k] = st_R[k * 4];  // R_i = var * I (camera.cpp:294-299); off-diagonals ignored
+        sm.wv[2 * k] = st_nu[2 * k];
+        sm.wv[2 * k + 1] = st_nu[2 * k + 1];
+      }
+      for (int e = tid; e < K * 26; e += UPD_THREADS) sm.Hx[e] = st_Hxv[e];
+      for (int e = tid; e < K * 6; e += UPD_THREADS) sm.Hy[e] = st_Hy[e];
+    } else {
+      for (int k = tid; k < K; k += UPD_THREADS) {
+        const int i = sm.mfeat[k];
+        sm.Rv[k] = d.Rvar[fb + i];
+        // nu = z - h (full_feature_model.cpp:197-200), z = (double)(u,v) (monoslam.cpp:382-383)
+        sm.wv[2 * k] = (rd((double)d.z_uv[(fb + i) * 2]) - rd(d.h[(fb + i) * 2])).v;
+        sm.wv[2 * k + 1] = (rd((double)d.z_uv[(fb + i) * 2 + 1]) - rd(d.h[(fb + i) * 2 + 1])).v;
+        for (int r = 0; r < 2; ++r) {
+          for (int c = 0; c < 13; ++c)
+            sm.Hx[k * 26 + r * 13 + c] = c < 7 ? d.dh_dxp[(fb + i) * 14 + r * 7 + c] : 0.0;
+          for (int c = 0; c < 3; ++c) sm.Hy[k * 6 + r * 3 + c] = d.dh_dy[(fb + i) * 6 + r * 3 + c];
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- phase 1a: H*P rows (structured: 13 + 3 columns of P per row pair) and nu column ----
+    for (int j = tid; j < n; j += UPD_THREADS) {
+      double px[13];
+#pragma unroll
+      for (int c = 0; c < 13; ++c) px[c] = P[j + (size_t)ld * c];  // P(c, j) by symmetry
+      for (int k = 0; k < K; ++k) {
+        const int pos = SL2_NXV + 3 * sm.mfeat[k];
+        const double py0 = P[j + (size_t)ld * pos], py1 = P[j + (size_t)ld * (pos + 1)],
+                     py2 = P[j + (size_t)ld * (pos + 2)];
+        const double *hx = sm.Hx + k * 26, *hy = sm.Hy + k * 6;
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int c = 0; c < 13; ++c) {
+          a0 += hx[c] * px[c];
+          a1 += hx[13 + c] * px[c];
+        }
+        a0 += hy[0] * py0;
+        a0 += hy[1] * py1;
+        a0 += hy[2] * py2;
+        a1 += hy[3] * py0;
+        a1 += hy[4] * py1;
+        a1 += hy[5] * py2;
+        G[(size_t)(2 * k) * ldg + m + j] = a0;
+        G[(size_t)(2 * k + 1) * ldg + m + j] = a1;
+      }
+    }
+    for (int i = tid; i < m; i += UPD_THREADS) G[(size_t)i * ldg + m + n] = sm.wv[i];
+    __syncthreads();
+    // ---- phase 1b: S = (H P) H^T + R ---------------------------------------------------------
+    for (int e = tid; e < m * K; e += UPD_THREADS) {
+      const int i = e / K, kp = e - i * K;
+      const double *g = G + (size_t)i * ldg + m;
+      const int pos = SL2_NXV + 3 * sm.mfeat[kp];
+      const double *hx = sm.Hx + kp * 26, *hy = sm.Hy + kp * 6;
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int c = 0; c < 13; ++c) {
+        const double v = g[c];
+        a0 += v * hx[c];
+        a1 += v * hx[13 + c];
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double v = g[pos + c];
+        a0 += v * hy[c];
+        a1 += v * hy[3 + c];
+      }
+      if (i == 2 * kp) a0 += sm.Rv[kp];
+      if (i == 2 * kp + 1) a1 += sm.Rv[kp];
+      G[(size_t)i * ldg + 2 * kp] = a0;
+      G[(size_t)i * ldg + 2 * kp + 1] = a1;
+    }
+    __syncthreads();
+
+    // ---- phase 2: left-looking Cholesky by row panels on G = [S | HP | nu] --------------------
+    const int width = m + n + 1;
+    constexpr int CPT = 3;  // columns per thread: (2*128 + 397 + 1) / 256 <= 3
+    for (int i0 = 0; i0 < m; i0 += SL2_NB) {
+      const int nbp = min(SL2_NB, m - i0);
+      // multipliers U(k, i0..i0+NB) of all finished rows k < i0
+      for (int e = tid; e < i0 * SL2_NB; e += UPD_THREADS) {
+        const int k = e / SL2_NB, r = e - k * SL2_NB;
+        sm.mult[e] = (r < nbp) ? G[(size_t)k * ldg + i0 + r] : 0.0;
+      }
+      __syncthreads();
+      double acc[CPT][SL2_NB];
+      int col[CPT];
+#pragma unroll
+      for (int q = 0; q < CPT; ++q) {
+        col[q] = i0 + tid + q * UPD_THREADS;
+#pragma unroll
+        for (int r = 0; r < SL2_NB; ++r)
+          acc[q][r] = (col[q] < width && r < nbp) ? G[(size_t)(i0 + r) * ldg + col[q]] : 0.0;
+      }
+      const bool c1 = col[1] < width, c2 = col[2] < width;
+#pragma unroll 4
+      for (int k = 0; k < i0; ++k) {
+        const double *gk = G + (size_t)k * ldg;
+        const double g0 = (col[0] < width) ? gk[col[0]] : 0.0;
+        const double g1 = c1 ? gk[col[1]] : 0.0;
+        const double g2 = c2 ? gk[col[2]] : 0.0;
+        const double2 *mk = reinterpret_cast<const double2 *>(sm.mult + (size_t)k * SL2_NB);
+#pragma unroll
+        for (int r2 = 0; r2 < SL2_NB / 2; ++r2) {
+          const double2 mm = mk[r2];
+          acc[0][2 * r2] -= mm.x * g0;
+          acc[0][2 * r2 + 1] -= mm.y * g0;
+          acc[1][2 * r2] -= mm.x * g1;
+          acc[1][2 * r2 + 1] -= mm.y * g1;
+          acc[2][2 * r2] -= mm.x * g2;
+          acc[2][2 * r2 + 1] -= mm.y * g2;
+        }
+      }
+      // diagonal block -> shared, factor on one thread
+      if (tid < SL2_NB) {
+#pragma unroll
+        for (int r = 0; r < SL2_NB; ++r) sm.ublk[r * SL2_NB + tid] = acc[0][r];
+      }
+      __syncthreads();
+      if (tid == 0) {
+        for (int r = 0; r < nbp; ++r) {
+          double dg = sm.ublk[r * SL2_NB + r];
+          for (int q = 0; q < r; ++q) dg -= sm.ublk[q * SL2_NB + r] * sm.ublk[q * SL2_NB + r];
+          const double u = sqrt(dg);
+          const double iu = 1.0 / u;
+          sm.ublk[r * SL2_NB + r] = u;
+          sm.invd[r] = iu;
+          for (int c = r + 1; c < nbp; ++c) {
+            double v = sm.ublk[r * SL2_NB + c];
+            for (int q = 0; q < r; ++q) v -= sm.ublk[q * SL2_NB + r] * sm.ublk[q * SL2_NB + c];
+            sm.ublk[r * SL2_NB + c] = v * iu;
+          }
+        }
+      }
+      __syncthreads();
+      // apply U_pp^-T to every column of the panel and write the finished rows
+#pragma unroll
+      for (int q = 0; q < CPT; ++q) {
+        if (col[q] < width) {
+          const int cc = col[q] - i0;
+          double f[SL2_NB];
+#pragma unroll
+          for (int r = 0; r < SL2_NB; ++r) {
+            double v = acc[q][r];
+#pragma unroll
+            for (int t = 0; t < r; ++t) v -= sm.ublk[t * SL2_NB + r] * f[t];
+            f[r] = v * sm.invd[r];
+            if (r < nbp) {
+              double outv = f[r];
+              if (cc < nbp) outv = (cc >= r) ? sm.ublk[r * SL2_NB + cc] : 0.0;
+              G[(size_t)(i0 + r) * ldg + col[q]] = outv;
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+
+    // ---- phase 3: x += Y^T w -----------------------------------------------------------------
+    for (int i = tid; i < m; i += UPD_THREADS) sm.wv[i] = G[(size_t)i * ldg + m + n];
+    __syncthreads();
+    for (int j = tid; j < n; j += UPD_THREADS) {
+      double a = 0.0;
+      for (int k = 0; k < m; ++k) a += G[(size_t)k * ldg + m + j] * sm.wv[k];
+      x[j] += a;
+    }
+
+    // ---- phase 4: P -= Y^T Y on 64x64 tiles, upper triangle computed, lower mirrored -----------
+    {
+      double *Ya = sm.tile;                 // [KC][64]
+      double *Yb = sm.tile + UPD_KC * 64;   // [KC][64]
+      const int tx = tid & 15, ty = tid >> 4;  // tx -> rows (a), ty -> cols (b)
+      const int nt = (n + 63) / 64;
+      for (int tb = 0; tb < nt; ++tb)
+        for (int ta = 0; ta <= tb; ++ta) {
+          double acc[4][4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+          for (int k0 = 0; k0 < m; k0 += UPD_KC) {
+            __syncthreads();
+            for (int e = tid; e < UPD_KC * 64; e += UPD_THREADS) {
+              const int kk = e >> 6, c = e & 63;
+              const int k = k0 + kk;
+              const int ca = ta * 64 + c, cb = tb * 64 + c;
+              Ya[e] = (k < m && ca < n) ? G[(size_t)k * ldg + m + ca] : 0.0;
+              Yb[e] = (k < m && cb < n) ? G[(size_t)k * ldg + m + cb] : 0.0;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < UPD_KC; ++kk) {
+              const double2 a01 = *reinterpret_cast<const double2 *>(Ya + kk * 64 + tx * 4);
+              const double2 a23 = *reinterpret_cast<const double2 *>(Ya + kk * 64 + tx * 4 + 2);
+              const double2 b01 = *reinterpret_cast<const double2 *>(Yb + kk * 64 + ty * 4);
+              const double2 b23 = *reinterpret_cast<const double2 *>(Yb + kk * 64 + ty * 4 + 2);
+              const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+              const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+            }
+          }
+          __syncthreads();
+          // new values; stage through shared memory for the mirrored (transposed) write
+          double *T = sm.tile;  // [64][65]
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int b = tb * 64 + ty * 4 + j;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int a = ta * 64 + tx * 4 + i;
+              double v = 0.0;
+              if (a < n && b < n) {
+                v = P[a + (size_t)ld * b] - acc[i][j];
+                P[a + (size_t)ld * b] = v;
+              }
+              T[(tx * 4 + i) * 65 + (ty * 4 + j)] = v;
+            }
+          }
+          if (ta != tb) {
+            __syncthreads();
+            // lower tile: rows = b range, cols = a range; thread (tx -> row b, ty -> col a)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int a = ta * 64 + ty * 4 + j;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int b = tb * 64 + tx * 4 + i;
+                if (a < n && b < n) P[b + (size_t)ld * a] = T[(ty * 4 + j) * 65 + (tx * 4 + i)];
+              }
+            }
+          }
+        }
+    }
+    __syncthreads();
+  }
+
+  // ---- phase 5: normalise_state (monoslam.cpp:616-637): P <- J P J^T, J = diag(I3, dqnorm, I6, I)
+  if (m > 0 || only_normalise) {
+    __shared__ double J4[16];
+    if (tid == 0) {
+      const rd q[4] = {rd(x[3]), rd(x[4]), rd(x[5]), rd(x[6])};
+      const rd qq = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+      for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j)  // motion_model.cpp:371-380 (quirk Q2)
+          J4[i * 4 + j] = (i == j) ? ((rd(1.0) - q[i] * q[i] / (qq * qq)) / qq).v
+                                   : ((-q[i]) * q[j] / (qq * qq * qq)).v;
+    }
+    __syncthreads();
+    // rows 3..6 of every column: P(3:7, j) = J4 * P(3:7, j)
+    for (int j = tid; j < n; j += UPD_THREADS) {
+      double v[4], o[4];
+      for (int k = 0; k < 4; ++k) v[k] = P[(3 + k) + (size_t)ld * j];
+      for (int i = 0; i < 4; ++i) {
+        rd a(0.0);
+        for (int k = 0; k < 4; ++k) a = a + rd(J4[i * 4 + k]) * rd(v[k]);
+        o[i] = a.v;
+      }
+      for (int k = 0; k < 4; ++k) P[(3 + k) + (size_t)ld * j] = o[k];
+    }
+    __syncthreads();
+    // columns 3..6: Pxx part gets (J Pxx) J^T; rows >= 13 are the mirror of the updated Pxy
+    for (int i = tid; i < n; i += UPD_THREADS) {
+      if (i < SL2_NXV) {
+        double v[4], o[4];
+        for (int k = 0; k < 4; ++k) v[k] = P[i + (size_t)ld * (3 + k)];
+        for (int c = 0; c < 4; ++c) {
+          rd a(0.0);
+          for (int k = 0; k < 4; ++k) a = a + rd(v[k]) * rd(J4[c * 4 + k]);
+          o[c] = a.v;
+        }
+        for (int k = 0; k < 4; ++k) P[i + (size_t)ld * (3 + k)] = o[k];
+      } else {
+        for (int k = 0; k < 4; ++k) P[i + (size_t)ld * (3 + k)] = P[(3 + k) + (size_t)ld * i];
+      }
+    }
+    __syncthreads();
+  }
+  // ---- symmetrise (monoslam.cpp:143-150): only the Pxx block can be asymmetric here ---------
+  {
+    const int i = tid % 13, j = (tid / 13) % 13;
+    const double a = P[i + (size_t)ld * j], b = P[j + (size_t)ld * i];
+    const double v = (rd(a) * rd(0.5) + rd(b) * rd(0.5)).v;
+    __syncthreads();
+    if (tid < 169) P[i + (size_t)ld * j] = v;
+    __syncthreads();
+  }
+
+  // ---- bookkeeping: attempt / success counters (monoslam.cpp:479-496) ------------------------
+  if (staged_m < 0 && !only_normalise) {
+    for (int i = tid; i < nf; i += UPD_THREADS) {
+      if (d.sel_rank[fb + i] >= 0) {
+        d.attempted[fb + i] += 1;
+        if (d.found[fb + i]) d.successful[fb + i] += 1;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel 3: delete_bad_features (monoslam.cpp:644-703) / delete_feature (:770-812)
+// removes the rows/columns of the culled features from x and P in place.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cull_kernel(const Sl2Dev d, int stream_lo, int force_index) {
+  const int s = stream_lo + blockIdx.x;
+  const int tid = threadIdx.x;
+  const int nf = d.nfeat[s];
+  const int ld = d.ld;
+  const size_t fb = (size_t)s * d.Nmax;
+  __shared__ int keep[SL2_MAX_FEAT_SMEM];  // new index of feature i or -1
+  __shared__ int s_new;
+  if (tid == 0) {
+    int k = 0;
+    for (int i = 0; i < nf; ++i) {
+      bool kill;
+      if (force_index >= 0) {
+        kill = (i == force_index);
+      } else {
+        const int att = d.attempted[fb + i], suc = d.successful[fb + i];
+        kill = att >= d.min_attempts && (double)suc / (double)att < d.match_fraction;
+      }
+      keep[i] = kill ? -1 : k++;
+    }
+    s_new = k;
+  }
+  __syncthreads();
+  const int nk = s_new;
+  if (nk == nf) return;
+  double *P = d.P + (size_t)s * ld * ld;
+  double *x = d.x + (size_t)s * ld;
+  double *scr = d.G + (size_t)s * d.mmax * d.ldg;  // scratch >= ld*ld? no: compact column by column
+  const int n = SL2_NXV + 3 * nf;
+  // destination indices are never larger than source indices, so walking columns in increasing
+  // order with a per-column staging buffer in scratch is race-free inside one CTA.
+  for (int c = 0; c < n; ++c) {
+    int cn;
+    if (c < SL2_NXV) {
+      cn = c;
+    } else {
+      const int f = (c - SL2_NXV) / 3;
+      cn = keep[f] < 0 ? -1 : SL2_NXV + 3 * keep[f] + (c - SL2_NXV) % 3;
+    }
+    if (cn < 0) continue;  // uniform across the CTA
+    for (int r = tid; r < n; r += blockDim.x) scr[r] = P[r + (size_t)ld * c];
+    __syncthreads();
+    for (int r = tid; r < n; r += blockDim.x) {
+      int rn;
+      if (r < SL2_NXV) {
+        rn = r;
+      } else {
+        const int f = (r - SL2_NXV) / 3;
+        rn = keep[f] < 0 ? -1 : SL2_NXV + 3 * keep[f] + (r - SL2_NXV) % 3;
+      }
+      if (rn >= 0) P[rn + (size_t)ld * cn] = scr[r];
+    }
+    __syncthreads();
+  }
+  // state vector and per-feature records
+  for (int r = tid; r < n; r += blockDim.x) scr[r] = x[r];
+  __syncthreads();
+  for (int r = SL2_NXV + tid; r < n; r += blockDim.x) {
+    const int f = (r - SL2_NXV) / 3;
+    if (keep[f] >= 0) x[SL2_NXV + 3 * keep[f] + (r - SL2_NXV) % 3] = scr[r];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    // serial compaction of the small per-feature records (rare path)
+    const int box16 = d.box * 16;
+    for (int i = 0; i < nf; ++i) {
+      const int k = keep[i];
+      if (k < 0 || k == i) continue;
+      for (int e = 0; e < 7; ++e) d.xp_org[(fb + k) * 7 + e] = d.xp_org[(fb + i) * 7 + e];
+      d.attempted[fb + k] = d.attempted[fb + i];
+      d.successful[fb + k] = d.successful[fb + i];
+      for (int e = 0; e < box16; ++e)
+        d.patches[(fb + k) * box16 + e] = d.patches[(fb + i) * box16 + e];
+      for (int e = 0; e < 2; ++e) {
+        d.h[(fb + k) * 2 + e] = d.h[(fb + i) * 2 + e];
+        d.z_uv[(fb + k) * 2 + e] = d.z_uv[(fb + i) * 2 + e];
+      }
+      for (int e = 0; e < 4; ++e) d.S[(fb + k) * 4 + e] = d.S[(fb + i) * 4 + e];
+      d.sel_rank[fb + k] = d.sel_rank[fb + i];
+      d.found[fb + k] = d.found[fb + i];
+    }
+    d.nfeat[s] = nk;
+  }
+}
+
+}  // namespace
+
+size_t sl2_update_smem_bytes(const Sl2Dev &d) {
+  const size_t K = d.Nmax, mmax = 2 * d.Nmax;
+  const size_t doubles = K * 26 + K * 6 + K + mmax + mmax * SL2_NB + SL2_NB * SL2_NB + SL2_NB + 64 * 65;
+  return doubles * 8 + K * 4 + 16;
+}
+
+cudaError_t sl2_launch_predict(const Sl2Dev &d, int stream_lo, int stream_cnt, const double *u3_dev,
+                               int do_predict, int do_measure, cudaStream_t st) {
+  if (stream_cnt <= 0) return cudaSuccess;
+  predict_kernel<<<stream_cnt, 256, 0, st>>>(d, stream_lo, u3_dev, do_predict, do_measure);
+  return cudaGetLastError();
+}
+
+cudaError_t sl2_launch_update(const Sl2Dev &d, int stream_lo, int stream_cnt, int staged_m,
+                              const int *st_feat, const double *st_Hxv, const double *st_Hy,
+                              const double *st_R, const double *st_nu, int only_normalise,
+                              cudaStream_t st) {
+  if (stream_cnt <= 0) return cudaSuccess;
+  const size_t smem = sl2_update_smem_bytes(d);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  update_kernel<<<stream_cnt, UPD_THREADS, smem, st>>>(d, stream_lo, staged_m, st_feat, st_Hxv,
+                                                        st_Hy, st_R, st_nu, only_normalise);
+  return cudaGetLastError();
+}
+
+cudaError_t sl2_launch_cull(const Sl2Dev &d, int stream_lo, int stream_cnt, int force_index,
+                            cudaStream_t st) {
+  if (stream_cnt <= 0) return cudaSuccess;
+  cull_kernel<<<stream_cnt, 256, 0, st>>>(d, stream_lo, force_index);
+  return cudaGetLastError();
+}

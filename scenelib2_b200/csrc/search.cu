@@ -1,0 +1,404 @@
+// search.cu — patch-correlation feature search on sm_100a.
+//
+// Replaces MonoSLAM::elliptical_search (monoslam.cpp:401-477) calling correlate2_warning
+// (improc/improc.cpp:55-134), and SearchMultipleOverlappingEllipses::search
+// (improc/search_multiple_overlapping_ellipses.cpp:106-196).
+//
+// Design (one WARP per feature, SL2_SEARCH_WARPS features per CTA):
+//   * the feature's search window (bounding box of the 3-sigma ellipse + BOXSIZE-1) is staged
+//     from the frame in HBM into shared memory by ONE TMA box load (cp.async.bulk.tensor.3d,
+//     tensor = [slot*stream][H][W] u8) that completes on a per-warp mbarrier; windows larger
+//     than the tile are walked tile by tile.
+//   * while the TMA is in flight the warp evaluates the exact FP64 ellipse predicate for every
+//     candidate of the tile and compacts the non-empty vertical strips (SL2_STRIP candidates of
+//     one column) into a task list with ballots, so later rounds run with full lanes.
+//   * integer phase, per lane = one strip: every image row is read once from shared memory as
+//     aligned 32-bit words, byte-aligned with funnel shifts, and feeds all strip candidates that
+//     overlap it: Sg0g1 by IDP.4A against the template held in registers, Sg1 / Sg1sq by IDP.4A
+//     against 0x01010101 / itself.  All sums are exact int32 like the reference's.
+//   * FP64 phase: the score of improc.cpp:99-133 op-for-op with __d*_rn (no FMA contraction,
+//     IEEE div / sqrt) so that scores are bit-identical to the x86-64 SSE2 reference build.
+//   * arg-min with the reference's tie-break (`corr <= corrmax` => the LAST candidate in
+//     urel-major / vrel-minor scan order wins) carried as (score, scan index) through a
+//     warp-shuffle reduction.
+#include "sl2_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar,
+                                            int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t phase) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(phase)
+      : "memory");
+  return ok != 0;
+}
+
+struct Best {
+  double corr;
+  int idx;
+};
+
+// reference acceptance rule folded into an order-independent comparison:
+// smaller score wins; equal scores -> the later scan index wins (monoslam.cpp:457, quirk Q3).
+__device__ __forceinline__ void consider(Best &b, double corr, int idx) {
+  if (corr < b.corr || (corr == b.corr && idx > b.idx)) {
+    b.corr = corr;
+    b.idx = idx;
+  }
+}
+
+struct DumpPtrs {
+  double *corr;
+  double *sd;
+  uint8_t *inside;
+  int *box;
+  int cap;
+};
+
+template <int BOX>
+__global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32)
+    search_kernel(const __grid_constant__ CUtensorMap tmap, const Sl2Dev d, const SearchLaunch L,
+                  const DumpPtrs dump) {
+  constexpr int NW = (BOX + 3) / 4;             // 32-bit words per template row
+  constexpr int HALF = (BOX - 1) / 2;
+  constexpr int V = SL2_STRIP;
+  constexpr uint32_t LASTMASK = (BOX % 4 == 0) ? 0xffffffffu : ((1u << (8 * (BOX % 4))) - 1u);
+  extern __shared__ __align__(128) uint8_t smem[];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int groups = (L.jobs_per_stream + SL2_SEARCH_WARPS - 1) / SL2_SEARCH_WARPS;
+  const int sl = blockIdx.x / groups;                       // stream, local to the launch
+  const int r = (blockIdx.x % groups) * SL2_SEARCH_WARPS + warp;  // job of this warp
+  if (r >= L.jobs_per_stream) return;
+  const int job = sl * L.jobs_per_stream + r;
+  const int feat = L.job_feat[job];
+  if (feat < 0) return;
+  const int s = L.stream_lo + sl;
+
+  const int TW = d.tile_w, TH = d.tile_h;
+  const int TCW = TW - BOX + 1, TCH = TH - BOX + 1;
+  const int tile_bytes = ((TW * TH + 16 + 127) / 128) * 128;
+  const int max_tasks = TCW * ((TCH + V - 1) / V);
+  const int list_bytes = ((max_tasks * 4 + 15) / 16) * 16;
+  const int per_warp = ((tile_bytes + list_bytes + 16 + 127) / 128) * 128;  // TMA dst: 128 B aligned
+  uint8_t *tile = smem + (size_t)warp * per_warp;
+  uint32_t *list = reinterpret_cast<uint32_t *>(tile + tile_bytes);
+  const uint32_t bar = smem_u32(tile + tile_bytes + list_bytes);
+  const uint32_t tile_s = smem_u32(tile);
+
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  __syncwarp();
+
+  // ---- template into registers, rows zero-padded to 16 bytes in HBM --------------------------
+  uint32_t T[BOX][NW];
+  {
+    const uint32_t *pp =
+        reinterpret_cast<const uint32_t *>(d.patches + ((size_t)s * d.Nmax + feat) * (BOX * 16));
+#pragma unroll
+    for (int rr = 0; rr < BOX; ++rr)
+#pragma unroll
+      for (int k = 0; k < NW; ++k) T[rr][k] = __ldg(pp + rr * 4 + k);
+  }
+  int Sg0 = 0, Sg0sq = 0;
+#pragma unroll
+  for (int rr = 0; rr < BOX; ++rr)
+#pragma unroll
+    for (int k = 0; k < NW; ++k) {
+      Sg0 = __dp4a(T[rr][k], 0x01010101u, (uint32_t)Sg0);
+      Sg0sq = __dp4a(T[rr][k], T[rr][k], (uint32_t)Sg0sq);
+    }
+  // per-feature constants of improc.cpp:99-131
+  const double n = (double)(BOX * BOX);
+  const double Sg0d = (double)Sg0, Sg0sqd = (double)Sg0sq;
+  const double g0bar = div_(Sg0d, n);
+  const double varg0 = sub_(div_(Sg0sqd, n), mul_(g0bar, g0bar));
+  const double sigmag0 = sqrt_(varg0);
+  const double A0 = div_(Sg0sqd, varg0);       // Sg0sqdoub / varg0
+  const double g0s = div_(g0bar, sigmag0);     // g0bar / sigmag0
+  const double Sg0x2 = mul_(Sg0d, 2.0);        // Sg0doub * 2.0
+
+  // ---- search box, monoslam.cpp:416-439 (smoe.cpp:118-147) -----------------------------------
+  const double P00 = L.job_puinv[job * 3 + 0], P01 = L.job_puinv[job * 3 + 1],
+               P11 = L.job_puinv[job * 3 + 2];
+  const double cx = L.job_centre[job * 2 + 0], cy = L.job_centre[job * 2 + 1];
+  const int halfwidth =
+      __double2int_rz(div_(3.0, sqrt_(sub_(P00, div_(mul_(P01, P01), P11)))));
+  const int halfheight =
+      __double2int_rz(div_(3.0, sqrt_(sub_(P11, div_(mul_(P01, P01), P00)))));
+  const int uc = L.smoe_mode ? __double2int_rz(cx) : __double2int_rz(add_(cx, 0.5));
+  const int vc = L.smoe_mode ? __double2int_rz(cy) : __double2int_rz(add_(cy, 0.5));
+  int us = -halfwidth, uf = halfwidth, vs = -halfheight, vf = halfheight;
+  if (uc + us - HALF < 0) us = HALF - uc;
+  if (uc + uf - HALF > d.W - BOX) uf = d.W - BOX - uc + HALF;
+  if (vc + vs - HALF < 0) vs = HALF - vc;
+  if (vc + vf - HALF > d.H - BOX) vf = d.H - BOX - vc + HALF;
+  const int CW = uf - us + 1, CH = vf - vs + 1;
+  const int x0 = uc + us - HALF, y0 = vc + vs - HALF;
+  const double twoP01 = mul_(2.0, P01);
+  if (dump.box && lane == 0) {
+    dump.box[0] = us; dump.box[1] = uf; dump.box[2] = vs; dump.box[3] = vf;
+    dump.box[4] = uc; dump.box[5] = vc;
+  }
+
+  Best best;
+  best.corr = 1000000.0;  // corrmax, monoslam.cpp:444
+  best.idx = -1;
+  uint32_t phase = 0;
+  const int img = L.slot * d.B + s;
+
+  if (CW > 0 && CH > 0) {
+    for (int ty0 = 0; ty0 < CH; ty0 += TCH) {
+      for (int tx0 = 0; tx0 < CW; tx0 += TCW) {
+        const int tcw = min(TCW, CW - tx0), tch = min(TCH, CH - ty0);
+        if (lane == 0) {
+          mbar_expect_tx(bar, (uint32_t)(TW * TH));
+          tma_load_3d(tile_s, &tmap, bar, x0 + tx0, y0 + ty0, img);
+        }
+        // ---- task list while the TMA is in flight ------------------------------------------
+        const int nstrips = (tch + V - 1) / V;
+        const int ntask = tcw * nstrips;
+        int nlist = 0;
+        for (int t0 = 0; t0 < ntask; t0 += 32) {
+          const int t = t0 + lane;
+          uint32_t entry = 0;
+          if (t < ntask) {
+            const int cu = t / nstrips, st = t - cu * nstrips;
+            const double du = (double)(us + tx0 + cu);
+            const double a = mul_(mul_(P00, du), du);
+            const double bcoef = mul_(twoP01, du);
+            uint32_t mask = 0;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+              const int cv = st * V + j;
+              if (cv < tch) {
+                const double dv = (double)(vs + ty0 + cv);
+                // PuInv(0,0)*u*u + 2*PuInv(0,1)*u*v + PuInv(1,1)*v*v < 9  (monoslam.cpp:453-454)
+                const double q = add_(add_(a, mul_(bcoef, dv)), mul_(mul_(P11, dv), dv));
+                if (q < 9.0 || dump.corr) mask |= (q < 9.0 ? 1u : 0x100u) << j;
+              }
+            }
+            // bits 0..7: inside ellipse; bits 8..15: outside but wanted by the dump mode
+            if (mask) entry = (uint32_t)cu | ((uint32_t)st << 8) | (mask << 16);
+          }
+          const uint32_t bal = __ballot_sync(0xffffffffu, entry != 0);
+          if (entry) list[nlist + __popc(bal & ((1u << lane) - 1u))] = entry;
+          nlist += __popc(bal);
+        }
+        __syncwarp();
+        while (!mbar_try_wait(bar, phase)) {
+        }
+        phase ^= 1;
+
+        // ---- strips ------------------------------------------------------------------------
+        for (int l0 = 0; l0 < nlist; l0 += 32) {
+          if (l0 + lane < nlist) {
+            const uint32_t e = list[l0 + lane];
+            const int cu = e & 0xff, st = (e >> 8) & 0xff;
+            const uint32_t m_in = (e >> 16) & 0xff, m_all = m_in | ((e >> 24) & 0xff);
+            const int cv0 = st * V;
+            const int sh = (cu & 3) * 8;
+            const uint32_t *wbase = reinterpret_cast<const uint32_t *>(tile) + (cu >> 2);
+            const int tw4 = TW >> 2;
+            uint32_t ax[V], a1[V], a2[V];
+#pragma unroll
+            for (int j = 0; j < V; ++j) ax[j] = a1[j] = a2[j] = 0;
+#pragma unroll
+            for (int rr = 0; rr < V + BOX - 1; ++rr) {
+              const int row = min(cv0 + rr, TH - 1);
+              const uint32_t *wp = wbase + row * tw4;
+              uint32_t w[NW + 1], sw[NW];
+#pragma unroll
+              for (int k = 0; k <= NW; ++k) w[k] = wp[k];
+#pragma unroll
+              for (int k = 0; k < NW; ++k) sw[k] = __funnelshift_r(w[k], w[k + 1], sh);
+              sw[NW - 1] &= LASTMASK;
+              uint32_t rs = 0, rq = 0;
+#pragma unroll
+              for (int k = 0; k < NW; ++k) {
+                rs = __dp4a(sw[k], 0x01010101u, rs);
+                rq = __dp4a(sw[k], sw[k], rq);
+              }
+#pragma unroll
+              for (int j = 0; j < V; ++j) {
+                const int t = rr - j;  // template row seen by candidate j in this image row
+                if (t >= 0 && t < BOX) {
+#pragma unroll
+                  for (int k = 0; k < NW; ++k) ax[j] = __dp4a(sw[k], T[t][k], ax[j]);
+                  a1[j] += rs;
+                  a2[j] += rq;
+                }
+              }
+            }
+            // ---- FP64 score, improc.cpp:99-133 ------------------------------------------------
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+              if ((m_all >> j) & 1u) {
+                const double Sg1d = (double)(int)a1[j], Sg1sqd = (double)(int)a2[j],
+                             Sg0g1d = (double)(int)ax[j];
+                const double g1bar = div_(Sg1d, n);
+                const double varg1 = sub_(div_(Sg1sqd, n), mul_(g1bar, g1bar));
+                const double sigmag1 = sqrt_(varg1);
+                double corr;
+                if (sigmag0 == 0.0) {
+                  corr = (sigmag1 == 0.0) ? 0.0 : 1.0;
+                } else if (sigmag1 == 0.0) {
+                  corr = 1.0;
+                } else {
+                  const double k = sub_(g0s, div_(g1bar, sigmag1));
+                  double C = add_(A0, div_(Sg1sqd, varg1));
+                  C = add_(C, mul_(n, mul_(k, k)));
+                  C = sub_(C, div_(mul_(Sg0g1d, 2.0), mul_(sigmag0, sigmag1)));
+                  C = sub_(C, div_(mul_(Sg0x2, k), sigmag0));
+                  C = add_(C, div_(mul_(mul_(Sg1d, 2.0), k), sigmag1));
+                  corr = div_(C, n);
+                }
+                const int ui = tx0 + cu, vi = ty0 + cv0 + j;
+                const int idx = ui * CH + vi;  // urel-major, vrel-minor scan position
+                const bool inside = (m_in >> j) & 1u;
+                if (dump.corr && idx < dump.cap) {
+                  dump.corr[idx] = corr;
+                  dump.sd[idx] = sigmag1;
+                  dump.inside[idx] = inside ? 1 : 0;
+                }
+                if (inside) {
+                  if (L.smoe_mode) {
+                    // smoe.cpp:173-184: penalise low image sigma, no patch-sigma gate
+                    if (sigmag1 < 10.0) corr = add_(corr, 5.0);
+                    if (corr <= 1000000.0) consider(best, corr, idx);
+                  } else if (corr <= 1000000.0 && !(sigmag0 < 10.0) && !(sigmag1 < 10.0)) {
+                    consider(best, corr, idx);  // monoslam.cpp:457-467
+                  }
+                }
+              }
+            }
+          }
+        }
+        __syncwarp();
+        fence_proxy_async();  // the next TMA write reuses the tile the warp has just read
+      }
+    }
+  }
+
+  // ---- warp arg-min with the scan-order tie-break -------------------------------------------
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double oc = __shfl_xor_sync(0xffffffffu, best.corr, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best.idx, o);
+    consider(best, oc, oi);
+  }
+  if (lane == 0) {
+    int u = L.smoe_mode ? 0 : -1, v = L.smoe_mode ? 0 : -1;  // smoe.cpp:43-44 default (0,0)
+    if (best.idx >= 0) {
+      u = us + best.idx / CH + uc;
+      v = vs + best.idx % CH + vc;
+    }
+    const uint8_t ok = (best.corr > 0.40) ? 0 : 1;  // monoslam.cpp:472-476
+    if (L.out_uv) {
+      L.out_uv[job * 2 + 0] = u;
+      L.out_uv[job * 2 + 1] = v;
+    }
+    if (L.out_found) L.out_found[job] = ok;
+    if (L.out_best) L.out_best[job] = best.corr;
+    if (L.scatter_to_features) {
+      const size_t f = (size_t)s * d.Nmax + feat;
+      d.z_uv[f * 2 + 0] = u;
+      d.z_uv[f * 2 + 1] = v;
+      d.found[f] = ok;
+      d.best[f] = best.corr;
+    }
+  }
+}
+
+size_t search_smem_bytes(const Sl2Dev &d) {
+  const int TCW = d.tile_w - d.box + 1, TCH = d.tile_h - d.box + 1;
+  const int tile_bytes = ((d.tile_w * d.tile_h + 16 + 127) / 128) * 128;
+  const int max_tasks = TCW * ((TCH + SL2_STRIP - 1) / SL2_STRIP);
+  const int list_bytes = ((max_tasks * 4 + 15) / 16) * 16;
+  return (size_t)SL2_SEARCH_WARPS * (((tile_bytes + list_bytes + 16 + 127) / 128) * 128);
+}
+
+template <int BOX>
+cudaError_t launch_t(const Sl2Dev &d, const CUtensorMap &tmap, const SearchLaunch &L,
+                     const DumpPtrs &dump, cudaStream_t st) {
+  const size_t smem = search_smem_bytes(d);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(search_kernel<BOX>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  const int groups = (L.jobs_per_stream + SL2_SEARCH_WARPS - 1) / SL2_SEARCH_WARPS;
+  const int grid = groups * L.stream_cnt;
+  if (grid <= 0) return cudaSuccess;
+  search_kernel<BOX><<<grid, SL2_SEARCH_WARPS * 32, smem, st>>>(tmap, d, L, dump);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_any(const Sl2Dev &d, const CUtensorMap &tmap, const SearchLaunch &L,
+                       const DumpPtrs &dump, cudaStream_t st) {
+  switch (d.box) {
+    case 11: return launch_t<11>(d, tmap, L, dump, st);
+    case 15: return launch_t<15>(d, tmap, L, dump, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace
+
+cudaError_t sl2_launch_search(const Sl2Dev &d, const CUtensorMap &tmap, const SearchLaunch &L,
+                              cudaStream_t st) {
+  DumpPtrs none = {nullptr, nullptr, nullptr, nullptr, 0};
+  return launch_any(d, tmap, L, none, st);
+}
+
+cudaError_t sl2_launch_score_map(const Sl2Dev &d, const CUtensorMap &tmap, int stream_id, int slot,
+                                 int feat, const double *cp, int *box_dev, double *corr_dev,
+                                 double *sd_dev, uint8_t *inside_dev, int cap, cudaStream_t st) {
+  // cp = device array: centre(2), puinv(3), then one int job_feat stored after them by the caller
+  SearchLaunch L = {};
+  L.job_centre = cp;
+  L.job_puinv = cp + 2;
+  L.job_feat = reinterpret_cast<const int *>(cp + 5);
+  L.jobs_per_stream = 1;
+  L.stream_lo = stream_id;
+  L.stream_cnt = 1;
+  L.slot = slot;
+  (void)feat;
+  DumpPtrs dump = {corr_dev, sd_dev, inside_dev, box_dev, cap};
+  return launch_any(d, tmap, L, dump, st);
+}

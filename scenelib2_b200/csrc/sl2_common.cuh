@@ -1,0 +1,97 @@
+// sl2_common.cuh — shared device/host declarations of libsl2b200.so (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define SL2_NXV 13          // vehicle state size (motion_model.cpp:44)
+#define SL2_NB 8            // Cholesky row-panel height
+#define SL2_SEARCH_WARPS 4  // features (warps) per search CTA
+#define SL2_STRIP 8         // candidates per vertical strip task
+#define SL2_MAX_FEAT_SMEM 128  // == SL2_MAX_FEATURES (include/sl2b200.h)
+
+// Device view of one context: everything the kernels need, passed by value.
+struct Sl2Dev {
+  // geometry / constants
+  int B;       // camera streams in this context
+  int Nmax;    // feature capacity per stream
+  int W, H, pitch, slots;
+  int box;     // BOXSIZE
+  int ld;      // leading dimension of P (>= 13 + 3*Nmax, multiple of 8)
+  int ldg;     // leading dimension of the update scratch G
+  int mmax;    // 2 * Nmax
+  int n_select;
+  int tile_w, tile_h;  // TMA window tile (bytes x rows)
+  int min_attempts;
+  double match_fraction;
+  double cam[8];  // width,height,fku,fkv,u0,v0,kd1,sd
+  double dt;
+  double ovr[3];
+  // resident state
+  uint8_t *frames;   // [slots][B][H][pitch]
+  uint8_t *patches;  // [B][Nmax][box][16]   rows zero-padded to 16 bytes
+  double *x;         // [B][ld]
+  double *P;         // [B][ld][ld] col-major, both triangles kept consistent
+  double *G;         // [B][mmax][ldg]  row-major scratch: [ S | H*P | nu ]
+  int *nfeat;        // [B]
+  double *xp_org;    // [B][Nmax][7]
+  int *attempted;    // [B][Nmax]
+  int *successful;   // [B][Nmax]
+  // per-step, per-feature (indexed by feature)
+  double *h;       // [B][Nmax][2]
+  double *S;       // [B][Nmax][4] col-major
+  double *Rvar;    // [B][Nmax]
+  double *dh_dxp;  // [B][Nmax][2][7] row-major
+  double *dh_dy;   // [B][Nmax][2][3] row-major
+  int *sel_rank;   // [B][Nmax]  rank in the selected list or -1
+  int *z_uv;       // [B][Nmax][2]
+  uint8_t *found;  // [B][Nmax]  1 = successful measurement this step
+  double *best;    // [B][Nmax]
+  // per-step, per job (rank order = measurement order)
+  int *job_feat;       // [B][Nmax]  feature index of job r, -1 = none
+  double *job_centre;  // [B][Nmax][2]
+  double *job_puinv;   // [B][Nmax][3]
+  int *nsel;           // [B]
+  int *nvisible;       // [B]
+  int *nmeas;          // [B]  successful measurements of the last step
+};
+
+// ---- correctly-rounded, never-fused FP64 helpers: the oracle is built with
+// -ffp-contract=off, so every bit-critical expression must avoid FMA contraction.
+__device__ __forceinline__ double mul_(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub_(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double div_(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double sqrt_(double a) { return __dsqrt_rn(a); }
+
+// launchers (defined in search.cu / ekf.cu), called from api.cu
+struct SearchLaunch {
+  // job arrays may be the context's own (fused step) or temporaries (staged API)
+  const int *job_feat;       // [njobs_per_stream * B] or [n]
+  const double *job_centre;  // x2
+  const double *job_puinv;   // x3
+  int jobs_per_stream;       // stride between streams in the job arrays
+  int stream_lo, stream_cnt; // streams covered by the launch
+  int slot;
+  int *out_uv;               // [jobs][2] (by job) or nullptr
+  uint8_t *out_found;        // by job
+  double *out_best;          // by job
+  int scatter_to_features;   // 1: also write d.z_uv/found/best indexed by feature
+  int smoe_mode;             // 1: A11 semantics (centre truncation, penalty, no patch gate)
+};
+
+cudaError_t sl2_launch_search(const Sl2Dev &d, const CUtensorMap &tmap, const SearchLaunch &L,
+                              cudaStream_t st);
+cudaError_t sl2_launch_score_map(const Sl2Dev &d, const CUtensorMap &tmap, int stream_id, int slot,
+                                 int feat, const double *centre_puinv_dev /*5*/, int *box_dev,
+                                 double *corr_dev, double *sd_dev, uint8_t *inside_dev, int cap,
+                                 cudaStream_t st);
+cudaError_t sl2_launch_predict(const Sl2Dev &d, int stream_lo, int stream_cnt, const double *u3_dev,
+                               int do_predict, int do_measure, cudaStream_t st);
+cudaError_t sl2_launch_update(const Sl2Dev &d, int stream_lo, int stream_cnt, int staged_m,
+                              const int *st_feat, const double *st_Hxv, const double *st_Hy,
+                              const double *st_R, const double *st_nu, int only_normalise,
+                              cudaStream_t st);
+cudaError_t sl2_launch_cull(const Sl2Dev &d, int stream_lo, int stream_cnt, int force_index,
+                            cudaStream_t st);
+size_t sl2_update_smem_bytes(const Sl2Dev &d);

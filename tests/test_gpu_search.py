@@ -1,0 +1,121 @@
+"""GPU parity, patch search: CUDA path through the C ABI vs the CPU oracle.  Bit-exact (integer
+match positions, found flags AND the FP64 score bits)."""
+import os
+
+import numpy as np
+import pytest
+
+from gpu_util import ctx_for_image, ctx_from_scenes, random_puinv, sl2, synth
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _compare_search(oracle, ctx, image, patches, feat, centres, pu):
+    u, v, f, best = ctx.patch_search(0, 0, feat, centres, pu)
+    ou, ov, of, obest = oracle.elliptical_search(image, patches[feat], centres, pu)
+    assert (f == of).all()
+    assert best.tobytes() == obest.tobytes()          # corrmax bits, incl. the 1e6 sentinel
+    acc = obest < 1e6
+    assert (u[acc] == ou[acc]).all() and (v[acc] == ov[acc]).all()
+    assert (u[~acc] == -1).all() and (v[~acc] == -1).all()
+    return f
+
+
+def test_c2_search_bit_exact(oracle):
+    sc = synth.make_scene("C2", n_frames=3)
+    ctx = ctx_from_scenes([sc])
+    rng = np.random.default_rng(1)
+    for t in range(3):
+        ctx.set_frame(0, 0, sc.frames[t])
+        n = sc.n_features
+        centres = sc.pix + rng.uniform(-4, 4, (n, 2))
+        pu = np.tile([9 / 400.0, 0.0, 9 / 400.0], (n, 1))
+        pu[::5] = random_puinv(rng, len(pu[::5]), 6, 20, iso_fraction=0.2)
+        f = _compare_search(oracle, ctx, sc.frames[t], sc.patches, np.arange(n, dtype=np.int32),
+                            centres, pu)
+        assert f.mean() > 0.9
+    ctx.close()
+
+
+def test_c3_full_size_search_bit_exact(oracle):
+    sc = synth.make_scene("C3", n_frames=1)
+    assert sc.patches.shape == (100, 15, 15) and sc.frames.shape[1:] == (480, 640)
+    ctx = ctx_from_scenes([sc])
+    ctx.set_frame(0, 0, sc.frames[0])
+    n = sc.n_features
+    centres = sc.pix + np.random.default_rng(2).uniform(-10, 10, (n, 2))
+    pu = np.tile([9 / 1600.0, 0.0, 9 / 1600.0], (n, 1))
+    f = _compare_search(oracle, ctx, sc.frames[0], sc.patches, np.arange(n, dtype=np.int32),
+                        centres, pu)
+    assert f.all()
+    ctx.close()
+
+
+@pytest.mark.parametrize("B", [11, 15])
+def test_score_map_bits_borders_ties_gating(oracle, B):
+    rng = np.random.default_rng(3)
+    img = synth.make_texture(rng, 120, 160)
+    img[30:75, 40:100] = 200          # flat plateau: sigma < 10 (gated) and exact ties
+    img[90:120, 0:30] = (np.arange(30)[None, :] * 8).astype(np.uint8)   # columns-only gradient: ties along v
+    half = B // 2
+    patches = np.stack([img[80 - half:80 + half + 1, 120 - half:120 + half + 1],
+                        img[100 - half:100 + half + 1, 12 - half:12 + half + 1],
+                        np.full((B, B), 77, np.uint8),                      # sigma0 = 0
+                        rng.integers(0, 256, (B, B), dtype=np.uint8)])
+    ctx = ctx_for_image(img, patches, radius=20)
+    cases = [(0, [120.3, 80.6], [0.02, 0.0, 0.02]), (0, [2.0, 3.0], [0.01, 0.002, 0.02]),
+             (0, [158.9, 118.2], [0.03, -0.01, 0.02]), (1, [14.0, 104.0], [0.05, 0.0, 0.01]),
+             (1, [70.0, 50.0], [0.04, 0.0, 0.04]), (2, [120.0, 80.0], [0.1, 0.0, 0.1]),
+             (3, [80.0, 5.0], [0.009, 0.0, 0.5]), (3, [3.0, 60.0], [0.5, 0.0, 0.009]),
+             (0, [120.0, 80.0], [0.3, 0.29, 0.3])]
+    for feat, c, p in cases:
+        box, corr, sd, inside = ctx.score_map(0, 0, feat, c, p)
+        obox, ocorr, osd, oinside = oracle.score_map(img, patches[feat], c, p)
+        assert (box == obox).all()
+        assert (inside == oinside).all()
+        assert corr.tobytes() == ocorr.tobytes()      # every candidate, inside or not: bit-exact
+        assert sd.tobytes() == osd.tobytes()
+        feat_i = np.array([feat], np.int32)
+        u, v, f, best = ctx.patch_search(0, 0, feat_i, np.array([c]), np.array([p]))
+        ou, ov, of, obest = oracle.elliptical_search(img, patches[feat_i], np.array([c]), np.array([p]))
+        assert (f[0], best[0]) == (of[0], obest[0])
+        if obest[0] < 1e6:
+            assert (u[0], v[0]) == (ou[0], ov[0])
+    ctx.close()
+
+
+def test_large_ellipse_walks_several_tiles(oracle):
+    sc = synth.make_scene("C2", n_frames=1, n_features=10)
+    ctx = ctx_from_scenes([sc], search_tile_radius=12)    # ellipses below need up to 4x4 tiles
+    ctx.set_frame(0, 0, sc.frames[0])
+    rng = np.random.default_rng(4)
+    n = sc.n_features
+    pu = random_puinv(rng, n, 25, 60, iso_fraction=0.3)
+    centres = sc.pix + rng.uniform(-15, 15, (n, 2))
+    _compare_search(oracle, ctx, sc.frames[0], sc.patches, np.arange(n, dtype=np.int32), centres, pu)
+    ctx.close()
+
+
+def test_smoe_search_matches_oracle_and_reference_golden(oracle):
+    k = np.load(os.path.join(G, "a11_ref_kat.npz"))
+    ctx = ctx_for_image(k["image"], k["patch"][None], radius=20)
+    ru, rv, rf = ctx.smoe_search(0, 0, 0, k["puinv3"], k["centres"])
+    assert (ru == k["res_u"]).all() and (rv == k["res_v"]).all() and (rf == k["res_flag"]).all()
+    rng = np.random.default_rng(5)
+    pu = random_puinv(rng, 16, 4, 18, iso_fraction=0.3)
+    centres = np.column_stack([rng.uniform(0, 160, 16), rng.uniform(0, 120, 16)])
+    ru, rv, rf = ctx.smoe_search(0, 0, 0, pu, centres)
+    ou, ov, of, _ = oracle.smoe_search(k["image"], k["patch"], pu, centres)
+    assert (ru == ou).all() and (rv == ov).all() and (rf == of).all()
+    ctx.close()
+
+
+def test_search_arguments_are_checked():
+    sc = synth.make_scene("C2", n_frames=1, n_features=4)
+    ctx = ctx_from_scenes([sc])
+    with pytest.raises(sl2.Sl2Error):
+        ctx.patch_search(0, 0, np.array([7], np.int32), np.zeros((1, 2)), np.ones((1, 3)))
+    with pytest.raises(sl2.Sl2Error):
+        ctx.patch_search(3, 0, np.array([0], np.int32), np.zeros((1, 2)), np.ones((1, 3)))
+    ctx.close()

@@ -1,0 +1,92 @@
+"""GPU parity, fused step (MonoSLAM::GoOneStep, monoslam.cpp:108-180) for several independent
+camera streams in one context vs one CPU oracle per stream."""
+import os
+
+import numpy as np
+import pytest
+
+from gpu_util import (RTOL_NORTH_STAR, assert_state_close, ctx_from_scenes, oracle_slam_from_scene,
+                      state_err, synth)
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _run(oracle, scenes, steps, slots=2):
+    ctx = ctx_from_scenes(scenes, frame_slots=slots)
+    oracles = [oracle_slam_from_scene(oracle, sc) for sc in scenes]
+    worst = (0.0, 0.0)
+    for t in range(steps):
+        k = t % scenes[0].frames.shape[0]
+        ctx.set_frames(t % slots, np.stack([sc.frames[k] for sc in scenes]))
+        ctx.step(t % slots)
+        ctx.sync()
+        for s, (sc, o) in enumerate(zip(scenes, oracles)):
+            o.step(sc.frames[k])
+            fg, fo = ctx.features(s), o.features()
+            assert ctx.num_features(s) == o.num_features
+            assert (fg["select_rank"] == fo["select_rank"]).all(), (t, s)
+            assert (fg["flags"] == fo["flags"]).all(), (t, s)
+            ok = (fo["flags"] & 2) > 0
+            assert (fg["z"][ok] == fo["z"][ok]).all(), (t, s)     # bit-exact match positions
+            assert (fg["attempted"] == fo["attempted"]).all()
+            assert (fg["successful"] == fo["successful"]).all()
+            xg, Pg = ctx.get_state(s)
+            xo, Po = o.get_state()
+            e = assert_state_close(xg, Pg, xo, Po)
+            worst = (max(worst[0], e[0]), max(worst[1], e[1]))
+            assert np.abs(Pg - Pg.T).max() == 0.0
+    ctx.close()
+    return worst
+
+
+def test_three_streams_c2_like(oracle):
+    scenes = [synth.make_scene("C2", stream_id=s, n_frames=6, n_features=24, override=False)
+              for s in range(3)]
+    w = _run(oracle, scenes, 6)
+    print("worst errors:", w)
+
+
+def test_c1_reference_config(oracle):
+    kp = np.load(os.path.join(G, "known_patches.npy"))
+    scenes = [synth.make_scene("C1", stream_id=s, n_frames=5, known_patches=kp) for s in range(2)]
+    _run(oracle, scenes, 8)
+
+
+def test_bad_feature_is_culled_like_the_reference(oracle):
+    sc = synth.make_scene("C2", n_frames=2, n_features=12)
+    bad = sc.patches.copy()
+    bad[3] = np.random.default_rng(0).integers(0, 256, bad[3].shape, dtype=np.uint8)
+    sc.patches = bad
+    good = synth.make_scene("C2", stream_id=1, n_frames=2, n_features=12)
+    ctx_scenes = [sc, good]
+    _run(oracle, ctx_scenes, 12)
+
+
+def test_c4_full_size_two_frames(oracle):
+    """BASELINE config C4: 320x240, N = 100 (n = 313, m = 200), fixed +-20 px search."""
+    sc = synth.make_scene("C4", n_frames=2)
+    assert sc.n == 313 and sc.search_override[0] > 0
+    w = _run(oracle, [sc], 2)
+    assert max(w) < RTOL_NORTH_STAR
+    print("C4 worst errors:", w)
+
+
+def test_c3_full_size_one_frame(oracle):
+    sc = synth.make_scene("C3", n_frames=1)
+    w = _run(oracle, [sc], 1, slots=1)
+    print("C3 worst errors:", w)
+
+
+def test_step_host_returns_camera_states(oracle):
+    scenes = [synth.make_scene("C2", stream_id=s, n_frames=2, n_features=16) for s in range(2)]
+    ctx = ctx_from_scenes(scenes)
+    frames = np.ascontiguousarray(np.stack([sc.frames[0] for sc in scenes]))
+    xv = np.zeros((2, 13))
+    ctx.step_host(0, frames.ctypes.data, xv.ctypes.data)
+    for s, sc in enumerate(scenes):
+        o = oracle_slam_from_scene(oracle, sc)
+        o.step(sc.frames[0])
+        xo, Po = o.get_state()
+        assert np.allclose(xv[s], xo[:13], rtol=1e-7, atol=1e-12)
+    ctx.close()
