@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json metric: EKF-SLAM frames/sec @320x240, N = 100 features (config C4:
+n = 313, m = 200, 11x11 patch, +-20 px search ellipse), aggregate over independent camera streams.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--streams B] [--impl ours|reference]
+
+A "step" = one GoOneStep pass (predict -> select -> patch search -> EKF update -> normalise ->
+cull -> symmetrise) of every camera stream resident on the GPU over one new frame each.
+`value`  : frames/s with the frames already resident in HBM (frame ring), CUDA-event timed.
+`e2e`    : the same metric through the C-ABI call sl2_step_host with HOST (pinned) frames in and
+           camera states out, host<->device copies inside the timed region.
+Multi-GPU: replicas only (independent camera sequences, no collective on the data path); the
+barrier + max-over-ranks timing uses torch.distributed (NCCL).
+`--impl reference`: the CPU oracle (a port: the reference cannot be built here) on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "EKF-SLAM frames/sec @320x240 N=100 feats"
+UNIT = "frames/s"
+WORKLOAD = "C4: synthetic 320x240, 100 features, EKF state dim 313, 11x11 patch, +-20px ellipse"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--streams", type=int, default=296, help="camera streams per GPU")
+    ap.add_argument("--config", default="C4")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ring", type=int, default=4, help="distinct frames per stream")
+    ap.add_argument("--unique", type=int, default=16, help="distinct synthetic scenes (tiled over streams)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons}
+
+
+def make_scenes(name, unique, ring, base_stream=0):
+    from scenelib2_b200 import synth
+    return [synth.make_scene(name, stream_id=base_stream + i, n_frames=ring) for i in range(unique)]
+
+
+def oracle_slams(po, scenes, count):
+    slams = []
+    for i in range(count):
+        sc = scenes[i % len(scenes)]
+        cfg = po.make_config(width=sc.width, height=sc.height, fku=sc.cam8[2], fkv=sc.cam8[3],
+                             u0=sc.cam8[4], v0=sc.cam8[5], kd1=sc.cam8[6], sd=sc.cam8[7],
+                             delta_t=sc.delta_t, n_select=sc.n_select, boxsize=sc.boxsize,
+                             search_override=sc.search_override)
+        s = po.Slam(cfg)
+        for k in range(sc.n_features):
+            s.add_feature(sc.x0[13 + 3 * k:16 + 3 * k], sc.xp_org[k], sc.patches[k])
+        s.set_state(sc.x0, sc.P0)
+        slams.append(s)
+    return slams
+
+
+def cpu_run(scenes, seconds, threads=None):
+    """Oracle (CPU port of the reference path) timed on the host cores over a bounded sample."""
+    from oracle import pyoracle as po
+    po.build()
+    threads = threads or po.hardware_threads() or os.cpu_count() or 1
+    slams = oracle_slams(po, scenes, threads)
+    frames = [scenes[i % len(scenes)].frames for i in range(threads)]
+    t1 = po.run_slams(slams, frames, 1, threads)            # calibration (also warms caches)
+    steps = max(2, int(seconds / max(t1, 1e-3)))
+    t = po.run_slams(slams, frames, steps, threads)
+    fps = threads * steps / t
+    return fps, threads, steps, t
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    scenes = make_scenes(args.config, min(args.unique, 8), args.ring)
+    budget = max(2.0, min(40.0, 120.0 / max(1, args.steps + args.warmup)))
+    vals = []
+    threads = None
+    for k in range(args.warmup + args.steps):
+        fps, threads, steps, t = cpu_run(scenes, budget, None)
+        if k >= args.warmup:
+            vals.append(fps)
+        if sum(1 for _ in vals) >= 3 and time.time() - T0 > 240:
+            break
+    v = float(np.mean(vals))
+    sample = "%d streams (1 per thread) x ~%.0f s of oracle steps per bench step" % (threads, budget)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1e3 * threads / v,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "streams": threads,
+                                        "note": "CPU oracle = port of the reference path (Eigen3/OpenCV absent: "
+                                                "the reference itself cannot be built); faithful block storage"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    import scenelib2_b200 as sl2
+    from scenelib2_b200 import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, R = args.streams, args.ring
+    scenes = make_scenes(args.config, min(args.unique, B), R, base_stream=rank * 1000)
+    sc0 = scenes[0]
+    N, n, H, W = sc0.n_features, sc0.n, sc0.height, sc0.width
+    # a dedicated (non-default) torch stream: the library launches on it, torch events time it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    cfg = sl2.config_for_scene(sc0, num_streams=B, frame_slots=R, device=local_rank,
+                               cuda_stream=stream.cuda_stream)
+    ctx = sl2.Context(cfg)
+    for s in range(B):
+        sl2.load_scene(ctx, s, scenes[s % len(scenes)])
+    # host frame ring in pinned memory: [R][B][H][W]
+    host = torch.empty((R, B, H, W), dtype=torch.uint8, pin_memory=True)
+    hv = host.numpy()
+    for s in range(B):
+        hv[:, s] = scenes[s % len(scenes)].frames
+    for k in range(R):
+        ctx.set_frames_ptr(k, host[k].data_ptr())
+    xv_out = torch.empty((B, 13), dtype=torch.float64, pin_memory=True)
+    ctx.sync()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for k in range(steps):
+            fn(k)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- device-resident leg (`value`) ----------------------------------------------------------
+    for k in range(args.warmup):
+        ctx.step(k % R)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctx.launch_count()
+    ms = timed(lambda k: ctx.step(k % R), args.steps)
+    launches = ctx.launch_count() - l0
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- per-kernel durations (CUDA events on the launching stream, one sync per step) ----------
+    ctx.enable_timing(True)
+    kt = np.zeros(4)
+    for k in range(args.steps):
+        ctx.step(k % R)
+        kt += ctx.last_step_times()
+    kt /= args.steps
+    ctx.enable_timing(False)
+
+    # ---- end-to-end leg: host frames in, camera states out, through the C ABI -----------------
+    for k in range(min(3, args.warmup)):
+        ctx.step_host(k % R, host[k % R].data_ptr(), xv_out.data_ptr())
+    ms_e2e = timed(lambda k: ctx.step_host(k % R, host[k % R].data_ptr(), xv_out.data_ptr()), args.steps)
+    e2e = world * B * args.steps / (ms_e2e * 1e-3)
+
+    matched = float(np.mean([(ctx.features(s)["flags"] & 2).astype(bool).mean() for s in (0, B // 2, B - 1)]))
+    nfeat_end = ctx.num_features(0)
+
+    if rank == 0:
+        pk, pk_kind = peaks()
+        rad = sc0.meta["config"]["radius"]
+        bytes_per_feature = synth.algorithmic_search_bytes(sc0.boxsize, rad)
+        search_bytes = B * N * bytes_per_feature                      # per launch
+        ach = search_bytes / (kt[1] * 1e-3) / 1e9
+        m = 2 * N
+        flops = synth.ekf_structured_flops(n, m) * B
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "search_dram_bytes_per_launch.json")
+        if os.path.exists(tp):
+            try:
+                tj = json.load(open(tp))
+                traffic = tj.get("dram_bytes_per_launch_per_stream", 0) * B or None
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64 (EKF, scores) + u8/int32 (correlation sums)",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "streams_per_gpu": B, "frames_per_step": B * world,
+                       "state_dim": n, "measurements": m, "parallelism": "replicas x%d (no collective)" % world,
+                       "l2": "per-step working set %.0f MB (P + scratch + frames of %d streams) exceeds the 126 MB L2"
+                             % ((B * (cfg.max_features * 3 + 13) ** 2 * 8 * 2.1) / 1e6, B),
+                       "matched_fraction": matched, "features_left_stream0": nfeat_end},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * H * W,
+                    "d2h_bytes_per_step": B * 13 * 8, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "roofline": {"kernel": "search_kernel<11> (patch search)", "bound": "hbm",
+                         "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": ach / pk["hbm_gbs"], "traffic": traffic, "peak_kind": pk_kind,
+                         "algorithmic_bytes_per_launch": search_bytes,
+                         "kernel_ms": float(kt[1]),
+                         "note": "compute-bound (FP64 score + IDP.4A), not HBM-bound: see DESIGN.md"},
+            "roofline_ekf": {"kernel": "update_kernel (EKF update)", "bound": "fp64",
+                             "achieved": flops / (kt[2] * 1e-3) / 1e12, "unit": "TFLOP/s",
+                             "peak_nominal": 37.0, "algorithmic_flops_per_launch": flops,
+                             "kernel_ms": float(kt[2])},
+            "kernel_ms": {"predict_select": float(kt[0]), "patch_search": float(kt[1]),
+                          "ekf_update": float(kt[2]), "cull": float(kt[3])},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            fps, threads, steps, t = cpu_run(scenes, args.cpu_seconds)
+            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "%d streams x %d oracle steps (%.1f s)" % (threads, steps, t)}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+T0 = time.time()
+
+if __name__ == "__main__":
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+    else:
+        run_ours(a, rank, local_rank, world)

@@ -207,7 +207,7 @@ int sl2_create(const sl2_config *cfg, sl2_ctx **out) {
   const int radius = cfg->search_tile_radius > 0 ? cfg->search_tile_radius : 20;
   d.tile_h = 2 * radius + d.box;
   if (d.tile_h > 255) d.tile_h = 255;
-  d.tile_w = (2 * radius + d.box + 15) & ~15;
+  d.tile_w = (2 * radius + d.box + 15 + 15) & ~15;  // +15: 16-byte aligned TMA box start
   if (d.tile_w > 256) d.tile_w = 256;
   d.min_attempts = cfg->minimum_attempted_measurements_of_feature;
   d.match_fraction = cfg->successful_match_fraction;

@@ -436,7 +436,8 @@ __global__ void __launch_bounds__(256) predict_kernel(const Sl2Dev d, int stream
       vis[i] = 0;
       score[i] = 0.0;
       d.sel_rank[fb + i] = -1;
-      d.found[fb + i] = 0;
+      // d.found keeps its previous value for features that are not measured this frame, like
+      // Feature::successful_measurement_flag_ (only written by make_measurements, monoslam.cpp:479-496)
       d.job_feat[fb + i] = -1;
     }
     if (i < nf) {
@@ -540,7 +541,7 @@ constexpr int UPD_KC = 16;
 
 __device__ __forceinline__ UpdSmem carve(uint8_t *base, int Nmax) {
   UpdSmem u;
-  const int K = Nmax, mmax = 2 * Nmax;
+  const int K = (Nmax + 1) & ~1, mmax = 2 * K;  // even counts keep every section 16 B aligned
   double *p = reinterpret_cast<double *>(base);
   u.Hx = p;  p += (size_t)K * 26;
   u.Hy = p;  p += (size_t)K * 6;
@@ -965,6 +966,15 @@ __global__ void __launch_bounds__(256) cull_kernel(const Sl2Dev d, int stream_lo
   __syncthreads();
   if (tid == 0) {
     // serial compaction of the small per-feature records (rare path)
+    // selected_feature_list_.erase (monoslam.cpp:258-281 via :797-798): later entries move up
+    for (int i = 0; i < nf; ++i) {
+      const int r = d.sel_rank[fb + i];
+      if (keep[i] < 0 && r >= 0) {
+        for (int j = 0; j < nf; ++j)
+          if (d.sel_rank[fb + j] > r) d.sel_rank[fb + j] -= 1;
+        d.sel_rank[fb + i] = -1;
+      }
+    }
     const int box16 = d.box * 16;
     for (int i = 0; i < nf; ++i) {
       const int k = keep[i];
@@ -989,7 +999,7 @@ __global__ void __launch_bounds__(256) cull_kernel(const Sl2Dev d, int stream_lo
 }  // namespace
 
 size_t sl2_update_smem_bytes(const Sl2Dev &d) {
-  const size_t K = d.Nmax, mmax = 2 * d.Nmax;
+  const size_t K = (d.Nmax + 1) & ~1, mmax = 2 * K;
   const size_t doubles = K * 26 + K * 6 + K + mmax + mmax * SL2_NB + SL2_NB * SL2_NB + SL2_NB + 64 * 65;
   return doubles * 8 + K * 4 + 16;
 }

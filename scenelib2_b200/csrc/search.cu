@@ -8,7 +8,8 @@
 //   * the feature's search window (bounding box of the 3-sigma ellipse + BOXSIZE-1) is staged
 //     from the frame in HBM into shared memory by ONE TMA box load (cp.async.bulk.tensor.3d,
 //     tensor = [slot*stream][H][W] u8) that completes on a per-warp mbarrier; windows larger
-//     than the tile are walked tile by tile.
+//     than the tile are walked tile by tile.  The TMA unit needs a 16-byte aligned box start
+//     (measured: tools/tma_probe3.cu), so the box is loaded from x & ~15 and is 15 B wider.
 //   * while the TMA is in flight the warp evaluates the exact FP64 ellipse predicate for every
 //     candidate of the tile and compacts the non-empty vertical strips (SL2_STRIP candidates of
 //     one column) into a task list with ballots, so later rounds run with full lanes.
@@ -106,7 +107,9 @@ __global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32)
   const int s = L.stream_lo + sl;
 
   const int TW = d.tile_w, TH = d.tile_h;
-  const int TCW = TW - BOX + 1, TCH = TH - BOX + 1;
+  // TMA needs the box start 16-byte aligned (innermost coordinate * 1 B): the tile is loaded from
+  // x & ~15 and is 15 bytes wider than the widest window it serves.
+  const int TCW = TW - 15 - BOX + 1, TCH = TH - BOX + 1;
   const int tile_bytes = ((TW * TH + 16 + 127) / 128) * 128;
   const int max_tasks = TCW * ((TCH + V - 1) / V);
   const int list_bytes = ((max_tasks * 4 + 15) / 16) * 16;
@@ -184,9 +187,10 @@ __global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32)
     for (int ty0 = 0; ty0 < CH; ty0 += TCH) {
       for (int tx0 = 0; tx0 < CW; tx0 += TCW) {
         const int tcw = min(TCW, CW - tx0), tch = min(TCH, CH - ty0);
+        const int xa = (x0 + tx0) & ~15, xoff = (x0 + tx0) & 15;
         if (lane == 0) {
           mbar_expect_tx(bar, (uint32_t)(TW * TH));
-          tma_load_3d(tile_s, &tmap, bar, x0 + tx0, y0 + ty0, img);
+          tma_load_3d(tile_s, &tmap, bar, xa, y0 + ty0, img);
         }
         // ---- task list while the TMA is in flight ------------------------------------------
         const int nstrips = (tch + V - 1) / V;
@@ -230,8 +234,9 @@ __global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32)
             const int cu = e & 0xff, st = (e >> 8) & 0xff;
             const uint32_t m_in = (e >> 16) & 0xff, m_all = m_in | ((e >> 24) & 0xff);
             const int cv0 = st * V;
-            const int sh = (cu & 3) * 8;
-            const uint32_t *wbase = reinterpret_cast<const uint32_t *>(tile) + (cu >> 2);
+            const int cx = cu + xoff;  // byte column of the candidate's window inside the tile
+            const int sh = (cx & 3) * 8;
+            const uint32_t *wbase = reinterpret_cast<const uint32_t *>(tile) + (cx >> 2);
             const int tw4 = TW >> 2;
             uint32_t ax[V], a1[V], a2[V];
 #pragma unroll
@@ -344,7 +349,7 @@ __global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32)
 }
 
 size_t search_smem_bytes(const Sl2Dev &d) {
-  const int TCW = d.tile_w - d.box + 1, TCH = d.tile_h - d.box + 1;
+  const int TCW = d.tile_w - 15 - d.box + 1, TCH = d.tile_h - d.box + 1;
   const int tile_bytes = ((d.tile_w * d.tile_h + 16 + 127) / 128) * 128;
   const int max_tasks = TCW * ((TCH + SL2_STRIP - 1) / SL2_STRIP);
   const int list_bytes = ((max_tasks * 4 + 15) / 16) * 16;
