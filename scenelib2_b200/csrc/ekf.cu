@@ -530,14 +530,30 @@ struct UpdSmem {
   double *Rv;    // [K]
   double *wv;    // [mmax]  nu, later w = U^-T nu
   int *mfeat;    // [K]
-  double *mult;  // [mmax][NB] multipliers of the current panel
+  double *mult;  // [mmax][NB] (negated) multipliers of the current panel
   double *ublk;  // [NB][NB]
   double *invd;  // [NB]
-  double *tile;  // phase 4: max(2*KC*64, 64*65) doubles
+  double *pan;   // phase 2: panel buffer [NB][panw]; phase 4: Y slabs (2 stages) / tile T[64][65]
+  int panw;
 };
 
 constexpr int UPD_THREADS = 256;
-constexpr int UPD_KC = 16;
+constexpr int UPD_KC = 16;   // k-chunk of the Y^T Y tiles
+constexpr int UPD_YS = 68;   // padded row stride of a staged Y slab (doubles): conflict-free DMMA reads
+constexpr int UPD_GB = 4;    // 8-column groups per warp iteration in the panel update
+
+__host__ __device__ inline int upd_panw(int Nmax) {
+  const int K = (Nmax + 1) & ~1;
+  // row stride = 2 (mod 16) doubles: the 8 rows of a DMMA C fragment hit distinct banks
+  return ((2 * K + SL2_NXV + 3 * Nmax + 1 + 15) & ~15) + 2;
+}
+__host__ __device__ inline size_t upd_pan_doubles(int Nmax) {
+  size_t a = (size_t)SL2_NB * upd_panw(Nmax);
+  const size_t b = 2 * 2 * UPD_KC * UPD_YS, c = 64 * 65;
+  if (b > a) a = b;
+  if (c > a) a = c;
+  return (a + 1) & ~(size_t)1;
+}
 
 __device__ __forceinline__ UpdSmem carve(uint8_t *base, int Nmax) {
   UpdSmem u;
@@ -550,9 +566,28 @@ __device__ __forceinline__ UpdSmem carve(uint8_t *base, int Nmax) {
   u.mult = p;  p += (size_t)mmax * SL2_NB;
   u.ublk = p;  p += SL2_NB * SL2_NB;
   u.invd = p;  p += SL2_NB;
-  u.tile = p;  p += 64 * 65;
+  u.pan = p;  p += upd_pan_doubles(Nmax);
+  u.panw = upd_panw(Nmax);
   u.mfeat = reinterpret_cast<int *>(p);
   return u;
+}
+
+// D(8x8) = A(8x4) * B(4x8) + C on the FP64 tensor path: lane holds A(lane/4, lane%4),
+// B(lane%4, lane/4) and C(lane/4, 2*(lane%4) + {0,1}).
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, int src_bytes) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
 __global__ void __launch_bounds__(UPD_THREADS) update_kernel(
@@ -671,84 +706,85 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(
     }
     __syncthreads();
 
-    // ---- phase 2: left-looking Cholesky by row panels on G = [S | HP | nu] --------------------
+    // ---- phase 2: left-looking Cholesky by row panels of 8 on G = [S | HP | nu] ----------------
+    // Trailing update of a panel = C(8 x cols) - A(8 x i0) * B(i0 x cols) with A(r,k) = U(k,i0+r)
+    // (multipliers, shared memory) and B = finished rows of G (global / L2): FP64 tensor-core
+    // tiles (DMMA m8n8k4), each warp owning groups of 8 columns.
     const int width = m + n + 1;
-    constexpr int CPT = 3;  // columns per thread: (2*128 + 397 + 1) / 256 <= 3
+    const int PW = sm.panw;  // panel buffer row stride (doubles)
+    const int warp = tid >> 5, lane = tid & 31;
+    const int lr = lane >> 2, lc = lane & 3;  // DMMA fragment coordinates
     for (int i0 = 0; i0 < m; i0 += SL2_NB) {
       const int nbp = min(SL2_NB, m - i0);
-      // multipliers U(k, i0..i0+NB) of all finished rows k < i0
+      // multipliers, negated so that D = (-A) * B + C
       for (int e = tid; e < i0 * SL2_NB; e += UPD_THREADS) {
         const int k = e / SL2_NB, r = e - k * SL2_NB;
-        sm.mult[e] = (r < nbp) ? G[(size_t)k * ldg + i0 + r] : 0.0;
+        sm.mult[e] = (r < nbp) ? -G[(size_t)k * ldg + i0 + r] : 0.0;
       }
       __syncthreads();
-      double acc[CPT][SL2_NB];
-      int col[CPT];
+      const int ngroups = (width - i0 + 7) >> 3;
+      for (int g0 = warp * UPD_GB; g0 < ngroups; g0 += (UPD_THREADS / 32) * UPD_GB) {
+        double c[UPD_GB][2];
+        int colb[UPD_GB];  // column of the B fragment element of this lane
 #pragma unroll
-      for (int q = 0; q < CPT; ++q) {
-        col[q] = i0 + tid + q * UPD_THREADS;
+        for (int q = 0; q < UPD_GB; ++q) {
+          const int cbase = i0 + (g0 + q) * 8;
+          colb[q] = cbase + lr;
+          const int cc = cbase + 2 * lc;  // C fragment: row lr, columns cc, cc+1
+          const bool rv = lr < nbp && (g0 + q) < ngroups;
+          c[q][0] = (rv && cc < width) ? G[(size_t)(i0 + lr) * ldg + cc] : 0.0;
+          c[q][1] = (rv && cc + 1 < width) ? G[(size_t)(i0 + lr) * ldg + cc + 1] : 0.0;
+          if (colb[q] >= width) colb[q] = -1;
+        }
+#pragma unroll 2
+        for (int k0 = 0; k0 < i0; k0 += 4) {
+          const double a = sm.mult[(k0 + lc) * SL2_NB + lr];
+          const double *gk = G + (size_t)(k0 + lc) * ldg;
+          double b[UPD_GB];
 #pragma unroll
-        for (int r = 0; r < SL2_NB; ++r)
-          acc[q][r] = (col[q] < width && r < nbp) ? G[(size_t)(i0 + r) * ldg + col[q]] : 0.0;
-      }
-      const bool c1 = col[1] < width, c2 = col[2] < width;
-#pragma unroll 4
-      for (int k = 0; k < i0; ++k) {
-        const double *gk = G + (size_t)k * ldg;
-        const double g0 = (col[0] < width) ? gk[col[0]] : 0.0;
-        const double g1 = c1 ? gk[col[1]] : 0.0;
-        const double g2 = c2 ? gk[col[2]] : 0.0;
-        const double2 *mk = reinterpret_cast<const double2 *>(sm.mult + (size_t)k * SL2_NB);
+          for (int q = 0; q < UPD_GB; ++q) b[q] = colb[q] >= 0 ? gk[colb[q]] : 0.0;
 #pragma unroll
-        for (int r2 = 0; r2 < SL2_NB / 2; ++r2) {
-          const double2 mm = mk[r2];
-          acc[0][2 * r2] -= mm.x * g0;
-          acc[0][2 * r2 + 1] -= mm.y * g0;
-          acc[1][2 * r2] -= mm.x * g1;
-          acc[1][2 * r2 + 1] -= mm.y * g1;
-          acc[2][2 * r2] -= mm.x * g2;
-          acc[2][2 * r2 + 1] -= mm.y * g2;
+          for (int q = 0; q < UPD_GB; ++q) dmma884(c[q][0], c[q][1], a, b[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < UPD_GB; ++q) {
+          if (g0 + q < ngroups) {
+            const int pc = (g0 + q) * 8 + 2 * lc;
+            *reinterpret_cast<double2 *>(sm.pan + (size_t)lr * PW + pc) = make_double2(c[q][0], c[q][1]);
+          }
         }
       }
-      // diagonal block -> shared, factor on one thread
-      if (tid < SL2_NB) {
-#pragma unroll
-        for (int r = 0; r < SL2_NB; ++r) sm.ublk[r * SL2_NB + tid] = acc[0][r];
-      }
       __syncthreads();
+      // factor the 8x8 diagonal block on one thread (rows of the panel buffer, columns 0..7)
       if (tid == 0) {
         for (int r = 0; r < nbp; ++r) {
-          double dg = sm.ublk[r * SL2_NB + r];
+          double dg = sm.pan[(size_t)r * PW + r];
           for (int q = 0; q < r; ++q) dg -= sm.ublk[q * SL2_NB + r] * sm.ublk[q * SL2_NB + r];
           const double u = sqrt(dg);
           const double iu = 1.0 / u;
           sm.ublk[r * SL2_NB + r] = u;
           sm.invd[r] = iu;
-          for (int c = r + 1; c < nbp; ++c) {
-            double v = sm.ublk[r * SL2_NB + c];
-            for (int q = 0; q < r; ++q) v -= sm.ublk[q * SL2_NB + r] * sm.ublk[q * SL2_NB + c];
-            sm.ublk[r * SL2_NB + c] = v * iu;
+          for (int cix = r + 1; cix < nbp; ++cix) {
+            double v = sm.pan[(size_t)r * PW + cix];
+            for (int q = 0; q < r; ++q) v -= sm.ublk[q * SL2_NB + r] * sm.ublk[q * SL2_NB + cix];
+            sm.ublk[r * SL2_NB + cix] = v * iu;
           }
         }
       }
       __syncthreads();
       // apply U_pp^-T to every column of the panel and write the finished rows
+      for (int cc = tid; cc < width - i0; cc += UPD_THREADS) {
+        double f[SL2_NB];
 #pragma unroll
-      for (int q = 0; q < CPT; ++q) {
-        if (col[q] < width) {
-          const int cc = col[q] - i0;
-          double f[SL2_NB];
+        for (int r = 0; r < SL2_NB; ++r) {
+          double v = sm.pan[(size_t)r * PW + cc];
 #pragma unroll
-          for (int r = 0; r < SL2_NB; ++r) {
-            double v = acc[q][r];
-#pragma unroll
-            for (int t = 0; t < r; ++t) v -= sm.ublk[t * SL2_NB + r] * f[t];
-            f[r] = v * sm.invd[r];
-            if (r < nbp) {
-              double outv = f[r];
-              if (cc < nbp) outv = (cc >= r) ? sm.ublk[r * SL2_NB + cc] : 0.0;
-              G[(size_t)(i0 + r) * ldg + col[q]] = outv;
-            }
+          for (int t = 0; t < r; ++t) v -= sm.ublk[t * SL2_NB + r] * f[t];
+          f[r] = v * sm.invd[r];
+          if (r < nbp) {
+            double outv = f[r];
+            if (cc < nbp) outv = (cc >= r) ? sm.ublk[r * SL2_NB + cc] : 0.0;
+            G[(size_t)(i0 + r) * ldg + i0 + cc] = outv;
           }
         }
       }
@@ -764,71 +800,87 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(
       x[j] += a;
     }
 
-    // ---- phase 4: P -= Y^T Y on 64x64 tiles, upper triangle computed, lower mirrored -----------
+    // ---- phase 4: P -= Y^T Y on 64x64 tiles (upper triangle computed, lower mirrored) ---------
+    // DMMA tiles: A(i,k) = Y(k, a0+i), B(k,j) = Y(k, b0+j); Y slabs are staged by cp.async into a
+    // double-buffered shared tile; warp w owns rows 16*(w%4).. and columns 32*(w/4)..
     {
-      double *Ya = sm.tile;                 // [KC][64]
-      double *Yb = sm.tile + UPD_KC * 64;   // [KC][64]
-      const int tx = tid & 15, ty = tid >> 4;  // tx -> rows (a), ty -> cols (b)
       const int nt = (n + 63) / 64;
+      const int wa = (warp & 3) * 16, wb = (warp >> 2) * 32;
+      const int nchunk = (m + UPD_KC - 1) / UPD_KC;
       for (int tb = 0; tb < nt; ++tb)
         for (int ta = 0; ta <= tb; ++ta) {
-          double acc[4][4];
+          double acc[2][4][2];
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+          for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-          for (int k0 = 0; k0 < m; k0 += UPD_KC) {
-            __syncthreads();
-            for (int e = tid; e < UPD_KC * 64; e += UPD_THREADS) {
-              const int kk = e >> 6, c = e & 63;
-              const int k = k0 + kk;
-              const int ca = ta * 64 + c, cb = tb * 64 + c;
-              Ya[e] = (k < m && ca < n) ? G[(size_t)k * ldg + m + ca] : 0.0;
-              Yb[e] = (k < m && cb < n) ? G[(size_t)k * ldg + m + cb] : 0.0;
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+          __syncthreads();  // previous tile's users of sm.pan (T) are done
+          // stage loader: 2 slabs x KC rows x 64 columns = 2*KC*32 16-byte segments
+          auto stage = [&](int chunk, int buf) {
+            double *dst = sm.pan + (size_t)buf * (2 * UPD_KC * UPD_YS);
+            for (int e = tid; e < 2 * UPD_KC * 32; e += UPD_THREADS) {
+              const int slab = e / (UPD_KC * 32), rem = e - slab * (UPD_KC * 32);
+              const int kk = rem >> 5, seg = rem & 31;
+              const int k = chunk * UPD_KC + kk;
+              const int col = (slab ? tb : ta) * 64 + seg * 2;
+              int bytes = 0;
+              if (k < m) bytes = col + 1 < n ? 16 : (col < n ? 8 : 0);
+              const double *src = G + (size_t)(k < m ? k : 0) * ldg + m + (col < n ? col : 0);
+              cp_async16(dst + (size_t)slab * (UPD_KC * UPD_YS) + kk * UPD_YS + seg * 2, src, bytes);
+            }
+            cp_async_commit();
+          };
+          stage(0, 0);
+          for (int ch = 0; ch < nchunk; ++ch) {
+            if (ch + 1 < nchunk) {
+              stage(ch + 1, (ch + 1) & 1);
+              cp_async_wait<1>();
+            } else {
+              cp_async_wait<0>();
             }
             __syncthreads();
+            const double *Ya = sm.pan + (size_t)(ch & 1) * (2 * UPD_KC * UPD_YS);
+            const double *Yb = Ya + UPD_KC * UPD_YS;
 #pragma unroll
-            for (int kk = 0; kk < UPD_KC; ++kk) {
-              const double2 a01 = *reinterpret_cast<const double2 *>(Ya + kk * 64 + tx * 4);
-              const double2 a23 = *reinterpret_cast<const double2 *>(Ya + kk * 64 + tx * 4 + 2);
-              const double2 b01 = *reinterpret_cast<const double2 *>(Yb + kk * 64 + ty * 4);
-              const double2 b23 = *reinterpret_cast<const double2 *>(Yb + kk * 64 + ty * 4 + 2);
-              const double a[4] = {a01.x, a01.y, a23.x, a23.y};
-              const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+            for (int kk = 0; kk < UPD_KC; kk += 4) {
+              double a[2], b[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
+              for (int i = 0; i < 2; ++i) a[i] = Ya[(kk + lc) * UPD_YS + wa + i * 8 + lr];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+              for (int j = 0; j < 4; ++j) b[j] = Yb[(kk + lc) * UPD_YS + wb + j * 8 + lr];
+#pragma unroll
+              for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
             }
+            __syncthreads();  // buffer (ch & 1) may be refilled by the next-next stage
           }
+          // accumulators -> shared T[a][b] (64 x 65), then coalesced read-modify-write of P
+          double *T = sm.pan;
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int ar = wa + i * 8 + lr, bc = wb + j * 8 + 2 * lc;
+              T[ar * 65 + bc] = acc[i][j][0];
+              T[ar * 65 + bc + 1] = acc[i][j][1];
+            }
           __syncthreads();
-          // new values; stage through shared memory for the mirrored (transposed) write
-          double *T = sm.tile;  // [64][65]
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int b = tb * 64 + ty * 4 + j;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int a = ta * 64 + tx * 4 + i;
-              double v = 0.0;
-              if (a < n && b < n) {
-                v = P[a + (size_t)ld * b] - acc[i][j];
-                P[a + (size_t)ld * b] = v;
-              }
-              T[(tx * 4 + i) * 65 + (ty * 4 + j)] = v;
+          const int tx = tid & 63, ty = tid >> 6;  // tx -> row a (contiguous in P), ty -> column phase
+          for (int bb = ty; bb < 64; bb += UPD_THREADS / 64) {
+            const int a = ta * 64 + tx, b = tb * 64 + bb;
+            if (a < n && b < n) {
+              const double v = P[a + (size_t)ld * b] - T[tx * 65 + bb];
+              P[a + (size_t)ld * b] = v;
+              T[tx * 65 + bb] = v;
             }
           }
           if (ta != tb) {
             __syncthreads();
-            // lower tile: rows = b range, cols = a range; thread (tx -> row b, ty -> col a)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int a = ta * 64 + ty * 4 + j;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int b = tb * 64 + tx * 4 + i;
-                if (a < n && b < n) P[b + (size_t)ld * a] = T[(ty * 4 + j) * 65 + (tx * 4 + i)];
-              }
+            // lower tile: rows = b range (contiguous in P), columns = a range
+            for (int aa = ty; aa < 64; aa += UPD_THREADS / 64) {
+              const int a = ta * 64 + aa, b = tb * 64 + tx;
+              if (a < n && b < n) P[b + (size_t)ld * a] = T[aa * 65 + tx];
             }
           }
         }
@@ -1000,7 +1052,8 @@ __global__ void __launch_bounds__(256) cull_kernel(const Sl2Dev d, int stream_lo
 
 size_t sl2_update_smem_bytes(const Sl2Dev &d) {
   const size_t K = (d.Nmax + 1) & ~1, mmax = 2 * K;
-  const size_t doubles = K * 26 + K * 6 + K + mmax + mmax * SL2_NB + SL2_NB * SL2_NB + SL2_NB + 64 * 65;
+  const size_t doubles = K * 26 + K * 6 + K + mmax + mmax * SL2_NB + SL2_NB * SL2_NB + SL2_NB +
+                         upd_pan_doubles(d.Nmax);
   return doubles * 8 + K * 4 + 16;
 }
 
