@@ -227,6 +227,12 @@ def run_ours(args, rank, local_rank, world):
         kt += ctx.last_step_times()
     kt /= args.steps
     ctx.enable_timing(False)
+    if os.environ.get("SL2_PHASES"):
+        import ctypes
+        buf = (ctypes.c_longlong * 64)()
+        ctx.L.sl2_debug_phase_cycles(ctx.h, buf)
+        st = [buf[i] for i in range(8)]
+        print("update phase cycles (CTA 0):", [st[i + 1] - st[i] for i in range(7)], file=sys.stderr)
 
     # ---- end-to-end leg: host frames in, camera states out, through the C ABI -----------------
     for k in range(min(3, args.warmup)):

@@ -249,6 +249,7 @@ int sl2_create(const sl2_config *cfg, sl2_ctx **out) {
   ALLOC(d.nsel, B);
   ALLOC(d.nvisible, B);
   ALLOC(d.nmeas, B);
+  ALLOC(d.dbg, 64);
 #undef ALLOC
   if (!ok) {
     const std::string m = std::string("cudaMalloc failed: ") + cudaGetErrorString(cudaGetLastError());
@@ -668,6 +669,14 @@ int sl2_last_step_times(sl2_ctx *c, float *ms4) {
   if (!c->timing) return fail(c, SL2_ERR_STATE, "timing not enabled");
   CU_TRY(c, cudaEventSynchronize(c->ev[4]));
   for (int i = 0; i < 4; ++i) CU_TRY(c, cudaEventElapsedTime(&ms4[i], c->ev[i], c->ev[i + 1]));
+  return SL2_OK;
+}
+
+// debug only (not part of the public header): clock64 stamps of the update kernel's phases
+int sl2_debug_phase_cycles(sl2_ctx *c, long long *out64) {
+  if (!c || !out64) return SL2_ERR_ARG;
+  CU_TRY(c, cudaMemcpyAsync(out64, c->d.dbg, 64 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
   return SL2_OK;
 }
 

@@ -575,7 +575,7 @@ __device__ __forceinline__ UpdSmem carve(uint8_t *base, int Nmax) {
 // D(8x8) = A(8x4) * B(4x8) + C on the FP64 tensor path: lane holds A(lane/4, lane%4),
 // B(lane%4, lane/4) and C(lane/4, 2*(lane%4) + {0,1}).
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }
@@ -600,11 +600,13 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(
   const int nf = d.nfeat[s];
   const int n = SL2_NXV + 3 * nf;
   const int ld = d.ld, ldg = d.ldg;
-  double *P = d.P + (size_t)s * ld * ld;
-  double *x = d.x + (size_t)s * ld;
-  double *G = d.G + (size_t)s * d.mmax * ldg;
+  double *__restrict__ P = d.P + (size_t)s * ld * ld;
+  double *__restrict__ x = d.x + (size_t)s * ld;
+  double *__restrict__ G = d.G + (size_t)s * d.mmax * ldg;
   const size_t fb = (size_t)s * d.Nmax;
   __shared__ int s_m;
+#define PH(i) do { if (blockIdx.x == 0 && tid == 0) d.dbg[(i)] = clock64(); } while (0)
+  PH(0);
 
   // ---- phase 0: measurement list in selected order, successful only (monoslam.cpp:556-571) ---
   if (tid == 0) {
@@ -652,11 +654,13 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(
     }
     __syncthreads();
 
+    PH(1);
     // ---- phase 1a: H*P rows (structured: 13 + 3 columns of P per row pair) and nu column ----
     for (int j = tid; j < n; j += UPD_THREADS) {
       double px[13];
 #pragma unroll
       for (int c = 0; c < 13; ++c) px[c] = P[j + (size_t)ld * c];  // P(c, j) by symmetry
+#pragma unroll 4
       for (int k = 0; k < K; ++k) {
         const int pos = SL2_NXV + 3 * sm.mfeat[k];
         const double py0 = P[j + (size_t)ld * pos], py1 = P[j + (size_t)ld * (pos + 1)],
@@ -680,6 +684,7 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(
     }
     for (int i = tid; i < m; i += UPD_THREADS) G[(size_t)i * ldg + m + n] = sm.wv[i];
     __syncthreads();
+    PH(2);
     // ---- phase 1b: S = (H P) H^T + R ---------------------------------------------------------
     for (int e = tid; e < m * K; e += UPD_THREADS) {
       const int i = e / K, kp = e - i * K;
@@ -706,6 +711,7 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(
     }
     __syncthreads();
 
+    PH(3);
     // ---- phase 2: left-looking Cholesky by row panels of 8 on G = [S | HP | nu] ----------------
     // Trailing update of a panel = C(8 x cols) - A(8 x i0) * B(i0 x cols) with A(r,k) = U(k,i0+r)
     // (multipliers, shared memory) and B = finished rows of G (global / L2): FP64 tensor-core
@@ -736,7 +742,7 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(
           c[q][1] = (rv && cc + 1 < width) ? G[(size_t)(i0 + lr) * ldg + cc + 1] : 0.0;
           if (colb[q] >= width) colb[q] = -1;
         }
-#pragma unroll 2
+#pragma unroll 8
         for (int k0 = 0; k0 < i0; k0 += 4) {
           const double a = sm.mult[(k0 + lc) * SL2_NB + lr];
           const double *gk = G + (size_t)(k0 + lc) * ldg;
@@ -791,6 +797,7 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(
       __syncthreads();
     }
 
+    PH(4);
     // ---- phase 3: x += Y^T w -----------------------------------------------------------------
     for (int i = tid; i < m; i += UPD_THREADS) sm.wv[i] = G[(size_t)i * ldg + m + n];
     __syncthreads();
@@ -800,6 +807,7 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(
       x[j] += a;
     }
 
+    PH(5);
     // ---- phase 4: P -= Y^T Y on 64x64 tiles (upper triangle computed, lower mirrored) ---------
     // DMMA tiles: A(i,k) = Y(k, a0+i), B(k,j) = Y(k, b0+j); Y slabs are staged by cp.async into a
     // double-buffered shared tile; warp w owns rows 16*(w%4).. and columns 32*(w/4)..
@@ -888,6 +896,7 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(
     __syncthreads();
   }
 
+  PH(6);
   // ---- phase 5: normalise_state (monoslam.cpp:616-637): P <- J P J^T, J = diag(I3, dqnorm, I6, I)
   if (m > 0 || only_normalise) {
     __shared__ double J4[16];
@@ -939,6 +948,7 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(
     __syncthreads();
   }
 
+  PH(7);
   // ---- bookkeeping: attempt / success counters (monoslam.cpp:479-496) ------------------------
   if (staged_m < 0 && !only_normalise) {
     for (int i = tid; i < nf; i += UPD_THREADS) {

@@ -86,7 +86,7 @@ struct DumpPtrs {
   int cap;
 };
 
-template <int BOX>
+template <int BOX, bool FILTER>
 __global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32)
     search_kernel(const __grid_constant__ CUtensorMap tmap, const Sl2Dev d, const SearchLaunch L,
                   const DumpPtrs dump) {
@@ -153,6 +153,11 @@ __global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32)
   const double A0 = div_(Sg0sqd, varg0);       // Sg0sqdoub / varg0
   const double g0s = div_(g0bar, sigmag0);     // g0bar / sigmag0
   const double Sg0x2 = mul_(Sg0d, 2.0);        // Sg0doub * 2.0
+  // exact integers (< 2^53, so FP64 holds them exactly): n^2 * var = n*Sxx - Sx^2
+  const double V0d = fma(n, Sg0sqd, -(Sg0d * Sg0d));
+  const double T100 = 100.0 * n * n;           // sigma >= 10  <=>  n^2 var >= 100 n^2
+  const bool patch_ok = !(sigmag0 < 10.0);     // kCorrelationSigmaThreshold_ gate on the template
+  float bmin = 3.0e38f;                        // running minimum of the approximate score
 
   // ---- search box, monoslam.cpp:416-439 (smoe.cpp:118-147) -----------------------------------
   const double P00 = L.job_puinv[job * 3 + 0], P01 = L.job_puinv[job * 3 + 1],
@@ -269,47 +274,86 @@ __global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32)
               }
             }
             // ---- FP64 score, improc.cpp:99-133 ------------------------------------------------
+            auto exact_score = [&](double Sg1d, double Sg1sqd, double Sg0g1d, double &sigmag1) {
+              const double g1bar = div_(Sg1d, n);
+              const double varg1 = sub_(div_(Sg1sqd, n), mul_(g1bar, g1bar));
+              sigmag1 = sqrt_(varg1);
+              if (sigmag0 == 0.0) return (sigmag1 == 0.0) ? 0.0 : 1.0;
+              if (sigmag1 == 0.0) return 1.0;
+              const double k = sub_(g0s, div_(g1bar, sigmag1));
+              double C = add_(A0, div_(Sg1sqd, varg1));
+              C = add_(C, mul_(n, mul_(k, k)));
+              C = sub_(C, div_(mul_(Sg0g1d, 2.0), mul_(sigmag0, sigmag1)));
+              C = sub_(C, div_(mul_(Sg0x2, k), sigmag0));
+              C = add_(C, div_(mul_(mul_(Sg1d, 2.0), k), sigmag1));
+              return div_(C, n);
+            };
+            if constexpr (FILTER) {
+              // The reference's score equals 2 - 2*rho (rho = normalised cross-correlation) up to
+              // FP64 rounding (<= 1e-9 for sigma >= 10).  rho is evaluated in FP32 from the EXACT
+              // integer moments; only candidates whose approximate score is within kWindow of the
+              // running minimum can be the reference's arg-min (or tie with it), and only those go
+              // through the exact FP64 chain.  kWindow = 1e-5 >= 2 * (FP32 error 1.1e-6 + 1e-9).
+              constexpr float kWindow = 1.0e-5f;
+              if (patch_ok) {
 #pragma unroll
-            for (int j = 0; j < V; ++j) {
-              if ((m_all >> j) & 1u) {
-                const double Sg1d = (double)(int)a1[j], Sg1sqd = (double)(int)a2[j],
-                             Sg0g1d = (double)(int)ax[j];
-                const double g1bar = div_(Sg1d, n);
-                const double varg1 = sub_(div_(Sg1sqd, n), mul_(g1bar, g1bar));
-                const double sigmag1 = sqrt_(varg1);
-                double corr;
-                if (sigmag0 == 0.0) {
-                  corr = (sigmag1 == 0.0) ? 0.0 : 1.0;
-                } else if (sigmag1 == 0.0) {
-                  corr = 1.0;
-                } else {
-                  const double k = sub_(g0s, div_(g1bar, sigmag1));
-                  double C = add_(A0, div_(Sg1sqd, varg1));
-                  C = add_(C, mul_(n, mul_(k, k)));
-                  C = sub_(C, div_(mul_(Sg0g1d, 2.0), mul_(sigmag0, sigmag1)));
-                  C = sub_(C, div_(mul_(Sg0x2, k), sigmag0));
-                  C = add_(C, div_(mul_(mul_(Sg1d, 2.0), k), sigmag1));
-                  corr = div_(C, n);
+                for (int j = 0; j < V; ++j) {
+                  if ((m_in >> j) & 1u) {
+                    const double Sg1d = (double)(int)a1[j], Sg1sqd = (double)(int)a2[j],
+                                 Sg0g1d = (double)(int)ax[j];
+                    const double V1 = fma(n, Sg1sqd, -(Sg1d * Sg1d));  // exact
+                    bool gate = V1 > T100;
+                    double sg1;
+                    if (V1 == T100) {  // knife edge of sdimage >= 10: decide with the exact chain
+                      exact_score(Sg1d, Sg1sqd, Sg0g1d, sg1);
+                      gate = !(sg1 < 10.0);
+                    }
+                    if (gate) {
+                      const double N01 = fma(n, Sg0g1d, -(Sg0d * Sg1d));  // exact
+                      const float rho = (float)N01 * rsqrtf((float)(V0d * V1));
+                      const float capprox = fmaf(-2.0f, rho, 2.0f);
+                      if (capprox <= bmin + kWindow) {
+                        const double corr = exact_score(Sg1d, Sg1sqd, Sg0g1d, sg1);
+                        const int idx = (tx0 + cu) * CH + (ty0 + cv0 + j);
+                        if (corr <= 1000000.0 && !(sg1 < 10.0)) consider(best, corr, idx);
+                      }
+                      bmin = fminf(bmin, capprox);
+                    }
+                  }
                 }
-                const int ui = tx0 + cu, vi = ty0 + cv0 + j;
-                const int idx = ui * CH + vi;  // urel-major, vrel-minor scan position
-                const bool inside = (m_in >> j) & 1u;
-                if (dump.corr && idx < dump.cap) {
-                  dump.corr[idx] = corr;
-                  dump.sd[idx] = sigmag1;
-                  dump.inside[idx] = inside ? 1 : 0;
-                }
-                if (inside) {
-                  if (L.smoe_mode) {
-                    // smoe.cpp:173-184: penalise low image sigma, no patch-sigma gate
-                    if (sigmag1 < 10.0) corr = add_(corr, 5.0);
-                    if (corr <= 1000000.0) consider(best, corr, idx);
-                  } else if (corr <= 1000000.0 && !(sigmag0 < 10.0) && !(sigmag1 < 10.0)) {
-                    consider(best, corr, idx);  // monoslam.cpp:457-467
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < V; ++j) {
+                if ((m_all >> j) & 1u) {
+                  const double Sg1d = (double)(int)a1[j], Sg1sqd = (double)(int)a2[j],
+                               Sg0g1d = (double)(int)ax[j];
+                  double sigmag1;
+                  double corr = exact_score(Sg1d, Sg1sqd, Sg0g1d, sigmag1);
+                  const int ui = tx0 + cu, vi = ty0 + cv0 + j;
+                  const int idx = ui * CH + vi;  // urel-major, vrel-minor scan position
+                  const bool inside = (m_in >> j) & 1u;
+                  if (dump.corr && idx < dump.cap) {
+                    dump.corr[idx] = corr;
+                    dump.sd[idx] = sigmag1;
+                    dump.inside[idx] = inside ? 1 : 0;
+                  }
+                  if (inside) {
+                    if (L.smoe_mode) {
+                      // smoe.cpp:173-184: penalise low image sigma, no patch-sigma gate
+                      if (sigmag1 < 10.0) corr = add_(corr, 5.0);
+                      if (corr <= 1000000.0) consider(best, corr, idx);
+                    } else if (corr <= 1000000.0 && !(sigmag0 < 10.0) && !(sigmag1 < 10.0)) {
+                      consider(best, corr, idx);  // monoslam.cpp:457-467
+                    }
                   }
                 }
               }
             }
+          }
+          if constexpr (FILTER) {  // share the running minimum so later rounds filter better
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) bmin = fminf(bmin, __shfl_xor_sync(0xffffffffu, bmin, o));
           }
         }
         __syncwarp();
@@ -356,13 +400,13 @@ size_t search_smem_bytes(const Sl2Dev &d) {
   return (size_t)SL2_SEARCH_WARPS * (((tile_bytes + list_bytes + 16 + 127) / 128) * 128);
 }
 
-template <int BOX>
+template <int BOX, bool FILTER>
 cudaError_t launch_t(const Sl2Dev &d, const CUtensorMap &tmap, const SearchLaunch &L,
                      const DumpPtrs &dump, cudaStream_t st) {
   const size_t smem = search_smem_bytes(d);
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(search_kernel<BOX>,
+    cudaError_t e = cudaFuncSetAttribute(search_kernel<BOX, FILTER>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = smem;
@@ -370,15 +414,18 @@ cudaError_t launch_t(const Sl2Dev &d, const CUtensorMap &tmap, const SearchLaunc
   const int groups = (L.jobs_per_stream + SL2_SEARCH_WARPS - 1) / SL2_SEARCH_WARPS;
   const int grid = groups * L.stream_cnt;
   if (grid <= 0) return cudaSuccess;
-  search_kernel<BOX><<<grid, SL2_SEARCH_WARPS * 32, smem, st>>>(tmap, d, L, dump);
+  search_kernel<BOX, FILTER><<<grid, SL2_SEARCH_WARPS * 32, smem, st>>>(tmap, d, L, dump);
   return cudaGetLastError();
 }
 
 cudaError_t launch_any(const Sl2Dev &d, const CUtensorMap &tmap, const SearchLaunch &L,
                        const DumpPtrs &dump, cudaStream_t st) {
+  const bool exact_all = L.smoe_mode || dump.corr;  // A11 semantics / score dump: no filter
   switch (d.box) {
-    case 11: return launch_t<11>(d, tmap, L, dump, st);
-    case 15: return launch_t<15>(d, tmap, L, dump, st);
+    case 11:
+      return exact_all ? launch_t<11, false>(d, tmap, L, dump, st) : launch_t<11, true>(d, tmap, L, dump, st);
+    case 15:
+      return exact_all ? launch_t<15, false>(d, tmap, L, dump, st) : launch_t<15, true>(d, tmap, L, dump, st);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -54,6 +54,7 @@ struct Sl2Dev {
   int *nsel;           // [B]
   int *nvisible;       // [B]
   int *nmeas;          // [B]  successful measurements of the last step
+  long long *dbg;      // [64] phase cycle stamps of CTA 0 of the update kernel (debug)
 };
 
 // ---- correctly-rounded, never-fused FP64 helpers: the oracle is built with
