@@ -29,6 +29,8 @@ sys.path.insert(0, ROOT)
 METRIC = "EKF-SLAM frames/sec @320x240 N=100 feats"
 UNIT = "frames/s"
 WORKLOAD = "C4: synthetic 320x240, 100 features, EKF state dim 313, 11x11 patch, +-20px ellipse"
+WORKLOADS = {"C2": "C2: synthetic 320x240, 50 features, 11x11 patch, +-20px ellipse",
+             "C3": "C3: synthetic 640x480, 100 features, 15x15 patch, +-40px ellipse", "C4": WORKLOAD}
 
 
 def parse():
@@ -43,6 +45,7 @@ def parse():
     ap.add_argument("--unique", type=int, default=16, help="distinct synthetic scenes (tiled over streams)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dist-selftest", action="store_true", help="CPU/gloo check of the N>1 plumbing")
     return ap.parse_args()
 
 
@@ -123,11 +126,29 @@ def cpu_run(scenes, seconds, threads=None):
     return fps, threads, steps, t
 
 
+def dist_selftest(rank, world):
+    """gloo on CPU: the same barrier / MAX-reduce / per-rank stream bases the GPU run uses."""
+    import torch
+    import torch.distributed as dist
+    dist.init_process_group("gloo")
+    dist.barrier()
+    t = torch.tensor([10.0 * (rank + 1)])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    n = torch.tensor([3.0])
+    dist.all_reduce(n, op=dist.ReduceOp.SUM)
+    bases = [None] * world
+    dist.all_gather_object(bases, rank * 1000)
+    if rank == 0:
+        print(json.dumps({"world": world, "max_ms": float(t.item()), "sum_streams": int(n.item()),
+                          "stream_bases": bases}))
+    dist.destroy_process_group()
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
     scenes = make_scenes(args.config, min(args.unique, 8), args.ring)
-    budget = max(2.0, min(40.0, 120.0 / max(1, args.steps + args.warmup)))
+    budget = args.cpu_seconds if args.cpu_seconds < 12.0 else max(2.0, min(40.0, 120.0 / max(1, args.steps + args.warmup)))
     vals = []
     threads = None
     for k in range(args.warmup + args.steps):
@@ -142,7 +163,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1e3 * threads / v,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "streams": threads,
+        "data": "synthetic", "config": {"workload": WORKLOADS.get(args.config, WORKLOAD), "streams": threads,
                                         "note": "CPU oracle = port of the reference path (Eigen3/OpenCV absent: "
                                                 "the reference itself cannot be built); faithful block storage"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
@@ -264,7 +285,7 @@ def run_ours(args, rank, local_rank, world):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64 (EKF, scores) + u8/int32 (correlation sums)",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "streams_per_gpu": B, "frames_per_step": B * world,
+            "config": {"workload": WORKLOADS.get(args.config, WORKLOAD), "streams_per_gpu": B, "frames_per_step": B * world,
                        "state_dim": n, "measurements": m, "parallelism": "replicas x%d (no collective)" % world,
                        "l2": "per-step working set %.0f MB (P + scratch + frames of %d streams) exceeds the 126 MB L2"
                              % ((B * (cfg.max_features * 3 + 13) ** 2 * 8 * 2.1) / 1e6, B),
@@ -303,7 +324,9 @@ if __name__ == "__main__":
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if a.impl == "reference":
+    if a.dist_selftest:
+        dist_selftest(rank, world)
+    elif a.impl == "reference":
         run_reference(a, rank, world)
     else:
         run_ours(a, rank, local_rank, world)

@@ -143,6 +143,11 @@ int sl2_step_host(sl2_ctx *ctx, int32_t slot, const uint8_t *gray, double *xv_ou
 int sl2_get_features(sl2_ctx *ctx, int32_t stream_id, double *h /* n x 2 */, double *z /* n x 2 */,
                      double *S /* n x 4 col-major */, uint8_t *flags /* bit0 selected, bit1 successful */,
                      int32_t *attempted, int32_t *successful, int32_t *select_rank);
+/* Feature::dh_by_dxv_ (2x13), dh_by_dy_ (2x3), R_ (2x2), nu_ (2) of the last prediction /
+ * measurement, all column-major like the Eigen members (feature.h:104-112). Arrays may be NULL. */
+int sl2_get_feature_jacobians(sl2_ctx *ctx, int32_t stream_id, double *dh_by_dxv /* n x 26 */,
+                              double *dh_by_dy /* n x 6 */, double *R /* n x 4 */,
+                              double *nu /* n x 2 */);
 /* device-time of the kernels of the last sl2_step (ms): [0] predict+select, [1] patch search,
  * [2] EKF update, [3] cull.  Valid after sl2_enable_timing(ctx, 1). */
 int sl2_enable_timing(sl2_ctx *ctx, int32_t on);

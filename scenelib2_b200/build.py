@@ -4,7 +4,8 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["csrc/api.cu", "csrc/search.cu", "csrc/ekf.cu"]
-HEADERS = ["csrc/sl2_common.cuh", "../include/sl2b200.h"]
+HEADERS = ["csrc/sl2_common.cuh", "../include/sl2b200.h", "host/scenelib2_b200.cpp",
+           "host/scenelib2_b200.h", "host/sl2_compat.h", "host/sl2_headless.cpp"]
 LIB = os.path.join(HERE, "libsl2b200.so")
 
 
@@ -26,7 +27,23 @@ def build(force=False, verbose=False):
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
     subprocess.check_call(cmd, cwd=HERE)
+    build_host()
     return LIB
+
+
+def build_host():
+    """C++ host shim (MonoSLAM / Kalman / Feature surface) + headless driver, linked to the C ABI."""
+    cxx = os.environ.get("CXX", "g++")
+    host = os.path.join(HERE, "host")
+    so = os.path.join(host, "libscenelib2_b200_host.so")
+    exe = os.path.join(host, "sl2_headless")
+    subprocess.check_call([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so,
+                           os.path.join(host, "scenelib2_b200.cpp"), "-L" + HERE, "-lsl2b200",
+                           "-Wl,-rpath,$ORIGIN/.."])
+    subprocess.check_call([cxx, "-O2", "-std=c++17", "-o", exe, os.path.join(host, "sl2_headless.cpp"),
+                           "-L" + host, "-lscenelib2_b200_host", "-L" + HERE, "-lsl2b200",
+                           "-Wl,-rpath,$ORIGIN:$ORIGIN/.."])
+    return exe
 
 
 if __name__ == "__main__":

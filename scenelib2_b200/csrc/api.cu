@@ -672,6 +672,35 @@ int sl2_last_step_times(sl2_ctx *c, float *ms4) {
   return SL2_OK;
 }
 
+int sl2_get_feature_jacobians(sl2_ctx *c, int32_t s, double *dh_by_dxv, double *dh_by_dy, double *R,
+                              double *nu) {
+  if (bad_stream(c, s)) return fail(c, SL2_ERR_ARG, "bad stream");
+  const Sl2Dev &d = c->d;
+  const int N = d.Nmax;
+  const size_t fb = (size_t)s * N;
+  int nf = 0;
+  std::vector<double> xp(14 * (size_t)N), dy(6 * (size_t)N), rv(N), hh(2 * (size_t)N);
+  std::vector<int> zz(2 * (size_t)N);
+  CU_TRY(c, cudaMemcpyAsync(&nf, d.nfeat + s, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(xp.data(), d.dh_dxp + fb * 14, 8 * xp.size(), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(dy.data(), d.dh_dy + fb * 6, 8 * dy.size(), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(rv.data(), d.Rvar + fb, 8 * rv.size(), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(hh.data(), d.h + fb * 2, 8 * hh.size(), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(zz.data(), d.z_uv + fb * 2, 4 * zz.size(), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < nf; ++i) {
+    if (dh_by_dxv)
+      for (int col = 0; col < 13; ++col)
+        for (int r = 0; r < 2; ++r) dh_by_dxv[i * 26 + col * 2 + r] = col < 7 ? xp[i * 14 + r * 7 + col] : 0.0;
+    if (dh_by_dy)
+      for (int col = 0; col < 3; ++col)
+        for (int r = 0; r < 2; ++r) dh_by_dy[i * 6 + col * 2 + r] = dy[i * 6 + r * 3 + col];
+    if (R) { R[i * 4 + 0] = rv[i]; R[i * 4 + 1] = 0.0; R[i * 4 + 2] = 0.0; R[i * 4 + 3] = rv[i]; }
+    if (nu) { nu[i * 2] = (double)zz[i * 2] - hh[i * 2]; nu[i * 2 + 1] = (double)zz[i * 2 + 1] - hh[i * 2 + 1]; }
+  }
+  return nf;
+}
+
 // debug only (not part of the public header): clock64 stamps of the update kernel's phases
 int sl2_debug_phase_cycles(sl2_ctx *c, long long *out64) {
   if (!c || !out64) return SL2_ERR_ARG;

@@ -78,6 +78,30 @@ __device__ __forceinline__ void consider(Best &b, double corr, int idx) {
   }
 }
 
+// improc.cpp:99-133 op for op (never-fused, IEEE div/sqrt).  Deliberately NOT inlined: the
+// filtered kernel reaches it for a handful of candidates per warp, and eight inlined copies of the
+// div/sqrt sequences blew the kernel up to ~66 KB of SASS (instruction-cache misses were the top
+// stall reason, profiles/r01b).
+struct PatchConst {
+  double n, sigmag0, A0, g0s, Sg0x2;
+};
+__device__ __noinline__ double exact_score_fn(const PatchConst pc, double Sg1d, double Sg1sqd,
+                                              double Sg0g1d, double *sigma1_out) {
+  const double g1bar = div_(Sg1d, pc.n);
+  const double varg1 = sub_(div_(Sg1sqd, pc.n), mul_(g1bar, g1bar));
+  const double sigmag1 = sqrt_(varg1);
+  *sigma1_out = sigmag1;
+  if (pc.sigmag0 == 0.0) return (sigmag1 == 0.0) ? 0.0 : 1.0;
+  if (sigmag1 == 0.0) return 1.0;
+  const double k = sub_(pc.g0s, div_(g1bar, sigmag1));
+  double C = add_(pc.A0, div_(Sg1sqd, varg1));
+  C = add_(C, mul_(pc.n, mul_(k, k)));
+  C = sub_(C, div_(mul_(Sg0g1d, 2.0), mul_(pc.sigmag0, sigmag1)));
+  C = sub_(C, div_(mul_(pc.Sg0x2, k), pc.sigmag0));
+  C = add_(C, div_(mul_(mul_(Sg1d, 2.0), k), sigmag1));
+  return div_(C, pc.n);
+}
+
 struct DumpPtrs {
   double *corr;
   double *sd;
@@ -158,6 +182,7 @@ __global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32)
   const double T100 = 100.0 * n * n;           // sigma >= 10  <=>  n^2 var >= 100 n^2
   const bool patch_ok = !(sigmag0 < 10.0);     // kCorrelationSigmaThreshold_ gate on the template
   float bmin = 3.0e38f;                        // running minimum of the approximate score
+  const PatchConst pconst = {n, sigmag0, A0, g0s, Sg0x2};
 
   // ---- search box, monoslam.cpp:416-439 (smoe.cpp:118-147) -----------------------------------
   const double P00 = L.job_puinv[job * 3 + 0], P01 = L.job_puinv[job * 3 + 1],
@@ -275,18 +300,7 @@ __global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32)
             }
             // ---- FP64 score, improc.cpp:99-133 ------------------------------------------------
             auto exact_score = [&](double Sg1d, double Sg1sqd, double Sg0g1d, double &sigmag1) {
-              const double g1bar = div_(Sg1d, n);
-              const double varg1 = sub_(div_(Sg1sqd, n), mul_(g1bar, g1bar));
-              sigmag1 = sqrt_(varg1);
-              if (sigmag0 == 0.0) return (sigmag1 == 0.0) ? 0.0 : 1.0;
-              if (sigmag1 == 0.0) return 1.0;
-              const double k = sub_(g0s, div_(g1bar, sigmag1));
-              double C = add_(A0, div_(Sg1sqd, varg1));
-              C = add_(C, mul_(n, mul_(k, k)));
-              C = sub_(C, div_(mul_(Sg0g1d, 2.0), mul_(sigmag0, sigmag1)));
-              C = sub_(C, div_(mul_(Sg0x2, k), sigmag0));
-              C = add_(C, div_(mul_(mul_(Sg1d, 2.0), k), sigmag1));
-              return div_(C, n);
+              return exact_score_fn(pconst, Sg1d, Sg1sqd, Sg0g1d, &sigmag1);
             };
             if constexpr (FILTER) {
               // The reference's score equals 2 - 2*rho (rho = normalised cross-correlation) up to

@@ -1,0 +1,454 @@
+// scenelib2_b200.cpp — implementation of the host shim over the C ABI (see scenelib2_b200.h).
+// Control flow mirrors MonoSLAM::GoOneStep (scenelib2/monoslam.cpp:108-180); every arithmetic
+// step is a call into libsl2b200.so.  No CPU fallback: a failing device call throws.
+#include "scenelib2_b200.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <stdexcept>
+
+#include "../../include/sl2b200.h"
+
+namespace SceneLib2 {
+
+namespace {
+
+void check(sl2_ctx *ctx, int rc, const char *what) {
+  if (rc < 0) throw std::runtime_error(std::string(what) + ": " + sl2_last_error(ctx));
+}
+
+// `key = value;` files as read by pangolin::ParseVarsFile (monoslam.cpp:1578): '#' comments,
+// one assignment per line, trailing ';'.
+std::map<std::string, std::string> parse_vars_file(const std::string &path) {
+  std::ifstream f(path);
+  if (!f) throw std::runtime_error("cannot open config " + path);
+  std::map<std::string, std::string> kv;
+  std::string line;
+  while (std::getline(f, line)) {
+    const size_t hash = line.find('#');
+    if (hash != std::string::npos) line.erase(hash);
+    const size_t eq = line.find('=');
+    if (eq == std::string::npos) continue;
+    auto trim = [](std::string s) {
+      const char *ws = " \t\r\n;";
+      const size_t a = s.find_first_not_of(ws), b = s.find_last_not_of(ws);
+      return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);
+    };
+    kv[trim(line.substr(0, eq))] = trim(line.substr(eq + 1));
+  }
+  return kv;
+}
+double num(const std::map<std::string, std::string> &kv, const std::string &k, double def) {
+  auto it = kv.find(k);
+  return it == kv.end() ? def : std::atof(it->second.c_str());
+}
+
+// binary PGM (P5) reader standing in for cv::imread(identifier, 0) (feature.cpp:119)
+cv::Mat read_pgm(const std::string &path) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) throw std::runtime_error("cannot open patch " + path);
+  std::string magic;
+  f >> magic;
+  if (magic != "P5") throw std::runtime_error("not a binary PGM: " + path);
+  int vals[3], got = 0;
+  while (got < 3) {
+    f >> std::ws;
+    if (f.peek() == '#') {
+      std::string c;
+      std::getline(f, c);
+      continue;
+    }
+    f >> vals[got++];
+  }
+  f.get();
+  cv::Mat m(vals[1], vals[0], CV_8UC1);
+  f.read(reinterpret_cast<char *>(m.data), (std::streamsize)vals[0] * vals[1]);
+  return m;
+}
+
+}  // namespace
+
+void Camera::SetCameraParameters(int w, int h, double fku, double fkv, double u0, double v0,
+                                 double kd1, int sd) {
+  width_ = w;
+  height_ = h;
+  fku_ = fku;
+  fkv_ = fkv;
+  centre_(0) = u0;
+  centre_(1) = v0;
+  kd1_ = kd1;
+  measurement_sd_ = sd;
+}
+
+void MotionModel::func_xp(const Eigen::VectorXd &xv) {  // motion_model.cpp:219-222
+  xpRES_.resize(7);
+  for (int i = 0; i < 7; ++i) xpRES_(i) = xv(i);
+  for (int i = 0; i < 3; ++i) rRES_(i) = xv(i);
+}
+
+MonoSLAM::MonoSLAM()
+    : kBoxSize_(11), kNoSigma_(3.0), kCorrThresh2_(0.40), kCorrelationSigmaThreshold_(10.0) {}
+
+MonoSLAM::~MonoSLAM() {
+  if (ctx_) sl2_destroy(ctx_);
+  for (Feature *f : feature_list_) delete f;
+  delete camera_;
+  delete motion_model_;
+  delete kalman_;
+}
+
+// monoslam.cpp:1574-1969, minus GUI / grabber / particle parameters
+void MonoSLAM::Init(const std::string &config_path) {
+  const auto kv = parse_vars_file(config_path);
+  camera_ = new Camera();
+  camera_->SetCameraParameters((int)num(kv, "cam.width", 0), (int)num(kv, "cam.height", 0),
+                               (int)num(kv, "cam.fku", 0), (int)num(kv, "cam.fkv", 0),
+                               (int)num(kv, "cam.u0", 0), (int)num(kv, "cam.v0", 0),
+                               num(kv, "cam.kd1", 0.0), (int)num(kv, "cam.sd", 0));
+  motion_model_ = new MotionModel();
+  kalman_ = new Kalman();
+  kDeltaT_ = num(kv, "params.delta_t", 0.0);
+  kNumberOfFeaturesToSelect_ = (int)num(kv, "params.number_of_features_to_select", 0);
+  kNumberOfFeaturesToKeepVisible_ = (int)num(kv, "params.number_of_features_to_keep_visible", 0);
+  xv_.resize(13);
+  const char *names[13] = {"state.rw_x", "state.rw_y", "state.rw_z", "state.qwr_w", "state.qwr_x",
+                           "state.qwr_y", "state.qwr_z", "state.vw_x", "state.vw_y", "state.vw_z",
+                           "state.ww_x", "state.ww_y", "state.ww_z"};
+  for (int i = 0; i < 13; ++i) xv_(i) = num(kv, names[i], 0.0);
+  Pxx_.resize(13, 13);
+  for (int i = 0; i < 13; ++i)
+    for (int j = 0; j < 13; ++j) {
+      std::ostringstream k;
+      k << "state.pxx" << i << "_" << j;
+      Pxx_(i, j) = num(kv, k.str(), 0.0);
+    }
+  const size_t slash = config_path.find_last_of('/');
+  const std::string dir = slash == std::string::npos ? "" : config_path.substr(0, slash + 1);
+  for (int fidx = 1; fidx <= 64; ++fidx) {
+    std::ostringstream p;
+    p << "f" << fidx << ".";
+    auto it = kv.find(p.str() + "identifier");
+    if (it == kv.end()) break;
+    Eigen::VectorXd y(3), xp(7);
+    y(0) = num(kv, p.str() + "yi_x", 0);
+    y(1) = num(kv, p.str() + "yi_y", 0);
+    y(2) = num(kv, p.str() + "yi_z", 0);
+    for (int i = 0; i < 7; ++i) {
+      std::ostringstream k;
+      k << p.str() << "xp_org_" << i;
+      xp(i) = num(kv, k.str(), 0);
+    }
+    const std::string id = it->second;
+    AddNewKnownFeature(y, xp, (id.size() && id[0] == '/') ? id : dir + id);
+  }
+  CreateDevice((int)num(kv, "device.max_features", 100), (int)num(kv, "device.ordinal", 0));
+  UploadMap();
+}
+
+void MonoSLAM::CreateDevice(int max_features, int device) {
+  if (!camera_) throw std::runtime_error("CreateDevice: camera parameters not set");
+  if (!motion_model_) motion_model_ = new MotionModel();
+  if (!kalman_) kalman_ = new Kalman();
+  sl2_config cfg;
+  sl2_default_config(&cfg);
+  cfg.device = device;
+  cfg.width = camera_->width_;
+  cfg.height = camera_->height_;
+  cfg.boxsize = kBoxSize_;
+  cfg.max_features = max_features;
+  cfg.number_of_features_to_select = kNumberOfFeaturesToSelect_;
+  cfg.fku = camera_->fku_;
+  cfg.fkv = camera_->fkv_;
+  cfg.u0 = camera_->centre_(0);
+  cfg.v0 = camera_->centre_(1);
+  cfg.kd1 = camera_->kd1_;
+  cfg.sd = camera_->measurement_sd_;
+  cfg.delta_t = kDeltaT_;
+  cfg.minimum_attempted_measurements_of_feature = minimum_attempted_measurements_of_feature_;
+  cfg.successful_match_fraction = successful_match_fraction_;
+  const int rc = sl2_create(&cfg, &ctx_);
+  if (rc != 0) throw std::runtime_error(std::string("sl2_create: ") + sl2_last_error(nullptr));
+}
+
+// monoslam.cpp:1278-1289 + feature.cpp:108-149
+void MonoSLAM::AddNewKnownFeature(const Eigen::VectorXd &y, const Eigen::VectorXd &xp,
+                                  const cv::Mat &patch) {
+  Feature *nf = new Feature();
+  nf->y_ = y;
+  nf->xp_org_ = xp;
+  nf->patch_ = patch;
+  nf->label_ = next_free_label_;
+  nf->position_in_list_ = (int)feature_list_.size();
+  nf->position_in_total_state_vector_ = total_state_size_;
+  nf->Pxy_.resize(13, 3);
+  nf->Pyy_.resize(3, 3);
+  for (int i = 0; i < nf->position_in_list_; ++i) nf->matrix_block_list_.push_back(Eigen::MatrixXd(3, 3));
+  nf->h_.resize(2);
+  nf->z_.resize(2);
+  nf->nu_.resize(2);
+  nf->dh_by_dxv_.resize(2, 13);
+  nf->dh_by_dy_.resize(2, 3);
+  nf->R_.resize(2, 2);
+  nf->S_.resize(2, 2);
+  feature_list_.push_back(nf);
+  total_state_size_ += 3;
+  ++next_free_label_;
+  map_dirty_ = true;
+}
+void MonoSLAM::AddNewKnownFeature(const Eigen::VectorXd &y, const Eigen::VectorXd &xp,
+                                  const std::string &identifier) {
+  AddNewKnownFeature(y, xp, read_pgm(identifier));
+}
+
+void MonoSLAM::construct_total_state(Eigen::VectorXd &V) {  // monoslam.cpp:501-512
+  V.resize(total_state_size_);
+  for (int i = 0; i < 13; ++i) V(i) = xv_(i);
+  int pos = 13;
+  for (Feature *f : feature_list_) {
+    for (int i = 0; i < 3; ++i) V(pos + i) = f->y_(i);
+    pos += 3;
+  }
+}
+
+void MonoSLAM::construct_total_covariance(Eigen::MatrixXd &M) {  // monoslam.cpp:518-546
+  M.resize(total_state_size_, total_state_size_);
+  for (int i = 0; i < 13; ++i)
+    for (int j = 0; j < 13; ++j) M(i, j) = Pxx_(i, j);
+  int xpos = 13;
+  for (Feature *f : feature_list_) {
+    for (int i = 0; i < 13; ++i)
+      for (int j = 0; j < 3; ++j) M(i, xpos + j) = M(xpos + j, i) = f->Pxy_(i, j);
+    int ypos = 13;
+    for (const Eigen::MatrixXd &b : f->matrix_block_list_) {
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) M(ypos + i, xpos + j) = M(xpos + j, ypos + i) = b(i, j);
+      ypos += 3;
+    }
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) M(ypos + i, xpos + j) = f->Pyy_(i, j);
+    xpos += 3;
+  }
+}
+
+void MonoSLAM::UploadMap() {
+  const int n = (int)feature_list_.size();
+  std::vector<double> y((size_t)n * 3), xp((size_t)n * 7);
+  std::vector<uint8_t> patches((size_t)n * kBoxSize_ * kBoxSize_);
+  for (int i = 0; i < n; ++i) {
+    Feature *f = feature_list_[i];
+    for (int k = 0; k < 3; ++k) y[i * 3 + k] = f->y_(k);
+    for (int k = 0; k < 7; ++k) xp[i * 7 + k] = f->xp_org_(k);
+    if (f->patch_.rows != kBoxSize_ || f->patch_.cols != kBoxSize_)
+      throw std::runtime_error("feature patch must be BOXSIZE x BOXSIZE");
+    for (int r = 0; r < kBoxSize_; ++r)
+      std::memcpy(&patches[((size_t)i * kBoxSize_ + r) * kBoxSize_], f->patch_.data + r * f->patch_.step,
+                  kBoxSize_);
+  }
+  check(ctx_, sl2_set_features(ctx_, 0, n, y.data(), xp.data(), patches.data()), "sl2_set_features");
+  Eigen::VectorXd V;
+  Eigen::MatrixXd M;
+  construct_total_state(V);
+  construct_total_covariance(M);
+  check(ctx_, sl2_set_state(ctx_, 0, V.data(), M.data()), "sl2_set_state");
+  map_dirty_ = false;
+}
+
+void MonoSLAM::SyncFromDevice() {  // fill_states / fill_covariances, monoslam.cpp:574-614
+  const int nfeat = sl2_num_features(ctx_, 0);
+  check(ctx_, nfeat, "sl2_num_features");
+  const int n = 13 + 3 * nfeat;
+  total_state_size_ = n;
+  std::vector<double> x(n), P((size_t)n * n);
+  check(ctx_, sl2_get_state(ctx_, 0, x.data(), P.data()), "sl2_get_state");
+  auto Pat = [&](int i, int j) { return P[(size_t)i + (size_t)j * n]; };
+  for (int i = 0; i < 13; ++i) xv_(i) = x[i];
+  for (int i = 0; i < 13; ++i)
+    for (int j = 0; j < 13; ++j) Pxx_(i, j) = Pat(i, j);
+  std::vector<double> h(2 * nfeat), z(2 * nfeat), S(4 * nfeat), J(26 * nfeat), Jy(6 * nfeat),
+      R(4 * nfeat), nu(2 * nfeat);
+  std::vector<uint8_t> flags(nfeat);
+  std::vector<int32_t> att(nfeat), suc(nfeat), rank(nfeat);
+  check(ctx_, sl2_get_features(ctx_, 0, h.data(), z.data(), S.data(), flags.data(), att.data(),
+                               suc.data(), rank.data()), "sl2_get_features");
+  check(ctx_, sl2_get_feature_jacobians(ctx_, 0, J.data(), Jy.data(), R.data(), nu.data()),
+        "sl2_get_feature_jacobians");
+  selected_feature_list_.assign(nfeat, nullptr);
+  int nsel = 0;
+  for (int i = 0; i < nfeat; ++i) {
+    Feature *f = feature_list_[i];
+    const int pos = 13 + 3 * i;
+    f->position_in_list_ = i;
+    f->position_in_total_state_vector_ = pos;
+    for (int k = 0; k < 3; ++k) f->y_(k) = x[pos + k];
+    for (int r = 0; r < 13; ++r)
+      for (int c = 0; c < 3; ++c) f->Pxy_(r, c) = Pat(r, pos + c);
+    f->matrix_block_list_.resize(i, Eigen::MatrixXd(3, 3));
+    for (int j = 0; j < i; ++j)
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) f->matrix_block_list_[j](r, c) = Pat(13 + 3 * j + r, pos + c);
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) f->Pyy_(r, c) = Pat(pos + r, pos + c);
+    for (int k = 0; k < 2; ++k) {
+      f->h_(k) = h[2 * i + k];
+      f->z_(k) = z[2 * i + k];
+      f->nu_(k) = nu[2 * i + k];
+    }
+    for (int k = 0; k < 4; ++k) {
+      f->S_.data()[k] = S[4 * i + k];
+      f->R_.data()[k] = R[4 * i + k];
+    }
+    for (int k = 0; k < 26; ++k) f->dh_by_dxv_.data()[k] = J[26 * i + k];
+    for (int k = 0; k < 6; ++k) f->dh_by_dy_.data()[k] = Jy[6 * i + k];
+    f->selected_flag_ = (flags[i] & 1) != 0;
+    f->successful_measurement_flag_ = (flags[i] & 2) != 0;
+    f->attempted_measurements_of_feature_ = att[i];
+    f->successful_measurements_of_feature_ = suc[i];
+    if (rank[i] >= 0) {
+      selected_feature_list_[rank[i]] = f;
+      ++nsel;
+    }
+  }
+  selected_feature_list_.resize(nsel);
+}
+
+void Kalman::KalmanFilterPredict(MonoSLAM *m, Eigen::Vector3d &u) {  // kalman.cpp:50-69
+  if (!m->ctx_) throw std::runtime_error("KalmanFilterPredict: no device context");
+  check(m->ctx_, sl2_ekf_predict(m->ctx_, 0, u.data()), "sl2_ekf_predict");
+}
+
+void Kalman::KalmanFilterUpdate(MonoSLAM *m) {  // kalman.cpp:72-119 (+ normalise, symmetrise)
+  check(m->ctx_, sl2_ekf_update_measured(m->ctx_, 0), "sl2_ekf_update_measured");
+}
+
+int MonoSLAM::auto_select_n_features(int n) {  // monoslam.cpp:187-254
+  (void)n;  // the device uses sl2_config::number_of_features_to_select (set from the same cfg key)
+  const int nv = sl2_predict_measurements(ctx_, 0);
+  check(ctx_, nv, "sl2_predict_measurements");
+  return nv;
+}
+
+int MonoSLAM::make_measurements(cv::Mat image) {  // monoslam.cpp:336-359
+  check(ctx_, sl2_set_frame(ctx_, 0, 0, image.data, image.step), "sl2_set_frame");
+  const int cnt = sl2_make_measurements(ctx_, 0, 0);
+  check(ctx_, cnt, "sl2_make_measurements");
+  successful_measurement_vector_size_ = 2 * cnt;
+  return cnt;
+}
+
+// monoslam.cpp:401-477.  `patch` must be the template of one of the map's features (the only way
+// the reference calls it, monoslam.cpp:349,378): it is identified by its pixel pointer.
+bool MonoSLAM::elliptical_search(const cv::Mat &image, const cv::Mat &patch,
+                                 const Eigen::Vector2d centre, const Eigen::Matrix2d &PuInv, int *u,
+                                 int *v, const int uBOXSIZE) {
+  if (uBOXSIZE != kBoxSize_) throw std::runtime_error("elliptical_search: BOXSIZE mismatch");
+  if (map_dirty_) UploadMap();
+  int32_t idx = -1;
+  for (size_t i = 0; i < feature_list_.size(); ++i)
+    if (feature_list_[i]->patch_.data == patch.data) idx = (int32_t)i;
+  if (idx < 0) throw std::runtime_error("elliptical_search: patch is not a map feature's template");
+  check(ctx_, sl2_set_frame(ctx_, 0, 0, image.data, image.step), "sl2_set_frame");
+  const double c[2] = {centre(0), centre(1)};
+  const double p[3] = {PuInv(0, 0), PuInv(0, 1), PuInv(1, 1)};
+  int32_t uu = -1, vv = -1;
+  uint8_t found = 0;
+  check(ctx_, sl2_patch_search(ctx_, 0, 0, 1, &idx, c, p, &uu, &vv, &found, nullptr), "sl2_patch_search");
+  if (uu >= 0) {  // quirk Q6: *u,*v are only written when a candidate was accepted
+    *u = uu;
+    *v = vv;
+  }
+  return found != 0;
+}
+
+// monoslam.cpp:368-386 (LLT of S, Sinv = Linv^T Linv, then elliptical_search)
+bool MonoSLAM::measure_feature(cv::Mat image, cv::Mat patch, Eigen::VectorXd &z,
+                               const Eigen::VectorXd &h, const Eigen::MatrixXd &S) {
+  const double l00 = std::sqrt(S(0, 0)), l10 = S(1, 0) / l00;
+  const double l11 = std::sqrt(S(1, 1) - l10 * l10);
+  const double x00 = 1.0 / l00, x10 = (0.0 - l10 * x00) / l11, x11 = 1.0 / l11;
+  Eigen::Matrix2d Sinv;
+  Sinv(0, 0) = x00 * x00 + x10 * x10;
+  Sinv(0, 1) = Sinv(1, 0) = x10 * x11;
+  Sinv(1, 1) = x11 * x11;
+  Eigen::Vector2d c;
+  c(0) = h(0);
+  c(1) = h(1);
+  int u = 0, v = 0;
+  if (!elliptical_search(image, patch, c, Sinv, &u, &v, kBoxSize_)) return false;
+  z(0) = (double)u;
+  z(1) = (double)v;
+  return true;
+}
+
+void MonoSLAM::normalise_state() {  // monoslam.cpp:616-637
+  check(ctx_, sl2_normalise_state(ctx_, 0), "sl2_normalise_state");
+}
+
+void MonoSLAM::mark_feature_by_lab(int lab) { marked_feature_label_ = lab; }  // monoslam.cpp:743-766
+
+bool MonoSLAM::delete_feature() {  // monoslam.cpp:770-812
+  if (marked_feature_label_ == -1) return false;
+  for (size_t i = 0; i < feature_list_.size(); ++i) {
+    if (feature_list_[i]->label_ != marked_feature_label_) continue;
+    check(ctx_, sl2_delete_feature(ctx_, 0, (int)i), "sl2_delete_feature");
+    delete feature_list_[i];
+    feature_list_.erase(feature_list_.begin() + i);
+    total_state_size_ -= 3;
+    marked_feature_label_ = -1;
+    return true;
+  }
+  return false;
+}
+
+void MonoSLAM::delete_bad_features() {  // monoslam.cpp:644-703
+  for (size_t i = 0; i < feature_list_.size();) {
+    Feature *f = feature_list_[i];
+    if (f->attempted_measurements_of_feature_ >= minimum_attempted_measurements_of_feature_ &&
+        double(f->successful_measurements_of_feature_) / double(f->attempted_measurements_of_feature_) <
+            successful_match_fraction_) {
+      mark_feature_by_lab(f->label_);
+      delete_feature();
+    } else {
+      ++i;
+    }
+  }
+}
+
+// monoslam.cpp:108-180, tracking only (enable_mapping is accepted and ignored: map growth is out of
+// scope)
+bool MonoSLAM::GoOneStep(cv::Mat frame, bool save_trajectory, bool enable_mapping) {
+  (void)enable_mapping;
+  if (!ctx_) throw std::runtime_error("GoOneStep: Init()/CreateDevice() has not been called");
+  if (map_dirty_) UploadMap();
+  Eigen::Vector3d u;
+  kalman_->KalmanFilterPredict(this, u);
+  number_of_visible_features_ = auto_select_n_features(kNumberOfFeaturesToSelect_);
+  successful_measurement_vector_size_ = 0;
+  if (number_of_visible_features_ > 0) {
+    make_measurements(frame);
+    // (Kalman update + normalise_state + symmetrise are one device call; it is a no-op on the
+    // state when nothing was measured, and it books the attempt counters either way)
+    kalman_->KalmanFilterUpdate(this);
+  }
+  SyncFromDevice();
+  delete_bad_features();
+  if (feature_list_.size() * 3 + 13 != (size_t)total_state_size_) total_state_size_ = 13 + 3 * (int)feature_list_.size();
+  SyncFromDevice();
+  motion_model_->func_xp(xv_);
+  if (save_trajectory) {
+    trajectory_store_.push_back(motion_model_->rRES_);
+    if (trajectory_store_.size() > 1000) trajectory_store_.erase(trajectory_store_.begin());
+  }
+  return true;
+}
+
+void MonoSLAM::print_robot_state() {  // monoslam.cpp:1543-1549
+  std::cout << "Robot state:" << std::endl;
+  for (int i = 0; i < 13; ++i) std::cout << xv_(i) << (i == 12 ? "\n" : " ");
+}
+
+}  // namespace SceneLib2

@@ -1,0 +1,117 @@
+// scenelib2_b200.h — C++ host shim keeping the reference's hot-path class surface
+// (SceneLib2::MonoSLAM / Kalman / Feature / Camera, scenelib2/monoslam.h:73-218, kalman.h:44-53,
+// feature.h:56-143, camera.h:42-78) on top of the C ABI of libsl2b200.so (include/sl2b200.h).
+//
+// Same names, same argument meaning, same `bool`/`int` returns as the reference; the arithmetic
+// runs in the sm_100a kernels.  Host mirrors (xv_, Pxx_, per-feature y_/Pxy_/Pyy_/
+// matrix_block_list_, h_/z_/S_/flags/counters) are refreshed before GoOneStep / the Kalman calls
+// return, because the reference's GUI reads them on every redraw (graphic/graphictool.cpp:130-168).
+// Out of scope here: GUI, frame grabbers, feature initialisation, particles.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "sl2_compat.h"
+
+struct sl2_ctx;
+
+namespace SceneLib2 {
+
+class MonoSLAM;
+
+class Camera {  // camera.h:42-78 (members used by the example and the hot path)
+ public:
+  void SetCameraParameters(int camera_width, int camera_height, double fku, double fkv, double u0,
+                           double v0, double kd1, int sd);
+  int width_ = 0, height_ = 0;
+  double kd1_ = 0, fku_ = 0, fkv_ = 0;
+  Eigen::Vector2d centre_;
+  double measurement_sd_ = 0;
+};
+
+class MotionModel {  // motion_model.h: constants + func_xp
+ public:
+  void func_xp(const Eigen::VectorXd &xv);
+  Eigen::VectorXd xpRES_;
+  Eigen::Vector3d rRES_;
+  const int kPositionStateSize_ = 7, kStateSize_ = 13, kControlSize_ = 3;
+};
+
+class Feature {  // feature.h:56-143
+ public:
+  Eigen::VectorXd y_, xp_org_;
+  Eigen::MatrixXd Pyy_, Pxy_;
+  cv::Mat patch_;
+  std::vector<Eigen::MatrixXd> matrix_block_list_;
+  Eigen::VectorXd h_, z_, nu_;
+  Eigen::MatrixXd dh_by_dxv_, dh_by_dy_, R_, S_;
+  int label_ = 0, position_in_list_ = 0, position_in_total_state_vector_ = 0;
+  int attempted_measurements_of_feature_ = 0, successful_measurements_of_feature_ = 0;
+  bool selected_flag_ = false, scheduled_for_termination_flag_ = false;
+  bool successful_measurement_flag_ = false, fully_initialised_flag_ = true;
+};
+
+class Kalman {  // kalman.h:44-53
+ public:
+  void KalmanFilterPredict(MonoSLAM *monoslam, Eigen::Vector3d &u);
+  void KalmanFilterUpdate(MonoSLAM *monoslam);
+};
+
+class MonoSLAM {  // monoslam.h:73-218 (hot-path subset)
+ public:
+  MonoSLAM();
+  ~MonoSLAM();
+
+  void Init(const std::string &config_path);
+  bool GoOneStep(cv::Mat frame, bool save_trajectory, bool enable_mapping);
+  void print_robot_state();
+
+  int auto_select_n_features(int n);
+  int make_measurements(cv::Mat image);
+  bool measure_feature(cv::Mat image, cv::Mat patch, Eigen::VectorXd &z, const Eigen::VectorXd &h,
+                       const Eigen::MatrixXd &S);
+  bool elliptical_search(const cv::Mat &image, const cv::Mat &patch, const Eigen::Vector2d centre,
+                         const Eigen::Matrix2d &PuInv, int *u, int *v, const int uBOXSIZE);
+  void construct_total_state(Eigen::VectorXd &V);
+  void construct_total_covariance(Eigen::MatrixXd &M);
+  void normalise_state();
+  void delete_bad_features();
+  void mark_feature_by_lab(int lab);
+  bool delete_feature();
+  void AddNewKnownFeature(const Eigen::VectorXd &y, const Eigen::VectorXd &xp,
+                          const std::string &identifier);
+  // same, with the template given in memory (the reference reads it with cv::imread)
+  void AddNewKnownFeature(const Eigen::VectorXd &y, const Eigen::VectorXd &xp, const cv::Mat &patch);
+
+  Camera *camera_ = nullptr;
+  MotionModel *motion_model_ = nullptr;
+  Kalman *kalman_ = nullptr;
+
+  Eigen::VectorXd xv_;
+  Eigen::MatrixXd Pxx_;
+  std::vector<Feature *> feature_list_;
+  std::vector<Feature *> selected_feature_list_;
+  std::vector<Eigen::Vector3d> trajectory_store_;
+
+  int number_of_visible_features_ = 0, next_free_label_ = 0, marked_feature_label_ = -1;
+  int total_state_size_ = 13, successful_measurement_vector_size_ = 0;
+  double kDeltaT_ = 0.033333333;
+  int kNumberOfFeaturesToSelect_ = 10, kNumberOfFeaturesToKeepVisible_ = 12;
+  int minimum_attempted_measurements_of_feature_ = 10;
+  double successful_match_fraction_ = 0.5;
+  const int kBoxSize_;
+  const double kNoSigma_, kCorrThresh2_, kCorrelationSigmaThreshold_;
+
+  // ---- device side (not in the reference) ----------------------------------------------------
+  // Creates the GPU context; called by Init(), or directly when the map is built in code.
+  // max_features bounds the map size; device = CUDA ordinal.  Throws std::runtime_error on failure.
+  void CreateDevice(int max_features = 100, int device = 0);
+  void UploadMap();    // host y_/xp_org_/patch_/xv_/P blocks -> device (after AddNewKnownFeature)
+  void SyncFromDevice();  // device state + per-feature results -> host mirrors
+  sl2_ctx *ctx_ = nullptr;
+
+ private:
+  bool map_dirty_ = true;
+};
+
+}  // namespace SceneLib2

@@ -43,7 +43,7 @@ EXPORTS = [
     "sl2_patch_search", "sl2_score_map", "sl2_smoe_search", "sl2_ekf_predict",
     "sl2_predict_measurements", "sl2_make_measurements", "sl2_ekf_update",
     "sl2_ekf_update_measured", "sl2_normalise_state", "sl2_step", "sl2_step_host",
-    "sl2_get_features", "sl2_enable_timing", "sl2_last_step_times", "sl2_launch_count",
+    "sl2_get_features", "sl2_get_feature_jacobians", "sl2_enable_timing", "sl2_last_step_times", "sl2_launch_count",
 ]
 
 _lib = None

@@ -1,0 +1,87 @@
+"""C++ host shim (scenelib2_b200/host): the MonoSLAM / Kalman / Feature class surface over the
+C ABI, driven by the headless analogue of examples/MonoSlamSceneLib1.cpp."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from scenelib2_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "scenelib2_b200", "host")
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _write_case(tmp, sc, Pxx):
+    """cfg in the reference's `key = value;` format (data/SceneLib2.cfg) + PGM templates + raw frames."""
+    lines = ["cam.width = %d;" % sc.width, "cam.height = %d;" % sc.height,
+             "cam.fku = %d;" % sc.cam8[2], "cam.fkv = %d;" % sc.cam8[3], "cam.u0 = %d;" % sc.cam8[4],
+             "cam.v0 = %d;" % sc.cam8[5], "cam.kd1 = %r;" % float(sc.cam8[6]), "cam.sd = 1;",
+             "params.delta_t = %r;   # frame period" % sc.delta_t,
+             "params.number_of_features_to_select = %d;" % sc.n_select,
+             "params.number_of_features_to_keep_visible = 12;"]
+    names = ["rw_x", "rw_y", "rw_z", "qwr_w", "qwr_x", "qwr_y", "qwr_z", "vw_x", "vw_y", "vw_z",
+             "ww_x", "ww_y", "ww_z"]
+    for k, nm in enumerate(names):
+        lines.append("state.%s = %r;" % (nm, float(sc.x0[k])))
+    for i in range(13):
+        for j in range(13):
+            lines.append("state.pxx%d_%d = %r;" % (i, j, float(Pxx[i, j])))
+    for i in range(sc.n_features):
+        p = "f%d" % (i + 1)
+        y = sc.x0[13 + 3 * i:16 + 3 * i]
+        lines += ["%s.yi_x = %r;" % (p, float(y[0])), "%s.yi_y = %r;" % (p, float(y[1])),
+                  "%s.yi_z = %r;" % (p, float(y[2]))]
+        for k in range(7):
+            lines.append("%s.xp_org_%d = %r;" % (p, k, float(sc.xp_org[i, k])))
+        lines.append("%s.identifier = patch%d.pgm;" % (p, i))
+        with open(os.path.join(tmp, "patch%d.pgm" % i), "wb") as f:
+            f.write(b"P5\n%d %d\n255\n" % (sc.boxsize, sc.boxsize) + sc.patches[i].tobytes())
+    lines.append("device.max_features = %d;" % max(sc.n_features, 4))
+    open(os.path.join(tmp, "case.cfg"), "w").write("\n".join(lines) + "\n")
+    sc.frames.tofile(os.path.join(tmp, "frames.raw"))
+
+
+def test_shim_builds_and_refuses_without_gpu(tmp_path):
+    import __graft_entry__ as g
+    g.build()
+    exe = os.path.join(HOST, "sl2_headless")
+    assert os.path.exists(exe) and os.path.exists(os.path.join(HOST, "libscenelib2_b200_host.so"))
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    kp = np.load(os.path.join(G, "known_patches.npy"))
+    sc = synth.make_scene("C1", n_frames=1, known_patches=kp)
+    _write_case(str(tmp_path), sc, np.eye(13) * 1e-4)
+    r = subprocess.run([exe, str(tmp_path / "case.cfg"), str(tmp_path / "frames.raw"), "320", "240", "1"],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_headless_matches_oracle(tmp_path, oracle):
+    from gpu_util import assert_state_close, oracle_slam_from_scene
+    kp = np.load(os.path.join(G, "known_patches.npy"))
+    sc = synth.make_scene("C1", n_frames=8, known_patches=kp)
+    Pxx = np.diag([4e-4] * 3 + [2e-5] * 4 + [1e-3] * 3 + [1e-3] * 3)     # cf. data/SceneLib2.cfg:85-115
+    sc.P0 = np.zeros_like(sc.P0)
+    sc.P0[:13, :13] = Pxx
+    _write_case(str(tmp_path), sc, Pxx)
+    exe = os.path.join(HOST, "sl2_headless")
+    out = tmp_path / "out.txt"
+    r = subprocess.run([exe, str(tmp_path / "case.cfg"), str(tmp_path / "frames.raw"), "320", "240", "8",
+                        str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    vals = np.loadtxt(str(out))
+    n = int(vals[0])
+    xg, Pg = vals[1:1 + n], vals[1 + n:].reshape(n, n).T
+    o = oracle_slam_from_scene(oracle, sc)
+    for t in range(8):
+        o.step(sc.frames[t])
+    xo, Po = o.get_state()
+    assert n == o.n
+    d = np.sqrt(np.abs(np.diag(Po))) + 1e-12
+    assert (np.abs(Pg - Po) <= 1e-6 * d[:, None] * d[None, :] + 1e-18).all()
+    assert np.allclose(xg, xo, rtol=1e-7, atol=1e-10)
+    assert "measured 10" in r.stdout
