@@ -525,49 +525,57 @@ __global__ void __launch_bounds__(256) predict_kernel(const Sl2Dev d, int stream
 // ---------------------------------------------------------------------------------------------
 struct UpdSmem {
   // carved from dynamic shared memory; sizes depend on Nmax
-  double *Hx;    // [K][2][13]
-  double *Hy;    // [K][2][3]
-  double *Rv;    // [K]
   double *wv;    // [mmax]  nu, later w = U^-T nu
   int *mfeat;    // [K]
-  double *mult;  // [mmax][NB] (negated) multipliers of the current panel
-  double *ublk;  // [NB][NB]
+  double *Rv;    // [K]
+  double *mult;  // [mmax][UPD_MS] (negated) multipliers of the current panel
   double *invd;  // [NB]
-  double *pan;   // phase 2: panel buffer [NB][panw]; phase 4: Y slabs (2 stages) / tile T[64][65]
-  int panw;
+  double *pan;   // phase 1: HxT / Hy (aliased); phase 2: panel buffer [NB][panw];
+                 // phase 4: Y slabs (2 stages) / tile T[64][65]
+  double *HxT;   // = pan          [16][hms]  Hx transposed, k-major, zero padded (cols 13..15, rows >= m)
+  double *Hy;    // = pan + 16*hms [K][2][3]
+  int panw, hms;
 };
 
 constexpr int UPD_THREADS = 256;
-constexpr int UPD_KC = 16;   // k-chunk of the Y^T Y tiles
+constexpr int UPD_NB = 16;   // Cholesky row-panel height (two DMMA M-tiles)
+constexpr int UPD_MS = 20;   // row stride of the multiplier table: 32 B (mod 128) => conflict-free A fragments
+constexpr int UPD_KC = 32;   // k-chunk of the Y^T Y tiles
 constexpr int UPD_YS = 68;   // padded row stride of a staged Y slab (doubles): conflict-free DMMA reads
 constexpr int UPD_GB = 4;    // 8-column groups per warp iteration in the panel update
 
+__host__ __device__ inline int upd_keven(int Nmax) { return (Nmax + 1) & ~1; }
 __host__ __device__ inline int upd_panw(int Nmax) {
-  const int K = (Nmax + 1) & ~1;
   // row stride = 2 (mod 16) doubles: the 8 rows of a DMMA C fragment hit distinct banks
-  return ((2 * K + SL2_NXV + 3 * Nmax + 1 + 15) & ~15) + 2;
+  return ((2 * upd_keven(Nmax) + SL2_NXV + 3 * Nmax + 1 + 15) & ~15) + 2;
+}
+__host__ __device__ inline int upd_hms(int Nmax) {
+  // k-major Hx table: row stride = 4 (mod 16) doubles => the 4 k-rows of a fragment are 32 B apart
+  return ((2 * upd_keven(Nmax) + 15) & ~15) + 4;
 }
 __host__ __device__ inline size_t upd_pan_doubles(int Nmax) {
-  size_t a = (size_t)SL2_NB * upd_panw(Nmax);
+  size_t a = (size_t)UPD_NB * upd_panw(Nmax);
   const size_t b = 2 * 2 * UPD_KC * UPD_YS, c = 64 * 65;
+  const size_t h = (size_t)16 * upd_hms(Nmax) + (size_t)upd_keven(Nmax) * 6;
   if (b > a) a = b;
   if (c > a) a = c;
+  if (h > a) a = h;
   return (a + 1) & ~(size_t)1;
 }
 
 __device__ __forceinline__ UpdSmem carve(uint8_t *base, int Nmax) {
   UpdSmem u;
-  const int K = (Nmax + 1) & ~1, mmax = 2 * K;  // even counts keep every section 16 B aligned
+  const int K = upd_keven(Nmax), mmax = 2 * K;  // even counts keep every section 16 B aligned
   double *p = reinterpret_cast<double *>(base);
-  u.Hx = p;  p += (size_t)K * 26;
-  u.Hy = p;  p += (size_t)K * 6;
-  u.Rv = p;  p += K;
   u.wv = p;  p += mmax;
-  u.mult = p;  p += (size_t)mmax * SL2_NB;
-  u.ublk = p;  p += SL2_NB * SL2_NB;
-  u.invd = p;  p += SL2_NB;
+  u.Rv = p;  p += K;
+  u.mult = p;  p += (size_t)mmax * UPD_MS;
+  u.invd = p;  p += UPD_NB;
   u.pan = p;  p += upd_pan_doubles(Nmax);
   u.panw = upd_panw(Nmax);
+  u.hms = upd_hms(Nmax);
+  u.HxT = u.pan;
+  u.Hy = u.pan + (size_t)16 * u.hms;
   u.mfeat = reinterpret_cast<int *>(p);
   return u;
 }
@@ -576,8 +584,8 @@ __device__ __forceinline__ UpdSmem carve(uint8_t *base, int Nmax) {
 // B(lane%4, lane/4) and C(lane/4, 2*(lane%4) + {0,1}).
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
 }
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, int src_bytes) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -590,7 +598,7 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-__global__ void __launch_bounds__(UPD_THREADS) update_kernel(
+__global__ void __launch_bounds__(UPD_THREADS, 2) update_kernel(
     const Sl2Dev d, int stream_lo, int staged_m, const int *st_feat, const double *st_Hxv,
     const double *st_Hy, const double *st_R, const double *st_nu, int only_normalise) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -604,6 +612,8 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(
   double *__restrict__ x = d.x + (size_t)s * ld;
   double *__restrict__ G = d.G + (size_t)s * d.mmax * ldg;
   const size_t fb = (size_t)s * d.Nmax;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int lr = lane >> 2, lc = lane & 3;  // DMMA fragment coordinates
   __shared__ int s_m;
 #define PH(i) do { if (blockIdx.x == 0 && tid == 0) d.dbg[(i)] = clock64(); } while (0)
   PH(0);
@@ -629,6 +639,10 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(
   const int m = s_m;
   const int K = m / 2;
   if (m > 0) {
+    const int HMS = sm.hms;
+    // HxT[c][i] = H_xv(i, c) (k-major, zero padded), Hy[k][r][c], Rv[k], wv = nu
+    for (int e = tid; e < 16 * HMS; e += UPD_THREADS) sm.HxT[e] = 0.0;
+    __syncthreads();
     if (staged_m >= 0) {
       for (int k = tid; k < K; k += UPD_THREADS) {
         sm.mfeat[k] = st_feat[k];
@@ -636,7 +650,10 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(
         sm.wv[2 * k] = st_nu[2 * k];
         sm.wv[2 * k + 1] = st_nu[2 * k + 1];
       }
-      for (int e = tid; e < K * 26; e += UPD_THREADS) sm.Hx[e] = st_Hxv[e];
+      for (int e = tid; e < m * 13; e += UPD_THREADS) {
+        const int i = e / 13, c = e - i * 13;
+        sm.HxT[c * HMS + i] = st_Hxv[e];
+      }
       for (int e = tid; e < K * 6; e += UPD_THREADS) sm.Hy[e] = st_Hy[e];
     } else {
       for (int k = tid; k < K; k += UPD_THREADS) {
@@ -646,8 +663,7 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(
         sm.wv[2 * k] = (rd((double)d.z_uv[(fb + i) * 2]) - rd(d.h[(fb + i) * 2])).v;
         sm.wv[2 * k + 1] = (rd((double)d.z_uv[(fb + i) * 2 + 1]) - rd(d.h[(fb + i) * 2 + 1])).v;
         for (int r = 0; r < 2; ++r) {
-          for (int c = 0; c < 13; ++c)
-            sm.Hx[k * 26 + r * 13 + c] = c < 7 ? d.dh_dxp[(fb + i) * 14 + r * 7 + c] : 0.0;
+          for (int c = 0; c < 7; ++c) sm.HxT[c * HMS + 2 * k + r] = d.dh_dxp[(fb + i) * 14 + r * 7 + c];
           for (int c = 0; c < 3; ++c) sm.Hy[k * 6 + r * 3 + c] = d.dh_dy[(fb + i) * 6 + r * 3 + c];
         }
       }
@@ -655,141 +671,190 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(
     __syncthreads();
 
     PH(1);
-    // ---- phase 1a: H*P rows (structured: 13 + 3 columns of P per row pair) and nu column ----
-    for (int j = tid; j < n; j += UPD_THREADS) {
-      double px[13];
+    // ---- phase 1a: H*P.  Dense part H_xv (m x 16) * P(0:16, :) on DMMA tiles; the 3 structural
+    //      columns of dh/dy are added per element; nu goes into the last column.
+    {
+      const int mtiles = (m + 7) >> 3, ngrp = (n + 7) >> 3;
+      for (int g = warp; g < ngrp; g += UPD_THREADS / 32) {
+        const int jb = g * 8 + lr;  // column of this lane's B element
+        double b[4];
 #pragma unroll
-      for (int c = 0; c < 13; ++c) px[c] = P[j + (size_t)ld * c];  // P(c, j) by symmetry
-#pragma unroll 4
-      for (int k = 0; k < K; ++k) {
-        const int pos = SL2_NXV + 3 * sm.mfeat[k];
-        const double py0 = P[j + (size_t)ld * pos], py1 = P[j + (size_t)ld * (pos + 1)],
-                     py2 = P[j + (size_t)ld * (pos + 2)];
-        const double *hx = sm.Hx + k * 26, *hy = sm.Hy + k * 6;
-        double a0 = 0.0, a1 = 0.0;
+        for (int ks = 0; ks < 4; ++ks) b[ks] = jb < n ? P[jb + (size_t)ld * (4 * ks + lc)] : 0.0;
+        const int j0 = g * 8 + 2 * lc;  // columns of this lane's C elements
+#pragma unroll 2
+        for (int mt = 0; mt < mtiles; ++mt) {
+          double c0 = 0.0, c1 = 0.0;
 #pragma unroll
-        for (int c = 0; c < 13; ++c) {
-          a0 += hx[c] * px[c];
-          a1 += hx[13 + c] * px[c];
+          for (int ks = 0; ks < 4; ++ks) dmma884(c0, c1, sm.HxT[(4 * ks + lc) * HMS + mt * 8 + lr], b[ks]);
+          const int i = mt * 8 + lr;
+          if (i < m && j0 < n) {
+            const int k = i >> 1;
+            const int pos = SL2_NXV + 3 * sm.mfeat[k];
+            const double *hy = sm.Hy + k * 6 + (i & 1) * 3;
+            if (j0 + 1 < n) {
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                const double2 pv = *reinterpret_cast<const double2 *>(P + j0 + (size_t)ld * (pos + c));
+                c0 += hy[c] * pv.x;
+                c1 += hy[c] * pv.y;
+              }
+              *reinterpret_cast<double2 *>(G + (size_t)i * ldg + m + j0) = make_double2(c0, c1);
+            } else {
+#pragma unroll
+              for (int c = 0; c < 3; ++c) c0 += hy[c] * P[j0 + (size_t)ld * (pos + c)];
+              G[(size_t)i * ldg + m + j0] = c0;
+            }
+          }
         }
-        a0 += hy[0] * py0;
-        a0 += hy[1] * py1;
-        a0 += hy[2] * py2;
-        a1 += hy[3] * py0;
-        a1 += hy[4] * py1;
-        a1 += hy[5] * py2;
-        G[(size_t)(2 * k) * ldg + m + j] = a0;
-        G[(size_t)(2 * k + 1) * ldg + m + j] = a1;
       }
     }
     for (int i = tid; i < m; i += UPD_THREADS) G[(size_t)i * ldg + m + n] = sm.wv[i];
     __syncthreads();
     PH(2);
-    // ---- phase 1b: S = (H P) H^T + R ---------------------------------------------------------
-    for (int e = tid; e < m * K; e += UPD_THREADS) {
-      const int i = e / K, kp = e - i * K;
-      const double *g = G + (size_t)i * ldg + m;
-      const int pos = SL2_NXV + 3 * sm.mfeat[kp];
-      const double *hx = sm.Hx + kp * 26, *hy = sm.Hy + kp * 6;
-      double a0 = 0.0, a1 = 0.0;
+    // ---- phase 1b: S = (H P) H^T + R, upper 8x8 tiles: dense part on DMMA (A = HP(:, 0:16) from
+    //      global, B = HxT), structural dh/dy part and R per element.
+    {
+      const int mtiles = (m + 7) >> 3;
+      const int ntile = mtiles * (mtiles + 1) / 2;
+      for (int t = warp; t < ntile; t += UPD_THREADS / 32) {
+        // unrank the upper-triangular tile index t -> (mt <= nt)
+        int mt = 0, rem = t;
+        while (rem >= mtiles - mt) {
+          rem -= mtiles - mt;
+          ++mt;
+        }
+        const int nt = mt + rem;
+        double c0 = 0.0, c1 = 0.0;
+        const int ia = mt * 8 + lr;
 #pragma unroll
-      for (int c = 0; c < 13; ++c) {
-        const double v = g[c];
-        a0 += v * hx[c];
-        a1 += v * hx[13 + c];
-      }
+        for (int ks = 0; ks < 4; ++ks) {
+          const double a = ia < m ? G[(size_t)ia * ldg + m + 4 * ks + lc] : 0.0;
+          dmma884(c0, c1, a, sm.HxT[(4 * ks + lc) * HMS + nt * 8 + lr]);
+        }
+        const int jp = nt * 8 + 2 * lc;  // columns jp, jp+1 belong to measured feature kp
+        if (ia < m && jp < m) {
+          const int kp = jp >> 1;
+          const int pos = SL2_NXV + 3 * sm.mfeat[kp];
+          const double *hy = sm.Hy + kp * 6;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const double v = g[pos + c];
-        a0 += v * hy[c];
-        a1 += v * hy[3 + c];
+          for (int c = 0; c < 3; ++c) {
+            const double v = G[(size_t)ia * ldg + m + pos + c];
+            c0 += v * hy[c];
+            c1 += v * hy[3 + c];
+          }
+          if (ia == jp) c0 += sm.Rv[kp];
+          if (ia == jp + 1) c1 += sm.Rv[kp];
+          *reinterpret_cast<double2 *>(G + (size_t)ia * ldg + jp) = make_double2(c0, c1);
+        }
       }
-      if (i == 2 * kp) a0 += sm.Rv[kp];
-      if (i == 2 * kp + 1) a1 += sm.Rv[kp];
-      G[(size_t)i * ldg + 2 * kp] = a0;
-      G[(size_t)i * ldg + 2 * kp + 1] = a1;
     }
     __syncthreads();
 
     PH(3);
-    // ---- phase 2: left-looking Cholesky by row panels of 8 on G = [S | HP | nu] ----------------
-    // Trailing update of a panel = C(8 x cols) - A(8 x i0) * B(i0 x cols) with A(r,k) = U(k,i0+r)
+    // ---- phase 2: left-looking Cholesky by row panels of 16 on G = [S | HP | nu] ---------------
+    // Trailing update of a panel = C(16 x cols) - A(16 x i0) * B(i0 x cols) with A(r,k) = U(k,i0+r)
     // (multipliers, shared memory) and B = finished rows of G (global / L2): FP64 tensor-core
-    // tiles (DMMA m8n8k4), each warp owning groups of 8 columns.
+    // tiles (DMMA m8n8k4, two M tiles per B fragment), each warp owning groups of 8 columns; the B
+    // fragments are software-pipelined three k-steps ahead.
     const int width = m + n + 1;
-    const int PW = sm.panw;  // panel buffer row stride (doubles)
-    const int warp = tid >> 5, lane = tid & 31;
-    const int lr = lane >> 2, lc = lane & 3;  // DMMA fragment coordinates
-    for (int i0 = 0; i0 < m; i0 += SL2_NB) {
-      const int nbp = min(SL2_NB, m - i0);
+    const int PW = sm.panw;
+    for (int i0 = 0; i0 < m; i0 += UPD_NB) {
+      const int nbp = min(UPD_NB, m - i0);
       // multipliers, negated so that D = (-A) * B + C
-      for (int e = tid; e < i0 * SL2_NB; e += UPD_THREADS) {
-        const int k = e / SL2_NB, r = e - k * SL2_NB;
-        sm.mult[e] = (r < nbp) ? -G[(size_t)k * ldg + i0 + r] : 0.0;
+      for (int e = tid; e < i0 * UPD_NB; e += UPD_THREADS) {
+        const int k = e / UPD_NB, r = e - k * UPD_NB;
+        sm.mult[k * UPD_MS + r] = (r < nbp) ? -G[(size_t)k * ldg + i0 + r] : 0.0;
       }
       __syncthreads();
       const int ngroups = (width - i0 + 7) >> 3;
+      const int nk = i0 >> 2;  // k-steps of 4 rows; i0 is a multiple of 16 so nk % 4 == 0
       for (int g0 = warp * UPD_GB; g0 < ngroups; g0 += (UPD_THREADS / 32) * UPD_GB) {
-        double c[UPD_GB][2];
-        int colb[UPD_GB];  // column of the B fragment element of this lane
+        double c[UPD_GB][2][2];
+        int colb[UPD_GB];  // column of the B fragment element of this lane (-1: none)
 #pragma unroll
         for (int q = 0; q < UPD_GB; ++q) {
           const int cbase = i0 + (g0 + q) * 8;
-          colb[q] = cbase + lr;
-          const int cc = cbase + 2 * lc;  // C fragment: row lr, columns cc, cc+1
-          const bool rv = lr < nbp && (g0 + q) < ngroups;
-          c[q][0] = (rv && cc < width) ? G[(size_t)(i0 + lr) * ldg + cc] : 0.0;
-          c[q][1] = (rv && cc + 1 < width) ? G[(size_t)(i0 + lr) * ldg + cc + 1] : 0.0;
-          if (colb[q] >= width) colb[q] = -1;
+          colb[q] = (cbase + lr < width && g0 + q < ngroups) ? cbase + lr : -1;
+          const int cc = cbase + 2 * lc;  // C fragment: rows lr / lr+8, columns cc, cc+1
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            const int r = mt * 8 + lr;
+            const bool rv = r < nbp && (g0 + q) < ngroups;
+            c[q][mt][0] = (rv && cc < width) ? G[(size_t)(i0 + r) * ldg + cc] : 0.0;
+            c[q][mt][1] = (rv && cc + 1 < width) ? G[(size_t)(i0 + r) * ldg + cc + 1] : 0.0;
+          }
         }
-#pragma unroll 8
-        for (int k0 = 0; k0 < i0; k0 += 4) {
-          const double a = sm.mult[(k0 + lc) * SL2_NB + lr];
-          const double *gk = G + (size_t)(k0 + lc) * ldg;
-          double b[UPD_GB];
+        double b[4][UPD_GB];
+        auto loadb = [&](int step, double *dst) {
+          const double *gk = G + (size_t)(4 * step + lc) * ldg;
 #pragma unroll
-          for (int q = 0; q < UPD_GB; ++q) b[q] = colb[q] >= 0 ? gk[colb[q]] : 0.0;
+          for (int q = 0; q < UPD_GB; ++q) dst[q] = colb[q] >= 0 ? gk[colb[q]] : 0.0;
+        };
+        if (nk > 0) {
+          loadb(0, b[0]);
+          loadb(1, b[1]);
+          loadb(2, b[2]);
+        }
+        for (int kb = 0; kb < nk; kb += 4) {
 #pragma unroll
-          for (int q = 0; q < UPD_GB; ++q) dmma884(c[q][0], c[q][1], a, b[q]);
+          for (int u = 0; u < 4; ++u) {
+            const int st = kb + u;
+            if (st + 3 < nk) loadb(st + 3, b[(u + 3) & 3]);
+            const double a0 = sm.mult[(4 * st + lc) * UPD_MS + lr];
+            const double a1 = sm.mult[(4 * st + lc) * UPD_MS + 8 + lr];
+#pragma unroll
+            for (int q = 0; q < UPD_GB; ++q) {
+              dmma884(c[q][0][0], c[q][0][1], a0, b[u][q]);
+              dmma884(c[q][1][0], c[q][1][1], a1, b[u][q]);
+            }
+          }
         }
 #pragma unroll
         for (int q = 0; q < UPD_GB; ++q) {
           if (g0 + q < ngroups) {
             const int pc = (g0 + q) * 8 + 2 * lc;
-            *reinterpret_cast<double2 *>(sm.pan + (size_t)lr * PW + pc) = make_double2(c[q][0], c[q][1]);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+              *reinterpret_cast<double2 *>(sm.pan + (size_t)(mt * 8 + lr) * PW + pc) =
+                  make_double2(c[q][mt][0], c[q][mt][1]);
           }
         }
       }
       __syncthreads();
-      // factor the 8x8 diagonal block on one thread (rows of the panel buffer, columns 0..7)
-      if (tid == 0) {
+      // factor the 16x16 diagonal block in place (upper triangle) with one warp, lane = column
+      if (warp == 0) {
         for (int r = 0; r < nbp; ++r) {
-          double dg = sm.pan[(size_t)r * PW + r];
-          for (int q = 0; q < r; ++q) dg -= sm.ublk[q * SL2_NB + r] * sm.ublk[q * SL2_NB + r];
+          const double dg = sm.pan[(size_t)r * PW + r];
           const double u = sqrt(dg);
           const double iu = 1.0 / u;
-          sm.ublk[r * SL2_NB + r] = u;
-          sm.invd[r] = iu;
-          for (int cix = r + 1; cix < nbp; ++cix) {
-            double v = sm.pan[(size_t)r * PW + cix];
-            for (int q = 0; q < r; ++q) v -= sm.ublk[q * SL2_NB + r] * sm.ublk[q * SL2_NB + cix];
-            sm.ublk[r * SL2_NB + cix] = v * iu;
+          __syncwarp();
+          if (lane > r && lane < nbp) sm.pan[(size_t)r * PW + lane] *= iu;
+          if (lane == r) {
+            sm.pan[(size_t)r * PW + r] = u;
+            sm.invd[r] = iu;
           }
+          __syncwarp();
+          if (lane > r && lane < nbp) {
+            const double urj = sm.pan[(size_t)r * PW + lane];
+            for (int i = r + 1; i <= lane; ++i)
+              sm.pan[(size_t)i * PW + lane] -= sm.pan[(size_t)r * PW + i] * urj;
+          }
+          __syncwarp();
         }
       }
       __syncthreads();
       // apply U_pp^-T to every column of the panel and write the finished rows
       for (int cc = tid; cc < width - i0; cc += UPD_THREADS) {
-        double f[SL2_NB];
+        double f[UPD_NB];
 #pragma unroll
-        for (int r = 0; r < SL2_NB; ++r) {
+        for (int r = 0; r < UPD_NB; ++r) {
           double v = sm.pan[(size_t)r * PW + cc];
 #pragma unroll
-          for (int t = 0; t < r; ++t) v -= sm.ublk[t * SL2_NB + r] * f[t];
-          f[r] = v * sm.invd[r];
+          for (int t = 0; t < r; ++t) v -= sm.pan[(size_t)t * PW + r] * f[t];
+          f[r] = r < nbp ? v * sm.invd[r] : 0.0;
           if (r < nbp) {
             double outv = f[r];
-            if (cc < nbp) outv = (cc >= r) ? sm.ublk[r * SL2_NB + cc] : 0.0;
+            if (cc < nbp) outv = (cc >= r) ? sm.pan[(size_t)r * PW + cc] : 0.0;
             G[(size_t)(i0 + r) * ldg + i0 + cc] = outv;
           }
         }
@@ -803,6 +868,7 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(
     __syncthreads();
     for (int j = tid; j < n; j += UPD_THREADS) {
       double a = 0.0;
+#pragma unroll 8
       for (int k = 0; k < m; ++k) a += G[(size_t)k * ldg + m + j] * sm.wv[k];
       x[j] += a;
     }
@@ -1061,9 +1127,8 @@ __global__ void __launch_bounds__(256) cull_kernel(const Sl2Dev d, int stream_lo
 }  // namespace
 
 size_t sl2_update_smem_bytes(const Sl2Dev &d) {
-  const size_t K = (d.Nmax + 1) & ~1, mmax = 2 * K;
-  const size_t doubles = K * 26 + K * 6 + K + mmax + mmax * SL2_NB + SL2_NB * SL2_NB + SL2_NB +
-                         upd_pan_doubles(d.Nmax);
+  const size_t K = upd_keven(d.Nmax), mmax = 2 * K;
+  const size_t doubles = mmax + K + mmax * UPD_MS + UPD_NB + upd_pan_doubles(d.Nmax);
   return doubles * 8 + K * 4 + 16;
 }
 
