@@ -138,6 +138,13 @@ int sl2_step(sl2_ctx *ctx, int32_t slot);
 /* end-to-end form: host frames in ([num_streams][height][width]), camera states out
  * (xv_out: [num_streams][13], may be NULL).  Copies run on the context's stream. */
 int sl2_step_host(sl2_ctx *ctx, int32_t slot, const uint8_t *gray, double *xv_out);
+/* asynchronous end-to-end form for a frame ring: enqueues the H2D copy of `gray` into `slot` on a
+ * copy stream, the fused step, and the D2H of the camera states into xv_out, then returns. gray and
+ * xv_out must be pinned and stay valid until sl2_wait_slot(ctx, slot) (or sl2_sync) returns.
+ * Consecutive calls should use different slots: the copy of frame t+1 then overlaps the kernels of
+ * frame t (the producer side of FrameGrabber::GetFrame, framegrabber.cpp:73-104). */
+int sl2_step_host_async(sl2_ctx *ctx, int32_t slot, const uint8_t *gray, double *xv_out);
+int sl2_wait_slot(sl2_ctx *ctx, int32_t slot);
 
 /* ---- read-back of per-feature results (Feature::h_/z_/S_/flags/counters, feature.h:96-140) */
 int sl2_get_features(sl2_ctx *ctx, int32_t stream_id, double *h /* n x 2 */, double *z /* n x 2 */,

@@ -36,6 +36,11 @@ struct sl2_ctx {
   bool timing = false;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   float last_ms[4] = {0, 0, 0, 0};
+  // asynchronous end-to-end path: frames of step t+1 are copied while step t computes
+  cudaStream_t copy_stream = nullptr;  // H2D of the frames
+  cudaStream_t out_stream = nullptr;   // D2H of the results (own stream: must not block the next H2D)
+  std::vector<cudaEvent_t> ev_h2d, ev_cmp, ev_out;  // per frame slot
+  double *xv_stage = nullptr;                        // [slots][B][13] device
 };
 
 namespace {
@@ -250,6 +255,7 @@ int sl2_create(const sl2_config *cfg, sl2_ctx **out) {
   ALLOC(d.nvisible, B);
   ALLOC(d.nmeas, B);
   ALLOC(d.dbg, 64);
+  ALLOC(c->xv_stage, (size_t)d.slots * B * SL2_NXV);
 #undef ALLOC
   if (!ok) {
     const std::string m = std::string("cudaMalloc failed: ") + cudaGetErrorString(cudaGetLastError());
@@ -261,6 +267,20 @@ int sl2_create(const sl2_config *cfg, sl2_ctx **out) {
   if (rc == SL2_OK) {
     for (int i = 0; i < 5 && rc == SL2_OK; ++i)
       if (cudaEventCreate(&c->ev[i]) != cudaSuccess) rc = SL2_ERR_CUDA;
+    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) rc = SL2_ERR_CUDA;
+    if (cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking) != cudaSuccess) rc = SL2_ERR_CUDA;
+    for (int i = 0; i < d.slots && rc == SL2_OK; ++i) {
+      cudaEvent_t e1, e2, e3;
+      if (cudaEventCreateWithFlags(&e1, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&e2, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&e3, cudaEventDisableTiming) != cudaSuccess) {
+        rc = SL2_ERR_CUDA;
+        break;
+      }
+      c->ev_h2d.push_back(e1);
+      c->ev_cmp.push_back(e2);
+      c->ev_out.push_back(e3);
+    }
   }
   if (rc == SL2_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = SL2_ERR_CUDA;
   if (rc != SL2_OK) {
@@ -275,6 +295,16 @@ int sl2_create(const sl2_config *cfg, sl2_ctx **out) {
 void sl2_destroy(sl2_ctx *c) {
   if (!c) return;
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->copy_stream) {
+    cudaStreamSynchronize(c->copy_stream);
+    cudaStreamDestroy(c->copy_stream);
+  }
+  if (c->out_stream) {
+    cudaStreamSynchronize(c->out_stream);
+    cudaStreamDestroy(c->out_stream);
+  }
+  for (auto &v : {c->ev_h2d, c->ev_cmp, c->ev_out})
+    for (cudaEvent_t e : v) cudaEventDestroy(e);
   for (void *p : c->allocs) cudaFree(p);
   if (c->stg_dev) cudaFree(c->stg_dev);
   if (c->stg_host) cudaFreeHost(c->stg_host);
@@ -287,6 +317,8 @@ void sl2_destroy(sl2_ctx *c) {
 int sl2_sync(sl2_ctx *c) {
   if (!c) return SL2_ERR_ARG;
   CU_TRY(c, cudaStreamSynchronize(c->stream));
+  if (c->copy_stream) CU_TRY(c, cudaStreamSynchronize(c->copy_stream));
+  if (c->out_stream) CU_TRY(c, cudaStreamSynchronize(c->out_stream));
   return SL2_OK;
 }
 
@@ -655,6 +687,41 @@ int sl2_step_host(sl2_ctx *c, int32_t slot, const uint8_t *gray, double *xv_out)
     CU_TRY(c, cudaMemcpy2DAsync(xv_out, sizeof(double) * SL2_NXV, d.x, sizeof(double) * d.ld,
                                 sizeof(double) * SL2_NXV, d.B, cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return SL2_OK;
+}
+
+int sl2_step_host_async(sl2_ctx *c, int32_t slot, const uint8_t *gray, double *xv_out) {
+  if (!c || bad_slot(c, slot) || !gray) return fail(c, SL2_ERR_ARG, "sl2_step_host_async: bad argument");
+  const Sl2Dev &d = c->d;
+  cudaStream_t cs = c->copy_stream;
+  // the frame slot may still be read by the step that used it last
+  CU_TRY(c, cudaStreamWaitEvent(cs, c->ev_cmp[slot], 0));
+  uint8_t *dst = d.frames + (size_t)slot * d.B * d.H * d.pitch;
+  if (d.pitch == d.W) {
+    CU_TRY(c, cudaMemcpyAsync(dst, gray, (size_t)d.B * d.H * d.W, cudaMemcpyHostToDevice, cs));
+  } else {
+    CU_TRY(c, cudaMemcpy2DAsync(dst, d.pitch, gray, d.W, d.W, (size_t)d.B * d.H, cudaMemcpyHostToDevice, cs));
+  }
+  CU_TRY(c, cudaEventRecord(c->ev_h2d[slot], cs));
+  CU_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_h2d[slot], 0));
+  CU_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_out[slot], 0));  // staging buffer of this slot is free
+  int rc = step_enqueue(c, slot);
+  if (rc) return rc;
+  double *stage = c->xv_stage + (size_t)slot * d.B * SL2_NXV;
+  CU_TRY(c, cudaMemcpy2DAsync(stage, sizeof(double) * SL2_NXV, d.x, sizeof(double) * d.ld,
+                              sizeof(double) * SL2_NXV, d.B, cudaMemcpyDeviceToDevice, c->stream));
+  CU_TRY(c, cudaEventRecord(c->ev_cmp[slot], c->stream));
+  CU_TRY(c, cudaStreamWaitEvent(c->out_stream, c->ev_cmp[slot], 0));
+  if (xv_out)
+    CU_TRY(c, cudaMemcpyAsync(xv_out, stage, sizeof(double) * SL2_NXV * d.B, cudaMemcpyDeviceToHost,
+                              c->out_stream));
+  CU_TRY(c, cudaEventRecord(c->ev_out[slot], c->out_stream));
+  return SL2_OK;
+}
+
+int sl2_wait_slot(sl2_ctx *c, int32_t slot) {
+  if (!c || bad_slot(c, slot)) return fail(c, SL2_ERR_ARG, "sl2_wait_slot: bad slot");
+  CU_TRY(c, cudaEventSynchronize(c->ev_out[slot]));
   return SL2_OK;
 }
 

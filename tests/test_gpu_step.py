@@ -90,3 +90,28 @@ def test_step_host_returns_camera_states(oracle):
         xo, Po = o.get_state()
         assert np.allclose(xv[s], xo[:13], rtol=1e-7, atol=1e-12)
     ctx.close()
+
+
+def test_async_host_ring_matches_blocking(oracle):
+    """sl2_step_host_async (copy of frame t+1 overlapped with the step of frame t) == blocking path."""
+    import torch
+    scenes = [synth.make_scene("C2", stream_id=s, n_frames=4, n_features=16) for s in range(3)]
+    a = ctx_from_scenes(scenes, frame_slots=4)
+    b = ctx_from_scenes(scenes, frame_slots=4)
+    host = torch.empty((4, 3, 240, 320), dtype=torch.uint8, pin_memory=True)
+    host.numpy()[:] = np.stack([np.stack([sc.frames[t] for sc in scenes]) for t in range(4)])
+    xa = torch.zeros((4, 3, 13), dtype=torch.float64, pin_memory=True)
+    xb = np.zeros((4, 3, 13))
+    for t in range(4):
+        a.step_host_async(t, host[t].data_ptr(), xa[t].data_ptr())
+    for t in range(4):
+        b.step_host(t, host[t].data_ptr(), xb[t].ctypes.data)
+    a.wait_slot(3)
+    a.sync()
+    assert (xa.numpy() == xb).all()
+    for s in range(3):
+        xs, Ps = a.get_state(s)
+        xt, Pt = b.get_state(s)
+        assert (xs == xt).all() and (Ps == Pt).all()
+    a.close()
+    b.close()
