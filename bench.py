@@ -301,8 +301,8 @@ def run_ours(args, rank, local_rank, world):
                        "l2": "per-step working set %.0f MB (P + scratch + frames of %d streams) exceeds the 126 MB L2"
                              % ((B * (cfg.max_features * 3 + 13) ** 2 * 8 * 2.1) / 1e6, B),
                        "matched_fraction": matched, "features_left_stream0": nfeat_end},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * H * W,
-                    "d2h_bytes_per_step": B * 13 * 8, "ms_per_step": ms_e2e / args.steps,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": world * B * H * W,
+                    "d2h_bytes_per_step": world * B * 13 * 8, "ms_per_step": ms_e2e / args.steps,
                     "api": "sl2_step_host_async over a ring of %d pinned frame sets" % R,
                     "blocking_call_value": e2e_sync},
             "gpu_launches": int(launches),

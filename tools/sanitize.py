@@ -1,0 +1,28 @@
+"""Small end-to-end exercise of every kernel for compute-sanitizer (memcheck / racecheck)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+from scenelib2_b200 import synth
+from gpu_util import ctx_from_scenes, random_puinv
+
+scenes = [synth.make_scene("C2", stream_id=s, n_frames=3, n_features=21, override=(s == 0)) for s in range(2)]
+ctx = ctx_from_scenes(scenes, frame_slots=2)
+for t in range(3):
+    ctx.set_frames(t % 2, np.stack([sc.frames[t] for sc in scenes]))
+    ctx.step(t % 2)
+ctx.sync()
+rng = np.random.default_rng(0)
+sc = scenes[0]
+n = sc.n_features
+u, v, f, b = ctx.patch_search(0, 0, np.arange(n, dtype=np.int32), sc.pix + rng.uniform(-3, 3, (n, 2)),
+                              random_puinv(rng, n, 5, 30, 0.3))
+ctx.score_map(0, 0, 2, sc.pix[2].astype(float), [0.02, 0.001, 0.03])
+ctx.smoe_search(0, 0, 1, random_puinv(rng, 4, 5, 12, 0.5), np.tile(sc.pix[1].astype(float), (4, 1)))
+ctx.delete_feature(1, 5)
+ctx.ekf_predict(0); ctx.predict_measurements(0); ctx.make_measurements(0, 0); ctx.ekf_update_measured(0)
+sc3 = synth.make_scene("C3", n_frames=1, n_features=9)
+c3 = ctx_from_scenes([sc3])
+c3.set_frames(0, sc3.frames[:1]); c3.step(0); c3.sync()
+print("found", int(f.sum()), "of", n, "| state finite:", bool(np.isfinite(ctx.get_state(0)[1]).all()),
+      bool(np.isfinite(c3.get_state(0)[1]).all()))
