@@ -230,7 +230,9 @@ __global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32, (BOX <= 11 && FILTER) ?
           const int t = t0 + lane;
           uint32_t entry = 0;
           if (t < ntask) {
-            const int cu = t / nstrips, st = t - cu * nstrips;
+            // strip-major order: the lanes of a round mostly share the image rows and read
+            // consecutive columns => shared-memory reads are broadcasts / conflict-free
+            const int st = t / tcw, cu = t - st * tcw;
             const double du = (double)(us + tx0 + cu);
             const double a = mul_(mul_(P00, du), du);
             const double bcoef = mul_(twoP01, du);
@@ -259,18 +261,25 @@ __global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32, (BOX <= 11 && FILTER) ?
 
         // ---- strips ------------------------------------------------------------------------
         for (int l0 = 0; l0 < nlist; l0 += 32) {
-          if (l0 + lane < nlist) {
+          const bool has_task = l0 + lane < nlist;
+          uint32_t ax[V], a1[V], a2[V];
+          float cap[V];           // FILTER: approximate scores of the strip
+          int cand0 = 0;          // scan index of candidate j = 0 of the strip
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            ax[j] = a1[j] = a2[j] = 0;
+            cap[j] = __int_as_float(0x7f800000);  // +inf: not a candidate
+          }
+          if (has_task) {
             const uint32_t e = list[l0 + lane];
             const int cu = e & 0xff, st = (e >> 8) & 0xff;
             const uint32_t m_in = (e >> 16) & 0xff, m_all = m_in | ((e >> 24) & 0xff);
             const int cv0 = st * V;
+            cand0 = (tx0 + cu) * CH + (ty0 + cv0);
             const int cx = cu + xoff;  // byte column of the candidate's window inside the tile
             const int sh = (cx & 3) * 8;
             const uint32_t *wbase = reinterpret_cast<const uint32_t *>(tile) + (cx >> 2);
             const int tw4 = TW >> 2;
-            uint32_t ax[V], a1[V], a2[V];
-#pragma unroll
-            for (int j = 0; j < V; ++j) ax[j] = a1[j] = a2[j] = 0;
 #pragma unroll
             for (int rr = 0; rr < V + BOX - 1; ++rr) {
               const int row = min(cv0 + rr, TH - 1);
@@ -307,34 +316,28 @@ __global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32, (BOX <= 11 && FILTER) ?
               // FP64 rounding (<= 1e-9 for sigma >= 10).  rho is evaluated in FP32 from the EXACT
               // integer moments; only candidates whose approximate score is within kWindow of the
               // running minimum can be the reference's arg-min (or tie with it), and only those go
-              // through the exact FP64 chain.  kWindow = 1e-5 >= 2 * (FP32 error 1.1e-6 + 1e-9).
-              constexpr float kWindow = 1.0e-5f;
+              // through the exact FP64 chain.  window 1e-5 >= 2 * (FP32 error 1.1e-6 + 1e-9).
+              // pass 1: approximate scores of the strip (no FP64 div/sqrt); pass 2, after the warp
+              // has agreed on the running minimum: exact chain for the survivors only.
               if (patch_ok) {
+                float lmin = bmin;
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
                   if ((m_in >> j) & 1u) {
                     const double Sg1d = (double)(int)a1[j], Sg1sqd = (double)(int)a2[j],
                                  Sg0g1d = (double)(int)ax[j];
                     const double V1 = fma(n, Sg1sqd, -(Sg1d * Sg1d));  // exact
-                    bool gate = V1 > T100;
-                    double sg1;
-                    if (V1 == T100) {  // knife edge of sdimage >= 10: decide with the exact chain
-                      exact_score(Sg1d, Sg1sqd, Sg0g1d, sg1);
-                      gate = !(sg1 < 10.0);
-                    }
-                    if (gate) {
+                    if (V1 > T100) {
                       const double N01 = fma(n, Sg0g1d, -(Sg0d * Sg1d));  // exact
                       const float rho = (float)N01 * rsqrtf((float)(V0d * V1));
-                      const float capprox = fmaf(-2.0f, rho, 2.0f);
-                      if (capprox <= bmin + kWindow) {
-                        const double corr = exact_score(Sg1d, Sg1sqd, Sg0g1d, sg1);
-                        const int idx = (tx0 + cu) * CH + (ty0 + cv0 + j);
-                        if (corr <= 1000000.0 && !(sg1 < 10.0)) consider(best, corr, idx);
-                      }
-                      bmin = fminf(bmin, capprox);
+                      cap[j] = fmaf(-2.0f, rho, 2.0f);
+                      lmin = fminf(lmin, cap[j]);
+                    } else if (V1 == T100) {
+                      cap[j] = -3.0e38f;  // knife edge of sdimage >= 10: the exact chain decides
                     }
                   }
                 }
+                bmin = lmin;
               }
             } else {
 #pragma unroll
@@ -365,9 +368,20 @@ __global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32, (BOX <= 11 && FILTER) ?
               }
             }
           }
-          if constexpr (FILTER) {  // share the running minimum so later rounds filter better
+          if constexpr (FILTER) {
+            // the warp agrees on the running minimum, then only the survivors take the exact chain
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) bmin = fminf(bmin, __shfl_xor_sync(0xffffffffu, bmin, o));
+            const float thr = bmin + 1.0e-5f;  // kWindow, see above
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+              if (cap[j] <= thr) {
+                double sg1;
+                const double corr = exact_score_fn(pconst, (double)(int)a1[j], (double)(int)a2[j],
+                                                   (double)(int)ax[j], &sg1);
+                if (corr <= 1000000.0 && !(sg1 < 10.0)) consider(best, corr, cand0 + j);
+              }
+            }
           }
         }
         __syncwarp();
