@@ -255,7 +255,8 @@ def run_ours(args, rank, local_rank, world):
         buf = (ctypes.c_longlong * 64)()
         ctx.L.sl2_debug_phase_cycles(ctx.h, buf)
         st = [buf[i] for i in range(8)]
-        print("update phase cycles (CTA 0):", [st[i + 1] - st[i] for i in range(7)], file=sys.stderr)
+        print("update phase cycles (CTA 0):", [st[i + 1] - st[i] for i in range(7)],
+              "panel sub-phases (mult, mma, wait, apply):", [buf[i] for i in range(16, 21)], file=sys.stderr)
 
     # ---- end-to-end leg: host frames in, camera states out, through the C ABI -----------------
     # every step: pinned host frames -> H2D -> GoOneStep of all streams -> D2H of the camera states;

@@ -530,6 +530,7 @@ struct UpdSmem {
   double *Rv;    // [K]
   double *mult;  // [mmax][UPD_MS] (negated) multipliers of the current panel
   double *invd;  // [NB]
+  double *Wm;    // [NB][UPD_WS]  W = U_pp^-T of the current panel
   double *pan;   // phase 1: HxT / Hy (aliased); phase 2: panel buffer [NB][panw];
                  // phase 4: Y slabs (2 stages) / tile T[64][65]
   double *HxT;   // = pan          [16][hms]  Hx transposed, k-major, zero padded (cols 13..15, rows >= m)
@@ -539,6 +540,7 @@ struct UpdSmem {
 
 constexpr int UPD_THREADS = 256;
 constexpr int UPD_NB = 16;   // Cholesky row-panel height (two DMMA M-tiles)
+constexpr int UPD_WS = 20;   // row stride of the W table
 constexpr int UPD_MS = 20;   // row stride of the multiplier table: 32 B (mod 128) => conflict-free A fragments
 constexpr int UPD_KC = 32;   // k-chunk of the Y^T Y tiles
 constexpr int UPD_YS = 68;   // padded row stride of a staged Y slab (doubles): conflict-free DMMA reads
@@ -571,6 +573,7 @@ __device__ __forceinline__ UpdSmem carve(uint8_t *base, int Nmax) {
   u.Rv = p;  p += K;
   u.mult = p;  p += (size_t)mmax * UPD_MS;
   u.invd = p;  p += UPD_NB;
+  u.Wm = p;  p += UPD_NB * UPD_WS;
   u.pan = p;  p += upd_pan_doubles(Nmax);
   u.panw = upd_panw(Nmax);
   u.hms = upd_hms(Nmax);
@@ -614,9 +617,10 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) update_kernel(
   const size_t fb = (size_t)s * d.Nmax;
   const int warp = tid >> 5, lane = tid & 31;
   const int lr = lane >> 2, lc = lane & 3;  // DMMA fragment coordinates
-  __shared__ int s_m;
+  __shared__ int s_m, s_next;
 #define PH(i) do { if (blockIdx.x == 0 && tid == 0) d.dbg[(i)] = clock64(); } while (0)
   PH(0);
+  if (blockIdx.x == 0 && tid == 32) d.dbg[16] = d.dbg[17] = d.dbg[18] = d.dbg[19] = d.dbg[20] = 0;
 
   // ---- phase 0: measurement list in selected order, successful only (monoslam.cpp:556-571) ---
   if (tid == 0) {
@@ -674,35 +678,58 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) update_kernel(
     // ---- phase 1a: H*P.  Dense part H_xv (m x 16) * P(0:16, :) on DMMA tiles; the 3 structural
     //      columns of dh/dy are added per element; nu goes into the last column.
     {
+      constexpr int QB = 4;  // column groups per warp pass
       const int mtiles = (m + 7) >> 3, ngrp = (n + 7) >> 3;
-      for (int g = warp; g < ngrp; g += UPD_THREADS / 32) {
-        const int jb = g * 8 + lr;  // column of this lane's B element
-        double b[4];
+      for (int gq = warp * QB; gq < ngrp; gq += (UPD_THREADS / 32) * QB) {
+        double b[QB][4];
+        int j0[QB];  // first of the two columns of this lane's C elements, per group (-1: none)
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) b[ks] = jb < n ? P[jb + (size_t)ld * (4 * ks + lc)] : 0.0;
-        const int j0 = g * 8 + 2 * lc;  // columns of this lane's C elements
-#pragma unroll 2
+        for (int q = 0; q < QB; ++q) {
+          const int jb = (gq + q) * 8 + lr;  // column of this lane's B element
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            b[q][ks] = (gq + q < ngrp && jb < n) ? P[jb + (size_t)ld * (4 * ks + lc)] : 0.0;
+          j0[q] = (gq + q) * 8 + 2 * lc;
+          if (gq + q >= ngrp || j0[q] >= n) j0[q] = -1;
+        }
         for (int mt = 0; mt < mtiles; ++mt) {
-          double c0 = 0.0, c1 = 0.0;
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) dmma884(c0, c1, sm.HxT[(4 * ks + lc) * HMS + mt * 8 + lr], b[ks]);
           const int i = mt * 8 + lr;
-          if (i < m && j0 < n) {
-            const int k = i >> 1;
-            const int pos = SL2_NXV + 3 * sm.mfeat[k];
-            const double *hy = sm.Hy + k * 6 + (i & 1) * 3;
-            if (j0 + 1 < n) {
+          const bool rv = i < m;
+          const int k = rv ? (i >> 1) : 0;
+          const int pos = SL2_NXV + 3 * sm.mfeat[k];
+          const double *hy = sm.Hy + k * 6 + (i & 1) * 3;
+          const double h0 = hy[0], h1 = hy[1], h2 = hy[2];
+          // structural dh/dy columns: all loads of the pass first (independent, 16 B each)
+          double2 pv[QB][3];
 #pragma unroll
-              for (int c = 0; c < 3; ++c) {
-                const double2 pv = *reinterpret_cast<const double2 *>(P + j0 + (size_t)ld * (pos + c));
-                c0 += hy[c] * pv.x;
-                c1 += hy[c] * pv.y;
+          for (int q = 0; q < QB; ++q)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              pv[q][c] = make_double2(0.0, 0.0);
+              if (rv && j0[q] >= 0) {
+                const double *src = P + j0[q] + (size_t)ld * (pos + c);
+                if (j0[q] + 1 < n) pv[q][c] = *reinterpret_cast<const double2 *>(src);
+                else pv[q][c].x = *src;
               }
-              *reinterpret_cast<double2 *>(G + (size_t)i * ldg + m + j0) = make_double2(c0, c1);
-            } else {
+            }
+          double a[4];
 #pragma unroll
-              for (int c = 0; c < 3; ++c) c0 += hy[c] * P[j0 + (size_t)ld * (pos + c)];
-              G[(size_t)i * ldg + m + j0] = c0;
+          for (int ks = 0; ks < 4; ++ks) a[ks] = sm.HxT[(4 * ks + lc) * HMS + mt * 8 + lr];
+#pragma unroll
+          for (int q = 0; q < QB; ++q) {
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) dmma884(c0, c1, a[ks], b[q][ks]);
+            c0 += h0 * pv[q][0].x;
+            c1 += h0 * pv[q][0].y;
+            c0 += h1 * pv[q][1].x;
+            c1 += h1 * pv[q][1].y;
+            c0 += h2 * pv[q][2].x;
+            c1 += h2 * pv[q][2].y;
+            if (rv && j0[q] >= 0) {
+              double *dst = G + (size_t)i * ldg + m + j0[q];
+              if (j0[q] + 1 < n) *reinterpret_cast<double2 *>(dst) = make_double2(c0, c1);
+              else *dst = c0;
             }
           }
         }
@@ -760,15 +787,33 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) update_kernel(
     const int PW = sm.panw;
     for (int i0 = 0; i0 < m; i0 += UPD_NB) {
       const int nbp = min(UPD_NB, m - i0);
+      long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0;
+      if (blockIdx.x == 0 && tid == 32) tq0 = clock64();
+      if (tid == 0) s_next = 1;  // batch 0 is reserved for warp 0
       // multipliers, negated so that D = (-A) * B + C
       for (int e = tid; e < i0 * UPD_NB; e += UPD_THREADS) {
         const int k = e / UPD_NB, r = e - k * UPD_NB;
         sm.mult[k * UPD_MS + r] = (r < nbp) ? -G[(size_t)k * ldg + i0 + r] : 0.0;
       }
       __syncthreads();
+      if (blockIdx.x == 0 && tid == 32) tq1 = clock64();
       const int ngroups = (width - i0 + 7) >> 3;
       const int nk = i0 >> 2;  // k-steps of 4 rows; i0 is a multiple of 16 so nk % 4 == 0
-      for (int g0 = warp * UPD_GB; g0 < ngroups; g0 += (UPD_THREADS / 32) * UPD_GB) {
+      const int nbatch = (ngroups + UPD_GB - 1) / UPD_GB;
+      // Batches of UPD_GB column groups are handed out dynamically.  Warp 0 takes batch 0 (it holds
+      // the 16 diagonal columns), factors the diagonal block straight away while the other warps
+      // keep multiplying, and only then joins the pool again.
+      bool first = true;
+      for (;;) {
+        int bt;
+        if (warp == 0 && first) {
+          bt = 0;
+        } else {
+          if (lane == 0) bt = atomicAdd(&s_next, 1);
+          bt = __shfl_sync(0xffffffffu, bt, 0);
+        }
+        if (bt >= nbatch) break;
+        const int g0 = bt * UPD_GB;
         double c[UPD_GB][2][2];
         int colb[UPD_GB];  // column of the B fragment element of this lane (-1: none)
 #pragma unroll
@@ -819,47 +864,97 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) update_kernel(
                   make_double2(c[q][mt][0], c[q][mt][1]);
           }
         }
-      }
-      __syncthreads();
-      // factor the 16x16 diagonal block in place (upper triangle) with one warp, lane = column
-      if (warp == 0) {
-        for (int r = 0; r < nbp; ++r) {
-          const double dg = sm.pan[(size_t)r * PW + r];
-          const double u = sqrt(dg);
-          const double iu = 1.0 / u;
+        if (warp == 0 && first) {
+          first = false;
           __syncwarp();
-          if (lane > r && lane < nbp) sm.pan[(size_t)r * PW + lane] *= iu;
-          if (lane == r) {
-            sm.pan[(size_t)r * PW + r] = u;
-            sm.invd[r] = iu;
+          // factor the 16x16 diagonal block in place (upper triangle), lane = column
+          for (int r = 0; r < nbp; ++r) {
+            const double dg = sm.pan[(size_t)r * PW + r];
+            const double iu = rsqrt(dg);
+            const double u = dg * iu;
+            __syncwarp();
+            if (lane > r && lane < nbp) sm.pan[(size_t)r * PW + lane] *= iu;
+            if (lane == r) {
+              sm.pan[(size_t)r * PW + r] = u;
+              sm.invd[r] = iu;
+            }
+            __syncwarp();
+            if (lane > r && lane < nbp) {
+              const double urj = sm.pan[(size_t)r * PW + lane];
+              for (int i = r + 1; i <= lane; ++i)
+                sm.pan[(size_t)i * PW + lane] -= sm.pan[(size_t)r * PW + i] * urj;
+            }
+            __syncwarp();
           }
-          __syncwarp();
-          if (lane > r && lane < nbp) {
-            const double urj = sm.pan[(size_t)r * PW + lane];
-            for (int i = r + 1; i <= lane; ++i)
-              sm.pan[(size_t)i * PW + lane] -= sm.pan[(size_t)r * PW + i] * urj;
+          // W = U_pp^-T (lower triangular), lane j = column j: U^T W = I by forward substitution.
+          // The panel is then finished with one more DMMA product  Y_panel = W * C_panel.
+          {
+            double w[UPD_NB];
+#pragma unroll
+            for (int i = 0; i < UPD_NB; ++i) {
+              double sacc = 0.0;
+#pragma unroll
+              for (int t = 0; t < i; ++t)
+                if (t >= lane) sacc += sm.pan[(size_t)t * PW + i] * w[t];
+              w[i] = (i == lane) ? sm.invd[i < nbp ? i : 0] : -sacc * sm.invd[i < nbp ? i : 0];
+              if (i < lane || i >= nbp || lane >= nbp) w[i] = 0.0;
+            }
+            if (lane < UPD_NB) {
+#pragma unroll
+              for (int i = 0; i < UPD_NB; ++i) sm.Wm[i * UPD_WS + lane] = w[i];
+            }
           }
-          __syncwarp();
         }
       }
+      if (blockIdx.x == 0 && tid == 32) tq2 = clock64();
       __syncthreads();
-      // apply U_pp^-T to every column of the panel and write the finished rows
-      for (int cc = tid; cc < width - i0; cc += UPD_THREADS) {
-        double f[UPD_NB];
+      if (blockIdx.x == 0 && tid == 32) tq3 = clock64();
+      // finish the panel: rows of U for the 16 diagonal columns, Y_panel = W * C_panel (DMMA) for
+      // all other columns, written straight to G from the C fragments
+      for (int e = tid; e < UPD_NB * UPD_NB; e += UPD_THREADS) {
+        const int r = e / UPD_NB, cc = e - r * UPD_NB;
+        if (r < nbp && cc < nbp && i0 + cc < width)
+          G[(size_t)(i0 + r) * ldg + i0 + cc] = (cc >= r) ? sm.pan[(size_t)r * PW + cc] : 0.0;
+      }
+      {
+        double aw[2][4];
 #pragma unroll
-        for (int r = 0; r < UPD_NB; ++r) {
-          double v = sm.pan[(size_t)r * PW + cc];
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-          for (int t = 0; t < r; ++t) v -= sm.pan[(size_t)t * PW + r] * f[t];
-          f[r] = r < nbp ? v * sm.invd[r] : 0.0;
-          if (r < nbp) {
-            double outv = f[r];
-            if (cc < nbp) outv = (cc >= r) ? sm.pan[(size_t)r * PW + cc] : 0.0;
-            G[(size_t)(i0 + r) * ldg + i0 + cc] = outv;
+          for (int ks = 0; ks < 4; ++ks) aw[mt][ks] = sm.Wm[(mt * 8 + lr) * UPD_WS + 4 * ks + lc];
+        const int ncol = width - i0;
+        for (int g = (nbp >> 3) + warp; g * 8 < ncol; g += UPD_THREADS / 32) {
+          double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+          const int cb = g * 8 + lr;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const double bv = cb < ncol ? sm.pan[(size_t)(4 * ks + lc) * PW + cb] : 0.0;
+            dmma884(c[0][0], c[0][1], aw[0][ks], bv);
+            dmma884(c[1][0], c[1][1], aw[1][ks], bv);
+          }
+          const int cc = g * 8 + 2 * lc;
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            const int r = mt * 8 + lr;
+            if (r < nbp && cc < ncol) {
+              double *dst = G + (size_t)(i0 + r) * ldg + i0 + cc;
+              if (cc + 1 < ncol) *reinterpret_cast<double2 *>(dst) = make_double2(c[mt][0], c[mt][1]);
+              else *dst = c[mt][0];
+            }
           }
         }
       }
+      long long tq35 = 0;
+      if (blockIdx.x == 0 && tid == 32) tq35 = clock64();
       __syncthreads();
+      if (blockIdx.x == 0 && tid == 32) {
+        const long long tq4 = clock64();
+        d.dbg[20] += tq35 - tq3;  // apply work of this warp (before the barrier)
+        d.dbg[16] += tq1 - tq0;  // multipliers + barrier
+        d.dbg[17] += tq2 - tq1;  // this warp's DMMA batches
+        d.dbg[18] += tq3 - tq2;  // waiting for the other warps / the diagonal factor
+        d.dbg[19] += tq4 - tq3;  // apply + write + barrier
+      }
     }
 
     PH(4);
@@ -889,18 +984,23 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) update_kernel(
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
           __syncthreads();  // previous tile's users of sm.pan (T) are done
-          // stage loader: 2 slabs x KC rows x 64 columns = 2*KC*32 16-byte segments
+          // stage loader: 2 slabs x KC rows x 64 columns; thread = (row warp + 8*j, 16-byte
+          // segment `lane`) of both slabs, so only the row pointer changes from chunk to chunk
+          const int colA = ta * 64 + 2 * lane, colB = tb * 64 + 2 * lane;
+          const int bytesA = colA + 1 < n ? 16 : (colA < n ? 8 : 0);
+          const int bytesB = colB + 1 < n ? 16 : (colB < n ? 8 : 0);
+          const double *srcA = G + m + (colA < n ? colA : 0);
+          const double *srcB = G + m + (colB < n ? colB : 0);
           auto stage = [&](int chunk, int buf) {
-            double *dst = sm.pan + (size_t)buf * (2 * UPD_KC * UPD_YS);
-            for (int e = tid; e < 2 * UPD_KC * 32; e += UPD_THREADS) {
-              const int slab = e / (UPD_KC * 32), rem = e - slab * (UPD_KC * 32);
-              const int kk = rem >> 5, seg = rem & 31;
+            double *dst = sm.pan + (size_t)buf * (2 * UPD_KC * UPD_YS) + 2 * lane;
+#pragma unroll
+            for (int j = 0; j < UPD_KC / 8; ++j) {
+              const int kk = warp + 8 * j;
               const int k = chunk * UPD_KC + kk;
-              const int col = (slab ? tb : ta) * 64 + seg * 2;
-              int bytes = 0;
-              if (k < m) bytes = col + 1 < n ? 16 : (col < n ? 8 : 0);
-              const double *src = G + (size_t)(k < m ? k : 0) * ldg + m + (col < n ? col : 0);
-              cp_async16(dst + (size_t)slab * (UPD_KC * UPD_YS) + kk * UPD_YS + seg * 2, src, bytes);
+              const bool kv = k < m;
+              const size_t ro = (size_t)(kv ? k : 0) * ldg;
+              cp_async16(dst + kk * UPD_YS, srcA + ro, kv ? bytesA : 0);
+              cp_async16(dst + UPD_KC * UPD_YS + kk * UPD_YS, srcB + ro, kv ? bytesB : 0);
             }
             cp_async_commit();
           };
@@ -941,12 +1041,22 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) update_kernel(
             }
           __syncthreads();
           const int tx = tid & 63, ty = tid >> 6;  // tx -> row a (contiguous in P), ty -> column phase
-          for (int bb = ty; bb < 64; bb += UPD_THREADS / 64) {
-            const int a = ta * 64 + tx, b = tb * 64 + bb;
-            if (a < n && b < n) {
-              const double v = P[a + (size_t)ld * b] - T[tx * 65 + bb];
-              P[a + (size_t)ld * b] = v;
-              T[tx * 65 + bb] = v;
+          {
+            const int a = ta * 64 + tx;
+            double pold[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              const int b = tb * 64 + ty + 4 * q;
+              pold[q] = (a < n && b < n) ? P[a + (size_t)ld * b] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              const int bb = ty + 4 * q, b = tb * 64 + bb;
+              if (a < n && b < n) {
+                const double v = pold[q] - T[tx * 65 + bb];
+                P[a + (size_t)ld * b] = v;
+                T[tx * 65 + bb] = v;
+              }
             }
           }
           if (ta != tb) {
@@ -1128,7 +1238,7 @@ __global__ void __launch_bounds__(256) cull_kernel(const Sl2Dev d, int stream_lo
 
 size_t sl2_update_smem_bytes(const Sl2Dev &d) {
   const size_t K = upd_keven(d.Nmax), mmax = 2 * K;
-  const size_t doubles = mmax + K + mmax * UPD_MS + UPD_NB + upd_pan_doubles(d.Nmax);
+  const size_t doubles = mmax + K + mmax * UPD_MS + UPD_NB + UPD_NB * UPD_WS + upd_pan_doubles(d.Nmax);
   return doubles * 8 + K * 4 + 16;
 }
 
