@@ -107,6 +107,14 @@ int sl2_smoe_search(sl2_ctx *ctx, int32_t stream_id, int32_t slot, int32_t feat_
                     const double *PuInv3 /* K x 3 */, const double *centres /* K x 2 */,
                     int32_t *res_u, int32_t *res_v, uint8_t *res_flag);
 
+/* MonoSLAM::find_best_patch_inside_region + find_eigenvalues (monoslam.cpp:1070-1205): Shi-Tomasi
+ * smallest-eigenvalue detector over n regions (ustart, vstart, ufinish, vfinish) of one stream's
+ * frame.  evbest[i] is always written; ubest/vbest[i] only when a position with a positive score
+ * exists or the clamped region is empty (the reference leaves the caller's values otherwise). */
+int sl2_find_best_patch(sl2_ctx *ctx, int32_t stream_id, int32_t slot, int32_t n,
+                        const int32_t *regions /* n x 4 */, int32_t *ubest, int32_t *vbest,
+                        double *evbest);
+
 /* ---- EKF ------------------------------------------------------------------------------------ */
 /* Kalman::KalmanFilterPredict (kalman.cpp:50-69) incl. MotionModel::func_fv_and_dfv_by_dxv and
  * func_Q (motion_model.cpp:84-217) evaluated on the device.  u3 = control accelerations (zero in

@@ -145,6 +145,14 @@ void orc_smoe_search(const uint8_t *image, int32_t width, int32_t height, const 
               res_best);
 }
 
+void orc_find_best_patch(const uint8_t *image, int32_t width, int32_t height, int32_t boxsize,
+                         const int32_t *r, int32_t *ubest, int32_t *vbest, double *evbest) {
+  int u = *ubest, v = *vbest;
+  find_best_patch_inside_region(image, width, height, &u, &v, evbest, boxsize, r[0], r[1], r[2], r[3]);
+  *ubest = u;
+  *vbest = v;
+}
+
 void orc_motion(const double *xv, const double *u, double delta_t, double *fv, double *F,
                 double *Q) {
   Mat Fm;

@@ -189,4 +189,86 @@ inline void smoe_search(const uint8_t *image, int width, int height, const uint8
   }
 }
 
+// N3. MonoSLAM::find_eigenvalues, monoslam.cpp:1196-1205
+inline void find_eigenvalues(double A, double B, double C, double *eval1ptr, double *eval2ptr) {
+  const double BB = std::sqrt((A + C) * (A + C) - 4 * (A * C - B * B));
+  *eval1ptr = (A + C + BB) / 2.0;
+  *eval2ptr = (A + C - BB) / 2.0;
+}
+
+// N3. MonoSLAM::find_best_patch_inside_region, monoslam.cpp:1070-1194 (Shi-Tomasi criterion with
+// running column sums).  *ubest / *vbest are only written when a position beats evbest = 0, like
+// the reference (they keep the caller's values otherwise), except in the empty-region early return.
+inline void find_best_patch_inside_region(const uint8_t *image, int width, int height, int *ubest,
+                                          int *vbest, double *evbest, const int BOXSIZE, int ustart,
+                                          int vstart, int ufinish, int vfinish) {
+  if (ustart < (BOXSIZE - 1) / 2 + 1) ustart = (BOXSIZE - 1) / 2 + 1;
+  if (ufinish > width - (BOXSIZE - 1) / 2 - 1) ufinish = width - (BOXSIZE - 1) / 2 - 1;
+  if (vstart < (BOXSIZE - 1) / 2 + 1) vstart = (BOXSIZE - 1) / 2 + 1;
+  if (vfinish > height - (BOXSIZE - 1) / 2 - 1) vfinish = height - (BOXSIZE - 1) / 2 - 1;
+  if (vstart >= vfinish || ustart >= ufinish) {
+    *ubest = ustart;
+    *vbest = vstart;
+    *evbest = 0;
+    return;
+  }
+  auto px = [&](int r, int c) { return (int)image[(size_t)r * width + c]; };
+  const int calc_width = ufinish - ustart + BOXSIZE - 1;
+  std::vector<double> CSgxsq(calc_width), CSgysq(calc_width), CSgxgy(calc_width);
+  double TSgxsq = 0.0, TSgysq = 0.0, TSgxgy = 0.0;
+  double gx, gy, eval1, eval2;
+  const int cstart = ustart - (BOXSIZE - 1) / 2;
+  const int cfinish = ufinish + (BOXSIZE - 1) / 2;
+  const int rstart = vstart - (BOXSIZE - 1) / 2;
+  int i, c, r;
+  for (c = cstart, i = 0; c < cfinish; ++c, ++i) {
+    CSgxsq[i] = 0;
+    CSgysq[i] = 0;
+    CSgxgy[i] = 0;
+    for (r = rstart; r < rstart + BOXSIZE; ++r) {
+      gx = (px(r, c + 1) - px(r, c - 1)) / 2.0;
+      gy = (px(r + 1, c) - px(r - 1, c)) / 2.0;
+      CSgxsq[i] += gx * gx;
+      CSgysq[i] += gy * gy;
+      CSgxgy[i] += gx * gy;
+    }
+  }
+  *evbest = 0;
+  for (int v = vstart; v < vfinish; ++v) {
+    TSgxsq = 0.0, TSgysq = 0.0, TSgxgy = 0.0;
+    for (i = 0; i < BOXSIZE; ++i) {
+      TSgxsq += CSgxsq[i];
+      TSgysq += CSgysq[i];
+      TSgxgy += CSgxgy[i];
+    }
+    for (int u = ustart; u < ufinish; ++u) {
+      if (u != ustart) {
+        TSgxsq += CSgxsq[u - ustart + BOXSIZE - 1] - CSgxsq[u - ustart - 1];
+        TSgysq += CSgysq[u - ustart + BOXSIZE - 1] - CSgysq[u - ustart - 1];
+        TSgxgy += CSgxgy[u - ustart + BOXSIZE - 1] - CSgxgy[u - ustart - 1];
+      }
+      find_eigenvalues(TSgxsq, TSgxgy, TSgysq, &eval1, &eval2);
+      if (eval2 > *evbest) {
+        *ubest = u;
+        *vbest = v;
+        *evbest = eval2;
+      }
+    }
+    if (v != vfinish - 1) {
+      for (c = cstart, i = 0; c < cfinish; ++c, ++i) {
+        gx = (px(v - (BOXSIZE - 1) / 2, c + 1) - px(v - (BOXSIZE - 1) / 2, c - 1)) / 2.0;
+        gy = (px(v - (BOXSIZE - 1) / 2 + 1, c) - px(v - (BOXSIZE - 1) / 2 - 1, c)) / 2.0;
+        CSgxsq[i] -= gx * gx;
+        CSgysq[i] -= gy * gy;
+        CSgxgy[i] -= gx * gy;
+        gx = (px(v + (BOXSIZE - 1) / 2 + 1, c + 1) - px(v + (BOXSIZE - 1) / 2 + 1, c - 1)) / 2.0;
+        gy = (px(v + (BOXSIZE - 1) / 2 + 1 + 1, c) - px(v + (BOXSIZE - 1) / 2 + 1 - 1, c)) / 2.0;
+        CSgxsq[i] += gx * gx;
+        CSgysq[i] += gy * gy;
+        CSgxgy[i] += gx * gy;
+      }
+    }
+  }
+}
+
 }  // namespace sl2o

@@ -189,6 +189,16 @@ def smoe_search(image, patch, puinv3, centres, use_ref=False):
     return ru, rv, rf, best
 
 
+def find_best_patch(image, boxsize, region, ubest=-1, vbest=-1):
+    """N3.  Shi-Tomasi best patch in region = (ustart, vstart, ufinish, vfinish)."""
+    image, ip = _u8(image)
+    region = np.ascontiguousarray(region, np.int32)
+    u, v, ev = C.c_int32(ubest), C.c_int32(vbest), C.c_double(0.0)
+    lib().orc_find_best_patch(ip, image.shape[1], image.shape[0], boxsize, _p(region, i32p),
+                              C.byref(u), C.byref(v), C.byref(ev))
+    return u.value, v.value, ev.value
+
+
 def motion(xv, dt, u=(0.0, 0.0, 0.0)):
     """A5.  -> fv (13), F (13,13), Q (13,13) as numpy (row/col = math indices)."""
     xv, xp = _f64(xv)

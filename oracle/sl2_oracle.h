@@ -50,6 +50,10 @@ void orc_smoe_search(const uint8_t *image, int32_t width, int32_t height, const 
                      int32_t boxsize, int32_t K, const double *PuInv3, const double *centres,
                      int32_t *res_u, int32_t *res_v, uint8_t *res_flag, double *res_best);
 
+/* N3  monoslam.cpp:1070-1194 ; region4 = (ustart,vstart,ufinish,vfinish); ubest/vbest in-out */
+void orc_find_best_patch(const uint8_t *image, int32_t width, int32_t height, int32_t boxsize,
+                         const int32_t *region4, int32_t *ubest, int32_t *vbest, double *evbest);
+
 /* A5  motion_model.cpp:84-217 ; F,Q 13x13 col-major */
 void orc_motion(const double *xv, const double *u, double delta_t, double *fv, double *F,
                 double *Q);

@@ -545,6 +545,35 @@ int sl2_score_map(sl2_ctx *c, int32_t s, int32_t slot, int32_t feat, const doubl
   return SL2_OK;
 }
 
+int sl2_find_best_patch(sl2_ctx *c, int32_t s, int32_t slot, int32_t n, const int32_t *regions,
+                        int32_t *ubest, int32_t *vbest, double *evbest) {
+  if (bad_stream(c, s) || bad_slot(c, slot) || n < 0 || (n && (!regions || !evbest)))
+    return fail(c, SL2_ERR_ARG, "sl2_find_best_patch: bad argument");
+  if (n == 0) return SL2_OK;
+  const size_t o_uv = 16 * (size_t)n, o_ev = o_uv + 8 * (size_t)n, total = o_ev + 8 * (size_t)n + 64;
+  int rc = stage_reserve(c, total);
+  if (rc) return rc;
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  memcpy(c->stg_host, regions, 16 * (size_t)n);
+  CU_TRY(c, cudaMemcpyAsync(c->stg_dev, c->stg_host, 16 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, sl2_launch_detect(c->d, s, slot, n, reinterpret_cast<const int *>(c->stg_dev),
+                              reinterpret_cast<int *>(c->stg_dev + o_uv),
+                              reinterpret_cast<double *>(c->stg_dev + o_ev), c->stream));
+  ++c->launches;
+  CU_TRY(c, cudaMemcpyAsync(c->stg_host + o_uv, c->stg_dev + o_uv, 16 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  const int *uv = reinterpret_cast<const int *>(c->stg_host + o_uv);
+  const double *ev = reinterpret_cast<const double *>(c->stg_host + o_ev);
+  for (int i = 0; i < n; ++i) {
+    evbest[i] = ev[i];
+    if (uv[2 * i] >= 0) {
+      if (ubest) ubest[i] = uv[2 * i];
+      if (vbest) vbest[i] = uv[2 * i + 1];
+    }
+  }
+  return SL2_OK;
+}
+
 // ---- EKF ----------------------------------------------------------------------------------------
 int sl2_ekf_predict(sl2_ctx *c, int32_t s, const double *u3) {
   if (bad_stream(c, s)) return fail(c, SL2_ERR_ARG, "bad stream");

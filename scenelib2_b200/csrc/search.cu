@@ -111,7 +111,7 @@ struct DumpPtrs {
 };
 
 template <int BOX, bool FILTER>
-__global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32, (BOX <= 11 && FILTER) ? 4 : 2)
+__global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32, FILTER ? (BOX <= 11 ? 4 : 3) : 2)
     search_kernel(const __grid_constant__ CUtensorMap tmap, const Sl2Dev d, const SearchLaunch L,
                   const DumpPtrs dump) {
   constexpr int NW = (BOX + 3) / 4;             // 32-bit words per template row

@@ -40,7 +40,7 @@ EXPORTS = [
     "sl2_default_config", "sl2_create", "sl2_destroy", "sl2_last_error", "sl2_sync", "sl2_version",
     "sl2_set_frame", "sl2_set_frames", "sl2_set_frames_dev", "sl2_set_features",
     "sl2_num_features", "sl2_state_size", "sl2_set_state", "sl2_get_state", "sl2_delete_feature",
-    "sl2_patch_search", "sl2_score_map", "sl2_smoe_search", "sl2_ekf_predict",
+    "sl2_patch_search", "sl2_score_map", "sl2_smoe_search", "sl2_find_best_patch", "sl2_ekf_predict",
     "sl2_predict_measurements", "sl2_make_measurements", "sl2_ekf_update",
     "sl2_ekf_update_measured", "sl2_normalise_state", "sl2_step", "sl2_step_host",
     "sl2_step_host_async", "sl2_wait_slot",
@@ -214,6 +214,18 @@ class Context:
         self._ck(self.L.sl2_smoe_search(self.h, stream_id, slot, feat_index, K, qp, cp,
                                         _p(ru, i32p), _p(rv, i32p), _p(rf, u8p)))
         return ru, rv, rf
+
+    def find_best_patch(self, stream_id, slot, regions, ubest=-1, vbest=-1):
+        """regions (n,4) = (ustart, vstart, ufinish, vfinish) -> u, v (kept at ubest/vbest where the
+        reference would not write them), ev."""
+        regions = np.ascontiguousarray(regions, np.int32).reshape(-1, 4)
+        n = regions.shape[0]
+        u = np.full(n, ubest, np.int32)
+        v = np.full(n, vbest, np.int32)
+        ev = np.zeros(n, np.float64)
+        self._ck(self.L.sl2_find_best_patch(self.h, stream_id, slot, n, _p(regions, i32p), _p(u, i32p),
+                                            _p(v, i32p), _p(ev, f64p)))
+        return u, v, ev
 
     # ---- EKF ----------------------------------------------------------------------------------
     def ekf_predict(self, stream_id, u3=None):

@@ -119,3 +119,23 @@ def test_search_arguments_are_checked():
     with pytest.raises(sl2.Sl2Error):
         ctx.patch_search(3, 0, np.array([0], np.int32), np.zeros((1, 2)), np.ones((1, 3)))
     ctx.close()
+
+
+@pytest.mark.parametrize("B", [11, 15])
+def test_shi_tomasi_best_patch_bit_exact(oracle, B):
+    """N3: MonoSLAM::find_best_patch_inside_region (monoslam.cpp:1070-1205) — position and the
+    FP64 eigenvalue bits, incl. border clamps, an empty region and a flat image."""
+    rng = np.random.default_rng(8)
+    img = synth.make_texture(rng, 120, 160)
+    img[0:50, 0:70] = 93                                   # flat corner: score 0 there
+    patches = np.zeros((1, B, B), np.uint8)
+    ctx = ctx_for_image(img, patches)
+    regions = np.array([[40, 30, 120, 90], [-5, -7, 60, 40], [100, 70, 400, 300], [0, 0, 160, 120],
+                        [50, 50, 50, 80], [3, 3, 40, 30], [90, 20, 91, 21], [10, 10, 30, 25]], np.int32)
+    u, v, ev = ctx.find_best_patch(0, 0, regions, ubest=-7, vbest=-9)
+    for i, reg in enumerate(regions):
+        ou, ov, oev = oracle.find_best_patch(img, B, reg, ubest=-7, vbest=-9)
+        assert (u[i], v[i]) == (ou, ov), (i, reg)
+        assert np.float64(ev[i]).tobytes() == np.float64(oev).tobytes(), (i, reg)
+    assert ev[0] > 0 and ev[4] == 0.0
+    ctx.close()

@@ -208,3 +208,31 @@ def _py_search(img, patch, c, p, B):
                 if corr <= best and sd0 >= 10 and sd1 >= 10:
                     best, bu, bv = corr, ur + uc, vr + vc
     return bu, bv, int(best <= 0.40), best
+
+
+def test_find_best_patch_vs_numpy(oracle):
+    """N3 (monoslam.cpp:1070-1205): the oracle's running-sum restatement equals a brute-force
+    evaluation (all partial sums are exact multiples of 0.25, so the order cannot matter)."""
+    rng = np.random.default_rng(9)
+    img = synth.make_texture(rng, 80, 100)
+    I = img.astype(np.int64)
+    dx = np.zeros_like(I)
+    dy = np.zeros_like(I)
+    dx[:, 1:-1] = I[:, 2:] - I[:, :-2]
+    dy[1:-1, :] = I[2:, :] - I[:-2, :]
+    for B, reg in ((11, (20, 15, 70, 60)), (15, (0, 0, 100, 80)), (11, (90, 70, 200, 200))):
+        half = (B - 1) // 2
+        us, vs = max(reg[0], half + 1), max(reg[1], half + 1)
+        uf, vf = min(reg[2], 100 - half - 1), min(reg[3], 80 - half - 1)
+        best = (0.0, -1, -1)
+        for v in range(vs, vf):
+            for u in range(us, uf):
+                w = (slice(v - half, v + half + 1), slice(u - half, u + half + 1))
+                A, C, Bm = (dx[w] ** 2).sum() / 4.0, (dy[w] ** 2).sum() / 4.0, (dx[w] * dy[w]).sum() / 4.0
+                BB = np.sqrt((A + C) * (A + C) - 4 * (A * C - Bm * Bm))
+                e2 = (A + C - BB) / 2.0
+                if e2 > best[0]:
+                    best = (e2, u, v)
+        u, v, ev = oracle.find_best_patch(img, B, reg)
+        assert (ev, u, v) == best
+    assert oracle.find_best_patch(img, 11, (50, 50, 50, 60), ubest=3, vbest=4) == (50, 50, 0.0)
