@@ -384,6 +384,28 @@ bool MonoSLAM::measure_feature(cv::Mat image, cv::Mat patch, Eigen::VectorXd &z,
   return true;
 }
 
+// monoslam.cpp:1070-1194 (Shi-Tomasi criterion); *ubest/*vbest keep their values when nothing
+// beats evbest = 0, like the reference
+void MonoSLAM::find_best_patch_inside_region(const cv::Mat &image, int *ubest, int *vbest,
+                                             double *evbest, const int BOXSIZE, int ustart,
+                                             int vstart, int ufinish, int vfinish) {
+  if (BOXSIZE != kBoxSize_) throw std::runtime_error("find_best_patch_inside_region: BOXSIZE mismatch");
+  check(ctx_, sl2_set_frame(ctx_, 0, 0, image.data, image.step), "sl2_set_frame");
+  const int32_t region[4] = {ustart, vstart, ufinish, vfinish};
+  int32_t u = *ubest, v = *vbest;
+  check(ctx_, sl2_find_best_patch(ctx_, 0, 0, 1, region, &u, &v, evbest), "sl2_find_best_patch");
+  *ubest = u;
+  *vbest = v;
+}
+
+double MonoSLAM::set_image_selection_automatically(cv::Mat frame, int ustart, int vstart,
+                                                   int ufinish, int vfinish) {  // monoslam.cpp:1043-1054
+  double evbest = 0;
+  find_best_patch_inside_region(frame, &uu_, &vv_, &evbest, kBoxSize_, ustart, vstart, ufinish, vfinish);
+  location_selected_flag_ = true;
+  return evbest;
+}
+
 void MonoSLAM::normalise_state() {  // monoslam.cpp:616-637
   check(ctx_, sl2_normalise_state(ctx_, 0), "sl2_normalise_state");
 }

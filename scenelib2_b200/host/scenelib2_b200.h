@@ -72,6 +72,12 @@ class MonoSLAM {  // monoslam.h:73-218 (hot-path subset)
                        const Eigen::MatrixXd &S);
   bool elliptical_search(const cv::Mat &image, const cv::Mat &patch, const Eigen::Vector2d centre,
                          const Eigen::Matrix2d &PuInv, int *u, int *v, const int uBOXSIZE);
+  // Shi-Tomasi detector (monoslam.cpp:1043-1205)
+  double set_image_selection_automatically(cv::Mat frame, int ustart, int vstart, int ufinish,
+                                           int vfinish);
+  void find_best_patch_inside_region(const cv::Mat &image, int *ubest, int *vbest, double *evbest,
+                                     const int BOXSIZE, int ustart, int vstart, int ufinish,
+                                     int vfinish);
   void construct_total_state(Eigen::VectorXd &V);
   void construct_total_covariance(Eigen::MatrixXd &M);
   void normalise_state();
@@ -99,6 +105,8 @@ class MonoSLAM {  // monoslam.h:73-218 (hot-path subset)
   int kNumberOfFeaturesToSelect_ = 10, kNumberOfFeaturesToKeepVisible_ = 12;
   int minimum_attempted_measurements_of_feature_ = 10;
   double successful_match_fraction_ = 0.5;
+  int uu_ = 0, vv_ = 0;
+  bool location_selected_flag_ = false;
   const int kBoxSize_;
   const double kNoSigma_, kCorrThresh2_, kCorrelationSigmaThreshold_;
 

@@ -236,3 +236,39 @@ def test_find_best_patch_vs_numpy(oracle):
         u, v, ev = oracle.find_best_patch(img, B, reg)
         assert (ev, u, v) == best
     assert oracle.find_best_patch(img, 11, (50, 50, 50, 60), ubest=3, vbest=4) == (50, 50, 0.0)
+
+
+def test_score_equals_two_minus_two_rho_within_1e9(oracle):
+    """Basis of the CUDA pre-filter (search.cu): for patches passing the sigma >= 10 gates the
+    reference score C/n (improc.cpp:127-133) equals 2 - 2*rho of the exact integer moments up to
+    FP64 rounding.  The kernel's acceptance window (1e-5) assumes |error| <= 1e-9."""
+    rng = np.random.default_rng(10)
+    worst = 0.0
+    for B in (11, 15):
+        n = B * B
+        for trial in range(6):
+            img = synth.make_texture(rng, 70, 90)
+            if trial % 3 == 1:                       # bright, low-contrast: large mean/sigma ratio
+                img = (200 + (img.astype(np.int64) - 128) // 5).clip(0, 255).astype(np.uint8)
+            if trial % 3 == 2:
+                img = (img.astype(np.int64) // 4 + 180).clip(0, 255).astype(np.uint8)
+            py, px = int(rng.integers(0, 70 - B)), int(rng.integers(0, 90 - B))
+            patch = img[py:py + B, px:px + B].copy()
+            c = [px + B // 2 + 1.2, py + B // 2 - 0.7]
+            box, corr, sd, inside = oracle.score_map(img, patch, c, [0.02, 0.0, 0.02])
+            g0 = patch.astype(np.int64)
+            s0, s00 = int(g0.sum()), int((g0 * g0).sum())
+            v0 = n * s00 - s0 * s0
+            if np.sqrt(v0) / n < 10:
+                continue
+            half = (B - 1) // 2
+            for iu in range(corr.shape[0]):
+                for iv in range(corr.shape[1]):
+                    if sd[iu, iv] < 10:
+                        continue
+                    x, y = box[4] + box[0] + iu - half, box[5] + box[2] + iv - half
+                    g1 = img[y:y + B, x:x + B].astype(np.int64)
+                    s1, s11, s01 = int(g1.sum()), int((g1 * g1).sum()), int((g0 * g1).sum())
+                    rho = np.longdouble(n * s01 - s0 * s1) / np.sqrt(np.longdouble(v0) * np.longdouble(n * s11 - s1 * s1))
+                    worst = max(worst, abs(float(np.longdouble(2) - 2 * rho) - corr[iu, iv]))
+    assert 0 < worst < 1e-9, worst
