@@ -115,3 +115,42 @@ def test_async_host_ring_matches_blocking(oracle):
         assert (xs == xt).all() and (Ps == Pt).all()
     a.close()
     b.close()
+
+
+def test_empty_map_and_invisible_features(oracle):
+    """Edge cases of GoOneStep: a stream with no features at all, and one whose features are all
+    outside the image (visibility test fails -> nothing selected, no update; monoslam.cpp:130-139)."""
+    import scenelib2_b200 as sl2
+    sc = synth.make_scene("C2", n_frames=2, n_features=8)
+    far = synth.make_scene("C2", stream_id=1, n_frames=2, n_features=8)
+    far.x0 = far.x0.copy()
+    far.x0[13:] += np.tile([3.0, 0.0, 0.0], 8)          # all features far to the side of the view
+    cfg = sl2.config_for_scene(sc, num_streams=3, frame_slots=1)
+    ctx = sl2.Context(cfg)
+    sl2.load_scene(ctx, 0, sc)
+    sl2.load_scene(ctx, 1, far)
+    ctx.set_features(2, np.zeros((0, 3)), np.zeros((0, 7)), np.zeros((0, 11, 11), np.uint8))
+    x2 = np.zeros(13)
+    x2[3], x2[12] = 1.0, 0.01
+    ctx.set_state(2, x2, np.eye(13) * 1e-4)
+    o0, o1 = oracle_slam_from_scene(oracle, sc), oracle_slam_from_scene(oracle, far)
+    for t in range(2):
+        ctx.set_frames(0, np.stack([sc.frames[t], far.frames[t], sc.frames[t]]))
+        ctx.step(0)
+        ctx.sync()
+        o0.step(sc.frames[t])
+        o1.step(far.frames[t])
+    assert_state_close(*ctx.get_state(0), *o0.get_state())
+    assert_state_close(*ctx.get_state(1), *o1.get_state())
+    f1 = ctx.features(1)
+    assert (f1["select_rank"] == -1).all() and (f1["attempted"] == 0).all()
+    x, P = ctx.get_state(2)
+    assert ctx.num_features(2) == 0 and np.isfinite(P).all() and P.shape == (13, 13)
+    # empty map: only the prediction acts (kalman.cpp:50-62)
+    fv, F, Q = oracle.motion(x2, sc.delta_t)
+    fv2, F2, Q2 = oracle.motion(fv, sc.delta_t)
+    Pe = F2 @ (F @ (np.eye(13) * 1e-4) @ F.T + Q) @ F2.T + Q2
+    Pe = 0.5 * (Pe + Pe.T)
+    assert np.allclose(x, fv2, rtol=1e-12, atol=1e-15)
+    assert np.abs(P - Pe).max() <= 1e-9 * np.abs(Pe).max()
+    ctx.close()
