@@ -154,3 +154,33 @@ def test_empty_map_and_invisible_features(oracle):
     assert np.allclose(x, fv2, rtol=1e-12, atol=1e-15)
     assert np.abs(P - Pe).max() <= 1e-9 * np.abs(Pe).max()
     ctx.close()
+
+
+def test_c4_many_streams_ground_truth_properties():
+    """Full BASELINE size (C4: n = 313, m = 200) with 37 streams in one context, checked through
+    size-independent properties instead of the oracle: every feature is found at its known ground-truth
+    pixel (template position + frame shift), P stays exactly symmetric and positive semi-definite, and
+    the map uncertainty never grows."""
+    B, T = 37, 4
+    scenes = [synth.make_scene("C4", stream_id=s, n_frames=T) for s in range(B)]
+    ctx = ctx_from_scenes(scenes, frame_slots=2)
+    tr_prev = [np.trace(sc.P0[13:, 13:]) for sc in scenes]
+    for t in range(T):
+        ctx.set_frames(t % 2, np.stack([sc.frames[t] for sc in scenes]))
+        ctx.step(t % 2)
+        ctx.sync()
+        for s in (0, 7, 18, 36) if t < T - 1 else range(B):
+            sc = scenes[s]
+            f = ctx.features(s)
+            assert ((f["flags"] & 3) == 3).all()                      # selected and successfully measured
+            assert (f["z"] == sc.pix + sc.shifts[t]).all()            # ground truth, bit-exact
+            x, P = ctx.get_state(s)
+            assert np.abs(P - P.T).max() == 0.0
+            tr = np.trace(P[13:, 13:])
+            assert tr <= tr_prev[s] * (1 + 1e-12)
+            tr_prev[s] = tr
+            if t == T - 1:
+                w = np.linalg.eigvalsh(P)
+                assert w.min() > -1e-10 * w.max()
+                assert abs(np.linalg.norm(x[3:7]) - 1.0) < 1e-2      # quaternion stays near unit (quirk Q1)
+    ctx.close()
