@@ -278,7 +278,7 @@ def run_ours(args, rank, local_rank, world):
 
     if rank == 0:
         pk, pk_kind = peaks()
-        rad = sc0.meta["config"]["radius"]
+        rad = sc0.meta["config"]["radius"] or 20   # C1: ellipses come from S_i; 20 px = the tile radius
         bytes_per_feature = synth.algorithmic_search_bytes(sc0.boxsize, rad)
         search_bytes = B * N * bytes_per_feature                      # per launch
         ach = search_bytes / (kt[1] * 1e-3) / 1e9
