@@ -57,7 +57,8 @@ def _random_measurements(rng, n, nf, K):
     return feats, Hxv, Hy, R, nu, H, np.kron(np.diag(var), np.eye(2))
 
 
-@pytest.mark.parametrize("nf,K", [(20, 4), (20, 20), (50, 50), (100, 100), (37, 13)])
+@pytest.mark.parametrize("nf,K", [(20, 4), (20, 20), (50, 50), (100, 100), (37, 13), (128, 128), (128, 77),
+                                  (5, 1), (9, 9)])
 def test_update_with_host_rows_matches_dense_oracle(oracle, nf, K):
     """kalman.cpp:72-119 as written (dense, explicit S^-1) vs the structured CUDA update."""
     sc = synth.make_scene("C4", n_frames=1, n_features=nf)

@@ -139,3 +139,25 @@ def test_shi_tomasi_best_patch_bit_exact(oracle, B):
         assert np.float64(ev[i]).tobytes() == np.float64(oev).tobytes(), (i, reg)
     assert ev[0] > 0 and ev[4] == 0.0
     ctx.close()
+
+
+def test_odd_frame_size_pitch_padding(oracle):
+    """Frame width not a multiple of 16 (device pitch != width): search, score map and detector."""
+    rng = np.random.default_rng(12)
+    img = synth.make_texture(rng, 101, 150)
+    B = 11
+    pts = [(30, 40), (140, 90), (75, 8), (6, 95), (144, 6)]
+    patches = np.stack([img[y - 5:y + 6, x - 5:x + 6] for x, y in pts])
+    ctx = ctx_for_image(img, patches)
+    n = len(pts)
+    centres = np.array(pts, float) + rng.uniform(-3, 3, (n, 2))
+    pu = random_puinv(rng, n, 6, 25, iso_fraction=0.4)
+    f = _compare_search(oracle, ctx, img, patches, np.arange(n, dtype=np.int32), centres, pu)
+    assert f.all()
+    box, corr, sd, inside = ctx.score_map(0, 0, 1, [141.0, 91.0], [0.02, 0.0, 0.02])
+    obox, ocorr, osd, oinside = oracle.score_map(img, patches[1], [141.0, 91.0], [0.02, 0.0, 0.02])
+    assert (box == obox).all() and corr.tobytes() == ocorr.tobytes() and (inside == oinside).all()
+    u, v, ev = ctx.find_best_patch(0, 0, [[0, 0, 150, 101], [100, 50, 150, 101]])
+    for i, reg in enumerate(([0, 0, 150, 101], [100, 50, 150, 101])):
+        assert (u[i], v[i], ev[i]) == oracle.find_best_patch(img, B, reg)
+    ctx.close()

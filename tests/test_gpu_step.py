@@ -184,3 +184,12 @@ def test_c4_many_streams_ground_truth_properties():
                 assert w.min() > -1e-10 * w.max()
                 assert abs(np.linalg.norm(x[3:7]) - 1.0) < 1e-2      # quaternion stays near unit (quirk Q1)
     ctx.close()
+
+
+def test_maximum_map_size_fused_step(oracle):
+    """SL2_MAX_FEATURES = 128 features per stream (n = 397, m = 256): the largest supported map."""
+    sc = synth.make_scene("C4", n_frames=2, n_features=128)
+    sc.n_select = 128
+    assert sc.n == 397
+    w = _run(oracle, [sc], 2)
+    print("max-size worst errors:", w)
