@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dist-selftest", action="store_true", help="CPU/gloo check of the N>1 plumbing")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="host threads of the CPU legs (0 = all)")
     return ap.parse_args()
 
 
@@ -152,7 +153,7 @@ def run_reference(args, rank, world):
     vals = []
     threads = None
     for k in range(args.warmup + args.steps):
-        fps, threads, steps, t = cpu_run(scenes, budget, None)
+        fps, threads, steps, t = cpu_run(scenes, budget, args.cpu_threads or None)
         if k >= args.warmup:
             vals.append(fps)
         if sum(1 for _ in vals) >= 3 and time.time() - T0 > 240:
@@ -334,7 +335,7 @@ def run_ours(args, rank, local_rank, world):
                           "ekf_update": float(kt[2]), "cull": float(kt[3])},
         }
         if not args.no_cpu_baseline and world == 1:
-            fps, threads, steps, t = cpu_run(scenes, args.cpu_seconds)
+            fps, threads, steps, t = cpu_run(scenes, args.cpu_seconds, args.cpu_threads or None)
             line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "%d streams x %d oracle steps (%.1f s)" % (threads, steps, t)}
         print(json.dumps(line))

@@ -26,6 +26,8 @@ def build(force=False, verbose=False):
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
+    if os.environ.get("SL2_PHASE_STAMPS"):  # profiling builds only: per-phase clock64 stamps
+        cmd.insert(1, "-DSL2_PHASE_STAMPS")
     subprocess.check_call(cmd, cwd=HERE)
     build_host()
     return LIB

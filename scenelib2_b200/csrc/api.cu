@@ -13,11 +13,6 @@ namespace {
 
 thread_local std::string g_create_error;
 
-struct DevBuf {
-  void *p = nullptr;
-  size_t bytes = 0;
-};
-
 }  // namespace
 
 struct sl2_ctx {
@@ -35,7 +30,6 @@ struct sl2_ctx {
   int64_t launches = 0;
   bool timing = false;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  float last_ms[4] = {0, 0, 0, 0};
   // asynchronous end-to-end path: frames of step t+1 are copied while step t computes
   cudaStream_t copy_stream = nullptr;  // H2D of the frames
   cudaStream_t out_stream = nullptr;   // D2H of the results (own stream: must not block the next H2D)

@@ -531,6 +531,7 @@ struct UpdSmem {
   double *mult;  // [mmax][UPD_MS] (negated) multipliers of the current panel
   double *invd;  // [NB]
   double *Wm;    // [NB][UPD_WS]  W = U_pp^-T of the current panel
+  double *xacc;  // [ld]  Y^T w accumulated panel by panel
   double *pan;   // phase 1: HxT / Hy (aliased); phase 2: panel buffer [NB][panw];
                  // phase 4: Y slabs (2 stages) / tile T[64][65]
   double *HxT;   // = pan          [16][hms]  Hx transposed, k-major, zero padded (cols 13..15, rows >= m)
@@ -574,6 +575,7 @@ __device__ __forceinline__ UpdSmem carve(uint8_t *base, int Nmax) {
   u.mult = p;  p += (size_t)mmax * UPD_MS;
   u.invd = p;  p += UPD_NB;
   u.Wm = p;  p += UPD_NB * UPD_WS;
+  u.xacc = p;  p += (SL2_NXV + 3 * Nmax + 7) & ~7;
   u.pan = p;  p += upd_pan_doubles(Nmax);
   u.panw = upd_panw(Nmax);
   u.hms = upd_hms(Nmax);
@@ -618,9 +620,15 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) update_kernel(
   const int warp = tid >> 5, lane = tid & 31;
   const int lr = lane >> 2, lc = lane & 3;  // DMMA fragment coordinates
   __shared__ int s_m, s_next;
+#ifdef SL2_PHASE_STAMPS  // clock64 stamps of CTA 0 (tools / bench SL2_PHASES=1); off in product builds
 #define PH(i) do { if (blockIdx.x == 0 && tid == 0) d.dbg[(i)] = clock64(); } while (0)
+#define PHQ(stmt) do { if (blockIdx.x == 0 && tid == 32) { stmt; } } while (0)
+#else
+#define PH(i) do { } while (0)
+#define PHQ(stmt) do { } while (0)
+#endif
   PH(0);
-  if (blockIdx.x == 0 && tid == 32) d.dbg[16] = d.dbg[17] = d.dbg[18] = d.dbg[19] = d.dbg[20] = 0;
+  PHQ(d.dbg[16] = d.dbg[17] = d.dbg[18] = d.dbg[19] = d.dbg[20] = 0);
 
   // ---- phase 0: measurement list in selected order, successful only (monoslam.cpp:556-571) ---
   if (tid == 0) {
@@ -785,10 +793,11 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) update_kernel(
     // fragments are software-pipelined three k-steps ahead.
     const int width = m + n + 1;
     const int PW = sm.panw;
+    for (int j = tid; j < n; j += UPD_THREADS) sm.xacc[j] = 0.0;
     for (int i0 = 0; i0 < m; i0 += UPD_NB) {
       const int nbp = min(UPD_NB, m - i0);
-      long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0;
-      if (blockIdx.x == 0 && tid == 32) tq0 = clock64();
+      long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0, tq35 = 0;
+      PHQ(tq0 = clock64());
       if (tid == 0) s_next = 1;  // batch 0 is reserved for warp 0
       // multipliers, negated so that D = (-A) * B + C
       for (int e = tid; e < i0 * UPD_NB; e += UPD_THREADS) {
@@ -796,7 +805,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) update_kernel(
         sm.mult[k * UPD_MS + r] = (r < nbp) ? -G[(size_t)k * ldg + i0 + r] : 0.0;
       }
       __syncthreads();
-      if (blockIdx.x == 0 && tid == 32) tq1 = clock64();
+      PHQ(tq1 = clock64());
       const int ngroups = (width - i0 + 7) >> 3;
       const int nk = i0 >> 2;  // k-steps of 4 rows; i0 is a multiple of 16 so nk % 4 == 0
       const int nbatch = (ngroups + UPD_GB - 1) / UPD_GB;
@@ -906,9 +915,9 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) update_kernel(
           }
         }
       }
-      if (blockIdx.x == 0 && tid == 32) tq2 = clock64();
+      PHQ(tq2 = clock64());
       __syncthreads();
-      if (blockIdx.x == 0 && tid == 32) tq3 = clock64();
+      PHQ(tq3 = clock64());
       // finish the panel: rows of U for the 16 diagonal columns, Y_panel = W * C_panel (DMMA) for
       // all other columns, written straight to G from the C fragments
       for (int e = tid; e < UPD_NB * UPD_NB; e += UPD_THREADS) {
@@ -923,6 +932,14 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) update_kernel(
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) aw[mt][ks] = sm.Wm[(mt * 8 + lr) * UPD_WS + 4 * ks + lc];
         const int ncol = width - i0;
+        // w_panel = W * nu_panel for this lane's two rows (the nu column is the last one)
+        double w_lo = 0.0, w_hi = 0.0;
+#pragma unroll
+        for (int k = 0; k < UPD_NB; ++k) {
+          const double nuk = sm.pan[(size_t)k * PW + ncol - 1];
+          w_lo += sm.Wm[lr * UPD_WS + k] * nuk;
+          w_hi += sm.Wm[(8 + lr) * UPD_WS + k] * nuk;
+        }
         for (int g = (nbp >> 3) + warp; g * 8 < ncol; g += UPD_THREADS / 32) {
           double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
           const int cb = g * 8 + lr;
@@ -942,31 +959,33 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) update_kernel(
               else *dst = c[mt][0];
             }
           }
+          // x += Y^T w, fused: the 16 rows of a column live in the 8 lanes sharing lc
+          double p0 = c[0][0] * w_lo + c[1][0] * w_hi, p1 = c[0][1] * w_lo + c[1][1] * w_hi;
+#pragma unroll
+          for (int o = 4; o < 32; o <<= 1) {
+            p0 += __shfl_xor_sync(0xffffffffu, p0, o);
+            p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+          }
+          if (lr == 0) {
+            const int j = i0 + cc - m;  // column of Y
+            if (j >= 0 && j < n) atomicAdd(sm.xacc + j, p0);
+            if (j + 1 >= 0 && j + 1 < n) atomicAdd(sm.xacc + j + 1, p1);
+          }
         }
       }
-      long long tq35 = 0;
-      if (blockIdx.x == 0 && tid == 32) tq35 = clock64();
+      PHQ(tq35 = clock64());
       __syncthreads();
-      if (blockIdx.x == 0 && tid == 32) {
-        const long long tq4 = clock64();
-        d.dbg[20] += tq35 - tq3;  // apply work of this warp (before the barrier)
-        d.dbg[16] += tq1 - tq0;  // multipliers + barrier
-        d.dbg[17] += tq2 - tq1;  // this warp's DMMA batches
-        d.dbg[18] += tq3 - tq2;  // waiting for the other warps / the diagonal factor
-        d.dbg[19] += tq4 - tq3;  // apply + write + barrier
-      }
+      PHQ(d.dbg[16] += tq1 - tq0;      // multipliers + barrier
+          d.dbg[17] += tq2 - tq1;      // this warp's DMMA batches
+          d.dbg[18] += tq3 - tq2;      // waiting for the other warps / the diagonal factor
+          d.dbg[19] += clock64() - tq3;  // finishing the panel + barrier
+          d.dbg[20] += tq35 - tq3);    // finishing work of this warp alone
+      (void)tq0; (void)tq1; (void)tq2; (void)tq3; (void)tq35;
     }
 
     PH(4);
-    // ---- phase 3: x += Y^T w -----------------------------------------------------------------
-    for (int i = tid; i < m; i += UPD_THREADS) sm.wv[i] = G[(size_t)i * ldg + m + n];
-    __syncthreads();
-    for (int j = tid; j < n; j += UPD_THREADS) {
-      double a = 0.0;
-#pragma unroll 8
-      for (int k = 0; k < m; ++k) a += G[(size_t)k * ldg + m + j] * sm.wv[k];
-      x[j] += a;
-    }
+    // ---- phase 3: x += Y^T w (accumulated panel by panel above) --------------------------------
+    for (int j = tid; j < n; j += UPD_THREADS) x[j] += sm.xacc[j];
 
     PH(5);
     // ---- phase 4: P -= Y^T Y on 64x64 tiles (upper triangle computed, lower mirrored) ---------
@@ -1238,7 +1257,8 @@ __global__ void __launch_bounds__(256) cull_kernel(const Sl2Dev d, int stream_lo
 
 size_t sl2_update_smem_bytes(const Sl2Dev &d) {
   const size_t K = upd_keven(d.Nmax), mmax = 2 * K;
-  const size_t doubles = mmax + K + mmax * UPD_MS + UPD_NB + UPD_NB * UPD_WS + upd_pan_doubles(d.Nmax);
+  const size_t doubles = mmax + K + mmax * UPD_MS + UPD_NB + UPD_NB * UPD_WS +
+                         ((SL2_NXV + 3 * d.Nmax + 7) & ~7) + upd_pan_doubles(d.Nmax);
   return doubles * 8 + K * 4 + 16;
 }
 
