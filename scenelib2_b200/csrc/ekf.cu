@@ -796,7 +796,9 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) update_kernel(
     for (int j = tid; j < n; j += UPD_THREADS) sm.xacc[j] = 0.0;
     for (int i0 = 0; i0 < m; i0 += UPD_NB) {
       const int nbp = min(UPD_NB, m - i0);
+#ifdef SL2_PHASE_STAMPS
       long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0, tq35 = 0;
+#endif
       PHQ(tq0 = clock64());
       if (tid == 0) s_next = 1;  // batch 0 is reserved for warp 0
       // multipliers, negated so that D = (-A) * B + C
@@ -980,7 +982,6 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) update_kernel(
           d.dbg[18] += tq3 - tq2;      // waiting for the other warps / the diagonal factor
           d.dbg[19] += clock64() - tq3;  // finishing the panel + barrier
           d.dbg[20] += tq35 - tq3);    // finishing work of this warp alone
-      (void)tq0; (void)tq1; (void)tq2; (void)tq3; (void)tq35;
     }
 
     PH(4);
