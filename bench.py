@@ -29,7 +29,8 @@ sys.path.insert(0, ROOT)
 METRIC = "EKF-SLAM frames/sec @320x240 N=100 feats"
 UNIT = "frames/s"
 WORKLOAD = "C4: synthetic 320x240, 100 features, EKF state dim 313, 11x11 patch, +-20px ellipse"
-WORKLOADS = {"C2": "C2: synthetic 320x240, 50 features, 11x11 patch, +-20px ellipse",
+WORKLOADS = {"C1": "C1: synthetic 320x240, 4 known + 16 features, 10 selected per frame, ellipses from S_i",
+             "C2": "C2: synthetic 320x240, 50 features, 11x11 patch, +-20px ellipse",
              "C3": "C3: synthetic 640x480, 100 features, 15x15 patch, +-40px ellipse", "C4": WORKLOAD}
 
 

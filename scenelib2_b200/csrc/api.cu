@@ -248,6 +248,7 @@ int sl2_create(const sl2_config *cfg, sl2_ctx **out) {
   ALLOC(d.nsel, B);
   ALLOC(d.nvisible, B);
   ALLOC(d.nmeas, B);
+  ALLOC(d.ncull, B);
   ALLOC(d.dbg, 64);
   ALLOC(c->xv_stage, (size_t)d.slots * B * SL2_NXV);
 #undef ALLOC

@@ -751,36 +751,71 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) update_kernel(
     {
       const int mtiles = (m + 7) >> 3;
       const int ntile = mtiles * (mtiles + 1) / 2;
-      for (int t = warp; t < ntile; t += UPD_THREADS / 32) {
-        // unrank the upper-triangular tile index t -> (mt <= nt)
-        int mt = 0, rem = t;
+      // tile t of the upper triangle -> (mt <= nt); the loads of the next tile of this warp are
+      // issued before the current tile is multiplied (software pipeline, depth 1)
+      auto unrank = [&](int t, int &mt, int &nt) {
+        mt = 0;
+        int rem = t;
         while (rem >= mtiles - mt) {
           rem -= mtiles - mt;
           ++mt;
         }
-        const int nt = mt + rem;
-        double c0 = 0.0, c1 = 0.0;
+        nt = mt + rem;
+      };
+      auto load_a = [&](int mt, double *a) {
         const int ia = mt * 8 + lr;
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const double a = ia < m ? G[(size_t)ia * ldg + m + 4 * ks + lc] : 0.0;
-          dmma884(c0, c1, a, sm.HxT[(4 * ks + lc) * HMS + nt * 8 + lr]);
+        for (int ks = 0; ks < 4; ++ks) a[ks] = ia < m ? G[(size_t)ia * ldg + m + 4 * ks + lc] : 0.0;
+      };
+      auto load_sp = [&](int mt, int nt, double *sp) {
+        const int ia = mt * 8 + lr, jp = nt * 8 + 2 * lc;
+        sp[0] = sp[1] = sp[2] = 0.0;
+        if (ia < m && jp < m) {
+          const int pos = SL2_NXV + 3 * sm.mfeat[jp >> 1];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) sp[c] = G[(size_t)ia * ldg + m + pos + c];
         }
-        const int jp = nt * 8 + 2 * lc;  // columns jp, jp+1 belong to measured feature kp
+      };
+      int t = warp, mt = 0, nt = 0;
+      double a[4], sp[3];
+      if (t < ntile) {
+        unrank(t, mt, nt);
+        load_a(mt, a);
+        load_sp(mt, nt, sp);
+      }
+      while (t < ntile) {
+        const int tn = t + UPD_THREADS / 32;
+        int mtn = mt, ntn = nt;
+        double an[4] = {a[0], a[1], a[2], a[3]}, spn[3] = {0.0, 0.0, 0.0};
+        if (tn < ntile) {
+          unrank(tn, mtn, ntn);
+          if (mtn != mt) load_a(mtn, an);
+          load_sp(mtn, ntn, spn);
+        }
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) dmma884(c0, c1, a[ks], sm.HxT[(4 * ks + lc) * HMS + nt * 8 + lr]);
+        const int ia = mt * 8 + lr, jp = nt * 8 + 2 * lc;  // columns jp, jp+1 belong to feature kp
         if (ia < m && jp < m) {
           const int kp = jp >> 1;
-          const int pos = SL2_NXV + 3 * sm.mfeat[kp];
           const double *hy = sm.Hy + kp * 6;
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            const double v = G[(size_t)ia * ldg + m + pos + c];
-            c0 += v * hy[c];
-            c1 += v * hy[3 + c];
+            c0 += sp[c] * hy[c];
+            c1 += sp[c] * hy[3 + c];
           }
           if (ia == jp) c0 += sm.Rv[kp];
           if (ia == jp + 1) c1 += sm.Rv[kp];
           *reinterpret_cast<double2 *>(G + (size_t)ia * ldg + jp) = make_double2(c0, c1);
         }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) a[ks] = an[ks];
+        sp[0] = spn[0];
+        sp[1] = spn[1];
+        sp[2] = spn[2];
+        t = tn;
+        mt = mtn;
+        nt = ntn;
       }
     }
     __syncthreads();
@@ -1147,12 +1182,21 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) update_kernel(
   PH(7);
   // ---- bookkeeping: attempt / success counters (monoslam.cpp:479-496) ------------------------
   if (staged_m < 0 && !only_normalise) {
+    if (tid == 0) s_next = 0;  // reused: number of features delete_bad_features would cull
+    __syncthreads();
     for (int i = tid; i < nf; i += UPD_THREADS) {
+      int att = d.attempted[fb + i], suc = d.successful[fb + i];
       if (d.sel_rank[fb + i] >= 0) {
-        d.attempted[fb + i] += 1;
-        if (d.found[fb + i]) d.successful[fb + i] += 1;
+        att += 1;
+        if (d.found[fb + i]) suc += 1;
+        d.attempted[fb + i] = att;
+        d.successful[fb + i] = suc;
       }
+      // monoslam.cpp:650-653; lets the cull kernel of the fused step return at once when idle
+      if (att >= d.min_attempts && (double)suc / (double)att < d.match_fraction) atomicAdd(&s_next, 1);
     }
+    __syncthreads();
+    if (tid == 0) d.ncull[s] = s_next;
   }
 }
 
@@ -1166,6 +1210,7 @@ __global__ void __launch_bounds__(256) cull_kernel(const Sl2Dev d, int stream_lo
   const int nf = d.nfeat[s];
   const int ld = d.ld;
   const size_t fb = (size_t)s * d.Nmax;
+  if (force_index < 0 && d.ncull[s] == 0) return;  // nothing to cull (decided by update_kernel)
   __shared__ int keep[SL2_MAX_FEAT_SMEM];  // new index of feature i or -1
   __shared__ int s_new;
   if (tid == 0) {

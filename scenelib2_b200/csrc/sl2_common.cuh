@@ -54,6 +54,7 @@ struct Sl2Dev {
   int *nsel;           // [B]
   int *nvisible;       // [B]
   int *nmeas;          // [B]  successful measurements of the last step
+  int *ncull;          // [B]  features the next cull would delete (set by update_kernel)
   long long *dbg;      // [64] phase cycle stamps of CTA 0 of the update kernel (debug)
 };
 
