@@ -358,7 +358,7 @@ __device__ int visibility_test(const double *cam, const double *xp, const rd yi[
 // ---------------------------------------------------------------------------------------------
 // kernel 1: predict (kalman.cpp:50-69) + measurement prediction / selection (monoslam.cpp:187-254)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) predict_kernel(const Sl2Dev d, int stream_lo,
+__global__ void __launch_bounds__(128) predict_kernel(const Sl2Dev d, int stream_lo,
                                                       const double *u3, int do_predict,
                                                       int do_measure) {
   const int s = stream_lo + blockIdx.x;
@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(256) predict_kernel(const Sl2Dev d, int stream
   __shared__ int s_nvis, s_r0;
 
   if (tid < 13) xv[tid] = x[tid];
-  if (tid < 169) Pxx[tid] = P[(tid % 13) + (size_t)ld * (tid / 13)];
+  for (int e = tid; e < 169; e += blockDim.x) Pxx[e] = P[(e % 13) + (size_t)ld * (e / 13)];
   __syncthreads();
 
   if (do_predict) {
@@ -383,8 +383,8 @@ __global__ void __launch_bounds__(256) predict_kernel(const Sl2Dev d, int stream
     __syncthreads();
     // Q = (G * Pnn) * G^T, Pnn = diag(lin x3, ang x3)   (motion_model.cpp:157-216)
     // TT = F * Pxx
-    if (tid < 169) {
-      const int i = tid % 13, j = tid / 13;
+    for (int e = tid; e < 169; e += blockDim.x) {
+      const int i = e % 13, j = e / 13;
       const rd dt(d.dt);
       const rd lin = rd(4.0) * rd(4.0) * dt * dt, ang = rd(6.0) * rd(6.0) * dt * dt;
       rd q(0.0), t(0.0);
@@ -393,17 +393,17 @@ __global__ void __launch_bounds__(256) predict_kernel(const Sl2Dev d, int stream
         q = q + gp * rd(Gn[j + 13 * k]);
       }
       for (int k = 0; k < 13; ++k) t = t + rd(F[i + 13 * k]) * rd(Pxx[k + 13 * j]);
-      Qm[tid] = q.v;
-      TT[tid] = t.v;
+      Qm[e] = q.v;
+      TT[e] = t.v;
     }
     __syncthreads();
     // Pxx = TT * F^T + Q
-    if (tid < 169) {
-      const int i = tid % 13, j = tid / 13;
+    for (int e = tid; e < 169; e += blockDim.x) {
+      const int i = e % 13, j = e / 13;
       rd a(0.0);
       for (int k = 0; k < 13; ++k) a = a + rd(TT[i + 13 * k]) * rd(F[j + 13 * k]);
-      const double v = (a + rd(Qm[tid])).v;
-      Pxx[tid] = v;  // own element only: no hazard with TT/F readers
+      const double v = (a + rd(Qm[e])).v;
+      Pxx[e] = v;  // own element only: no hazard with TT/F readers
       P[i + (size_t)ld * j] = v;
     }
     // Pxy_i = F * Pxy_i  (one thread per column of the 13 x 3N panel), mirrored below the diagonal
@@ -1311,7 +1311,9 @@ size_t sl2_update_smem_bytes(const Sl2Dev &d) {
 cudaError_t sl2_launch_predict(const Sl2Dev &d, int stream_lo, int stream_cnt, const double *u3_dev,
                                int do_predict, int do_measure, cudaStream_t st) {
   if (stream_cnt <= 0) return cudaSuccess;
-  predict_kernel<<<stream_cnt, 256, 0, st>>>(d, stream_lo, u3_dev, do_predict, do_measure);
+  // 128 threads = one per feature (SL2_MAX_FEATURES); the kernel needs ~255 registers per thread,
+  // so 128-thread CTAs are what lets two streams share an SM
+  predict_kernel<<<stream_cnt, 128, 0, st>>>(d, stream_lo, u3_dev, do_predict, do_measure);
   return cudaGetLastError();
 }
 
