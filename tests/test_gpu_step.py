@@ -193,3 +193,30 @@ def test_maximum_map_size_fused_step(oracle):
     assert sc.n == 397
     w = _run(oracle, [sc], 2)
     print("max-size worst errors:", w)
+
+
+def test_long_run_does_not_drift_from_oracle(oracle):
+    """40 consecutive frames (ring of 8) on a C2-sized map with the EKF's own search ellipses: the
+    CUDA path and the oracle must keep making the same decisions (same selected set, same matches,
+    same culling) and stay within the north-star tolerance at every frame, i.e. rounding
+    differences do not accumulate."""
+    sc = synth.make_scene("C2", n_frames=8, n_features=50, override=False)
+    ctx = ctx_from_scenes([sc], frame_slots=2)
+    o = oracle_slam_from_scene(oracle, sc)
+    worst = 0.0
+    for t in range(40):
+        k = t % 8
+        ctx.set_frames(t % 2, sc.frames[k][None])
+        ctx.step(t % 2)
+        ctx.sync()
+        o.step(sc.frames[k])
+        fg, fo = ctx.features(0), o.features()
+        assert ctx.num_features(0) == o.num_features
+        assert (fg["select_rank"] == fo["select_rank"]).all() and (fg["flags"] == fo["flags"]).all(), t
+        ok = (fo["flags"] & 2) > 0
+        assert (fg["z"][ok] == fo["z"][ok]).all(), t
+        ex, eP = state_err(*ctx.get_state(0), *o.get_state())
+        worst = max(worst, ex, eP)
+        assert max(ex, eP) < 1e-7, (t, ex, eP)
+    print("long run worst error:", worst)
+    ctx.close()
