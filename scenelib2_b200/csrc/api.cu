@@ -95,7 +95,14 @@ int make_tensor_map(sl2_ctx *c) {
   return SL2_OK;
 }
 
-bool bad_stream(sl2_ctx *c, int s) { return !c || s < 0 || s >= c->cfg.num_streams; }
+// every entry point runs on the context's device whatever the calling thread's current device is
+inline void enter(sl2_ctx *c) {
+  if (c) cudaSetDevice(c->cfg.device);
+}
+bool bad_stream(sl2_ctx *c, int s) {
+  enter(c);
+  return !c || s < 0 || s >= c->cfg.num_streams;
+}
 bool bad_slot(sl2_ctx *c, int s) { return s < 0 || s >= c->cfg.frame_slots; }
 
 int stage_reserve(sl2_ctx *c, size_t bytes) {
@@ -258,6 +265,8 @@ int sl2_create(const sl2_config *cfg, sl2_ctx **out) {
     return fail(nullptr, SL2_ERR_CUDA, m);
   }
   int rc = make_tensor_map(c);
+  if (rc == SL2_OK && (sl2_configure_search(d) != cudaSuccess || sl2_configure_update(d) != cudaSuccess))
+    rc = fail(c, SL2_ERR_CUDA, std::string("kernel configuration failed: ") + cudaGetErrorString(cudaGetLastError()));
   if (rc == SL2_OK) rc = stage_reserve(c, 1 << 20);
   if (rc == SL2_OK) {
     for (int i = 0; i < 5 && rc == SL2_OK; ++i)
@@ -289,6 +298,7 @@ int sl2_create(const sl2_config *cfg, sl2_ctx **out) {
 
 void sl2_destroy(sl2_ctx *c) {
   if (!c) return;
+  enter(c);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->copy_stream) {
     cudaStreamSynchronize(c->copy_stream);
@@ -311,6 +321,7 @@ void sl2_destroy(sl2_ctx *c) {
 
 int sl2_sync(sl2_ctx *c) {
   if (!c) return SL2_ERR_ARG;
+  enter(c);
   CU_TRY(c, cudaStreamSynchronize(c->stream));
   if (c->copy_stream) CU_TRY(c, cudaStreamSynchronize(c->copy_stream));
   if (c->out_stream) CU_TRY(c, cudaStreamSynchronize(c->out_stream));
@@ -329,6 +340,7 @@ int sl2_set_frame(sl2_ctx *c, int32_t s, int32_t slot, const uint8_t *gray, size
 }
 
 static int set_frames_any(sl2_ctx *c, int32_t slot, const uint8_t *gray, cudaMemcpyKind kind) {
+  enter(c);
   if (!c || bad_slot(c, slot) || !gray) return fail(c, SL2_ERR_ARG, "sl2_set_frames: bad argument");
   const Sl2Dev &d = c->d;
   uint8_t *dst = d.frames + (size_t)slot * d.B * d.H * d.pitch;
@@ -696,11 +708,13 @@ static int step_enqueue(sl2_ctx *c, int32_t slot) {
 }
 
 int sl2_step(sl2_ctx *c, int32_t slot) {
+  enter(c);
   if (!c || bad_slot(c, slot)) return fail(c, SL2_ERR_ARG, "sl2_step: bad slot");
   return step_enqueue(c, slot);
 }
 
 int sl2_step_host(sl2_ctx *c, int32_t slot, const uint8_t *gray, double *xv_out) {
+  enter(c);
   if (!c || bad_slot(c, slot) || !gray) return fail(c, SL2_ERR_ARG, "sl2_step_host: bad argument");
   int rc = sl2_set_frames(c, slot, gray);
   if (rc) return rc;
@@ -715,6 +729,7 @@ int sl2_step_host(sl2_ctx *c, int32_t slot, const uint8_t *gray, double *xv_out)
 }
 
 int sl2_step_host_async(sl2_ctx *c, int32_t slot, const uint8_t *gray, double *xv_out) {
+  enter(c);
   if (!c || bad_slot(c, slot) || !gray) return fail(c, SL2_ERR_ARG, "sl2_step_host_async: bad argument");
   const Sl2Dev &d = c->d;
   cudaStream_t cs = c->copy_stream;
@@ -744,6 +759,7 @@ int sl2_step_host_async(sl2_ctx *c, int32_t slot, const uint8_t *gray, double *x
 }
 
 int sl2_wait_slot(sl2_ctx *c, int32_t slot) {
+  enter(c);
   if (!c || bad_slot(c, slot)) return fail(c, SL2_ERR_ARG, "sl2_wait_slot: bad slot");
   CU_TRY(c, cudaEventSynchronize(c->ev_out[slot]));
   return SL2_OK;
@@ -756,6 +772,7 @@ int sl2_enable_timing(sl2_ctx *c, int32_t on) {
 }
 
 int sl2_last_step_times(sl2_ctx *c, float *ms4) {
+  enter(c);
   if (!c || !ms4) return SL2_ERR_ARG;
   if (!c->timing) return fail(c, SL2_ERR_STATE, "timing not enabled");
   CU_TRY(c, cudaEventSynchronize(c->ev[4]));

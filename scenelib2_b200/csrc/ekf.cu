@@ -1308,6 +1308,11 @@ size_t sl2_update_smem_bytes(const Sl2Dev &d) {
   return doubles * 8 + K * 4 + 16;
 }
 
+cudaError_t sl2_configure_update(const Sl2Dev &d) {
+  return cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)sl2_update_smem_bytes(d));
+}
+
 cudaError_t sl2_launch_predict(const Sl2Dev &d, int stream_lo, int stream_cnt, const double *u3_dev,
                                int do_predict, int do_measure, cudaStream_t st) {
   if (stream_cnt <= 0) return cudaSuccess;
@@ -1323,13 +1328,6 @@ cudaError_t sl2_launch_update(const Sl2Dev &d, int stream_lo, int stream_cnt, in
                               cudaStream_t st) {
   if (stream_cnt <= 0) return cudaSuccess;
   const size_t smem = sl2_update_smem_bytes(d);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
   update_kernel<<<stream_cnt, UPD_THREADS, smem, st>>>(d, stream_lo, staged_m, st_feat, st_Hxv,
                                                         st_Hy, st_R, st_nu, only_normalise);
   return cudaGetLastError();

@@ -432,13 +432,6 @@ template <int BOX, bool FILTER>
 cudaError_t launch_t(const Sl2Dev &d, const CUtensorMap &tmap, const SearchLaunch &L,
                      const DumpPtrs &dump, cudaStream_t st) {
   const size_t smem = search_smem_bytes(d);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(search_kernel<BOX, FILTER>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
   const int groups = (L.jobs_per_stream + SL2_SEARCH_WARPS - 1) / SL2_SEARCH_WARPS;
   const int grid = groups * L.stream_cnt;
   if (grid <= 0) return cudaSuccess;
@@ -459,6 +452,25 @@ cudaError_t launch_any(const Sl2Dev &d, const CUtensorMap &tmap, const SearchLau
 }
 
 }  // namespace
+
+// once per context (per device): opt the search kernels in to their dynamic shared memory size
+cudaError_t sl2_configure_search(const Sl2Dev &d) {
+  const int smem = (int)search_smem_bytes(d);
+  cudaError_t e = cudaSuccess;
+  auto set = [&](const void *f) {
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  };
+  if (d.box == 11) {
+    set((const void *)search_kernel<11, true>);
+    set((const void *)search_kernel<11, false>);
+  } else if (d.box == 15) {
+    set((const void *)search_kernel<15, true>);
+    set((const void *)search_kernel<15, false>);
+  } else {
+    e = cudaErrorInvalidValue;
+  }
+  return e;
+}
 
 cudaError_t sl2_launch_search(const Sl2Dev &d, const CUtensorMap &tmap, const SearchLaunch &L,
                               cudaStream_t st) {

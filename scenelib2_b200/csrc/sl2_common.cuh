@@ -97,5 +97,7 @@ cudaError_t sl2_launch_update(const Sl2Dev &d, int stream_lo, int stream_cnt, in
 cudaError_t sl2_launch_cull(const Sl2Dev &d, int stream_lo, int stream_cnt, int force_index,
                             cudaStream_t st);
 size_t sl2_update_smem_bytes(const Sl2Dev &d);
+cudaError_t sl2_configure_search(const Sl2Dev &d);  // per context: dynamic smem opt-in
+cudaError_t sl2_configure_update(const Sl2Dev &d);
 cudaError_t sl2_launch_detect(const Sl2Dev &d, int stream, int slot, int n, const int *regions_dev,
                               int *out_uv_dev, double *out_ev_dev, cudaStream_t st);

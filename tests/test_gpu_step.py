@@ -220,3 +220,30 @@ def test_long_run_does_not_drift_from_oracle(oracle):
         assert max(ex, eP) < 1e-7, (t, ex, eP)
     print("long run worst error:", worst)
     ctx.close()
+
+
+def test_two_devices_in_one_process(oracle):
+    """Two contexts on two GPUs driven from ONE process (each call selects its device itself)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import scenelib2_b200 as sl2
+    scenes = [synth.make_scene("C2", stream_id=s, n_frames=3, n_features=20) for s in range(2)]
+    ctxs = []
+    for dev, sc in enumerate(scenes):
+        cfg = sl2.config_for_scene(sc, num_streams=1, frame_slots=1, device=dev)
+        c = sl2.Context(cfg)
+        sl2.load_scene(c, 0, sc)
+        ctxs.append(c)
+    oracles = [oracle_slam_from_scene(oracle, sc) for sc in scenes]
+    for t in range(3):
+        for c, sc in zip(ctxs, scenes):         # interleaved calls: device 0, device 1, ...
+            c.set_frames(0, sc.frames[t][None])
+            c.step(0)
+        for c, sc, o in zip(ctxs, scenes, oracles):
+            c.sync()
+            o.step(sc.frames[t])
+            assert (c.features(0)["z"] == o.features()["z"]).all()
+            assert_state_close(*c.get_state(0), *o.get_state())
+    for c in ctxs:
+        c.close()
