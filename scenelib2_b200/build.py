@@ -28,6 +28,8 @@ def build(force=False, verbose=False):
         cmd.insert(2, "-v")
     if os.environ.get("SL2_PHASE_STAMPS"):  # profiling builds only: per-phase clock64 stamps
         cmd.insert(1, "-DSL2_PHASE_STAMPS")
+    if os.environ.get("SL2_EXTRA_NVCC"):  # experiments only
+        cmd[1:1] = os.environ["SL2_EXTRA_NVCC"].split()
     subprocess.check_call(cmd, cwd=HERE)
     build_host()
     return LIB

@@ -529,7 +529,7 @@ struct UpdSmem {
   int *mfeat;    // [K]
   double *Rv;    // [K]
   double *mult;  // [mmax][UPD_MS] (negated) multipliers of the current panel
-  double *invd;  // [NB]
+  double *dg;    // [NB][UPD_DS] diagonal block of the current panel (factor scratch)
   double *Wm;    // [NB][UPD_WS]  W = U_pp^-T of the current panel
   double *xacc;  // [ld]  Y^T w accumulated panel by panel
   double *pan;   // phase 1: HxT / Hy (aliased); phase 2: panel buffer [NB][panw];
@@ -542,9 +542,14 @@ struct UpdSmem {
 constexpr int UPD_THREADS = 256;
 constexpr int UPD_NB = 16;   // Cholesky row-panel height (two DMMA M-tiles)
 constexpr int UPD_WS = 20;   // row stride of the W table
+constexpr int UPD_DS = 20;   // row stride of the diagonal-block scratch (conflict-free fragments)
 constexpr int UPD_MS = 20;   // row stride of the multiplier table: 32 B (mod 128) => conflict-free A fragments
 constexpr int UPD_KC = 32;   // k-chunk of the Y^T Y tiles
 constexpr int UPD_YS = 68;   // padded row stride of a staged Y slab (doubles): conflict-free DMMA reads
+#ifndef SL2_UPD_SUPER_MIN
+#define SL2_UPD_SUPER_MIN 1000
+#endif
+constexpr int UPD_SUPER_MIN = SL2_UPD_SUPER_MIN;  // fewest rows of a block that get the tile update
 constexpr int UPD_GB = 4;    // 8-column groups per warp iteration in the panel update
 
 __host__ __device__ inline int upd_keven(int Nmax) { return (Nmax + 1) & ~1; }
@@ -573,7 +578,7 @@ __device__ __forceinline__ UpdSmem carve(uint8_t *base, int Nmax) {
   u.wv = p;  p += mmax;
   u.Rv = p;  p += K;
   u.mult = p;  p += (size_t)mmax * UPD_MS;
-  u.invd = p;  p += UPD_NB;
+  u.dg = p;  p += UPD_NB * UPD_DS;
   u.Wm = p;  p += UPD_NB * UPD_WS;
   u.xacc = p;  p += (SL2_NXV + 3 * Nmax + 7) & ~7;
   u.pan = p;  p += upd_pan_doubles(Nmax);
@@ -601,6 +606,147 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// 1/sqrt(d) for a positive pivot: MUFU seed + two Newton steps (about 1 ulp); a handful of FP64
+// instructions instead of the library routine -- this sits on the serial path of every panel.
+__device__ __forceinline__ double pivot_rsqrt(double dv) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(dv));
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const double e = fma(-(dv * y), y, 1.0);
+    y = fma(0.5 * y, e, y);
+  }
+  return y;
+}
+
+// One warp: Cholesky of the 8x8 block at (o, o) of dg (upper triangle, U^T U = A) and W = U^-T into
+// the same block of Wm.  Lane j (mod 8) holds column j in registers; pivots and multipliers travel
+// by shuffles.  All 32 lanes must call.
+__device__ __forceinline__ void chol8_inv(double *dg, double *Wm, int o, int lane) {
+  const int j = lane & 7;
+  double a[8], w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = (i <= j) ? dg[(o + i) * UPD_DS + o + j] : 0.0;
+  double iud = 0.0;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const double dv = __shfl_sync(0xffffffffu, a[r], r);
+    const double iu = pivot_rsqrt(dv);
+    const double urj = (j == r) ? dv * iu : a[r] * iu;
+    a[r] = urj;
+    if (j == r) iud = iu;
+#pragma unroll
+    for (int i = r + 1; i < 8; ++i) {
+      const double uri = __shfl_sync(0xffffffffu, urj, i);
+      a[i] -= uri * urj;
+    }
+  }
+  // column j of W = U^-T (lower triangular): U^T W = I by forward substitution
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const double iui = __shfl_sync(0xffffffffu, iud, i);
+    double sacc = 0.0;
+#pragma unroll
+    for (int t = 0; t < i; ++t) {
+      const double u = __shfl_sync(0xffffffffu, a[t], i);  // U(t, i), t < i
+      sacc += u * w[t];
+    }
+    w[i] = (i == j) ? iui : ((i > j) ? -sacc * iui : 0.0);
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i <= j) dg[(o + i) * UPD_DS + o + j] = a[i];
+      Wm[(o + i) * UPD_WS + o + j] = w[i];
+    }
+  }
+}
+
+// 64x64 tile products T_t = sum_{k < kr} A_t(k, :)^T B_t(k, :) for a list of tiles, A_t / B_t = 64-column
+// slabs of the row-major matrix Gm (row stride ldg) starting at the columns tile_cols(t) returns.  FP64
+// DMMA tiles; the slabs are staged by cp.async (LDGSTS) into a double-buffered, conflict-free (stride
+// UPD_YS) shared tile; the stage sequence is flattened over (tile, k-chunk) so the first chunk of the
+// next tile is in flight while the epilogue of the current one runs.  Warp w owns rows 16*(w%4).. and
+// columns 32*(w/4).. of the tile; epi(t, acc) gets the DMMA C fragments:
+// acc[i][j][e] = T(16*(w%4) + 8*i + lane/4, 32*(w/4) + 8*j + 2*(lane%4) + e).
+// Columns >= limA / limB and rows >= kr are zero-filled.  `stage_buf` = 2*2*UPD_KC*UPD_YS doubles.
+template <class ColsFn, class EpiFn>
+__device__ __forceinline__ void tile_products(double *stage_buf, const double *__restrict__ Gm, int ldg,
+                                              int kr, int ntiles, int limA, int limB, ColsFn tile_cols,
+                                              EpiFn epi) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
+  const int wa = (warp & 3) * 16, wb = (warp >> 2) * 32;
+  const int nchunk = (kr + UPD_KC - 1) / UPD_KC;
+  const int total = ntiles * nchunk;
+  if (total <= 0) return;
+  // stage loader: 2 slabs x KC rows x 64 columns; thread = (row warp + 8*j, 16-byte segment `lane`)
+  int st_tile = 0, st_chunk = 0;  // the (tile, chunk) the next stage() call loads
+  auto stage = [&](int buf) {
+    int colA, colB;
+    tile_cols(st_tile, colA, colB);
+    colA += 2 * lane;
+    colB += 2 * lane;
+    const int bytesA = colA + 1 < limA ? 16 : (colA < limA ? 8 : 0);
+    const int bytesB = colB + 1 < limB ? 16 : (colB < limB ? 8 : 0);
+    const double *srcA = Gm + (bytesA ? colA : 0);
+    const double *srcB = Gm + (bytesB ? colB : 0);
+    double *dst = stage_buf + (size_t)buf * (2 * UPD_KC * UPD_YS) + 2 * lane;
+#pragma unroll
+    for (int j = 0; j < UPD_KC / 8; ++j) {
+      const int kk = warp + 8 * j;
+      const int k = st_chunk * UPD_KC + kk;
+      const bool kv = k < kr;
+      const size_t ro = (size_t)(kv ? k : 0) * ldg;
+      cp_async16(dst + kk * UPD_YS, srcA + ro, kv ? bytesA : 0);
+      cp_async16(dst + UPD_KC * UPD_YS + kk * UPD_YS, srcB + ro, kv ? bytesB : 0);
+    }
+    cp_async_commit();
+    if (++st_chunk == nchunk) {
+      st_chunk = 0;
+      ++st_tile;
+    }
+  };
+  double acc[2][4][2];
+  __syncthreads();  // previous users of the staging area are done
+  stage(0);
+  int tile = 0, ch = 0;
+  for (int sidx = 0; sidx < total; ++sidx) {
+    if (sidx + 1 < total) {
+      stage((sidx + 1) & 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (ch == 0) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    }
+    const double *Ya = stage_buf + (size_t)(sidx & 1) * (2 * UPD_KC * UPD_YS);
+    const double *Yb = Ya + UPD_KC * UPD_YS;
+#pragma unroll
+    for (int kk = 0; kk < UPD_KC; kk += 4) {
+      double a[2], b[4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) a[i] = Ya[(kk + lc) * UPD_YS + wa + i * 8 + lr];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Yb[(kk + lc) * UPD_YS + wb + j * 8 + lr];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    __syncthreads();  // buffer (sidx & 1) may be refilled by the stage issued in the next iteration
+    if (++ch == nchunk) {
+      epi(tile, acc);
+      ch = 0;
+      ++tile;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(UPD_THREADS, 2) update_kernel(
@@ -746,76 +892,55 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) update_kernel(
     for (int i = tid; i < m; i += UPD_THREADS) G[(size_t)i * ldg + m + n] = sm.wv[i];
     __syncthreads();
     PH(2);
-    // ---- phase 1b: S = (H P) H^T + R, upper 8x8 tiles: dense part on DMMA (A = HP(:, 0:16) from
-    //      global, B = HxT), structural dh/dy part and R per element.
+    // ---- phase 1b: S = (H P) H^T + R, upper triangle, one warp per row.  The dense 13 columns of
+    //      the row of H*P are staged once in shared memory (broadcast reads), lane = measured feature
+    //      (two columns of S); the 3 structural dh/dy columns and R are added per element.
     {
-      const int mtiles = (m + 7) >> 3;
-      const int ntile = mtiles * (mtiles + 1) / 2;
-      // tile t of the upper triangle -> (mt <= nt); the loads of the next tile of this warp are
-      // issued before the current tile is multiplied (software pipeline, depth 1)
-      auto unrank = [&](int t, int &mt, int &nt) {
-        mt = 0;
-        int rem = t;
-        while (rem >= mtiles - mt) {
-          rem -= mtiles - mt;
-          ++mt;
-        }
-        nt = mt + rem;
-      };
-      auto load_a = [&](int mt, double *a) {
-        const int ia = mt * 8 + lr;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) a[ks] = ia < m ? G[(size_t)ia * ldg + m + 4 * ks + lc] : 0.0;
-      };
-      auto load_sp = [&](int mt, int nt, double *sp) {
-        const int ia = mt * 8 + lr, jp = nt * 8 + 2 * lc;
-        sp[0] = sp[1] = sp[2] = 0.0;
-        if (ia < m && jp < m) {
-          const int pos = SL2_NXV + 3 * sm.mfeat[jp >> 1];
-#pragma unroll
-          for (int c = 0; c < 3; ++c) sp[c] = G[(size_t)ia * ldg + m + pos + c];
-        }
-      };
-      int t = warp, mt = 0, nt = 0;
-      double a[4], sp[3];
-      if (t < ntile) {
-        unrank(t, mt, nt);
-        load_a(mt, a);
-        load_sp(mt, nt, sp);
+      constexpr int HXS = 14;  // row stride of the staged H*P(:, 0:13) table (aliases sm.mult)
+      double *hpx = sm.mult;
+      for (int e = tid; e < m * 13; e += UPD_THREADS) {
+        const int i = e / 13, c = e - i * 13;
+        hpx[i * HXS + c] = G[(size_t)i * ldg + m + c];
       }
-      while (t < ntile) {
-        const int tn = t + UPD_THREADS / 32;
-        int mtn = mt, ntn = nt;
-        double an[4] = {a[0], a[1], a[2], a[3]}, spn[3] = {0.0, 0.0, 0.0};
-        if (tn < ntile) {
-          unrank(tn, mtn, ntn);
-          if (mtn != mt) load_a(mtn, an);
-          load_sp(mtn, ntn, spn);
-        }
-        double c0 = 0.0, c1 = 0.0;
+      __syncthreads();
+      constexpr int SCH = 4;  // feature chunks of 32 per pass (covers K <= 128 in one pass)
+      for (int i = warp; i < m; i += UPD_THREADS / 32) {
+        const double *grow = G + (size_t)i * ldg + m;
+        const int k0 = i >> 1;
+        for (int kb = k0; kb < K; kb += 32 * SCH) {
+          double hp[SCH][3];
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) dmma884(c0, c1, a[ks], sm.HxT[(4 * ks + lc) * HMS + nt * 8 + lr]);
-        const int ia = mt * 8 + lr, jp = nt * 8 + 2 * lc;  // columns jp, jp+1 belong to feature kp
-        if (ia < m && jp < m) {
-          const int kp = jp >> 1;
-          const double *hy = sm.Hy + kp * 6;
+          for (int t = 0; t < SCH; ++t) {  // all scattered loads of the pass first
+            const int k = kb + 32 * t + lane;
+            const int pos = SL2_NXV + 3 * sm.mfeat[k < K ? k : 0];
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            c0 += sp[c] * hy[c];
-            c1 += sp[c] * hy[3 + c];
+            for (int c = 0; c < 3; ++c) hp[t][c] = k < K ? grow[pos + c] : 0.0;
           }
-          if (ia == jp) c0 += sm.Rv[kp];
-          if (ia == jp + 1) c1 += sm.Rv[kp];
-          *reinterpret_cast<double2 *>(G + (size_t)ia * ldg + jp) = make_double2(c0, c1);
-        }
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) a[ks] = an[ks];
-        sp[0] = spn[0];
-        sp[1] = spn[1];
-        sp[2] = spn[2];
-        t = tn;
-        mt = mtn;
-        nt = ntn;
+          for (int t = 0; t < SCH; ++t) {
+            const int k = kb + 32 * t + lane;
+            if (kb + 32 * t < K) {  // warp-uniform
+              const int kk = k < K ? k : 0;
+              double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+              for (int c = 0; c < 13; ++c) {
+                const double hx = hpx[i * HXS + c];
+                const double2 hv = *reinterpret_cast<const double2 *>(sm.HxT + c * HMS + 2 * kk);
+                s0 += hx * hv.x;
+                s1 += hx * hv.y;
+              }
+              const double *hy = sm.Hy + kk * 6;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                s0 += hp[t][c] * hy[c];
+                s1 += hp[t][c] * hy[3 + c];
+              }
+              if (i == 2 * kk) s0 += sm.Rv[kk];
+              if (i == 2 * kk + 1) s1 += sm.Rv[kk];
+              if (k < K) *reinterpret_cast<double2 *>(G + (size_t)i * ldg + 2 * k) = make_double2(s0, s1);
+            }
+          }
+        }
       }
     }
     __syncthreads();
@@ -829,22 +954,79 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) update_kernel(
     const int width = m + n + 1;
     const int PW = sm.panw;
     for (int j = tid; j < n; j += UPD_THREADS) sm.xacc[j] = 0.0;
+    // Super-panels: once a block of up to 64 rows is reached, its update by ALL finished rows is done
+    // as 64x64 tile products (tile_products: both operands staged through shared memory, finished
+    // rows are read once per super-panel instead of once per panel); the 16-row panels inside the
+    // block then only look back to the start of the block (kbase).  The first block is 64..112 rows,
+    // chosen so that the column range left of it splits into 64-wide tiles with little waste.
+    int sp_next = 64;
+    {
+      int best = -1;
+      for (int cand = 64; cand <= 112; cand += 16) {
+        int r = (width - cand) & 63;
+        if (r == 0) r = 64;
+        if (r > best) {
+          best = r;
+          sp_next = cand;
+        }
+      }
+    }
+    int kbase = 0;
     for (int i0 = 0; i0 < m; i0 += UPD_NB) {
       const int nbp = min(UPD_NB, m - i0);
+      if (i0 == sp_next) {
+        sp_next += 64;
+        const int R = min(64, m - i0);
+        kbase = 0;
+        if (R >= UPD_SUPER_MIN) {
+          kbase = i0;
+          const int wa = (warp & 3) * 16, wb = (warp >> 2) * 32;
+          tile_products(
+              sm.pan, G, ldg, i0, (width - i0 + 63) / 64, width, width,
+              [&](int t, int &colA, int &colB) {
+                colA = i0;
+                colB = i0 + 64 * t;
+              },
+              [&](int t, double (&acc)[2][4][2]) {
+                double2 old[2][4];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const int r = wa + i * 8 + lr, cc = i0 + 64 * t + wb + j * 8 + 2 * lc;
+                    const double *src = G + (size_t)(i0 + r) * ldg + cc;
+                    old[i][j] = make_double2(0.0, 0.0);
+                    if (r < R && cc + 1 < width) old[i][j] = *reinterpret_cast<const double2 *>(src);
+                    else if (r < R && cc < width) old[i][j].x = *src;
+                  }
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const int r = wa + i * 8 + lr, cc = i0 + 64 * t + wb + j * 8 + 2 * lc;
+                    double *dst = G + (size_t)(i0 + r) * ldg + cc;
+                    const double v0 = old[i][j].x - acc[i][j][0], v1 = old[i][j].y - acc[i][j][1];
+                    if (r < R && cc + 1 < width) *reinterpret_cast<double2 *>(dst) = make_double2(v0, v1);
+                    else if (r < R && cc < width) *dst = v0;
+                  }
+              });
+          __syncthreads();
+        }
+      }
 #ifdef SL2_PHASE_STAMPS
       long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0, tq35 = 0;
 #endif
       PHQ(tq0 = clock64());
       if (tid == 0) s_next = 1;  // batch 0 is reserved for warp 0
       // multipliers, negated so that D = (-A) * B + C
-      for (int e = tid; e < i0 * UPD_NB; e += UPD_THREADS) {
+      for (int e = tid; e < (i0 - kbase) * UPD_NB; e += UPD_THREADS) {
         const int k = e / UPD_NB, r = e - k * UPD_NB;
-        sm.mult[k * UPD_MS + r] = (r < nbp) ? -G[(size_t)k * ldg + i0 + r] : 0.0;
+        sm.mult[k * UPD_MS + r] = (r < nbp) ? -G[(size_t)(kbase + k) * ldg + i0 + r] : 0.0;
       }
       __syncthreads();
       PHQ(tq1 = clock64());
       const int ngroups = (width - i0 + 7) >> 3;
-      const int nk = i0 >> 2;  // k-steps of 4 rows; i0 is a multiple of 16 so nk % 4 == 0
+      const int nk = (i0 - kbase) >> 2;  // k-steps of 4 rows; a multiple of 16 rows so nk % 4 == 0
       const int nbatch = (ngroups + UPD_GB - 1) / UPD_GB;
       // Batches of UPD_GB column groups are handed out dynamically.  Warp 0 takes batch 0 (it holds
       // the 16 diagonal columns), factors the diagonal block straight away while the other warps
@@ -877,7 +1059,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) update_kernel(
         }
         double b[4][UPD_GB];
         auto loadb = [&](int step, double *dst) {
-          const double *gk = G + (size_t)(4 * step + lc) * ldg;
+          const double *gk = G + (size_t)(kbase + 4 * step + lc) * ldg;
 #pragma unroll
           for (int q = 0; q < UPD_GB; ++q) dst[q] = colb[q] >= 0 ? gk[colb[q]] : 0.0;
         };
@@ -913,41 +1095,61 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) update_kernel(
         if (warp == 0 && first) {
           first = false;
           __syncwarp();
-          // factor the 16x16 diagonal block in place (upper triangle), lane = column
-          for (int r = 0; r < nbp; ++r) {
-            const double dg = sm.pan[(size_t)r * PW + r];
-            const double iu = rsqrt(dg);
-            const double u = dg * iu;
-            __syncwarp();
-            if (lane > r && lane < nbp) sm.pan[(size_t)r * PW + lane] *= iu;
-            if (lane == r) {
-              sm.pan[(size_t)r * PW + r] = u;
-              sm.invd[r] = iu;
-            }
-            __syncwarp();
-            if (lane > r && lane < nbp) {
-              const double urj = sm.pan[(size_t)r * PW + lane];
-              for (int i = r + 1; i <= lane; ++i)
-                sm.pan[(size_t)i * PW + lane] -= sm.pan[(size_t)r * PW + i] * urj;
-            }
-            __syncwarp();
-          }
-          // W = U_pp^-T (lower triangular), lane j = column j: U^T W = I by forward substitution.
-          // The panel is then finished with one more DMMA product  Y_panel = W * C_panel.
+          // Factor the 16x16 diagonal block and form W = U_pp^-T (the panel is then finished with one
+          // more DMMA product Y_panel = W * C_panel).  This is the serial path of the panel, so it is
+          // kept short: two 8x8 register/shuffle factorizations (chol8_inv) and 8x8 DMMA products
+          //   U12 = W11 A12,  A22 -= U12^T U12,  W21 = -W22 (U12^T W11)
+          // on a private copy of the block (identity padding for the ragged last panel).
           {
-            double w[UPD_NB];
-#pragma unroll
-            for (int i = 0; i < UPD_NB; ++i) {
-              double sacc = 0.0;
-#pragma unroll
-              for (int t = 0; t < i; ++t)
-                if (t >= lane) sacc += sm.pan[(size_t)t * PW + i] * w[t];
-              w[i] = (i == lane) ? sm.invd[i < nbp ? i : 0] : -sacc * sm.invd[i < nbp ? i : 0];
-              if (i < lane || i >= nbp || lane >= nbp) w[i] = 0.0;
+            double *dg = sm.dg;
+            for (int e = lane; e < UPD_NB * UPD_NB; e += 32) {
+              const int i = e >> 4, j = e & 15;
+              dg[i * UPD_DS + j] = (i < nbp && j < nbp) ? sm.pan[(size_t)i * PW + j] : (i == j ? 1.0 : 0.0);
             }
-            if (lane < UPD_NB) {
+            for (int e = lane; e < UPD_NB * UPD_WS; e += 32) sm.Wm[e] = 0.0;
+            __syncwarp();
+            chol8_inv(dg, sm.Wm, 0, lane);
+            __syncwarp();
+            {  // U12 = W11 * A12
+              double c0 = 0.0, c1 = 0.0;
 #pragma unroll
-              for (int i = 0; i < UPD_NB; ++i) sm.Wm[i * UPD_WS + lane] = w[i];
+              for (int ks = 0; ks < 2; ++ks)
+                dmma884(c0, c1, sm.Wm[lr * UPD_WS + 4 * ks + lc], dg[(4 * ks + lc) * UPD_DS + 8 + lr]);
+              __syncwarp();
+              *reinterpret_cast<double2 *>(dg + lr * UPD_DS + 8 + 2 * lc) = make_double2(c0, c1);
+            }
+            __syncwarp();
+            {  // A22 -= U12^T U12   (A(i,k) = U12(k,i) and B(k,n) = U12(k,n): the same fragment)
+              double2 cv = *reinterpret_cast<const double2 *>(dg + (8 + lr) * UPD_DS + 8 + 2 * lc);
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                const double v = dg[(4 * ks + lc) * UPD_DS + 8 + lr];
+                dmma884(cv.x, cv.y, -v, v);
+              }
+              *reinterpret_cast<double2 *>(dg + (8 + lr) * UPD_DS + 8 + 2 * lc) = cv;
+            }
+            __syncwarp();
+            chol8_inv(dg, sm.Wm, 8, lane);
+            __syncwarp();
+            {  // T = U12^T W11 (parked in the unused lower-left block of dg), W21 = -W22 T
+              double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks)
+                dmma884(t0, t1, dg[(4 * ks + lc) * UPD_DS + 8 + lr], sm.Wm[(4 * ks + lc) * UPD_WS + lr]);
+              *reinterpret_cast<double2 *>(dg + (8 + lr) * UPD_DS + 2 * lc) = make_double2(t0, t1);
+              __syncwarp();
+              double w0 = 0.0, w1 = 0.0;
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks)
+                dmma884(w0, w1, -sm.Wm[(8 + lr) * UPD_WS + 8 + 4 * ks + lc], dg[(8 + 4 * ks + lc) * UPD_DS + lr]);
+              *reinterpret_cast<double2 *>(sm.Wm + (8 + lr) * UPD_WS + 2 * lc) = make_double2(w0, w1);
+            }
+            __syncwarp();
+            // U back into the panel (upper triangle); rows / columns of the padding carry no W
+            for (int e = lane; e < UPD_NB * UPD_NB; e += 32) {
+              const int i = e >> 4, j = e & 15;
+              if (i <= j && j < nbp) sm.pan[(size_t)i * PW + j] = dg[i * UPD_DS + j];
+              if (i >= nbp || j >= nbp) sm.Wm[i * UPD_WS + j] = 0.0;
             }
           }
         }
@@ -977,36 +1179,58 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) update_kernel(
           w_lo += sm.Wm[lr * UPD_WS + k] * nuk;
           w_hi += sm.Wm[(8 + lr) * UPD_WS + k] * nuk;
         }
-        for (int g = (nbp >> 3) + warp; g * 8 < ncol; g += UPD_THREADS / 32) {
-          double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-          const int cb = g * 8 + lr;
+        // FG column groups per iteration: independent DMMA chains; a column belongs to exactly one
+        // warp within a panel and panels are separated by barriers, so xacc needs no atomics
+        constexpr int FG = 4;
+        for (int gb = (nbp >> 3) + warp; gb * 8 < ncol; gb += FG * (UPD_THREADS / 32)) {
+          double c[FG][2][2];
+#pragma unroll
+          for (int f = 0; f < FG; ++f) c[f][0][0] = c[f][0][1] = c[f][1][0] = c[f][1][1] = 0.0;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            const double bv = cb < ncol ? sm.pan[(size_t)(4 * ks + lc) * PW + cb] : 0.0;
-            dmma884(c[0][0], c[0][1], aw[0][ks], bv);
-            dmma884(c[1][0], c[1][1], aw[1][ks], bv);
-          }
-          const int cc = g * 8 + 2 * lc;
+            double bv[FG];
 #pragma unroll
-          for (int mt = 0; mt < 2; ++mt) {
-            const int r = mt * 8 + lr;
-            if (r < nbp && cc < ncol) {
-              double *dst = G + (size_t)(i0 + r) * ldg + i0 + cc;
-              if (cc + 1 < ncol) *reinterpret_cast<double2 *>(dst) = make_double2(c[mt][0], c[mt][1]);
-              else *dst = c[mt][0];
+            for (int f = 0; f < FG; ++f) {
+              const int cb = (gb + f * (UPD_THREADS / 32)) * 8 + lr;
+              bv[f] = cb < ncol ? sm.pan[(size_t)(4 * ks + lc) * PW + cb] : 0.0;
+            }
+#pragma unroll
+            for (int f = 0; f < FG; ++f) {
+              dmma884(c[f][0][0], c[f][0][1], aw[0][ks], bv[f]);
+              dmma884(c[f][1][0], c[f][1][1], aw[1][ks], bv[f]);
             }
           }
-          // x += Y^T w, fused: the 16 rows of a column live in the 8 lanes sharing lc
-          double p0 = c[0][0] * w_lo + c[1][0] * w_hi, p1 = c[0][1] * w_lo + c[1][1] * w_hi;
+          double p0[FG], p1[FG];
 #pragma unroll
-          for (int o = 4; o < 32; o <<= 1) {
-            p0 += __shfl_xor_sync(0xffffffffu, p0, o);
-            p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+          for (int f = 0; f < FG; ++f) {
+            const int cc = (gb + f * (UPD_THREADS / 32)) * 8 + 2 * lc;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+              const int r = mt * 8 + lr;
+              if (r < nbp && cc < ncol) {
+                double *dst = G + (size_t)(i0 + r) * ldg + i0 + cc;
+                if (cc + 1 < ncol) *reinterpret_cast<double2 *>(dst) = make_double2(c[f][mt][0], c[f][mt][1]);
+                else *dst = c[f][mt][0];
+              }
+            }
+            // x += Y^T w, fused: the 16 rows of a column live in the 8 lanes sharing lc
+            p0[f] = c[f][0][0] * w_lo + c[f][1][0] * w_hi;
+            p1[f] = c[f][0][1] * w_lo + c[f][1][1] * w_hi;
           }
+#pragma unroll
+          for (int o = 4; o < 32; o <<= 1)
+#pragma unroll
+            for (int f = 0; f < FG; ++f) {
+              p0[f] += __shfl_xor_sync(0xffffffffu, p0[f], o);
+              p1[f] += __shfl_xor_sync(0xffffffffu, p1[f], o);
+            }
           if (lr == 0) {
-            const int j = i0 + cc - m;  // column of Y
-            if (j >= 0 && j < n) atomicAdd(sm.xacc + j, p0);
-            if (j + 1 >= 0 && j + 1 < n) atomicAdd(sm.xacc + j + 1, p1);
+#pragma unroll
+            for (int f = 0; f < FG; ++f) {
+              const int j = i0 + (gb + f * (UPD_THREADS / 32)) * 8 + 2 * lc - m;  // column of Y
+              if (j >= 0 && j < n) sm.xacc[j] += p0[f];
+              if (j + 1 >= 0 && j + 1 < n) sm.xacc[j + 1] += p1[f];
+            }
           }
         }
       }
@@ -1024,105 +1248,55 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) update_kernel(
     for (int j = tid; j < n; j += UPD_THREADS) x[j] += sm.xacc[j];
 
     PH(5);
-    // ---- phase 4: P -= Y^T Y on 64x64 tiles (upper triangle computed, lower mirrored) ---------
-    // DMMA tiles: A(i,k) = Y(k, a0+i), B(k,j) = Y(k, b0+j); Y slabs are staged by cp.async into a
-    // double-buffered shared tile; warp w owns rows 16*(w%4).. and columns 32*(w/4)..
+    // ---- phase 4: P -= Y^T Y on 64x64 tiles (upper triangle computed, lower mirrored), written back
+    //      straight from the DMMA fragments (64-byte row segments either way, P is column-major)
     {
       const int nt = (n + 63) / 64;
       const int wa = (warp & 3) * 16, wb = (warp >> 2) * 32;
-      const int nchunk = (m + UPD_KC - 1) / UPD_KC;
-      for (int tb = 0; tb < nt; ++tb)
-        for (int ta = 0; ta <= tb; ++ta) {
-          double acc[2][4][2];
+      auto unrank = [&](int t, int &ta, int &tb) {  // tiles in (tb outer, ta <= tb inner) order
+        tb = 0;
+        while ((tb + 1) * (tb + 2) / 2 <= t) ++tb;
+        ta = t - tb * (tb + 1) / 2;
+      };
+      tile_products(
+          sm.pan, G, ldg, m, nt * (nt + 1) / 2, m + n, m + n,
+          [&](int t, int &colA, int &colB) {
+            int ta, tb;
+            unrank(t, ta, tb);
+            colA = m + ta * 64;
+            colB = m + tb * 64;
+          },
+          [&](int t, double (&acc)[2][4][2]) {
+            int ta, tb;
+            unrank(t, ta, tb);
+            const bool mirror = ta != tb;
+            double pold[2][4][2];
 #pragma unroll
-          for (int i = 0; i < 2; ++i)
+            for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-          __syncthreads();  // previous tile's users of sm.pan (T) are done
-          // stage loader: 2 slabs x KC rows x 64 columns; thread = (row warp + 8*j, 16-byte
-          // segment `lane`) of both slabs, so only the row pointer changes from chunk to chunk
-          const int colA = ta * 64 + 2 * lane, colB = tb * 64 + 2 * lane;
-          const int bytesA = colA + 1 < n ? 16 : (colA < n ? 8 : 0);
-          const int bytesB = colB + 1 < n ? 16 : (colB < n ? 8 : 0);
-          const double *srcA = G + m + (colA < n ? colA : 0);
-          const double *srcB = G + m + (colB < n ? colB : 0);
-          auto stage = [&](int chunk, int buf) {
-            double *dst = sm.pan + (size_t)buf * (2 * UPD_KC * UPD_YS) + 2 * lane;
+              for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int j = 0; j < UPD_KC / 8; ++j) {
-              const int kk = warp + 8 * j;
-              const int k = chunk * UPD_KC + kk;
-              const bool kv = k < m;
-              const size_t ro = (size_t)(kv ? k : 0) * ldg;
-              cp_async16(dst + kk * UPD_YS, srcA + ro, kv ? bytesA : 0);
-              cp_async16(dst + UPD_KC * UPD_YS + kk * UPD_YS, srcB + ro, kv ? bytesB : 0);
-            }
-            cp_async_commit();
-          };
-          stage(0, 0);
-          for (int ch = 0; ch < nchunk; ++ch) {
-            if (ch + 1 < nchunk) {
-              stage(ch + 1, (ch + 1) & 1);
-              cp_async_wait<1>();
-            } else {
-              cp_async_wait<0>();
-            }
-            __syncthreads();
-            const double *Ya = sm.pan + (size_t)(ch & 1) * (2 * UPD_KC * UPD_YS);
-            const double *Yb = Ya + UPD_KC * UPD_YS;
+                for (int e = 0; e < 2; ++e) {
+                  const int a = ta * 64 + wa + i * 8 + lr, bq = tb * 64 + wb + j * 8 + 2 * lc + e;
+                  pold[i][j][e] = (a < n && bq < n) ? P[a + (size_t)ld * bq] : 0.0;
+                }
 #pragma unroll
-            for (int kk = 0; kk < UPD_KC; kk += 4) {
-              double a[2], b[4];
+            for (int i = 0; i < 2; ++i)
 #pragma unroll
-              for (int i = 0; i < 2; ++i) a[i] = Ya[(kk + lc) * UPD_YS + wa + i * 8 + lr];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) b[j] = Yb[(kk + lc) * UPD_YS + wb + j * 8 + lr];
-#pragma unroll
-              for (int i = 0; i < 2; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-            }
-            __syncthreads();  // buffer (ch & 1) may be refilled by the next-next stage
-          }
-          // accumulators -> shared T[a][b] (64 x 65), then coalesced read-modify-write of P
-          double *T = sm.pan;
-#pragma unroll
-          for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int ar = wa + i * 8 + lr, bc = wb + j * 8 + 2 * lc;
-              T[ar * 65 + bc] = acc[i][j][0];
-              T[ar * 65 + bc + 1] = acc[i][j][1];
-            }
-          __syncthreads();
-          const int tx = tid & 63, ty = tid >> 6;  // tx -> row a (contiguous in P), ty -> column phase
-          {
-            const int a = ta * 64 + tx;
-            double pold[16];
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-              const int b = tb * 64 + ty + 4 * q;
-              pold[q] = (a < n && b < n) ? P[a + (size_t)ld * b] : 0.0;
-            }
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-              const int bb = ty + 4 * q, b = tb * 64 + bb;
-              if (a < n && b < n) {
-                const double v = pold[q] - T[tx * 65 + bb];
-                P[a + (size_t)ld * b] = v;
-                T[tx * 65 + bb] = v;
+              for (int j = 0; j < 4; ++j) {
+                const int a = ta * 64 + wa + i * 8 + lr, bq = tb * 64 + wb + j * 8 + 2 * lc;
+                const double v0 = pold[i][j][0] - acc[i][j][0], v1 = pold[i][j][1] - acc[i][j][1];
+                if (a < n && bq < n) {
+                  P[a + (size_t)ld * bq] = v0;
+                  if (bq + 1 < n) P[a + (size_t)ld * (bq + 1)] = v1;
+                  if (mirror) {  // lower tile: rows = b range (contiguous in P), column a
+                    double *dst = P + bq + (size_t)ld * a;
+                    if (bq + 1 < n) *reinterpret_cast<double2 *>(dst) = make_double2(v0, v1);
+                    else *dst = v0;
+                  }
+                }
               }
-            }
-          }
-          if (ta != tb) {
-            __syncthreads();
-            // lower tile: rows = b range (contiguous in P), columns = a range
-            for (int aa = ty; aa < 64; aa += UPD_THREADS / 64) {
-              const int a = ta * 64 + aa, b = tb * 64 + tx;
-              if (a < n && b < n) P[b + (size_t)ld * a] = T[aa * 65 + tx];
-            }
-          }
-        }
+          });
     }
     __syncthreads();
   }
@@ -1303,7 +1477,7 @@ __global__ void __launch_bounds__(256) cull_kernel(const Sl2Dev d, int stream_lo
 
 size_t sl2_update_smem_bytes(const Sl2Dev &d) {
   const size_t K = upd_keven(d.Nmax), mmax = 2 * K;
-  const size_t doubles = mmax + K + mmax * UPD_MS + UPD_NB + UPD_NB * UPD_WS +
+  const size_t doubles = mmax + K + mmax * UPD_MS + UPD_NB * UPD_DS + UPD_NB * UPD_WS +
                          ((SL2_NXV + 3 * d.Nmax + 7) & ~7) + upd_pan_doubles(d.Nmax);
   return doubles * 8 + K * 4 + 16;
 }

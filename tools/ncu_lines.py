@@ -1,4 +1,5 @@
-"""Join an ncu SASS-level source page (samples per instruction) with nvdisasm line info so that
+"""(-gi: instructions of inlined functions are attributed to the outermost call-site line.)
+Join an ncu SASS-level source page (samples per instruction) with nvdisasm line info so that
 stall samples can be read per CUDA source line.  Usage:
   python tools/ncu_lines.py <report.ncu-rep> <kernel-substring> <cubin> [top]
 """
@@ -10,7 +11,7 @@ from collections import defaultdict
 
 
 def line_map(cubin, kernel):
-    out = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
+    out = subprocess.run(["nvdisasm", "-gi", "-c", cubin], capture_output=True, text=True).stdout
     m, cur, infn = {}, None, False
     for ln in out.splitlines():
         if ln.startswith(".text."):
