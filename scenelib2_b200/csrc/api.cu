@@ -35,6 +35,16 @@ struct sl2_ctx {
   cudaStream_t out_stream = nullptr;   // D2H of the results (own stream: must not block the next H2D)
   std::vector<cudaEvent_t> ev_h2d, ev_cmp, ev_out;  // per frame slot
   double *xv_stage = nullptr;                        // [slots][B][13] device
+  // Fused step as two staggered groups of camera streams: group A (first half) on `stream`, group B on
+  // `stream_b`; B's predict+search wait for A's search of the same step and A's next step waits for
+  // B's search, so the integer-bound search of one group runs under the FP64-bound update of the other
+  // and the two update kernels are half a step out of phase.  Results are identical to the serial order
+  // (the groups share nothing); every other entry point joins the two streams first (enter()).
+  int step_groups = 2;
+  cudaStream_t stream_b = nullptr;
+  cudaEvent_t ev_main = nullptr, ev_a_search = nullptr, ev_b_search = nullptr, ev_b_done = nullptr;
+  bool b_pending = false, b_search_valid = false;
+  std::vector<cudaEvent_t> ev_cmp_b;  // per frame slot: group B is done with the slot
 };
 
 namespace {
@@ -96,8 +106,14 @@ int make_tensor_map(sl2_ctx *c) {
 }
 
 // every entry point runs on the context's device whatever the calling thread's current device is
-inline void enter(sl2_ctx *c) {
-  if (c) cudaSetDevice(c->cfg.device);
+inline void enter(sl2_ctx *c, bool join = true) {
+  if (!c) return;
+  cudaSetDevice(c->cfg.device);
+  if (join && c->b_pending) {  // the second stream group's step work becomes visible to `stream`
+    cudaStreamWaitEvent(c->stream, c->ev_b_done, 0);
+    c->b_pending = false;
+    c->b_search_valid = false;
+  }
 }
 bool bad_stream(sl2_ctx *c, int s) {
   enter(c);
@@ -273,17 +289,22 @@ int sl2_create(const sl2_config *cfg, sl2_ctx **out) {
       if (cudaEventCreate(&c->ev[i]) != cudaSuccess) rc = SL2_ERR_CUDA;
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) rc = SL2_ERR_CUDA;
     if (cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking) != cudaSuccess) rc = SL2_ERR_CUDA;
+    if (cudaStreamCreateWithFlags(&c->stream_b, cudaStreamNonBlocking) != cudaSuccess) rc = SL2_ERR_CUDA;
+    for (cudaEvent_t *e : {&c->ev_main, &c->ev_a_search, &c->ev_b_search, &c->ev_b_done})
+      if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) rc = SL2_ERR_CUDA;
     for (int i = 0; i < d.slots && rc == SL2_OK; ++i) {
-      cudaEvent_t e1, e2, e3;
+      cudaEvent_t e1, e2, e3, e4;
       if (cudaEventCreateWithFlags(&e1, cudaEventDisableTiming) != cudaSuccess ||
           cudaEventCreateWithFlags(&e2, cudaEventDisableTiming) != cudaSuccess ||
-          cudaEventCreateWithFlags(&e3, cudaEventDisableTiming) != cudaSuccess) {
+          cudaEventCreateWithFlags(&e3, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&e4, cudaEventDisableTiming) != cudaSuccess) {
         rc = SL2_ERR_CUDA;
         break;
       }
       c->ev_h2d.push_back(e1);
       c->ev_cmp.push_back(e2);
       c->ev_out.push_back(e3);
+      c->ev_cmp_b.push_back(e4);
     }
   }
   if (rc == SL2_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = SL2_ERR_CUDA;
@@ -308,8 +329,14 @@ void sl2_destroy(sl2_ctx *c) {
     cudaStreamSynchronize(c->out_stream);
     cudaStreamDestroy(c->out_stream);
   }
-  for (auto &v : {c->ev_h2d, c->ev_cmp, c->ev_out})
+  if (c->stream_b) {
+    cudaStreamSynchronize(c->stream_b);
+    cudaStreamDestroy(c->stream_b);
+  }
+  for (auto &v : {c->ev_h2d, c->ev_cmp, c->ev_out, c->ev_cmp_b})
     for (cudaEvent_t e : v) cudaEventDestroy(e);
+  for (cudaEvent_t e : {c->ev_main, c->ev_a_search, c->ev_b_search, c->ev_b_done})
+    if (e) cudaEventDestroy(e);
   for (void *p : c->allocs) cudaFree(p);
   if (c->stg_dev) cudaFree(c->stg_dev);
   if (c->stg_host) cudaFreeHost(c->stg_host);
@@ -682,33 +709,62 @@ int sl2_normalise_state(sl2_ctx *c, int32_t s) {
 }
 
 // ---- fused step ---------------------------------------------------------------------------------
-static int step_enqueue(sl2_ctx *c, int32_t slot) {
+static int step_group(sl2_ctx *c, int32_t slot, int lo, int cnt, cudaStream_t st, cudaEvent_t after_search,
+                      bool t) {
   const Sl2Dev &d = c->d;
-  const bool t = c->timing;
-  if (t) CU_TRY(c, cudaEventRecord(c->ev[0], c->stream));
-  CU_TRY(c, sl2_launch_predict(d, 0, d.B, nullptr, 1, 1, c->stream));
-  if (t) CU_TRY(c, cudaEventRecord(c->ev[1], c->stream));
+  if (t) CU_TRY(c, cudaEventRecord(c->ev[0], st));
+  CU_TRY(c, sl2_launch_predict(d, lo, cnt, nullptr, 1, 1, st));
+  if (t) CU_TRY(c, cudaEventRecord(c->ev[1], st));
   SearchLaunch L = {};
-  L.job_feat = d.job_feat;
-  L.job_centre = d.job_centre;
-  L.job_puinv = d.job_puinv;
+  // job arrays are indexed by the stream number local to the launch
+  L.job_feat = d.job_feat + (size_t)lo * d.Nmax;
+  L.job_centre = d.job_centre + (size_t)lo * d.Nmax * 2;
+  L.job_puinv = d.job_puinv + (size_t)lo * d.Nmax * 3;
   L.jobs_per_stream = d.Nmax;
-  L.stream_lo = 0;
-  L.stream_cnt = d.B;
+  L.stream_lo = lo;
+  L.stream_cnt = cnt;
   L.slot = slot;
   L.scatter_to_features = 1;
-  CU_TRY(c, sl2_launch_search(d, c->tmap, L, c->stream));
-  if (t) CU_TRY(c, cudaEventRecord(c->ev[2], c->stream));
-  CU_TRY(c, sl2_launch_update(d, 0, d.B, -1, nullptr, nullptr, nullptr, nullptr, nullptr, 0, c->stream));
-  if (t) CU_TRY(c, cudaEventRecord(c->ev[3], c->stream));
-  CU_TRY(c, sl2_launch_cull(d, 0, d.B, -1, c->stream));
-  if (t) CU_TRY(c, cudaEventRecord(c->ev[4], c->stream));
+  CU_TRY(c, sl2_launch_search(d, c->tmap, L, st));
+  if (t) CU_TRY(c, cudaEventRecord(c->ev[2], st));
+  if (after_search) CU_TRY(c, cudaEventRecord(after_search, st));
+  CU_TRY(c, sl2_launch_update(d, lo, cnt, -1, nullptr, nullptr, nullptr, nullptr, nullptr, 0, st));
+  if (t) CU_TRY(c, cudaEventRecord(c->ev[3], st));
+  CU_TRY(c, sl2_launch_cull(d, lo, cnt, -1, st));
+  if (t) CU_TRY(c, cudaEventRecord(c->ev[4], st));
   c->launches += 4;
   return SL2_OK;
 }
 
+// number of camera streams in group A when the step runs as two staggered groups, else 0
+static int split_point(const sl2_ctx *c) {
+  return (c->step_groups >= 2 && !c->timing && c->d.B >= 2) ? (c->d.B + 1) / 2 : 0;
+}
+
+static int step_enqueue(sl2_ctx *c, int32_t slot, bool serial = false) {
+  const Sl2Dev &d = c->d;
+  const int BA = serial ? 0 : split_point(c);
+  if (BA == 0) {
+    enter(c);  // serial order on `stream` (timing mode, one stream, or grouping switched off)
+    return step_group(c, slot, 0, d.B, c->stream, nullptr, c->timing);
+  }
+  // group B sees everything `stream` has done so far (uploads, staged calls, the frame copy)
+  CU_TRY(c, cudaEventRecord(c->ev_main, c->stream));
+  CU_TRY(c, cudaStreamWaitEvent(c->stream_b, c->ev_main, 0));
+  if (c->b_search_valid) CU_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_b_search, 0));
+  int rc = step_group(c, slot, 0, BA, c->stream, c->ev_a_search, false);
+  if (rc) return rc;
+  CU_TRY(c, cudaStreamWaitEvent(c->stream_b, c->ev_a_search, 0));
+  rc = step_group(c, slot, BA, d.B - BA, c->stream_b, c->ev_b_search, false);
+  if (rc) return rc;
+  c->b_search_valid = true;
+  CU_TRY(c, cudaEventRecord(c->ev_b_done, c->stream_b));
+  c->b_pending = true;
+  return SL2_OK;
+}
+
 int sl2_step(sl2_ctx *c, int32_t slot) {
-  enter(c);
+  enter(c, false);
   if (!c || bad_slot(c, slot)) return fail(c, SL2_ERR_ARG, "sl2_step: bad slot");
   return step_enqueue(c, slot);
 }
@@ -718,7 +774,7 @@ int sl2_step_host(sl2_ctx *c, int32_t slot, const uint8_t *gray, double *xv_out)
   if (!c || bad_slot(c, slot) || !gray) return fail(c, SL2_ERR_ARG, "sl2_step_host: bad argument");
   int rc = sl2_set_frames(c, slot, gray);
   if (rc) return rc;
-  rc = step_enqueue(c, slot);
+  rc = step_enqueue(c, slot, true);  // a blocking call has nothing to overlap with: serial kernel order
   if (rc) return rc;
   const Sl2Dev &d = c->d;
   if (xv_out)
@@ -729,12 +785,13 @@ int sl2_step_host(sl2_ctx *c, int32_t slot, const uint8_t *gray, double *xv_out)
 }
 
 int sl2_step_host_async(sl2_ctx *c, int32_t slot, const uint8_t *gray, double *xv_out) {
-  enter(c);
+  enter(c, false);
   if (!c || bad_slot(c, slot) || !gray) return fail(c, SL2_ERR_ARG, "sl2_step_host_async: bad argument");
   const Sl2Dev &d = c->d;
   cudaStream_t cs = c->copy_stream;
-  // the frame slot may still be read by the step that used it last
+  // the frame slot may still be read by the step that used it last (either stream group)
   CU_TRY(c, cudaStreamWaitEvent(cs, c->ev_cmp[slot], 0));
+  CU_TRY(c, cudaStreamWaitEvent(cs, c->ev_cmp_b[slot], 0));
   uint8_t *dst = d.frames + (size_t)slot * d.B * d.H * d.pitch;
   if (d.pitch == d.W) {
     CU_TRY(c, cudaMemcpyAsync(dst, gray, (size_t)d.B * d.H * d.W, cudaMemcpyHostToDevice, cs));
@@ -746,15 +803,39 @@ int sl2_step_host_async(sl2_ctx *c, int32_t slot, const uint8_t *gray, double *x
   CU_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_out[slot], 0));  // staging buffer of this slot is free
   int rc = step_enqueue(c, slot);
   if (rc) return rc;
+  // camera states of this step -> per-slot staging (each group on its own stream) -> host
   double *stage = c->xv_stage + (size_t)slot * d.B * SL2_NXV;
+  const int BA = c->b_pending ? split_point(c) : 0;
+  const int nA = BA ? BA : d.B;
   CU_TRY(c, cudaMemcpy2DAsync(stage, sizeof(double) * SL2_NXV, d.x, sizeof(double) * d.ld,
-                              sizeof(double) * SL2_NXV, d.B, cudaMemcpyDeviceToDevice, c->stream));
+                              sizeof(double) * SL2_NXV, nA, cudaMemcpyDeviceToDevice, c->stream));
   CU_TRY(c, cudaEventRecord(c->ev_cmp[slot], c->stream));
   CU_TRY(c, cudaStreamWaitEvent(c->out_stream, c->ev_cmp[slot], 0));
+  if (BA) {
+    CU_TRY(c, cudaMemcpy2DAsync(stage + (size_t)BA * SL2_NXV, sizeof(double) * SL2_NXV,
+                                d.x + (size_t)BA * d.ld, sizeof(double) * d.ld, sizeof(double) * SL2_NXV,
+                                d.B - BA, cudaMemcpyDeviceToDevice, c->stream_b));
+    CU_TRY(c, cudaEventRecord(c->ev_cmp_b[slot], c->stream_b));
+    CU_TRY(c, cudaEventRecord(c->ev_b_done, c->stream_b));
+    CU_TRY(c, cudaStreamWaitEvent(c->out_stream, c->ev_cmp_b[slot], 0));
+  }
   if (xv_out)
     CU_TRY(c, cudaMemcpyAsync(xv_out, stage, sizeof(double) * SL2_NXV * d.B, cudaMemcpyDeviceToHost,
                               c->out_stream));
   CU_TRY(c, cudaEventRecord(c->ev_out[slot], c->out_stream));
+  return SL2_OK;
+}
+
+int sl2_join(sl2_ctx *c) {
+  if (!c) return SL2_ERR_ARG;
+  enter(c);
+  return SL2_OK;
+}
+
+int sl2_set_step_groups(sl2_ctx *c, int32_t groups) {
+  if (!c || groups < 1 || groups > 2) return fail(c, SL2_ERR_ARG, "sl2_set_step_groups: 1 or 2");
+  enter(c);
+  c->step_groups = groups;
   return SL2_OK;
 }
 
@@ -767,7 +848,8 @@ int sl2_wait_slot(sl2_ctx *c, int32_t slot) {
 
 int sl2_enable_timing(sl2_ctx *c, int32_t on) {
   if (!c) return SL2_ERR_ARG;
-  c->timing = on != 0;
+  enter(c);
+  c->timing = on != 0;  // timing mode runs the step in serial order on the context's stream
   return SL2_OK;
 }
 

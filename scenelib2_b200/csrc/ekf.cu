@@ -542,6 +542,7 @@ struct UpdSmem {
 constexpr int UPD_THREADS = 256;
 constexpr int UPD_NB = 16;   // Cholesky row-panel height (two DMMA M-tiles)
 constexpr int UPD_WS = 20;   // row stride of the W table
+constexpr int UPD_HXS = 14;  // row stride of the H*P(:, 0:13) table phase 1a leaves in sm.mult for phase 1b
 constexpr int UPD_DS = 20;   // row stride of the diagonal-block scratch (conflict-free fragments)
 constexpr int UPD_MS = 20;   // row stride of the multiplier table: 32 B (mod 128) => conflict-free A fragments
 constexpr int UPD_KC = 32;   // k-chunk of the Y^T Y tiles
@@ -728,8 +729,7 @@ __device__ __forceinline__ void tile_products(double *stage_buf, const double *_
     }
     const double *Ya = stage_buf + (size_t)(sidx & 1) * (2 * UPD_KC * UPD_YS);
     const double *Yb = Ya + UPD_KC * UPD_YS;
-#pragma unroll
-    for (int kk = 0; kk < UPD_KC; kk += 4) {
+    auto kstep = [&](int kk) {
       double a[2], b[4];
 #pragma unroll
       for (int i = 0; i < 2; ++i) a[i] = Ya[(kk + lc) * UPD_YS + wa + i * 8 + lr];
@@ -739,6 +739,14 @@ __device__ __forceinline__ void tile_products(double *stage_buf, const double *_
       for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    };
+    const int krem = kr - ch * UPD_KC;  // rows of this chunk that exist (the rest is zero fill)
+    if (krem >= UPD_KC) {
+#pragma unroll
+      for (int kk = 0; kk < UPD_KC; kk += 4) kstep(kk);
+    } else {
+#pragma unroll 2
+      for (int kk = 0; kk < krem; kk += 4) kstep(kk);
     }
     __syncthreads();  // buffer (sidx & 1) may be refilled by the stage issued in the next iteration
     if (++ch == nchunk) {
@@ -884,6 +892,10 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) update_kernel(
               double *dst = G + (size_t)i * ldg + m + j0[q];
               if (j0[q] + 1 < n) *reinterpret_cast<double2 *>(dst) = make_double2(c0, c1);
               else *dst = c0;
+              if (j0[q] < SL2_NXV) {  // dense 13 columns of H*P: kept in shared memory for phase 1b
+                sm.mult[i * UPD_HXS + j0[q]] = c0;
+                if (j0[q] + 1 < SL2_NXV) sm.mult[i * UPD_HXS + j0[q] + 1] = c1;
+              }
             }
           }
         }
@@ -893,16 +905,11 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) update_kernel(
     __syncthreads();
     PH(2);
     // ---- phase 1b: S = (H P) H^T + R, upper triangle, one warp per row.  The dense 13 columns of
-    //      the row of H*P are staged once in shared memory (broadcast reads), lane = measured feature
+    //      the row of H*P come from shared memory (written by phase 1a; broadcast reads), lane = measured feature
     //      (two columns of S); the 3 structural dh/dy columns and R are added per element.
     {
-      constexpr int HXS = 14;  // row stride of the staged H*P(:, 0:13) table (aliases sm.mult)
-      double *hpx = sm.mult;
-      for (int e = tid; e < m * 13; e += UPD_THREADS) {
-        const int i = e / 13, c = e - i * 13;
-        hpx[i * HXS + c] = G[(size_t)i * ldg + m + c];
-      }
-      __syncthreads();
+      constexpr int HXS = UPD_HXS;  // H*P(:, 0:13), left in sm.mult by phase 1a
+      const double *hpx = sm.mult;
       constexpr int SCH = 4;  // feature chunks of 32 per pass (covers K <= 128 in one pass)
       for (int i = warp; i < m; i += UPD_THREADS / 32) {
         const double *grow = G + (size_t)i * ldg + m;

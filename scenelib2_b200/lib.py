@@ -43,7 +43,7 @@ EXPORTS = [
     "sl2_patch_search", "sl2_score_map", "sl2_smoe_search", "sl2_find_best_patch", "sl2_ekf_predict",
     "sl2_predict_measurements", "sl2_make_measurements", "sl2_ekf_update",
     "sl2_ekf_update_measured", "sl2_normalise_state", "sl2_step", "sl2_step_host",
-    "sl2_step_host_async", "sl2_wait_slot",
+    "sl2_step_host_async", "sl2_wait_slot", "sl2_set_step_groups", "sl2_join",
     "sl2_get_features", "sl2_get_feature_jacobians", "sl2_enable_timing", "sl2_last_step_times", "sl2_launch_count",
 ]
 
@@ -77,6 +77,8 @@ def load():
         L.sl2_step_host.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.sl2_step_host_async.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.sl2_wait_slot.argtypes = [C.c_void_p, C.c_int32]
+        L.sl2_set_step_groups.argtypes = [C.c_void_p, C.c_int32]
+        L.sl2_join.argtypes = [C.c_void_p]
         L.sl2_sync.argtypes = [C.c_void_p]
         L.sl2_score_map.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, f64p, f64p, i32p,
                                     f64p, f64p, u8p, C.c_size_t]
@@ -268,6 +270,12 @@ class Context:
 
     def wait_slot(self, slot):
         self._ck(self.L.sl2_wait_slot(self.h, slot))
+
+    def set_step_groups(self, groups):
+        self._ck(self.L.sl2_set_step_groups(self.h, groups))
+
+    def join(self):
+        self._ck(self.L.sl2_join(self.h))
 
     def sync(self):
         self._ck(self.L.sl2_sync(self.h))

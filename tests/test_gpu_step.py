@@ -247,3 +247,40 @@ def test_two_devices_in_one_process(oracle):
             assert_state_close(*c.get_state(0), *o.get_state())
     for c in ctxs:
         c.close()
+
+
+def test_staggered_stream_groups_match_serial_order():
+    """sl2_set_step_groups: the fused step run as two staggered stream groups on internal CUDA streams
+    gives bit-identical states to the serial kernel order, for back-to-back sl2_step calls, for the
+    asynchronous host ring, and when other entry points are interleaved (they join the groups)."""
+    import torch
+    nS, T = 5, 6
+    scenes = [synth.make_scene("C2", stream_id=s, n_frames=4, n_features=20) for s in range(nS)]
+    ctxs = []
+    for groups in (1, 2):
+        c = ctx_from_scenes(scenes, frame_slots=4)
+        c.set_step_groups(groups)
+        ctxs.append(c)
+    host = torch.empty((4, nS, 240, 320), dtype=torch.uint8, pin_memory=True)
+    host.numpy()[:] = np.stack([np.stack([sc.frames[t] for sc in scenes]) for t in range(4)])
+    xs = [torch.zeros((4, nS, 13), dtype=torch.float64, pin_memory=True) for _ in ctxs]
+    for c in ctxs:                                   # device-resident frames, steps back to back
+        for t in range(4):
+            c.set_frames(t, host[t].numpy())
+        for t in range(T):
+            c.step(t % 4)
+    for s in range(nS):                              # get_state joins the groups
+        (x1, P1), (x2, P2) = ctxs[0].get_state(s), ctxs[1].get_state(s)
+        assert (x1 == x2).all() and (P1 == P2).all(), s
+    for c, xo in zip(ctxs, xs):                      # host ring on top of the same contexts
+        for t in range(T):
+            c.step_host_async(t % 4, host[t % 4].data_ptr(), xo[t % 4].data_ptr())
+        c.sync()
+    assert (xs[0].numpy() == xs[1].numpy()).all()
+    for s in range(nS):
+        (x1, P1), (x2, P2) = ctxs[0].get_state(s), ctxs[1].get_state(s)
+        assert (x1 == x2).all() and (P1 == P2).all(), s
+        f1, f2 = ctxs[0].features(s), ctxs[1].features(s)
+        assert all((f1[k] == f2[k]).all() for k in ("z", "flags", "attempted", "successful"))
+    for c in ctxs:
+        c.close()
