@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dist-selftest", action="store_true", help="CPU/gloo check of the N>1 plumbing")
     ap.add_argument("--cpu-threads", type=int, default=0, help="host threads of the CPU legs (0 = all)")
-    ap.add_argument("--step-groups", type=int, default=2, choices=[1, 2],
+    ap.add_argument("--step-groups", type=int, default=1, choices=[1, 2],
                     help="staggered stream groups of the fused step (1 = serial kernel order)")
     return ap.parse_args()
 

@@ -153,9 +153,9 @@ int sl2_step_host(sl2_ctx *ctx, int32_t slot, const uint8_t *gray, double *xv_ou
  * frame t (the producer side of FrameGrabber::GetFrame, framegrabber.cpp:73-104). */
 int sl2_step_host_async(sl2_ctx *ctx, int32_t slot, const uint8_t *gray, double *xv_out);
 int sl2_wait_slot(sl2_ctx *ctx, int32_t slot);
-/* The fused step runs the camera streams of a context as `groups` (1 or 2, default 2) staggered groups
- * on internal CUDA streams: the patch search of one group is scheduled under the EKF update of the
- * other.  The groups share no state, so results do not depend on the setting; the reference's GoOneStep
+/* The fused step can run the camera streams of a context as `groups` (1 or 2, default 1) staggered groups
+ * on internal CUDA streams: with 2, the patch search of one group is scheduled under the EKF update of
+ * the other (measured neutral at 296 streams on B200; useful when the update does not fill the GPU).  The groups share no state, so results do not depend on the setting; the reference's GoOneStep
  * order (monoslam.cpp:108-180) holds within every camera stream.  Every other entry point first makes
  * the context's stream wait for both groups; sl2_join does only that (no host synchronisation) -- call
  * it before recording your own events on the context's stream after a run of sl2_step calls. */

@@ -40,7 +40,7 @@ struct sl2_ctx {
   // B's search, so the integer-bound search of one group runs under the FP64-bound update of the other
   // and the two update kernels are half a step out of phase.  Results are identical to the serial order
   // (the groups share nothing); every other entry point joins the two streams first (enter()).
-  int step_groups = 2;
+  int step_groups = 1;  // measured neutral on B200 at 296 streams (update loses its second CTA/SM): off by default
   cudaStream_t stream_b = nullptr;
   cudaEvent_t ev_main = nullptr, ev_a_search = nullptr, ev_b_search = nullptr, ev_b_done = nullptr;
   bool b_pending = false, b_search_valid = false;

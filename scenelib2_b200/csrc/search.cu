@@ -137,10 +137,12 @@ __global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32, FILTER ? (BOX <= 11 ? 4
   const int tile_bytes = ((TW * TH + 16 + 127) / 128) * 128;
   const int max_tasks = TCW * ((TCH + V - 1) / V);
   const int list_bytes = ((max_tasks * 4 + 15) / 16) * 16;
-  const int per_warp = ((tile_bytes + list_bytes + 16 + 127) / 128) * 128;  // TMA dst: 128 B aligned
+  const int vtab_bytes = TCH * 16;  // per candidate row: (double)v and P11*v*v of the ellipse test
+  const int per_warp = ((tile_bytes + list_bytes + 16 + vtab_bytes + 127) / 128) * 128;  // TMA dst: 128 B aligned
   uint8_t *tile = smem + (size_t)warp * per_warp;
   uint32_t *list = reinterpret_cast<uint32_t *>(tile + tile_bytes);
   const uint32_t bar = smem_u32(tile + tile_bytes + list_bytes);
+  double2 *vtab = reinterpret_cast<double2 *>(tile + tile_bytes + list_bytes + 16);
   const uint32_t tile_s = smem_u32(tile);
 
   if (lane == 0) {
@@ -180,6 +182,7 @@ __global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32, FILTER ? (BOX <= 11 ? 4
   // exact integers (< 2^53, so FP64 holds them exactly): n^2 * var = n*Sxx - Sx^2
   const double V0d = fma(n, Sg0sqd, -(Sg0d * Sg0d));
   const double T100 = 100.0 * n * n;           // sigma >= 10  <=>  n^2 var >= 100 n^2
+  const float V0f = (float)V0d;
   const bool patch_ok = !(sigmag0 < 10.0);     // kCorrelationSigmaThreshold_ gate on the template
   float bmin = 3.0e38f;                        // running minimum of the approximate score
   const PatchConst pconst = {n, sigmag0, A0, g0s, Sg0x2};
@@ -225,6 +228,12 @@ __global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32, FILTER ? (BOX <= 11 ? 4
         // ---- task list while the TMA is in flight ------------------------------------------
         const int nstrips = (tch + V - 1) / V;
         const int ntask = tcw * nstrips;
+        // the v-only term of the ellipse test, once per candidate row instead of once per candidate
+        for (int cv = lane; cv < tch; cv += 32) {
+          const double dv = (double)(vs + ty0 + cv);
+          vtab[cv] = make_double2(dv, mul_(mul_(P11, dv), dv));
+        }
+        __syncwarp();
         int nlist = 0;
         for (int t0 = 0; t0 < ntask; t0 += 32) {
           const int t = t0 + lane;
@@ -232,7 +241,11 @@ __global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32, FILTER ? (BOX <= 11 ? 4
           if (t < ntask) {
             // strip-major order: the lanes of a round mostly share the image rows and read
             // consecutive columns => shared-memory reads are broadcasts / conflict-free
-            const int st = t / tcw, cu = t - st * tcw;
+            // strips are visited centre-out (the match is expected near the predicted position, so the
+            // running minimum of the filter is tight from the first round on and few candidates need the
+            // exact chain); the arg-min carries its scan index, so the visiting order is free
+            const int sk = t / tcw, cu = t - sk * tcw;
+            const int st = (sk & 1) ? (nstrips - 1) / 2 + (sk + 1) / 2 : (nstrips - 1) / 2 - sk / 2;
             const double du = (double)(us + tx0 + cu);
             const double a = mul_(mul_(P00, du), du);
             const double bcoef = mul_(twoP01, du);
@@ -241,9 +254,9 @@ __global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32, FILTER ? (BOX <= 11 ? 4
             for (int j = 0; j < V; ++j) {
               const int cv = st * V + j;
               if (cv < tch) {
-                const double dv = (double)(vs + ty0 + cv);
+                const double2 tv = vtab[cv];
                 // PuInv(0,0)*u*u + 2*PuInv(0,1)*u*v + PuInv(1,1)*v*v < 9  (monoslam.cpp:453-454)
-                const double q = add_(add_(a, mul_(bcoef, dv)), mul_(mul_(P11, dv), dv));
+                const double q = add_(add_(a, mul_(bcoef, tv.x)), tv.y);
                 if (q < 9.0 || dump.corr) mask |= (q < 9.0 ? 1u : 0x100u) << j;
               }
             }
@@ -324,16 +337,31 @@ __global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32, FILTER ? (BOX <= 11 ? 4
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
                   if ((m_in >> j) & 1u) {
-                    const double Sg1d = (double)(int)a1[j], Sg1sqd = (double)(int)a2[j],
-                                 Sg0g1d = (double)(int)ax[j];
-                    const double V1 = fma(n, Sg1sqd, -(Sg1d * Sg1d));  // exact
-                    if (V1 > T100) {
-                      const double N01 = fma(n, Sg0g1d, -(Sg0d * Sg1d));  // exact
-                      const float rho = (float)N01 * rsqrtf((float)(V0d * V1));
-                      cap[j] = fmaf(-2.0f, rho, 2.0f);
-                      lmin = fminf(lmin, cap[j]);
-                    } else if (V1 == T100) {
-                      cap[j] = -3.0e38f;  // knife edge of sdimage >= 10: the exact chain decides
+                    if constexpr (BOX <= 11) {
+                      // n^2 var = n Sxx - Sx^2 and n Sxy - Sx0 Sx1 fit 32-bit integers for n <= 121
+                      // (n^2 255^2 < 2^31): exact in the integer pipe, one conversion each to FP32
+                      constexpr uint32_t NN = BOX * BOX, T100u = 100u * NN * NN;
+                      const uint32_t V1u = NN * a2[j] - a1[j] * a1[j];
+                      if (V1u > T100u) {
+                        const int N01i = (int)NN * (int)ax[j] - Sg0 * (int)a1[j];
+                        const float rho = (float)N01i * rsqrtf(V0f * (float)V1u);
+                        cap[j] = fmaf(-2.0f, rho, 2.0f);
+                        lmin = fminf(lmin, cap[j]);
+                      } else if (V1u == T100u) {
+                        cap[j] = -3.0e38f;  // knife edge of sdimage >= 10: the exact chain decides
+                      }
+                    } else {
+                      const double Sg1d = (double)(int)a1[j], Sg1sqd = (double)(int)a2[j],
+                                   Sg0g1d = (double)(int)ax[j];
+                      const double V1 = fma(n, Sg1sqd, -(Sg1d * Sg1d));  // exact
+                      if (V1 > T100) {
+                        const double N01 = fma(n, Sg0g1d, -(Sg0d * Sg1d));  // exact
+                        const float rho = (float)N01 * rsqrtf((float)(V0d * V1));
+                        cap[j] = fmaf(-2.0f, rho, 2.0f);
+                        lmin = fminf(lmin, cap[j]);
+                      } else if (V1 == T100) {
+                        cap[j] = -3.0e38f;  // knife edge of sdimage >= 10: the exact chain decides
+                      }
                     }
                   }
                 }
@@ -425,7 +453,7 @@ size_t search_smem_bytes(const Sl2Dev &d) {
   const int tile_bytes = ((d.tile_w * d.tile_h + 16 + 127) / 128) * 128;
   const int max_tasks = TCW * ((TCH + SL2_STRIP - 1) / SL2_STRIP);
   const int list_bytes = ((max_tasks * 4 + 15) / 16) * 16;
-  return (size_t)SL2_SEARCH_WARPS * (((tile_bytes + list_bytes + 16 + 127) / 128) * 128);
+  return (size_t)SL2_SEARCH_WARPS * (((tile_bytes + list_bytes + 16 + TCH * 16 + 127) / 128) * 128);
 }
 
 template <int BOX, bool FILTER>
