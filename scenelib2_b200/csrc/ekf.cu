@@ -656,6 +656,7 @@ __device__ __forceinline__ void chol8_inv(double *dg, double *Wm, int o, int lan
     }
     w[i] = (i == j) ? iui : ((i > j) ? -sacc * iui : 0.0);
   }
+  __syncwarp();  // every lane has read its (mirrored) column before the block is overwritten
   if (lane < 8) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {

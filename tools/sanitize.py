@@ -12,6 +12,12 @@ for t in range(3):
     ctx.set_frames(t % 2, np.stack([sc.frames[t] for sc in scenes]))
     ctx.step(t % 2)
 ctx.sync()
+ctx.set_step_groups(2)                       # staggered stream groups on the internal streams
+for t in range(3):
+    ctx.step(t % 2)
+ctx.sync()
+ctx.set_step_groups(1)
+ctx.find_best_patch(0, 0, [[100, 80, 180, 140], [5, 5, 60, 50]])   # Shi-Tomasi detector
 rng = np.random.default_rng(0)
 sc = scenes[0]
 n = sc.n_features
