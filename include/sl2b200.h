@@ -107,6 +107,23 @@ int sl2_smoe_search(sl2_ctx *ctx, int32_t stream_id, int32_t slot, int32_t feat_
                     const double *PuInv3 /* K x 3 */, const double *centres /* K x 2 */,
                     int32_t *res_u, int32_t *res_v, uint8_t *res_flag);
 
+/* One partially-initialised feature represented by K depth particles:
+ * MonoSLAM::measure_feature_with_multiple_priors (monoslam.cpp:1408-1438: SMOE search of the template of
+ * feat_index over the K ellipses (Sinv_k, h_k)) followed by the body of
+ * update_partially_initialised_feature_probabilities for that feature (monoslam.cpp:1447-1493):
+ * prob_k *= N(z_k - h_k; S_k) (0 where the match failed), normalise_particle_vector_and_calculate_cumulative,
+ * prune_particle_vector(prune_probability_threshold), calculate_mean_and_covariance (feature_init_info.cpp:
+ * 95-172, scalar lambda).  Both kernels run back to back on the device.
+ * in: h (K x 2), Sinv3 (K x (S00,S01,S11)), detS (K), lambda (K); in/out: prob (K);
+ * out (each may be NULL): z_uv (K x 2), found (K), keep (K; 1 = particle survives), cumulative (K; of the
+ * survivors in order, 0 for pruned ones), mean_var (2).
+ * Returns the number of surviving particles, 0 when every probability is zero (the reference then deletes the
+ * feature and leaves prob un-normalised), < 0 on error. */
+int sl2_measure_particles(sl2_ctx *ctx, int32_t stream_id, int32_t slot, int32_t feat_index, int32_t K,
+                          const double *h, const double *Sinv3, const double *detS, const double *lambda,
+                          double prune_probability_threshold, double *prob, int32_t *z_uv, uint8_t *found,
+                          uint8_t *keep, double *cumulative, double *mean_var);
+
 /* MonoSLAM::find_best_patch_inside_region + find_eigenvalues (monoslam.cpp:1070-1205): Shi-Tomasi
  * smallest-eigenvalue detector over n regions (ustart, vstart, ufinish, vfinish) of one stream's
  * frame.  evbest[i] is always written; ubest/vbest[i] only when a position with a positive score

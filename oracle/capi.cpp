@@ -4,6 +4,7 @@
 
 #include "sl2_oracle.h"
 #include "slam.hpp"
+#include "particles.hpp"
 
 using namespace sl2o;
 
@@ -151,6 +152,14 @@ void orc_find_best_patch(const uint8_t *image, int32_t width, int32_t height, in
   find_best_patch_inside_region(image, width, height, &u, &v, evbest, boxsize, r[0], r[1], r[2], r[3]);
   *ubest = u;
   *vbest = v;
+}
+
+int32_t orc_particle_update(int32_t K, const double *h, const double *Sinv3, const double *detS,
+                            const double *lambda, const int32_t *z_uv, const uint8_t *found,
+                            double prune_probability_threshold, double *prob, uint8_t *keep,
+                            double *cumulative, double *mean_var) {
+  return particle_update(K, h, Sinv3, detS, lambda, z_uv, found, prune_probability_threshold, prob, keep,
+                         cumulative, mean_var);
 }
 
 void orc_motion(const double *xv, const double *u, double delta_t, double *fv, double *F,

@@ -199,6 +199,26 @@ def find_best_patch(image, boxsize, region, ubest=-1, vbest=-1):
     return u.value, v.value, ev.value
 
 
+def particle_update(h, Sinv3, detS, lam, z_uv, found, prune_threshold, prob):
+    """N2.  -> survivors, prob (normalised), keep, cumulative, (mean, variance)."""
+    h, hp = _f64(h)
+    Sinv3, sp = _f64(Sinv3)
+    detS, dp = _f64(detS)
+    lam, lp = _f64(lam)
+    z_uv = np.ascontiguousarray(z_uv, np.int32)
+    found = np.ascontiguousarray(found, np.uint8)
+    prob = np.array(prob, np.float64)
+    K = prob.shape[0]
+    keep = np.zeros(K, np.uint8)
+    cum = np.zeros(K)
+    mv = np.zeros(2)
+    f = lib().orc_particle_update
+    f.restype = C.c_int32
+    left = f(K, hp, sp, dp, lp, _p(z_uv, i32p), _p(found, u8p), C.c_double(prune_threshold), _p(prob, f64p),
+             _p(keep, u8p), _p(cum, f64p), _p(mv, f64p))
+    return left, prob, keep, cum, mv
+
+
 def motion(xv, dt, u=(0.0, 0.0, 0.0)):
     """A5.  -> fv (13), F (13,13), Q (13,13) as numpy (row/col = math indices)."""
     xv, xp = _f64(xv)

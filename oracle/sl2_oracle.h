@@ -54,6 +54,14 @@ void orc_smoe_search(const uint8_t *image, int32_t width, int32_t height, const 
 void orc_find_best_patch(const uint8_t *image, int32_t width, int32_t height, int32_t boxsize,
                          const int32_t *region4, int32_t *ubest, int32_t *vbest, double *evbest);
 
+/* N2  monoslam.cpp:1447-1493 (one feature) + feature_init_info.cpp:95-172: Bayes re-weighting of K depth
+ * particles from their SMOE matches, normalise, prune below thr/K, re-normalise, mean / variance of
+ * lambda.  Returns survivors (0: all probabilities zero, the reference deletes the feature). */
+int32_t orc_particle_update(int32_t K, const double *h, const double *Sinv3, const double *detS,
+                            const double *lambda, const int32_t *z_uv, const uint8_t *found,
+                            double prune_probability_threshold, double *prob, uint8_t *keep,
+                            double *cumulative, double *mean_var);
+
 /* A5  motion_model.cpp:84-217 ; F,Q 13x13 col-major */
 void orc_motion(const double *xv, const double *u, double delta_t, double *fv, double *F,
                 double *Q);

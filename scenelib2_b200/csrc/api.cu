@@ -541,6 +541,73 @@ int sl2_smoe_search(sl2_ctx *c, int32_t s, int32_t slot, int32_t feat_index, int
                        nullptr, 1);
 }
 
+int sl2_measure_particles(sl2_ctx *c, int32_t s, int32_t slot, int32_t feat_index, int32_t K,
+                          const double *h, const double *Sinv3, const double *detS, const double *lambda,
+                          double prune_probability_threshold, double *prob, int32_t *z_uv, uint8_t *found,
+                          uint8_t *keep, double *cumulative, double *mean_var) {
+  if (bad_stream(c, s) || bad_slot(c, slot) || K < 0 || (K && (!h || !Sinv3 || !detS || !lambda || !prob)))
+    return fail(c, SL2_ERR_ARG, "sl2_measure_particles: bad argument");
+  if (K == 0) return 0;
+  int nf = 0;
+  int rc = device_nfeat(c, s, &nf);
+  if (rc) return rc;
+  if (feat_index < 0 || feat_index >= nf)
+    return fail(c, SL2_ERR_ARG, "sl2_measure_particles: feature index out of range");
+  // staging: h(2K) Sinv3(3K) detS(K) lambda(K) prob(K) | cum(K) mean_var(2) | feat(K) uv(2K) left(1+pad) |
+  //          found(K) keep(K)
+  const size_t n = (size_t)K;
+  const size_t o_h = 0, o_p = o_h + 16 * n, o_d = o_p + 24 * n, o_l = o_d + 8 * n, o_pr = o_l + 8 * n,
+               o_cu = o_pr + 8 * n, o_mv = o_cu + 8 * n, o_f = o_mv + 16, o_uv = o_f + 4 * n,
+               o_left = o_uv + 8 * n, o_fd = o_left + 8, o_kp = o_fd + n, total = o_kp + n + 64;
+  rc = stage_reserve(c, total);
+  if (rc) return rc;
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  uint8_t *hp = c->stg_host;
+  memcpy(hp + o_h, h, 16 * n);
+  memcpy(hp + o_p, Sinv3, 24 * n);
+  memcpy(hp + o_d, detS, 8 * n);
+  memcpy(hp + o_l, lambda, 8 * n);
+  memcpy(hp + o_pr, prob, 8 * n);
+  int *hf = reinterpret_cast<int *>(hp + o_f);
+  for (int i = 0; i < K; ++i) hf[i] = feat_index;
+  CU_TRY(c, cudaMemcpyAsync(c->stg_dev, hp, o_uv, cudaMemcpyHostToDevice, c->stream));
+  // measure_feature_with_multiple_priors (monoslam.cpp:1408-1438): ellipses (SInv_k, h_k), one template
+  SearchLaunch L = {};
+  L.job_centre = reinterpret_cast<const double *>(c->stg_dev + o_h);
+  L.job_puinv = reinterpret_cast<const double *>(c->stg_dev + o_p);
+  L.job_feat = reinterpret_cast<const int *>(c->stg_dev + o_f);
+  L.jobs_per_stream = K;
+  L.stream_lo = s;
+  L.stream_cnt = 1;
+  L.slot = slot;
+  L.out_uv = reinterpret_cast<int *>(c->stg_dev + o_uv);
+  L.out_found = c->stg_dev + o_fd;
+  L.scatter_to_features = 0;
+  L.smoe_mode = 1;
+  CU_TRY(c, sl2_launch_search(c->d, c->tmap, L, c->stream));
+  CU_TRY(c, sl2_launch_particles(K, reinterpret_cast<const double *>(c->stg_dev + o_h),
+                                 reinterpret_cast<const double *>(c->stg_dev + o_p),
+                                 reinterpret_cast<const double *>(c->stg_dev + o_d),
+                                 reinterpret_cast<const double *>(c->stg_dev + o_l),
+                                 reinterpret_cast<const int *>(c->stg_dev + o_uv), c->stg_dev + o_fd,
+                                 prune_probability_threshold, reinterpret_cast<double *>(c->stg_dev + o_pr),
+                                 c->stg_dev + o_kp, reinterpret_cast<double *>(c->stg_dev + o_cu),
+                                 reinterpret_cast<double *>(c->stg_dev + o_mv),
+                                 reinterpret_cast<int *>(c->stg_dev + o_left), c->stream));
+  c->launches += 2;
+  CU_TRY(c, cudaMemcpyAsync(hp + o_pr, c->stg_dev + o_pr, total - 64 - o_pr, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  memcpy(prob, hp + o_pr, 8 * n);
+  if (cumulative) memcpy(cumulative, hp + o_cu, 8 * n);
+  if (mean_var) memcpy(mean_var, hp + o_mv, 16);
+  if (z_uv) memcpy(z_uv, hp + o_uv, 8 * n);
+  if (found) memcpy(found, hp + o_fd, n);
+  if (keep) memcpy(keep, hp + o_kp, n);
+  int left = 0;
+  memcpy(&left, hp + o_left, sizeof(int));
+  return left;
+}
+
 int sl2_score_map(sl2_ctx *c, int32_t s, int32_t slot, int32_t feat, const double *centre,
                   const double *PuInv3, int32_t *box6, double *corr, double *sd_image,
                   uint8_t *inside, size_t cap) {

@@ -99,5 +99,9 @@ cudaError_t sl2_launch_cull(const Sl2Dev &d, int stream_lo, int stream_cnt, int 
 size_t sl2_update_smem_bytes(const Sl2Dev &d);
 cudaError_t sl2_configure_search(const Sl2Dev &d);  // per context: dynamic smem opt-in
 cudaError_t sl2_configure_update(const Sl2Dev &d);
+cudaError_t sl2_launch_particles(int K, const double *h, const double *sinv3, const double *detS,
+                                 const double *lambda, const int *z_uv, const uint8_t *found,
+                                 double prune_threshold, double *prob, uint8_t *keep, double *cumulative,
+                                 double *mean_var, int *left_out, cudaStream_t st);
 cudaError_t sl2_launch_detect(const Sl2Dev &d, int stream, int slot, int n, const int *regions_dev,
                               int *out_uv_dev, double *out_ev_dev, cudaStream_t st);

@@ -161,3 +161,48 @@ def test_odd_frame_size_pitch_padding(oracle):
     for i, reg in enumerate(([0, 0, 150, 101], [100, 50, 150, 101])):
         assert (u[i], v[i], ev[i]) == oracle.find_best_patch(img, B, reg)
     ctx.close()
+
+
+def test_particle_measurement_and_reweighting_matches_oracle(oracle):
+    """N2: sl2_measure_particles = measure_feature_with_multiple_priors (monoslam.cpp:1408-1438) + the
+    particle branch of update_partially_initialised_feature_probabilities (monoslam.cpp:1447-1493,
+    feature_init_info.cpp:95-172).  Match positions / flags / surviving set bit-exact against the oracle
+    (reference-pinned SMOE search), probabilities within 1e-13 (device exp is not glibc's)."""
+    k = np.load(os.path.join(G, "a11_ref_kat.npz"))
+    img, patch = k["image"], k["patch"]
+    ctx = ctx_for_image(img, patch[None], radius=20)
+    rng = np.random.default_rng(21)
+    # where the template really is: a successful match of the reference's own golden run
+    hit = int(np.flatnonzero(k["res_flag"])[0])
+    cu, cv = [float(k["res_u"][hit])], [float(k["res_v"][hit])]
+    for K, spread in ((40, 6.0), (100, 25.0), (1, 0.5)):
+        h = np.column_stack([cu[0] + rng.normal(0, spread, K), cv[0] + rng.normal(0, spread, K)])
+        pu = random_puinv(rng, K, 4, 12, iso_fraction=0.3)
+        det = 1.0 / (pu[:, 0] * pu[:, 2] - pu[:, 1] ** 2)          # det S = 1 / det Sinv
+        lam = np.linspace(0.5, 4.5, K)
+        p0 = rng.uniform(0.2, 1.0, K)
+        p0 /= p0.sum()
+        left, prob, z, found, keep, cum, mv = ctx.measure_particles(0, 0, 0, h, pu, det, lam, 0.05, p0)
+        ou, ov, of, _ = oracle.smoe_search(img, patch, pu, h)
+        oleft, oprob, okeep, ocum, omv = oracle.particle_update(h, pu, det, lam, np.column_stack([ou, ov]),
+                                                                of, 0.05, p0)
+        assert (found == of).all()
+        assert (z[of > 0, 0] == ou[of > 0]).all() and (z[of > 0, 1] == ov[of > 0]).all()
+        assert left == oleft and (keep == okeep).all()
+        np.testing.assert_allclose(prob, oprob, rtol=1e-13, atol=1e-300)
+        np.testing.assert_allclose(cum, ocum, rtol=1e-13, atol=1e-300)
+        np.testing.assert_allclose(mv, omv, rtol=1e-12, atol=1e-15)
+        if left:
+            assert abs(prob[keep > 0].sum() - 1.0) < 1e-12 and (prob[keep == 0] * 0 == 0).all()
+    # every match fails (ellipses on a flat, textureless area): the reference deletes the feature
+    flat = img.copy()
+    flat[:] = 127
+    ctx.set_frame(0, 0, flat)
+    K = 8
+    h = np.column_stack([rng.uniform(40, 120, K), rng.uniform(40, 80, K)])
+    pu = random_puinv(rng, K, 4, 8, iso_fraction=1.0)
+    det = 1.0 / (pu[:, 0] * pu[:, 2] - pu[:, 1] ** 2)
+    left, prob, z, found, keep, cum, mv = ctx.measure_particles(0, 0, 0, h, pu, det, np.ones(K), 0.05,
+                                                                np.full(K, 1.0 / K))
+    assert left == 0 and not found.any() and not keep.any() and (prob == 0).all()
+    ctx.close()

@@ -272,3 +272,38 @@ def test_score_equals_two_minus_two_rho_within_1e9(oracle):
                     rho = np.longdouble(n * s01 - s0 * s1) / np.sqrt(np.longdouble(v0) * np.longdouble(n * s11 - s1 * s1))
                     worst = max(worst, abs(float(np.longdouble(2) - 2 * rho) - corr[iu, iv]))
     assert 0 < worst < 1e-9, worst
+
+
+def test_particle_update_against_numpy(oracle):
+    """N2 (monoslam.cpp:1447-1493, feature_init_info.cpp:95-172): Bayes re-weighting, normalisation,
+    pruning below thr/K, re-normalisation, mean / variance of lambda — against a NumPy restatement."""
+    rng = np.random.default_rng(3)
+    for K in (1, 7, 100):
+        h = rng.uniform(50, 150, (K, 2))
+        a, b, c = rng.uniform(0.01, 0.05, K), rng.uniform(-0.005, 0.005, K), rng.uniform(0.01, 0.05, K)
+        Sinv3 = np.column_stack([a, b, c])
+        det = 1.0 / (a * c - b * b)
+        z = np.rint(h + rng.normal(0, 4, (K, 2))).astype(np.int32)
+        found = (rng.uniform(size=K) < 0.8).astype(np.uint8)
+        if K == 1:
+            found[:] = 1
+        lam = np.linspace(0.5, 4.5, K)
+        p0 = rng.uniform(0.1, 1, K)
+        p0 /= p0.sum()
+        left, prob, keep, cum, mv = oracle.particle_update(h, Sinv3, det, lam, z, found, 0.05, p0)
+        nu = z - h
+        q = a * nu[:, 0] ** 2 + 2 * b * nu[:, 0] * nu[:, 1] + c * nu[:, 1] ** 2
+        w = p0 * np.where(found > 0, np.exp(-0.5 * q) / np.sqrt(2 * np.pi * det), 0.0)
+        w /= w.sum()
+        k2 = w >= 0.05 / K
+        w2 = np.where(k2, w, 0.0)
+        w2 /= w2.sum()
+        assert left == int(k2.sum()) and (keep.astype(bool) == k2).all()
+        np.testing.assert_allclose(prob[k2], w2[k2], rtol=1e-12)
+        np.testing.assert_allclose(cum[k2], np.cumsum(w2[k2]), rtol=1e-12)
+        assert (cum[~k2] == 0).all()
+        mean = (w2 * lam).sum()
+        np.testing.assert_allclose(mv, [mean, (w2 * lam * lam).sum() - mean * mean], rtol=1e-10, atol=1e-14)
+    # all matches failed -> 0 survivors, probabilities zero (the reference deletes the feature)
+    left, prob, keep, cum, mv = oracle.particle_update(h, Sinv3, det, lam, z, np.zeros(K, np.uint8), 0.05, p0)
+    assert left == 0 and not keep.any() and (prob == 0).all()

@@ -25,6 +25,10 @@ u, v, f, b = ctx.patch_search(0, 0, np.arange(n, dtype=np.int32), sc.pix + rng.u
                               random_puinv(rng, n, 5, 30, 0.3))
 ctx.score_map(0, 0, 2, sc.pix[2].astype(float), [0.02, 0.001, 0.03])
 ctx.smoe_search(0, 0, 1, random_puinv(rng, 4, 5, 12, 0.5), np.tile(sc.pix[1].astype(float), (4, 1)))
+K = 12
+pu = random_puinv(rng, K, 4, 10, 0.5)
+ctx.measure_particles(0, 0, 1, np.tile(sc.pix[1].astype(float), (K, 1)) + rng.normal(0, 3, (K, 2)), pu,
+                      1.0 / (pu[:, 0] * pu[:, 2] - pu[:, 1] ** 2), np.linspace(0.5, 4.5, K), 0.05, np.full(K, 1.0 / K))
 ctx.delete_feature(1, 5)
 ctx.ekf_predict(0); ctx.predict_measurements(0); ctx.make_measurements(0, 0); ctx.ekf_update_measured(0)
 sc3 = synth.make_scene("C3", n_frames=1, n_features=9)
