@@ -284,3 +284,39 @@ def test_staggered_stream_groups_match_serial_order():
         assert all((f1[k] == f2[k]).all() for k in ("z", "flags", "attempted", "successful"))
     for c in ctxs:
         c.close()
+
+
+def test_c1_trajectory_1000_steps_matches_oracle_fixture():
+    """The CUDA path over the 1 000-step C1 trajectory of tests/golden/c1_trajectory_1000.npz (generated by
+    the CPU oracle): selection ranks, found flags and match positions of EVERY step hash to the oracle's
+    value (bit-exact integer results over 10 000 measurements); camera state within the north-star
+    tolerance at every 100th step."""
+    import hashlib
+    import sys
+    sys.path.insert(0, G)
+    import make_c1_trajectory as gen
+    k = np.load(os.path.join(G, "c1_trajectory_1000.npz"))
+    kp = np.load(os.path.join(G, "known_patches.npy"))
+    sc = synth.make_scene("C1", n_frames=gen.RING, known_patches=kp)
+    ctx = ctx_from_scenes([sc], frame_slots=gen.RING)
+    for t in range(gen.RING):
+        ctx.set_frames(t, sc.frames[t:t + 1])
+    hz = hashlib.sha256()
+    xs = []
+    for t in range(gen.STEPS):
+        ctx.step(gen.frame_index(t))
+        f = ctx.features(0)
+        hz.update(np.ascontiguousarray(f["select_rank"], np.int32).tobytes())
+        hz.update(np.ascontiguousarray(f["flags"], np.uint8).tobytes())
+        ok = (f["flags"] & 2) > 0
+        hz.update(np.ascontiguousarray(f["z"][ok], np.float64).tobytes())
+        if (t + 1) % gen.EVERY == 0:
+            x, P = ctx.get_state(0)
+            xs.append((x[:13].copy(), np.diag(P)[:13].copy()))
+    f = ctx.features(0)
+    assert (np.frombuffer(hz.digest(), np.uint8) == k["integer_hash"]).all()
+    assert (f["attempted"] == k["attempted"]).all() and (f["successful"] == k["successful"]).all()
+    for i, (xv, pd) in enumerate(xs):
+        np.testing.assert_allclose(xv, k["xv"][i], rtol=RTOL_NORTH_STAR, atol=1e-9)
+        np.testing.assert_allclose(pd, k["Pxx_diag"][i], rtol=RTOL_NORTH_STAR, atol=1e-15)
+    ctx.close()

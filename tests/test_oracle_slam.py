@@ -86,3 +86,18 @@ def test_bad_features_are_deleted(oracle):
     assert s.num_features == 11 and s.n == n0 - 3            # monoslam.cpp:644-660: >=10 attempts, <50 %
     x, P = s.get_state()
     assert P.shape == (n0 - 3, n0 - 3) and np.isfinite(P).all()
+
+
+def test_c1_trajectory_1000_steps_matches_fixture(oracle):
+    """1 000 GoOneStep calls on C1; integer results (selection ranks, flags, match
+    positions of every step) by hash, camera state / covariance at every 100th step numerically."""
+    import sys
+    sys.path.insert(0, G)
+    import make_c1_trajectory as gen
+    k = np.load(os.path.join(G, "c1_trajectory_1000.npz"))
+    out = gen.run(oracle)
+    assert (out["integer_hash"] == k["integer_hash"]).all()
+    assert (out["nfeat"] == k["nfeat"]).all()
+    assert (out["attempted"] == k["attempted"]).all() and (out["successful"] == k["successful"]).all()
+    for name in ("xv", "Pxx_diag", "x_final", "P_diag_final"):
+        np.testing.assert_allclose(out[name], k[name], rtol=1e-9, atol=1e-15)
