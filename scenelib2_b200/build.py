@@ -41,10 +41,10 @@ def build_host():
     host = os.path.join(HERE, "host")
     so = os.path.join(host, "libscenelib2_b200_host.so")
     exe = os.path.join(host, "sl2_headless")
-    subprocess.check_call([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so,
+    subprocess.check_call([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", so,
                            os.path.join(host, "scenelib2_b200.cpp"), "-L" + HERE, "-lsl2b200",
                            "-Wl,-rpath,$ORIGIN/.."])
-    subprocess.check_call([cxx, "-O2", "-std=c++17", "-o", exe, os.path.join(host, "sl2_headless.cpp"),
+    subprocess.check_call([cxx, "-O2", "-std=c++17", "-pthread", "-o", exe, os.path.join(host, "sl2_headless.cpp"),
                            "-L" + host, "-lscenelib2_b200_host", "-L" + HERE, "-lsl2b200",
                            "-Wl,-rpath,$ORIGIN:$ORIGIN/.."])
     return exe

@@ -3,9 +3,12 @@
 // step is a call into libsl2b200.so.  No CPU fallback: a failing device call throws.
 #include "scenelib2_b200.h"
 
+#include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <filesystem>
 #include <fstream>
 #include <iostream>
 #include <map>
@@ -48,13 +51,15 @@ double num(const std::map<std::string, std::string> &kv, const std::string &k, d
   return it == kv.end() ? def : std::atof(it->second.c_str());
 }
 
-// binary PGM (P5) reader standing in for cv::imread(identifier, 0) (feature.cpp:119)
-cv::Mat read_pgm(const std::string &path) {
+// PGM decoder standing in for cv::imread(path, 0) (feature.cpp:119, filegrabber.cpp:106-109): binary P5
+// and ASCII P2, maxval <= 255, '#' comments in the header.  Returns an empty Mat for anything else
+// (cv::imread returns an empty Mat when it cannot decode).
+cv::Mat decode_pgm(const std::string &path) {
   std::ifstream f(path, std::ios::binary);
-  if (!f) throw std::runtime_error("cannot open patch " + path);
+  if (!f) return cv::Mat();
   std::string magic;
   f >> magic;
-  if (magic != "P5") throw std::runtime_error("not a binary PGM: " + path);
+  if (magic != "P5" && magic != "P2") return cv::Mat();
   int vals[3], got = 0;
   while (got < 3) {
     f >> std::ws;
@@ -63,11 +68,28 @@ cv::Mat read_pgm(const std::string &path) {
       std::getline(f, c);
       continue;
     }
-    f >> vals[got++];
+    if (!(f >> vals[got++])) return cv::Mat();
   }
-  f.get();
+  if (vals[0] <= 0 || vals[1] <= 0 || vals[2] <= 0 || vals[2] > 255) return cv::Mat();
   cv::Mat m(vals[1], vals[0], CV_8UC1);
-  f.read(reinterpret_cast<char *>(m.data), (std::streamsize)vals[0] * vals[1]);
+  const size_t count = (size_t)vals[0] * vals[1];
+  if (magic == "P5") {
+    f.get();  // the single whitespace byte after maxval
+    f.read(reinterpret_cast<char *>(m.data), (std::streamsize)count);
+    if ((size_t)f.gcount() != count) return cv::Mat();
+  } else {
+    for (size_t i = 0; i < count; ++i) {
+      int v;
+      if (!(f >> v)) return cv::Mat();
+      m.data[i] = (unsigned char)v;
+    }
+  }
+  return m;
+}
+
+cv::Mat read_pgm(const std::string &path) {  // known-feature templates: a missing patch is an error
+  cv::Mat m = decode_pgm(path);
+  if (m.empty()) throw std::runtime_error("cannot read PGM patch " + path);
   return m;
 }
 
@@ -471,6 +493,85 @@ bool MonoSLAM::GoOneStep(cv::Mat frame, bool save_trajectory, bool enable_mappin
 void MonoSLAM::print_robot_state() {  // monoslam.cpp:1543-1549
   std::cout << "Robot state:" << std::endl;
   for (int i = 0; i < 13; ++i) std::cout << xv_(i) << (i == 12 ? "\n" : " ");
+}
+
+// ---- frame ingestion (framegrabber/framegrabber.cpp:40-105, filegrabber.cpp:40-110) -----------------
+FileGrabber::FileGrabber() {}
+
+FileGrabber::~FileGrabber() {
+  initialised_ = false;  // the reference never stops its thread; here the loop ends and is joined
+  if (fg_thread_.joinable()) fg_thread_.join();
+  files_vec_.clear();
+}
+
+void FileGrabber::Init(const std::string &path, FrameGrabber *frame_grabber) {
+  ProcessFiles(path);
+  std::sort(files_vec_.begin(), files_vec_.end());
+  frame_grabber_ = frame_grabber;
+  initialised_ = true;
+  fg_thread_ = std::thread(std::ref(*this));
+}
+
+void FileGrabber::ProcessFiles(const std::string &directory) {  // filegrabber.cpp:63-83, recursive
+  namespace fs = std::filesystem;
+  if (!fs::exists(directory)) throw std::runtime_error("provided directory doesn't exist!");
+  for (const auto &entry : fs::directory_iterator(directory)) {
+    if (entry.is_directory()) ProcessFiles(entry.path().string());
+    else files_vec_.push_back(entry.path().string());
+  }
+}
+
+void FileGrabber::operator()() {  // filegrabber.cpp:85-104
+  while (initialised_) {
+    if (!frame_grabber_->IsFrameBufferFull() && files_vec_.size() > (size_t)frame_id_) {
+      Frame frame;
+      frame.frame_id = frame_id_;
+      frame.data = GetImageFile(files_vec_.at(frame_id_));
+      ++frame_id_;
+      frame_grabber_->SetFrame(frame);
+    } else {
+      std::this_thread::sleep_for(std::chrono::milliseconds(1));
+    }
+  }
+}
+
+cv::Mat FileGrabber::GetImageFile(const std::string &file_full_path) { return decode_pgm(file_full_path); }
+
+FrameGrabber::FrameGrabber() {}
+
+FrameGrabber::~FrameGrabber() {
+  delete file_grabber_;
+  while (!frame_buffer_.empty()) frame_buffer_.pop();
+}
+
+void FrameGrabber::Init(const std::string &dev, const bool mode) {  // framegrabber.cpp:59-69
+  if (mode) throw std::runtime_error("FrameGrabber: the USB camera grabber is not built (file mode only)");
+  file_grabber_ = new FileGrabber;
+  file_grabber_->Init(dev, this);
+}
+
+bool FrameGrabber::GetFrame(int /*frame_id*/, Frame *frame) {  // framegrabber.cpp:71-84
+  std::lock_guard<std::mutex> lock(fg_mutex_);
+  if (frame_buffer_.size() < 1) return false;
+  *frame = frame_buffer_.front();
+  frame_buffer_.pop();
+  ++handed_out_;
+  return true;
+}
+
+void FrameGrabber::SetFrame(const Frame &frame) {
+  std::lock_guard<std::mutex> lock(fg_mutex_);
+  frame_buffer_.push(frame);
+}
+
+bool FrameGrabber::IsFrameBufferFull() {  // framegrabber.cpp:94-103
+  std::lock_guard<std::mutex> lock(fg_mutex_);
+  return !(frame_buffer_.size() < 50);
+}
+
+bool FrameGrabber::Exhausted() {
+  std::lock_guard<std::mutex> lock(fg_mutex_);
+  return file_grabber_ && (size_t)handed_out_ >= file_grabber_->NumberOfFiles();
 }
 
 }  // namespace SceneLib2

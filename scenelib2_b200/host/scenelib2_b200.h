@@ -6,9 +6,14 @@
 // runs in the sm_100a kernels.  Host mirrors (xv_, Pxx_, per-feature y_/Pxy_/Pyy_/
 // matrix_block_list_, h_/z_/S_/flags/counters) are refreshed before GoOneStep / the Kalman calls
 // return, because the reference's GUI reads them on every redraw (graphic/graphictool.cpp:130-168).
-// Out of scope here: GUI, frame grabbers, feature initialisation, particles.
+// Also here: the file-based FrameGrabber / FileGrabber (framegrabber/*.h).
+// Out of scope: GUI, USB camera grabber, feature initialisation, particle prediction.
 #pragma once
+#include <atomic>
+#include <mutex>
+#include <queue>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "sl2_compat.h"
@@ -55,6 +60,54 @@ class Kalman {  // kalman.h:44-53
  public:
   void KalmanFilterPredict(MonoSLAM *monoslam, Eigen::Vector3d &u);
   void KalmanFilterUpdate(MonoSLAM *monoslam);
+};
+
+// ---- frame ingestion (framegrabber/framegrabber.h:47-77, filegrabber.h:50-72) ------------------
+// The producer side of the main loop (examples/MonoSlamSceneLib1.cpp:132-142): a reader thread fills a
+// bounded queue (50 frames, framegrabber.cpp:94-103) from the sorted files of a directory tree.
+// cv::imread(path, 0) is replaced by a PGM decoder (P5 binary and P2 ASCII, 8-bit); a file that is not
+// a PGM yields an empty Mat like a failed imread.  The USB camera grabber is not built.
+struct Frame {
+  int frame_id;
+  cv::Mat data;
+};
+
+class FrameGrabber;
+
+class FileGrabber {
+ public:
+  FileGrabber();
+  ~FileGrabber();
+  void Init(const std::string &path, FrameGrabber *frame_grabber);  // throws std::runtime_error
+  void operator()();                                                // reader loop (own thread)
+  cv::Mat GetImageFile(const std::string &file_full_path);
+  size_t NumberOfFiles() const { return files_vec_.size(); }
+
+ private:
+  void ProcessFiles(const std::string &directory);
+  std::vector<std::string> files_vec_;
+  FrameGrabber *frame_grabber_ = nullptr;
+  std::atomic<bool> initialised_{false};
+  int frame_id_ = 0;
+  std::thread fg_thread_;
+};
+
+class FrameGrabber {
+ public:
+  FrameGrabber();
+  ~FrameGrabber();
+  void Init(const std::string &dev, const bool mode);  // mode == false: directory of image files
+  bool GetFrame(int frame_id, Frame *frame);            // false while the queue is empty
+  void SetFrame(const Frame &frame);
+  bool IsFrameBufferFull();
+  // not in the reference: true once every file has been handed out (lets a batch driver stop)
+  bool Exhausted();
+
+ private:
+  std::queue<Frame> frame_buffer_;
+  std::mutex fg_mutex_;
+  FileGrabber *file_grabber_ = nullptr;
+  int handed_out_ = 0;
 };
 
 class MonoSLAM {  // monoslam.h:73-218 (hot-path subset)

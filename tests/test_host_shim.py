@@ -85,3 +85,98 @@ def test_headless_matches_oracle(tmp_path, oracle):
     assert (np.abs(Pg - Po) <= 1e-6 * d[:, None] * d[None, :] + 1e-18).all()
     assert np.allclose(xg, xo, rtol=1e-7, atol=1e-10)
     assert "measured 10" in r.stdout
+
+
+_GRABBER_DRIVER = r"""
+#include <chrono>
+#include <cstdio>
+#include <thread>
+#include "scenelib2_b200.h"
+int main(int argc, char **argv) {
+  try {
+    SceneLib2::FrameGrabber g;
+    g.Init(argv[1], argc > 2);
+    SceneLib2::Frame f;
+    int id = 0;
+    while (!g.Exhausted()) {
+      if (!g.GetFrame(id, &f)) { std::this_thread::sleep_for(std::chrono::milliseconds(1)); continue; }
+      unsigned long long sum = 0;
+      for (int i = 0; i < f.data.rows * f.data.cols; ++i) sum = sum * 31 + f.data.data[i];
+      std::printf("%d %d %d %llu\n", f.frame_id, f.data.cols, f.data.rows, sum);
+      ++id;
+    }
+  } catch (const std::exception &e) { std::fprintf(stderr, "error: %s\n", e.what()); return 1; }
+  return 0;
+}
+"""
+
+
+def _checksum(a):
+    s = 0
+    for v in a.reshape(-1).tolist():
+        s = (s * 31 + v) & 0xFFFFFFFFFFFFFFFF
+    return s
+
+
+def test_frame_grabber_reads_sorted_pgm_files(tmp_path):
+    """N4: FrameGrabber / FileGrabber (framegrabber.cpp:59-103, filegrabber.cpp:54-110): recursive sorted file
+    list, reader thread + bounded queue, frames in order; P5 and P2 PGMs with header comments decode, a
+    non-image yields an empty frame, a missing directory throws, the USB mode is refused."""
+    import __graft_entry__ as g
+    g.build()
+    rng = np.random.default_rng(4)
+    d = tmp_path / "seq"
+    (d / "sub").mkdir(parents=True)
+    frames = [rng.integers(0, 256, (12, 20), dtype=np.uint8) for _ in range(60)]   # > queue bound of 50
+    expect = {}
+    for i, fr in enumerate(frames):
+        name = (d / "sub" / ("b%04d.pgm" % i)) if i % 7 == 3 else (d / ("a%04d.pgm" % i))
+        if i % 5 == 0:
+            body = b"P2\n# ascii frame\n20 12\n255\n" + b" ".join(b"%d" % v for v in fr.reshape(-1)) + b"\n"
+        else:
+            body = b"P5\n# comment line\n20 12\n255\n" + fr.tobytes()
+        name.write_bytes(body)
+        expect[str(name)] = fr
+    (d / "notes.txt").write_text("not an image")
+    expect[str(d / "notes.txt")] = np.zeros((0, 0), np.uint8)
+    src = tmp_path / "drv.cpp"
+    src.write_text(_GRABBER_DRIVER)
+    exe = tmp_path / "drv"
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-pthread", "-I" + HOST, "-o", str(exe), str(src),
+                           "-L" + HOST, "-lscenelib2_b200_host", "-L" + os.path.dirname(HOST), "-lsl2b200",
+                           "-Wl,-rpath," + HOST + ":" + os.path.dirname(HOST)])
+    r = subprocess.run([str(exe), str(d)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    rows = [ln.split() for ln in r.stdout.strip().splitlines()]
+    order = sorted(expect)                                     # std::sort of the full path names
+    assert [int(x[0]) for x in rows] == list(range(len(order)))
+    for row, path in zip(rows, order):
+        fr = expect[path]
+        assert (int(row[1]), int(row[2])) == (fr.shape[1] if fr.size else 0, fr.shape[0] if fr.size else 0)
+        assert int(row[3]) == _checksum(fr)
+    r = subprocess.run([str(exe), str(tmp_path / "nowhere")], capture_output=True, text=True)
+    assert r.returncode == 1 and "doesn't exist" in r.stderr   # filegrabber.cpp:81
+    r = subprocess.run([str(exe), str(d), "usb"], capture_output=True, text=True)
+    assert r.returncode == 1 and "USB" in r.stderr
+
+
+@pytest.mark.gpu
+def test_headless_directory_mode_equals_raw_mode(tmp_path):
+    """sl2_headless fed by the FrameGrabber from a directory of PGM frames == the raw-file mode."""
+    kp = np.load(os.path.join(G, "known_patches.npy"))
+    sc = synth.make_scene("C1", n_frames=6, known_patches=kp)
+    Pxx = np.diag([4e-4] * 3 + [2e-5] * 4 + [1e-3] * 3 + [1e-3] * 3)
+    _write_case(str(tmp_path), sc, Pxx)
+    d = tmp_path / "frames"
+    d.mkdir()
+    for t in range(6):
+        (d / ("rawoutput%04d.pgm" % t)).write_bytes(b"P5\n320 240\n255\n" + sc.frames[t].tobytes())
+    exe = os.path.join(HOST, "sl2_headless")
+    a, b = tmp_path / "a.txt", tmp_path / "b.txt"
+    r = subprocess.run([exe, str(tmp_path / "case.cfg"), str(tmp_path / "frames.raw"), "320", "240", "6",
+                        str(a)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r2 = subprocess.run([exe, str(tmp_path / "case.cfg"), str(d), str(b)], capture_output=True, text=True)
+    assert r2.returncode == 0, r2.stderr
+    assert r.stdout == r2.stdout
+    assert (np.loadtxt(str(a)) == np.loadtxt(str(b))).all()
