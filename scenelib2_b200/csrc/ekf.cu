@@ -547,10 +547,6 @@ constexpr int UPD_DS = 20;   // row stride of the diagonal-block scratch (confli
 constexpr int UPD_MS = 20;   // row stride of the multiplier table: 32 B (mod 128) => conflict-free A fragments
 constexpr int UPD_KC = 32;   // k-chunk of the Y^T Y tiles
 constexpr int UPD_YS = 68;   // padded row stride of a staged Y slab (doubles): conflict-free DMMA reads
-#ifndef SL2_UPD_SUPER_MIN
-#define SL2_UPD_SUPER_MIN 1000
-#endif
-constexpr int UPD_SUPER_MIN = SL2_UPD_SUPER_MIN;  // fewest rows of a block that get the tile update
 constexpr int UPD_GB = 4;    // 8-column groups per warp iteration in the panel update
 
 __host__ __device__ inline int upd_keven(int Nmax) { return (Nmax + 1) & ~1; }
@@ -962,79 +958,22 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) update_kernel(
     const int width = m + n + 1;
     const int PW = sm.panw;
     for (int j = tid; j < n; j += UPD_THREADS) sm.xacc[j] = 0.0;
-    // Super-panels: once a block of up to 64 rows is reached, its update by ALL finished rows is done
-    // as 64x64 tile products (tile_products: both operands staged through shared memory, finished
-    // rows are read once per super-panel instead of once per panel); the 16-row panels inside the
-    // block then only look back to the start of the block (kbase).  The first block is 64..112 rows,
-    // chosen so that the column range left of it splits into 64-wide tiles with little waste.
-    int sp_next = 64;
-    {
-      int best = -1;
-      for (int cand = 64; cand <= 112; cand += 16) {
-        int r = (width - cand) & 63;
-        if (r == 0) r = 64;
-        if (r > best) {
-          best = r;
-          sp_next = cand;
-        }
-      }
-    }
-    int kbase = 0;
     for (int i0 = 0; i0 < m; i0 += UPD_NB) {
       const int nbp = min(UPD_NB, m - i0);
-      if (i0 == sp_next) {
-        sp_next += 64;
-        const int R = min(64, m - i0);
-        kbase = 0;
-        if (R >= UPD_SUPER_MIN) {
-          kbase = i0;
-          const int wa = (warp & 3) * 16, wb = (warp >> 2) * 32;
-          tile_products(
-              sm.pan, G, ldg, i0, (width - i0 + 63) / 64, width, width,
-              [&](int t, int &colA, int &colB) {
-                colA = i0;
-                colB = i0 + 64 * t;
-              },
-              [&](int t, double (&acc)[2][4][2]) {
-                double2 old[2][4];
-#pragma unroll
-                for (int i = 0; i < 2; ++i)
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const int r = wa + i * 8 + lr, cc = i0 + 64 * t + wb + j * 8 + 2 * lc;
-                    const double *src = G + (size_t)(i0 + r) * ldg + cc;
-                    old[i][j] = make_double2(0.0, 0.0);
-                    if (r < R && cc + 1 < width) old[i][j] = *reinterpret_cast<const double2 *>(src);
-                    else if (r < R && cc < width) old[i][j].x = *src;
-                  }
-#pragma unroll
-                for (int i = 0; i < 2; ++i)
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const int r = wa + i * 8 + lr, cc = i0 + 64 * t + wb + j * 8 + 2 * lc;
-                    double *dst = G + (size_t)(i0 + r) * ldg + cc;
-                    const double v0 = old[i][j].x - acc[i][j][0], v1 = old[i][j].y - acc[i][j][1];
-                    if (r < R && cc + 1 < width) *reinterpret_cast<double2 *>(dst) = make_double2(v0, v1);
-                    else if (r < R && cc < width) *dst = v0;
-                  }
-              });
-          __syncthreads();
-        }
-      }
 #ifdef SL2_PHASE_STAMPS
       long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0, tq35 = 0;
 #endif
       PHQ(tq0 = clock64());
       if (tid == 0) s_next = 1;  // batch 0 is reserved for warp 0
       // multipliers, negated so that D = (-A) * B + C
-      for (int e = tid; e < (i0 - kbase) * UPD_NB; e += UPD_THREADS) {
+      for (int e = tid; e < i0 * UPD_NB; e += UPD_THREADS) {
         const int k = e / UPD_NB, r = e - k * UPD_NB;
-        sm.mult[k * UPD_MS + r] = (r < nbp) ? -G[(size_t)(kbase + k) * ldg + i0 + r] : 0.0;
+        sm.mult[k * UPD_MS + r] = (r < nbp) ? -G[(size_t)k * ldg + i0 + r] : 0.0;
       }
       __syncthreads();
       PHQ(tq1 = clock64());
       const int ngroups = (width - i0 + 7) >> 3;
-      const int nk = (i0 - kbase) >> 2;  // k-steps of 4 rows; a multiple of 16 rows so nk % 4 == 0
+      const int nk = i0 >> 2;  // k-steps of 4 rows; i0 is a multiple of 16 so nk % 4 == 0
       const int nbatch = (ngroups + UPD_GB - 1) / UPD_GB;
       // Batches of UPD_GB column groups are handed out dynamically.  Warp 0 takes batch 0 (it holds
       // the 16 diagonal columns), factors the diagonal block straight away while the other warps
@@ -1067,7 +1006,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) update_kernel(
         }
         double b[4][UPD_GB];
         auto loadb = [&](int step, double *dst) {
-          const double *gk = G + (size_t)(kbase + 4 * step + lc) * ldg;
+          const double *gk = G + (size_t)(4 * step + lc) * ldg;
 #pragma unroll
           for (int q = 0; q < UPD_GB; ++q) dst[q] = colb[q] >= 0 ? gk[colb[q]] : 0.0;
         };
