@@ -525,15 +525,15 @@ __global__ void __launch_bounds__(128) predict_kernel(const Sl2Dev d, int stream
 // ---------------------------------------------------------------------------------------------
 struct UpdSmem {
   // carved from dynamic shared memory; sizes depend on Nmax
-  double *wv;    // [mmax]  nu, later w = U^-T nu
+  double *wv;    // [mmax]  nu (copied into the last column of G)
   int *mfeat;    // [K]
   double *Rv;    // [K]
-  double *mult;  // [mmax][UPD_MS] (negated) multipliers of the current panel
+  double *mult;  // [mmax][UPD_MS] (negated) multipliers of the current panel; phases 1a/1b: H*P(:, 0:13)
   double *dg;    // [NB][UPD_DS] diagonal block of the current panel (factor scratch)
   double *Wm;    // [NB][UPD_WS]  W = U_pp^-T of the current panel
   double *xacc;  // [ld]  Y^T w accumulated panel by panel
   double *pan;   // phase 1: HxT / Hy (aliased); phase 2: panel buffer [NB][panw];
-                 // phase 4: Y slabs (2 stages) / tile T[64][65]
+                 // phase 4: Y slabs of tile_products (2 stages x 2 slabs)
   double *HxT;   // = pan          [16][hms]  Hx transposed, k-major, zero padded (cols 13..15, rows >= m)
   double *Hy;    // = pan + 16*hms [K][2][3]
   int panw, hms;
