@@ -8,7 +8,11 @@
 //                     /root/reference/scenelib2/feature_model.cpp:99-238
 // Every function cites the lines it follows.  Scalar expressions keep the reference's
 // left-to-right evaluation order; Eigen quaternion helpers follow Eigen3's generic
-// (non-vectorised) formulas.  PARITY UNPINNED (no reference goldens; Eigen absent).
+// (non-vectorised) formulas.
+// Pinning: every function here is checked against the reference's OWN source files compiled
+// unmodified against oracle/stubs_arith (tests/test_oracle_ref.py, _ref/libsl2refmodels.so): the
+// formulas are pinned (agreement < 1e-13, scalar Jacobians bit-exact); PARITY UNPINNED only for
+// Eigen's summation order inside matrix products (Eigen absent, no reference goldens).
 #pragma once
 #include "dense.hpp"
 

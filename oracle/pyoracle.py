@@ -87,6 +87,19 @@ def ref():
     return _ref
 
 
+_REFM = os.path.join(_HERE, "_ref", "libsl2refmodels.so")
+_refm = None
+
+
+def ref_models():
+    """The reference's own MotionModel / Camera / FullFeatureModel code compiled against the arithmetic
+    stand-in of oracle/stubs_arith (None when the prebuilt .so is absent)."""
+    global _refm
+    if _refm is None and os.path.exists(_REFM):
+        _refm = C.CDLL(_REFM)
+    return _refm
+
+
 def make_config(width=320, height=240, fku=195.0, fkv=195.0, u0=162.0, v0=125.0, kd1=9e-6, sd=1.0,
                 delta_t=0.033333333, n_select=10, boxsize=11, search_override=(0.0, 0.0, 0.0),
                 min_attempts=10, match_fraction=0.5):
@@ -219,20 +232,25 @@ def particle_update(h, Sinv3, detS, lam, z_uv, found, prune_threshold, prob):
     return left, prob, keep, cum, mv
 
 
-def motion(xv, dt, u=(0.0, 0.0, 0.0)):
+def motion(xv, dt, u=(0.0, 0.0, 0.0), use_ref=False):
     """A5.  -> fv (13), F (13,13), Q (13,13) as numpy (row/col = math indices)."""
     xv, xp = _f64(xv)
     uu, up = _f64(u)
     fv = np.zeros(13)
     F = np.zeros((13, 13), order="F")
     Q = np.zeros((13, 13), order="F")
-    lib().orc_motion(xp, up, C.c_double(dt), _p(fv, f64p), _p(F, f64p), _p(Q, f64p))
+    f = ref_models().ref_motion if use_ref else lib().orc_motion
+    f(xp, up, C.c_double(dt), _p(fv, f64p), _p(F, f64p), _p(Q, f64p))
     return fv, F, Q
 
 
-def dxvnorm_by_dxv(xv):
+def dxvnorm_by_dxv(xv, use_ref=False):
     xv, xp = _f64(xv)
     J = np.zeros((13, 13), order="F")
+    if use_ref:
+        xn = np.zeros(13)
+        ref_models().ref_dxvnorm_by_dxv(xp, _p(J, f64p), _p(xn, f64p))
+        return J, xn
     lib().orc_dxvnorm_by_dxv(xp, _p(J, f64p))
     return J
 
@@ -242,7 +260,7 @@ def _colmajor(a):
     return a, _p(a, f64p)
 
 
-def predict_feature(cam8, xv, y, Pxx, Pxy, Pyy):
+def predict_feature(cam8, xv, y, Pxx, Pxy, Pyy, use_ref=False):
     cam8, cp = _f64(cam8)
     xv, xp = _f64(xv)
     y, yp = _f64(y)
@@ -254,18 +272,19 @@ def predict_feature(cam8, xv, y, Pxx, Pxy, Pyy):
     dy = np.zeros((2, 3), order="F")
     R = np.zeros((2, 2), order="F")
     S = np.zeros((2, 2), order="F")
-    lib().orc_predict_feature(cp, xp, yp, a, b, c, _p(h, f64p), _p(dxv, f64p), _p(dy, f64p),
-                              _p(R, f64p), _p(S, f64p))
+    f = ref_models().ref_predict_feature if use_ref else lib().orc_predict_feature
+    f(cp, xp, yp, a, b, c, _p(h, f64p), _p(dxv, f64p), _p(dy, f64p), _p(R, f64p), _p(S, f64p))
     return h, dxv, dy, R, S
 
 
-def visibility_test(cam8, xp, y, xp_org, h):
+def visibility_test(cam8, xp, y, xp_org, h, use_ref=False):
     cam8, cp = _f64(cam8)
     xp, a = _f64(xp)
     y, b = _f64(y)
     xp_org, c = _f64(xp_org)
     h, d = _f64(h)
-    return lib().orc_visibility_test(cp, a, b, c, d)
+    f = ref_models().ref_visibility_test if use_ref else lib().orc_visibility_test
+    return f(cp, a, b, c, d)
 
 
 def kalman_update_dense(x, P, H, R, nu):

@@ -25,3 +25,11 @@ def refimpl(oracle):
     if r is None:
         pytest.skip("oracle/_ref/libsl2ref.so not built (reference tree absent)")
     return r
+
+
+@pytest.fixture(scope="session")
+def refmodels(oracle):
+    r = oracle.ref_models()
+    if r is None:
+        pytest.skip("oracle/_ref/libsl2refmodels.so not built (reference tree absent)")
+    return r
