@@ -212,7 +212,16 @@ def find_best_patch(image, boxsize, region, ubest=-1, vbest=-1):
     return u.value, v.value, ev.value
 
 
-def particle_update(h, Sinv3, detS, lam, z_uv, found, prune_threshold, prob):
+def particle_set_S_ref(S):
+    """The reference's own Particle::set_S (feature_init_info.cpp:55-63): S (2,2) -> Sinv (2,2), det S."""
+    S, sp = _colmajor(S)
+    Sinv = np.zeros((2, 2), order="F")
+    det = C.c_double(0.0)
+    ref_models().ref_particle_set_S(sp, _p(Sinv, f64p), C.byref(det))
+    return Sinv, det.value
+
+
+def particle_update(h, Sinv3, detS, lam, z_uv, found, prune_threshold, prob, use_ref=False):
     """N2.  -> survivors, prob (normalised), keep, cumulative, (mean, variance)."""
     h, hp = _f64(h)
     Sinv3, sp = _f64(Sinv3)
@@ -225,7 +234,7 @@ def particle_update(h, Sinv3, detS, lam, z_uv, found, prune_threshold, prob):
     keep = np.zeros(K, np.uint8)
     cum = np.zeros(K)
     mv = np.zeros(2)
-    f = lib().orc_particle_update
+    f = ref_models().ref_particle_update if use_ref else lib().orc_particle_update
     f.restype = C.c_int32
     left = f(K, hp, sp, dp, lp, _p(z_uv, i32p), _p(found, u8p), C.c_double(prune_threshold), _p(prob, f64p),
              _p(keep, u8p), _p(cum, f64p), _p(mv, f64p))
