@@ -13,6 +13,8 @@
 // PARITY UNPINNED at the last ulp versus a true Eigen3 build: Eigen's blocked/vectorised
 // accumulation order cannot be reproduced without Eigen, and the reference ships no
 // golden outputs.  The 1e-5 relative tolerance of the north star absorbs this.
+// Everything else -- formulas, control flow, operation order -- is pinned to the reference's own
+// sources compiled against oracle/stubs_arith (oracle/_ref/libsl2refmodels.so, tests/test_oracle_ref.py).
 #pragma once
 #include <cmath>
 #include <cstddef>

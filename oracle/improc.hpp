@@ -11,12 +11,13 @@
 //
 // Pinning: A1 and A11 are checked bit-for-bit against the reference's OWN source files
 // compiled unmodified into oracle/_ref/libsl2ref.so (storage-only cv::Mat / Eigen stubs, see
-// oracle/Makefile and tests/test_oracle_ref.py).  A2/A3 live in monoslam.cpp, which cannot be
-// compiled here (Eigen3 / OpenCV / Pangolin absent); A2 differs from A11 only in the four
-// documented places (centre rounding, sigma gating, no cache, single ellipse), so its search
-// loop is pinned through A11; the S -> PuInv step of A3 is PARITY UNPINNED (closed form
-// chosen per SURVEY.md §8(c): l11 = sqrt(s11), l21 = s21/l11, l22 = sqrt(s22 - l21^2),
-// inverse by forward substitution, Sinv = Linv^T * Linv).
+// oracle/Makefile and tests/test_oracle_ref.py).  A2/A3 live in monoslam.cpp; they are pinned
+// through the reference's own monoslam.cpp compiled against oracle/stubs_arith
+// (_ref/libsl2refmodels.so): identical match positions on every frame of the whole-step tests and
+// of the 1 000-step trajectory, and S -> PuInv against Particle::set_S (same operation sequence) to
+// 4e-15 (closed form per SURVEY.md 8(c): l11 = sqrt(s11), l21 = s21/l11, l22 = sqrt(s22 - l21^2),
+// inverse by forward substitution, Sinv = Linv^T * Linv; last-ulp differences to the stand-in's
+// Gauss-Jordan inverse / to real Eigen remain unpinned).
 #pragma once
 #include <cstdint>
 

@@ -381,6 +381,94 @@ class Slam:
         return out
 
 
+class RefSlam:
+    """The REFERENCE'S OWN MonoSLAM (monoslam.cpp, kalman.cpp, feature.cpp, models, improc compiled
+    unmodified against oracle/stubs_arith; see oracle/ref_slam_shim.cpp).  Same surface as Slam.
+    Built from a scene through the reference's own Init(cfg): the cfg (data/SceneLib2.cfg format) carries the
+    camera, parameters, initial state and the first four features; further features go through
+    AddNewKnownFeature; the total state / covariance are then set through fill_states / fill_covariances."""
+
+    def __init__(self, sc, workdir):
+        R = ref_models()
+        R.ref_slam_create.restype = C.c_void_p
+        os.makedirs(workdir, exist_ok=True)
+        assert sc.n_features >= 4, "MonoSLAM::Init always adds four known features"
+        paths = []
+        for i in range(sc.n_features):
+            pth = os.path.join(workdir, "patch%03d.pgm" % i)
+            with open(pth, "wb") as f:
+                f.write(b"P5\n%d %d\n255\n" % (sc.boxsize, sc.boxsize) + np.ascontiguousarray(sc.patches[i]).tobytes())
+            paths.append(pth)
+        lines = ["cam.width = %d;" % sc.width, "cam.height = %d;" % sc.height, "cam.fku = %d;" % sc.cam8[2],
+                 "cam.fkv = %d;" % sc.cam8[3], "cam.u0 = %d;" % sc.cam8[4], "cam.v0 = %d;" % sc.cam8[5],
+                 "cam.kd1 = %r;" % float(sc.cam8[6]), "cam.sd = %d;" % sc.cam8[7],
+                 "params.delta_t = %r;" % float(sc.delta_t),
+                 "params.number_of_features_to_select = %d;" % sc.n_select,
+                 "params.number_of_features_to_keep_visible = 12;"]
+        names = ["rw_x", "rw_y", "rw_z", "qwr_w", "qwr_x", "qwr_y", "qwr_z", "vw_x", "vw_y", "vw_z", "ww_x",
+                 "ww_y", "ww_z"]
+        for k, nm in enumerate(names):
+            lines.append("state.%s = %r;" % (nm, float(sc.x0[k])))
+        for i in range(4):
+            y = sc.x0[13 + 3 * i:16 + 3 * i]
+            lines += ["f%d.yi_%s = %r;" % (i + 1, c, float(v)) for c, v in zip("xyz", y)]
+            lines += ["f%d.xp_org_%d = %r;" % (i + 1, k, float(sc.xp_org[i, k])) for k in range(7)]
+            lines.append("f%d.identifier = %s;" % (i + 1, paths[i]))
+        cfg = os.path.join(workdir, "ref.cfg")
+        open(cfg, "w").write("\n".join(lines) + "\n")
+        self.R = R
+        self.h = C.c_void_p(R.ref_slam_create(cfg.encode()))
+        for i in range(4, sc.n_features):
+            y, a = _f64(sc.x0[13 + 3 * i:16 + 3 * i])
+            xp, b = _f64(sc.xp_org[i])
+            R.ref_slam_add_feature(self.h, a, b, paths[i].encode())
+        self.width, self.height = sc.width, sc.height
+        self.set_state(sc.x0, sc.P0)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.R.ref_slam_destroy(self.h)
+            self.h = None
+
+    def set_params(self, n_select=-1, min_attempts=-1, match_fraction=-1.0):
+        self.R.ref_slam_set_params(self.h, n_select, min_attempts, C.c_double(match_fraction))
+
+    @property
+    def num_features(self):
+        return self.R.ref_slam_num_features(self.h)
+
+    @property
+    def n(self):
+        return self.R.ref_slam_state_size(self.h)
+
+    def set_state(self, x, P):
+        x, a = _f64(x)
+        P, b = _colmajor(P)
+        self.R.ref_slam_set_state(self.h, a, b)
+
+    def get_state(self):
+        n = self.n
+        x = np.zeros(n)
+        P = np.zeros((n, n), order="F")
+        self.R.ref_slam_get_state(self.h, _p(x, f64p), _p(P, f64p))
+        return x, P
+
+    def step(self, frame):
+        frame, fp = _u8(frame)
+        self.R.ref_slam_step(self.h, fp, self.width, self.height)
+
+    def features(self):
+        nf = self.num_features
+        out = dict(label=np.zeros(nf, np.int32), h=np.zeros((nf, 2)), z=np.zeros((nf, 2)),
+                   S=np.zeros((nf, 4)), flags=np.zeros(nf, np.uint8),
+                   attempted=np.zeros(nf, np.int32), successful=np.zeros(nf, np.int32),
+                   select_rank=np.zeros(nf, np.int32))
+        self.R.ref_slam_get_features(self.h, _p(out["label"], i32p), _p(out["h"], f64p), _p(out["z"], f64p),
+                                     _p(out["S"], f64p), _p(out["flags"], u8p), _p(out["attempted"], i32p),
+                                     _p(out["successful"], i32p), _p(out["select_rank"], i32p))
+        return out
+
+
 def run_slams(slams, frames, nsteps, nthreads):
     """Step every Slam nsteps times over its own frame ring; returns wall seconds."""
     n = len(slams)

@@ -12,7 +12,12 @@
 //   feature state layout  /root/reference/scenelib2/feature.h:56-143, feature.cpp:108-149
 // "Faithful" storage: per-feature Pxy_ / Pyy_ / matrix_block_list_ blocks exactly like the
 // reference, dense P assembled and scattered around the update (4 gather/scatter passes per
-// frame).  PARITY UNPINNED at the last ulp (Eigen product order), see dense.hpp.
+// frame).
+// Pinning: tests/test_oracle_ref.py runs this step against the reference's OWN monoslam.cpp / kalman.cpp /
+// feature.cpp (+ models, improc) compiled unmodified against oracle/stubs_arith (_ref/libsl2refmodels.so,
+// ref_slam_shim.cpp): selection, match positions, counters, deletion identical frame by frame and over a
+// 1 000-step trajectory; state / covariance agree to ~1e-13.  PARITY UNPINNED only at the last ulp
+// (Eigen's own product order cannot be reproduced without Eigen), see dense.hpp.
 #pragma once
 #include <memory>
 

@@ -5,8 +5,10 @@ frames always differ by one step of the bounded random walk.
 
     python tests/golden/make_c1_trajectory.py
 
-The reference has no golden outputs; this fixture is produced by the oracle itself, so it pins
-the oracle against unintended change, it does not pin it to the reference.
+The reference has no golden outputs; this fixture is produced by the oracle.  It is reproduced by
+the reference's own sources compiled against oracle/stubs_arith (identical integer hash, state within 1e-11:
+tests/test_oracle_ref.py::test_c1_trajectory_1000_steps_reproduced_by_reference_source) and by the CUDA path
+(tests/test_gpu_step.py).
 """
 import hashlib
 import os

@@ -320,3 +320,33 @@ def test_c1_trajectory_1000_steps_matches_oracle_fixture():
         np.testing.assert_allclose(xv, k["xv"][i], rtol=RTOL_NORTH_STAR, atol=1e-9)
         np.testing.assert_allclose(pd, k["Pxx_diag"][i], rtol=RTOL_NORTH_STAR, atol=1e-15)
     ctx.close()
+
+
+def test_cuda_path_against_the_reference_source(oracle, refmodels, tmp_path):
+    """The CUDA path vs the REFERENCE'S OWN MonoSLAM code (monoslam.cpp / kalman.cpp / feature.cpp / models /
+    improc compiled unmodified against oracle/stubs_arith, prebuilt oracle/_ref/libsl2refmodels.so; see
+    oracle/ref_slam_shim.cpp): selection ranks, flags, match positions and counters identical on every frame,
+    state and covariance within the test tolerance (C1, and a 24-feature scene where every feature is measured)."""
+    kp = np.load(os.path.join(G, "known_patches.npy"))
+    cases = [(synth.make_scene("C1", n_frames=10, known_patches=kp), 10),
+             (synth.make_scene("C2", n_frames=4, n_features=24, override=False), 4)]
+    for ci, (sc, steps) in enumerate(cases):
+        ctx = ctx_from_scenes([sc], frame_slots=1)
+        ref = oracle.RefSlam(sc, str(tmp_path / ("case%d" % ci)))
+        for t in range(steps):
+            ctx.set_frames(0, sc.frames[t:t + 1])
+            ctx.step(0)
+            ref.step(sc.frames[t])
+            fg, fr = ctx.features(0), ref.features()
+            assert ctx.num_features(0) == ref.num_features
+            assert (fg["select_rank"] == fr["select_rank"]).all(), (ci, t)
+            assert ((fg["flags"] & 1) == (fr["flags"] & 1)).all(), (ci, t)
+            seen = fr["attempted"] > 0
+            assert ((fg["flags"] & 2)[seen] == (fr["flags"] & 2)[seen]).all(), (ci, t)
+            ok = (fr["flags"] & 2) > 0
+            assert (fg["z"][ok] == fr["z"][ok]).all(), (ci, t)
+            assert (fg["attempted"] == fr["attempted"]).all() and (fg["successful"] == fr["successful"]).all()
+            xg, Pg = ctx.get_state(0)
+            xr, Pr = ref.get_state()
+            assert_state_close(xg, Pg, xr, Pr)
+        ctx.close()

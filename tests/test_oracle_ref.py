@@ -195,3 +195,102 @@ def test_sinv_and_particles_match_reference_source(oracle, refmodels):
     o = oracle.particle_update(h, Sinv3, det, lam, z, np.zeros(K, np.uint8), 0.05, p0)
     r = oracle.particle_update(h, Sinv3, det, lam, z, np.zeros(K, np.uint8), 0.05, p0, use_ref=True)
     assert o[0] == r[0] == 0 and (o[1] == r[1]).all()
+
+
+# ---- the whole tracking step: the reference's OWN monoslam.cpp / kalman.cpp / feature.cpp (+ models, improc)
+# compiled unmodified against oracle/stubs_arith and driven through MonoSLAM::Init / AddNewKnownFeature /
+# fill_* / GoOneStep (oracle/ref_slam_shim.cpp), vs the oracle.  Integer results must be identical; state and
+# covariance agree up to summation order (the stand-in matrix class is not Eigen).
+
+def _compare_step(r, o, t, tol):
+    fr, fo = r.features(), o.features()
+    assert r.num_features == o.num_features and r.n == o.n
+    assert (fr["label"] == fo["label"]).all()
+    assert (fr["select_rank"] == fo["select_rank"]).all(), t
+    assert ((fr["flags"] & 1) == (fo["flags"] & 1)).all(), t
+    seen = fo["attempted"] > 0      # the reference leaves the success flag uninitialised until first measured
+    assert ((fr["flags"] & 2)[seen] == (fo["flags"] & 2)[seen]).all(), t
+    ok = (fo["flags"] & 2) > 0
+    assert (fr["z"][ok] == fo["z"][ok]).all(), t                       # bit-exact match positions
+    assert (fr["attempted"] == fo["attempted"]).all() and (fr["successful"] == fo["successful"]).all()
+    sel = fo["select_rank"] >= 0
+    np.testing.assert_allclose(fr["h"][sel], fo["h"][sel], rtol=tol, atol=tol)
+    np.testing.assert_allclose(fr["S"][sel], fo["S"][sel], rtol=tol, atol=tol)
+    xr, Pr = r.get_state()
+    xo, Po = o.get_state()
+    d = np.sqrt(np.abs(np.diag(Po))) + 1e-300
+    assert np.abs(xr - xo).max() <= tol * max(1.0, np.abs(xo).max())
+    assert (np.abs(Pr - Po) <= tol * d[:, None] * d[None, :]).all()
+    assert np.abs(Pr - Pr.T).max() == 0.0
+
+
+def test_whole_step_matches_reference_source(oracle, refmodels, tmp_path):
+    from scenelib2_b200 import synth
+    from test_oracle_slam import make_oracle_slam
+    kp = np.load(os.path.join(G, "known_patches.npy"))
+    # C1: 20 features, 10 selected per frame by trace(S), ellipses from the EKF's own S_i
+    sc = synth.make_scene("C1", n_frames=12, known_patches=kp)
+    r, o = oracle.RefSlam(sc, str(tmp_path / "c1")), make_oracle_slam(oracle, sc)
+    xr, Pr = r.get_state()
+    xo, Po = o.get_state()
+    assert (xr == xo).all() and (Pr == Po).all()          # Init + AddNewKnownFeature + fill_* round trip
+    for t in range(12):
+        r.step(sc.frames[t])
+        o.step(sc.frames[t])
+        _compare_step(r, o, t, 1e-12)
+    # C2-like without the benchmark's ellipse override: every feature selected (m = 2N), bigger update
+    sc = synth.make_scene("C2", n_frames=4, n_features=24, override=False)
+    r, o = oracle.RefSlam(sc, str(tmp_path / "c2")), make_oracle_slam(oracle, sc)
+    for t in range(4):
+        r.step(sc.frames[t])
+        o.step(sc.frames[t])
+        _compare_step(r, o, t, 1e-11)
+    assert (o.features()["select_rank"] >= 0).sum() == 24
+
+
+def test_bad_feature_deletion_matches_reference_source(oracle, refmodels, tmp_path):
+    """delete_bad_features / delete_feature (monoslam.cpp:644-703, 770-812): a template that never matches is
+    culled after 10 attempts; the compaction of state, covariance blocks and lists is the reference's own."""
+    from scenelib2_b200 import synth
+    from test_oracle_slam import make_oracle_slam
+    sc = synth.make_scene("C2", n_frames=2, n_features=12, override=False)
+    bad = sc.patches.copy()
+    bad[3] = np.random.default_rng(0).integers(0, 256, bad[3].shape, dtype=np.uint8)
+    sc.patches = bad
+    r, o = oracle.RefSlam(sc, str(tmp_path)), make_oracle_slam(oracle, sc)
+    n0 = o.n
+    for t in range(12):
+        r.step(sc.frames[t % 2])
+        o.step(sc.frames[t % 2])
+        _compare_step(r, o, t, 1e-11)
+    assert r.num_features == 11 and r.n == n0 - 3
+
+
+def test_c1_trajectory_1000_steps_reproduced_by_reference_source(oracle, refmodels, tmp_path):
+    """The fixture tests/golden/c1_trajectory_1000.npz was generated by the ORACLE; the reference's own code
+    reproduces it: identical hash of the selection ranks / flags / match positions of all 1 000 steps
+    (10 000 measurements), identical counters, camera state within 1e-11."""
+    import hashlib
+    import sys
+    from scenelib2_b200 import synth
+    sys.path.insert(0, G)
+    import make_c1_trajectory as gen
+    k = np.load(os.path.join(G, "c1_trajectory_1000.npz"))
+    kp = np.load(os.path.join(G, "known_patches.npy"))
+    sc = synth.make_scene("C1", n_frames=gen.RING, known_patches=kp)
+    r = oracle.RefSlam(sc, str(tmp_path))
+    hz = hashlib.sha256()
+    for t in range(gen.STEPS):
+        r.step(sc.frames[gen.frame_index(t)])
+        f = r.features()
+        hz.update(np.ascontiguousarray(f["select_rank"], np.int32).tobytes())
+        hz.update(np.ascontiguousarray(f["flags"], np.uint8).tobytes())
+        hz.update(np.ascontiguousarray(f["z"][(f["flags"] & 2) > 0], np.float64).tobytes())
+        if (t + 1) % gen.EVERY == 0:
+            x, P = r.get_state()
+            i = (t + 1) // gen.EVERY - 1
+            np.testing.assert_allclose(x[:13], k["xv"][i], rtol=1e-11, atol=1e-12)
+            np.testing.assert_allclose(np.diag(P)[:13], k["Pxx_diag"][i], rtol=1e-10)
+    f = r.features()
+    assert (np.frombuffer(hz.digest(), np.uint8) == k["integer_hash"]).all()
+    assert (f["attempted"] == k["attempted"]).all() and (f["successful"] == k["successful"]).all()
