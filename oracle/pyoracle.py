@@ -202,14 +202,38 @@ def smoe_search(image, patch, puinv3, centres, use_ref=False):
     return ru, rv, rf, best
 
 
-def find_best_patch(image, boxsize, region, ubest=-1, vbest=-1):
+def find_best_patch(image, boxsize, region, ubest=-1, vbest=-1, use_ref=False):
     """N3.  Shi-Tomasi best patch in region = (ustart, vstart, ufinish, vfinish)."""
     image, ip = _u8(image)
     region = np.ascontiguousarray(region, np.int32)
     u, v, ev = C.c_int32(ubest), C.c_int32(vbest), C.c_double(0.0)
-    lib().orc_find_best_patch(ip, image.shape[1], image.shape[0], boxsize, _p(region, i32p),
-                              C.byref(u), C.byref(v), C.byref(ev))
+    f = ref_models().ref_find_best_patch if use_ref else lib().orc_find_best_patch
+    f(ip, image.shape[1], image.shape[0], boxsize, _p(region, i32p), C.byref(u), C.byref(v), C.byref(ev))
     return u.value, v.value, ev.value
+
+
+def elliptical_search_ref(image, patch, centre, puinv3, u0=-7, v0=-9):
+    """The reference's own MonoSLAM::elliptical_search (monoslam.cpp:401-477) -> found, u, v (u, v keep their
+    input values on failure: quirk Q6)."""
+    image, ip = _u8(image)
+    patch, pp = _u8(patch)
+    centre, cp = _f64(centre)
+    puinv3, qp = _f64(puinv3)
+    u, v = C.c_int32(u0), C.c_int32(v0)
+    ok = ref_models().ref_elliptical_search(ip, image.shape[1], image.shape[0], pp, patch.shape[0], cp, qp,
+                                            C.byref(u), C.byref(v))
+    return ok, u.value, v.value
+
+
+def measure_feature_ref(image, patch, h, S):
+    """The reference's own MonoSLAM::measure_feature (monoslam.cpp:368-386), 11x11 patch -> found, z (2)."""
+    image, ip = _u8(image)
+    patch, pp = _u8(patch)
+    h, hp = _f64(h)
+    S, sp = _colmajor(S)
+    z = np.full(2, -1.0)
+    ok = ref_models().ref_measure_feature(ip, image.shape[1], image.shape[0], pp, hp, sp, _p(z, f64p))
+    return ok, z
 
 
 def particle_set_S_ref(S):

@@ -111,4 +111,53 @@ void ref_slam_get_features(void *p, int32_t *label, double *h, double *z, double
   }
 }
 
+// MonoSLAM::elliptical_search (monoslam.cpp:401-477) on its own: PuInv3 = (P00, P01, P11); returns the bool
+int32_t ref_elliptical_search(const uint8_t *image, int32_t width, int32_t height, const uint8_t *patch,
+                              int32_t boxsize, const double *centre, const double *PuInv3, int32_t *u,
+                              int32_t *v) {
+  MonoSLAM m;  // no Init needed: the search only uses the constructor's constants
+  cv::Mat img(height, width, CV_8UC1, const_cast<uint8_t *>(image));
+  cv::Mat pat(boxsize, boxsize, CV_8UC1, const_cast<uint8_t *>(patch));
+  Eigen::Vector2d c(centre[0], centre[1]);
+  Eigen::Matrix2d P;
+  P(0, 0) = PuInv3[0];
+  P(0, 1) = P(1, 0) = PuInv3[1];
+  P(1, 1) = PuInv3[2];
+  int uu = *u, vv = *v;
+  const bool ok = m.elliptical_search(img, pat, c, P, &uu, &vv, boxsize);
+  *u = uu;
+  *v = vv;
+  return ok ? 1 : 0;
+}
+
+// MonoSLAM::measure_feature (monoslam.cpp:368-386): S (2x2 column-major) -> LLT -> PuInv -> elliptical_search
+int32_t ref_measure_feature(const uint8_t *image, int32_t width, int32_t height, const uint8_t *patch,
+                            const double *h, const double *S4, double *z) {
+  MonoSLAM m;
+  cv::Mat img(height, width, CV_8UC1, const_cast<uint8_t *>(image));
+  cv::Mat pat(11, 11, CV_8UC1, const_cast<uint8_t *>(patch));  // kBoxSize_ (monoslam.cpp:48)
+  Eigen::VectorXd zz(2), hh(2);
+  hh(0) = h[0];
+  hh(1) = h[1];
+  zz(0) = z[0];
+  zz(1) = z[1];
+  Eigen::MatrixXd S(2, 2);
+  std::memcpy(S.data(), S4, sizeof(double) * 4);
+  const bool ok = m.measure_feature(img, pat, zz, hh, S);
+  z[0] = zz(0);
+  z[1] = zz(1);
+  return ok ? 1 : 0;
+}
+
+// MonoSLAM::find_best_patch_inside_region (monoslam.cpp:1070-1205), region4 = (ustart, vstart, ufinish, vfinish)
+void ref_find_best_patch(const uint8_t *image, int32_t width, int32_t height, int32_t boxsize,
+                         const int32_t *region4, int32_t *ubest, int32_t *vbest, double *evbest) {
+  MonoSLAM m;
+  cv::Mat img(height, width, CV_8UC1, const_cast<uint8_t *>(image));
+  int u = *ubest, v = *vbest;
+  m.find_best_patch_inside_region(img, &u, &v, evbest, boxsize, region4[0], region4[1], region4[2], region4[3]);
+  *ubest = u;
+  *vbest = v;
+}
+
 }  // extern "C"

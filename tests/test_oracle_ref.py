@@ -294,3 +294,56 @@ def test_c1_trajectory_1000_steps_reproduced_by_reference_source(oracle, refmode
     f = r.features()
     assert (np.frombuffer(hz.digest(), np.uint8) == k["integer_hash"]).all()
     assert (f["attempted"] == k["attempted"]).all() and (f["successful"] == k["successful"]).all()
+
+
+def test_elliptical_search_and_detector_match_reference_source(oracle, refmodels):
+    """A2 / A3 / N3 one by one against the reference's own monoslam.cpp: MonoSLAM::elliptical_search (rotated and
+    border-clamped ellipses, plateaus, 11x11 and 15x15), measure_feature (S -> PuInv -> search) and
+    find_best_patch_inside_region (positions and FP64 eigenvalue bits)."""
+    from scenelib2_b200 import synth
+    rng = np.random.default_rng(41)
+    img = synth.make_texture(rng, 120, 160)
+    img[30:60, 40:90] = 128                                   # plateau: low sigma, ties
+    n_found = 0
+    for B in (11, 15):
+        h = (B - 1) // 2
+        for k in range(120):
+            cu, cv = int(rng.integers(h, 160 - h)), int(rng.integers(h, 120 - h))
+            patch = img[cv - h:cv + h + 1, cu - h:cu + h + 1].copy()
+            if k % 4 == 0:
+                patch = rng.integers(0, 256, (B, B), dtype=np.uint8)      # no good match anywhere
+            a, b = rng.uniform(2, 14, 2)
+            th = rng.uniform(0, np.pi)
+            R = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+            Si = np.linalg.inv(R @ np.diag([a * a / 9, b * b / 9]) @ R.T)
+            pu = np.array([Si[0, 0], Si[0, 1], Si[1, 1]])
+            centre = np.array([cu + rng.uniform(-4, 4), cv + rng.uniform(-4, 4)])
+            if k % 7 == 0:
+                centre = np.array([rng.choice([1.5, 158.2]), rng.choice([2.4, 117.9])])   # clamped at a corner
+            ok, ru, rv = oracle.elliptical_search_ref(img, patch, centre, pu)
+            ou, ov, of, _ = oracle.elliptical_search(img, patch[None], centre[None], pu[None])
+            assert bool(of[0]) == bool(ok), (B, k)
+            if ok:
+                assert (ou[0], ov[0]) == (ru, rv), (B, k)
+                n_found += 1
+    assert n_found > 60
+    for k in range(100):                                       # A3: S -> PuInv -> search, 11x11
+        cu, cv = int(rng.integers(10, 150)), int(rng.integers(10, 110))
+        patch = img[cv - 5:cv + 6, cu - 5:cu + 6].copy()
+        a, b = rng.uniform(4, 60, 2)
+        r = rng.uniform(-0.8, 0.8)
+        S = np.array([[a, r * np.sqrt(a * b)], [r * np.sqrt(a * b), b]])
+        hh = np.array([cu + rng.uniform(-3, 3), cv + rng.uniform(-3, 3)])
+        ok, z = oracle.measure_feature_ref(img, patch, hh, S)
+        pu = oracle.puinv_from_S(S)
+        ou, ov, of, _ = oracle.elliptical_search(img, patch[None], hh[None], pu[None])
+        assert bool(of[0]) == bool(ok), k
+        if ok:
+            assert (z == [ou[0], ov[0]]).all(), k
+    regions = np.array([[40, 30, 120, 90], [-5, -7, 60, 40], [100, 70, 400, 300], [0, 0, 160, 120],
+                        [50, 50, 50, 80], [3, 3, 40, 30], [90, 20, 91, 21], [10, 10, 30, 25]], np.int32)
+    for B in (11, 15):
+        for reg in regions:
+            a = oracle.find_best_patch(img, B, reg, ubest=-7, vbest=-9)
+            b = oracle.find_best_patch(img, B, reg, ubest=-7, vbest=-9, use_ref=True)
+            assert a[:2] == b[:2] and np.float64(a[2]).tobytes() == np.float64(b[2]).tobytes(), (B, reg)
