@@ -4,8 +4,8 @@
 // FeatureInitInfo::normalise_particle_vector_and_calculate_cumulative (feature_init_info.cpp:95-119),
 // prune_particle_vector (:126-141) and calculate_mean_and_covariance (:152-172); lambda is scalar
 // (kParticleDimension_ = 1 in MonoSLAM).  Pinned: bit-exact against the reference's own feature_init_info.cpp
-// (normalise / prune / mean-covariance; _ref/libsl2refmodels.so, tests/test_oracle_ref.py); the likelihood
-// loop of monoslam.cpp:1456-1478 is transcribed (monoslam.cpp cannot be compiled here).
+// (normalise / prune / mean-covariance) and against the reference's whole particle cycle in monoslam.cpp
+// (likelihood loop of :1456-1478 included; _ref/libsl2refmodels.so, tests/test_oracle_ref.py).
 #pragma once
 #include <cmath>
 #include <cstdint>

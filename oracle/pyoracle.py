@@ -428,7 +428,12 @@ class RefSlam:
                  "cam.kd1 = %r;" % float(sc.cam8[6]), "cam.sd = %d;" % sc.cam8[7],
                  "params.delta_t = %r;" % float(sc.delta_t),
                  "params.number_of_features_to_select = %d;" % sc.n_select,
-                 "params.number_of_features_to_keep_visible = 12;"]
+                 "params.number_of_features_to_keep_visible = 12;",
+                 # data/SceneLib2.cfg:63-69
+                 "params.min_lambda = 0.5;", "params.max_lambda = 5.0;", "params.number_of_particles = 100;",
+                 "params.standard_deviation_depth_ratio = 0.3;", "params.min_number_of_particles = 20;",
+                 "params.prune_probability_threshold = 0.05;",
+                 "params.erase_partially_init_feature_after_this_many_attempts = 10;"]
         names = ["rw_x", "rw_y", "rw_z", "qwr_w", "qwr_x", "qwr_y", "qwr_z", "vw_x", "vw_y", "vw_z", "ww_x",
                  "ww_y", "ww_z"]
         for k, nm in enumerate(names):
@@ -480,6 +485,30 @@ class RefSlam:
     def step(self, frame):
         frame, fp = _u8(frame)
         self.R.ref_slam_step(self.h, fp, self.width, self.height)
+
+    def init_partial_feature(self, frame, u, v):
+        """MonoSLAM::InitialiseFeature at pixel (u, v) (monoslam.cpp:1211-1236)."""
+        frame, fp = _u8(frame)
+        self.R.ref_slam_init_partial(self.h, fp, self.width, self.height, int(u), int(v))
+
+    def particle_cycle(self, frame, cap=256):
+        """One predict / measure / re-weight cycle of the first partially-initialised feature (see
+        ref_slam_particle_cycle).  None when no measurement is made on this step."""
+        frame, fp = _u8(frame)
+        o = dict(h=np.zeros((cap, 2)), sinv3=np.zeros((cap, 3)), detS=np.zeros(cap), lam=np.zeros(cap),
+                 prob_before=np.zeros(cap), z=np.zeros((cap, 2), np.int32), found=np.zeros(cap, np.uint8),
+                 prob_after=np.zeros(cap), keep=np.zeros(cap, np.uint8), cum=np.zeros(cap), mean_var=np.zeros(2))
+        ka = C.c_int32(0)
+        K = self.R.ref_slam_particle_cycle(self.h, fp, self.width, self.height, cap, _p(o["h"], f64p),
+                                           _p(o["sinv3"], f64p), _p(o["detS"], f64p), _p(o["lam"], f64p),
+                                           _p(o["prob_before"], f64p), _p(o["z"], i32p), _p(o["found"], u8p),
+                                           _p(o["prob_after"], f64p), _p(o["keep"], u8p), _p(o["cum"], f64p),
+                                           _p(o["mean_var"], f64p), C.byref(ka))
+        if K < 0:
+            return None
+        out = {k: (v[:K] if k != "mean_var" else v) for k, v in o.items()}
+        out["K"], out["K_after"] = K, ka.value
+        return out
 
     def features(self):
         nf = self.num_features

@@ -111,6 +111,76 @@ void ref_slam_get_features(void *p, int32_t *label, double *h, double *z, double
   }
 }
 
+// MonoSLAM::InitialiseFeature (monoslam.cpp:1211-1236): a partially-initialised feature with
+// kNumberOfParticles_ depth particles at pixel (u, v) of `frame`
+void ref_slam_init_partial(void *p, const uint8_t *frame, int32_t width, int32_t height, int32_t u, int32_t v) {
+  MonoSLAM *m = static_cast<MonoSLAM *>(p);
+  cv::Mat f(height, width, CV_8UC1, const_cast<uint8_t *>(frame));
+  m->uu_ = u;
+  m->vv_ = v;
+  m->location_selected_flag_ = true;
+  m->InitialiseFeature(f);
+}
+
+// One particle cycle of the FIRST partially-initialised feature, split exactly like
+// MonoSLAM::MatchPartiallyInitialisedFeatures (monoslam.cpp:1299-1340) so that the inputs and outputs of the
+// measurement / re-weighting step can be read: predict_partially_initialised_feature_measurements ->
+// [h, SInv, detS, lambda, probability] -> measure_feature_with_multiple_priors -> [z, flags] ->
+// update_partially_initialised_feature_probabilities -> [probability, cumulative, survivors, mean, covariance].
+// Returns the number of particles before the cycle, -1 when the feature makes no measurement on this step
+// (the first step after initialisation, monoslam.cpp:1367-1369), -2 when there is no such feature.
+int32_t ref_slam_particle_cycle(void *p, const uint8_t *frame, int32_t width, int32_t height, int32_t cap,
+                                double *h, double *sinv3, double *detS, double *lambda, double *prob_before,
+                                int32_t *z_uv, uint8_t *found, double *prob_after, uint8_t *keep,
+                                double *cumulative, double *mean_var, int32_t *k_after) {
+  MonoSLAM *m = static_cast<MonoSLAM *>(p);
+  if (m->feature_init_info_vector_.empty()) return -2;
+  cv::Mat f(height, width, CV_8UC1, const_cast<uint8_t *>(frame));
+  m->predict_partially_initialised_feature_measurements();
+  FeatureInitInfo *feat = &m->feature_init_info_vector_.front();
+  if (!feat->making_measurement_on_this_step_flag_) return -1;
+  const int K = (int)feat->particle_vector_.size();
+  if (K > cap) return -3;
+  for (int k = 0; k < K; ++k) {
+    const Particle &q = feat->particle_vector_[k];
+    h[2 * k] = q.m_h_(0);
+    h[2 * k + 1] = q.m_h_(1);
+    sinv3[3 * k] = q.m_SInv_(0, 0);
+    sinv3[3 * k + 1] = q.m_SInv_(0, 1);
+    sinv3[3 * k + 2] = q.m_SInv_(1, 1);
+    detS[k] = q.m_detS_;
+    lambda[k] = q.lambda_(0);
+    prob_before[k] = q.probability_;
+  }
+  m->measure_feature_with_multiple_priors(f, feat->fp_->patch_, feat->particle_vector_);
+  for (int k = 0; k < K; ++k) {
+    const Particle &q = feat->particle_vector_[k];
+    found[k] = q.m_successful_measurement_flag_ ? 1 : 0;
+    z_uv[2 * k] = found[k] ? (int)q.m_z_(0) : 0;
+    z_uv[2 * k + 1] = found[k] ? (int)q.m_z_(1) : 0;
+    keep[k] = 0;
+    prob_after[k] = 0.0;
+    cumulative[k] = 0.0;
+  }
+  m->update_partially_initialised_feature_probabilities(m->kPruneProbabilityThreshold_);
+  mean_var[0] = mean_var[1] = 0.0;
+  *k_after = 0;
+  if (m->feature_init_info_vector_.empty()) return K;  // every match failed: the feature was deleted
+  feat = &m->feature_init_info_vector_.front();
+  size_t j = 0;
+  for (int k = 0; k < K && j < feat->particle_vector_.size(); ++k)
+    if (feat->particle_vector_[j].lambda_(0) == lambda[k]) {
+      keep[k] = 1;
+      prob_after[k] = feat->particle_vector_[j].probability_;
+      cumulative[k] = feat->particle_vector_[j].cumulative_probability_;
+      ++j;
+    }
+  mean_var[0] = feat->mean_(0);
+  mean_var[1] = feat->covariance_(0, 0);
+  *k_after = (int)feat->particle_vector_.size();
+  return K;
+}
+
 // MonoSLAM::elliptical_search (monoslam.cpp:401-477) on its own: PuInv3 = (P00, P01, P11); returns the bool
 int32_t ref_elliptical_search(const uint8_t *image, int32_t width, int32_t height, const uint8_t *patch,
                               int32_t boxsize, const double *centre, const double *PuInv3, int32_t *u,

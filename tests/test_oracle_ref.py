@@ -347,3 +347,43 @@ def test_elliptical_search_and_detector_match_reference_source(oracle, refmodels
             a = oracle.find_best_patch(img, B, reg, ubest=-7, vbest=-9)
             b = oracle.find_best_patch(img, B, reg, ubest=-7, vbest=-9, use_ref=True)
             assert a[:2] == b[:2] and np.float64(a[2]).tobytes() == np.float64(b[2]).tobytes(), (B, reg)
+
+
+def test_particle_cycle_matches_reference_source(oracle, refmodels, tmp_path):
+    """N2 end to end on the reference's own code: InitialiseFeature creates a partially-initialised feature with
+    100 depth particles; after the camera has moved, predict_partially_initialised_feature_measurements
+    (part_feature_model.cpp), measure_feature_with_multiple_priors (SMOE) and
+    update_partially_initialised_feature_probabilities run as in MatchPartiallyInitialisedFeatures
+    (monoslam.cpp:1299-1340).  Fed with the same particle inputs, the oracle's SMOE search and particle update
+    give identical matches, survivors, probabilities (bit-exact), mean and variance."""
+    from scenelib2_b200 import synth
+    kp = np.load(os.path.join(G, "known_patches.npy"))
+    sc = synth.make_scene("C1", n_frames=6, known_patches=kp)
+    cycles = 0
+    for (u, v, dx) in ((150, 110, (0.03, -0.01, 0.0)), (90, 70, (-0.02, 0.02, 0.01)), (200, 150, (0.0, 0.04, 0.0))):
+        r = oracle.RefSlam(sc, str(tmp_path / ("p%d_%d" % (u, v))))
+        r.init_partial_feature(sc.frames[0], u, v)
+        assert r.num_features == sc.n_features + 1 and r.n == 13 + 3 * sc.n_features + 6
+        assert r.particle_cycle(sc.frames[0]) is None          # no match attempt right after initialisation
+        patch = sc.frames[0][v - 5:v + 6, u - 5:u + 6]
+        for t in (1, 2, 3):
+            x, P = r.get_state()
+            x[:3] += dx                                        # the camera moves: the depth line spreads out
+            r.set_state(x, P)
+            c = r.particle_cycle(sc.frames[t])
+            if c is None:
+                break
+            ou, ov, of, _ = oracle.smoe_search(sc.frames[t], patch, c["sinv3"], c["h"])
+            assert (of == c["found"]).all()
+            assert (ou[of > 0] == c["z"][of > 0, 0]).all() and (ov[of > 0] == c["z"][of > 0, 1]).all()
+            o = oracle.particle_update(c["h"], c["sinv3"], c["detS"], c["lam"], c["z"], c["found"], 0.05,
+                                       c["prob_before"])
+            assert o[0] == c["K_after"] and (o[2] == c["keep"]).all()
+            kk = c["keep"] > 0
+            assert o[1][kk].tobytes() == c["prob_after"][kk].tobytes()
+            assert o[3][kk].tobytes() == c["cum"][kk].tobytes()
+            assert o[4].tobytes() == c["mean_var"].tobytes()
+            cycles += 1
+            if c["K_after"] == 0:
+                break
+    assert cycles >= 4
