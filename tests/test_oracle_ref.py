@@ -387,3 +387,19 @@ def test_particle_cycle_matches_reference_source(oracle, refmodels, tmp_path):
             if c["K_after"] == 0:
                 break
     assert cycles >= 4
+
+
+def test_c4_size_step_matches_reference_source(oracle, refmodels, tmp_path):
+    """Full-size update (n = 313, all 100 features measured, m = 200; ellipses from the EKF's own S_i since the
+    reference has no fixed-ellipse switch): Kalman::KalmanFilterUpdate as written (kalman.cpp:72-119) with its
+    gather / scatter, on the reference's own code vs the oracle."""
+    from scenelib2_b200 import synth
+    from test_oracle_slam import make_oracle_slam
+    sc = synth.make_scene("C4", n_frames=3, override=False)
+    r, o = oracle.RefSlam(sc, str(tmp_path)), make_oracle_slam(oracle, sc)
+    for t in range(3):
+        r.step(sc.frames[t])
+        o.step(sc.frames[t])
+        _compare_step(r, o, t, 1e-11)
+    f = o.features()
+    assert ((f["flags"] & 2) > 0).sum() == 100 and o.n == 313
