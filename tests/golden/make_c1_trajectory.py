@@ -1,14 +1,15 @@
-"""Generates tests/golden/c1_trajectory_1000.npz: SURVEY 8(c)(iv), a 1 000-step C1 trajectory of the CPU
-oracle (20 features, 10 selected per frame, ellipses from the EKF's own S_i, known patches) as a regression
-pin of the whole-step restatement.  Frames: 32 synthetic frames walked forwards and backwards, so consecutive
-frames always differ by one step of the bounded random walk.
+"""Generates tests/golden/c1_trajectory_1000.npz: SURVEY 8(c)(iv), a 1 000-step C1 trajectory (20 features, 10
+selected per frame, ellipses from the EKF's own S_i, known patches).  Frames: 32 synthetic frames walked forwards
+and backwards, so consecutive frames always differ by one step of the bounded random walk.
 
-    python tests/golden/make_c1_trajectory.py
+    python tests/golden/make_c1_trajectory.py            # needs /root/reference (oracle/_ref is built from it)
 
-The reference has no golden outputs; this fixture is produced by the oracle.  It is reproduced by
-the reference's own sources compiled against oracle/stubs_arith (identical integer hash, state within 1e-11:
-tests/test_oracle_ref.py::test_c1_trajectory_1000_steps_reproduced_by_reference_source) and by the CUDA path
-(tests/test_gpu_step.py).
+The fixture is an output of THE REFERENCE'S OWN CODE: monoslam.cpp / kalman.cpp / feature.cpp / models / improc
+compiled unmodified against the stand-ins of oracle/stubs_arith (oracle/_ref/libsl2refmodels.so, driven through
+MonoSLAM::Init / GoOneStep by oracle/ref_slam_shim.cpp).  The CPU oracle (tests/test_oracle_slam.py) and the CUDA
+path (tests/test_gpu_step.py) are tested against it: the hash of every frame's selection ranks / flags / match
+positions must be identical, the camera state agrees numerically.  (`python make_c1_trajectory.py --oracle`
+regenerates it from the oracle instead; the integer hash is the same.)
 """
 import hashlib
 import os
@@ -28,12 +29,19 @@ def frame_index(t):
     return k if k < RING else 2 * RING - 2 - k
 
 
-def run(oracle):
-    from scenelib2_b200 import synth
+def make_slam(oracle, sc, use_ref=False, workdir=None):
+    if use_ref:
+        import tempfile
+        return oracle.RefSlam(sc, workdir or tempfile.mkdtemp(prefix="sl2ref_"))
     from test_oracle_slam import make_oracle_slam
+    return make_oracle_slam(oracle, sc)
+
+
+def run(oracle, use_ref=False, workdir=None):
+    from scenelib2_b200 import synth
     kp = np.load(os.path.join(HERE, "known_patches.npy"))
     sc = synth.make_scene("C1", n_frames=RING, known_patches=kp)
-    s = make_oracle_slam(oracle, sc)
+    s = make_slam(oracle, sc, use_ref, workdir)
     hz = hashlib.sha256()
     xs, diag, nfeat = [], [], []
     for t in range(STEPS):
@@ -58,6 +66,9 @@ def run(oracle):
 if __name__ == "__main__":
     from oracle import pyoracle as po
     po.build()
-    out = run(po)
+    use_ref = "--oracle" not in sys.argv
+    assert not use_ref or po.ref_models() is not None, "oracle/_ref/libsl2refmodels.so missing (make -C oracle)"
+    out = run(po, use_ref=use_ref)
+    out["source"] = np.array("reference sources + oracle/stubs_arith" if use_ref else "oracle")
     np.savez_compressed(os.path.join(HERE, "c1_trajectory_1000.npz"), **out)
-    print("written; features left:", out["nfeat"][-1], "successful:", out["successful"].sum())
+    print("written from", out["source"], "; features left:", out["nfeat"][-1], "successful:", out["successful"].sum())

@@ -287,10 +287,10 @@ def test_staggered_stream_groups_match_serial_order():
 
 
 def test_c1_trajectory_1000_steps_matches_oracle_fixture():
-    """The CUDA path over the 1 000-step C1 trajectory of tests/golden/c1_trajectory_1000.npz (generated by
-    the CPU oracle): selection ranks, found flags and match positions of EVERY step hash to the oracle's
-    value (bit-exact integer results over 10 000 measurements); camera state within the north-star
-    tolerance at every 100th step."""
+    """The CUDA path over the 1 000-step C1 trajectory of tests/golden/c1_trajectory_1000.npz (an output of the
+    REFERENCE'S OWN code, see tests/golden/make_c1_trajectory.py): selection ranks, found flags and match
+    positions of EVERY step hash to the reference's value (bit-exact integer results over 10 000
+    measurements); camera state within the north-star tolerance at every 100th step."""
     import hashlib
     import sys
     sys.path.insert(0, G)

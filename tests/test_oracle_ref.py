@@ -267,9 +267,10 @@ def test_bad_feature_deletion_matches_reference_source(oracle, refmodels, tmp_pa
 
 
 def test_c1_trajectory_1000_steps_reproduced_by_reference_source(oracle, refmodels, tmp_path):
-    """The fixture tests/golden/c1_trajectory_1000.npz was generated by the ORACLE; the reference's own code
-    reproduces it: identical hash of the selection ranks / flags / match positions of all 1 000 steps
-    (10 000 measurements), identical counters, camera state within 1e-11."""
+    """tests/golden/c1_trajectory_1000.npz is an output of the reference's own code (make_c1_trajectory.py);
+    re-running it live must reproduce the fixture: identical hash of the selection ranks / flags / match
+    positions of all 1 000 steps (10 000 measurements), identical counters, camera state within 1e-11.
+    (The oracle and the CUDA path are tested against the same fixture.)"""
     import hashlib
     import sys
     from scenelib2_b200 import synth

@@ -89,8 +89,9 @@ def test_bad_features_are_deleted(oracle):
 
 
 def test_c1_trajectory_1000_steps_matches_fixture(oracle):
-    """1 000 GoOneStep calls on C1; integer results (selection ranks, flags, match
-    positions of every step) by hash, camera state / covariance at every 100th step numerically."""
+    """1 000 GoOneStep calls on C1 against the fixture produced by the REFERENCE'S OWN code
+    (tests/golden/make_c1_trajectory.py): integer results (selection ranks, flags, match positions of every
+    step) by hash, camera state / covariance at every 100th step numerically."""
     import sys
     sys.path.insert(0, G)
     import make_c1_trajectory as gen
