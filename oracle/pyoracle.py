@@ -245,7 +245,7 @@ def particle_set_S_ref(S):
     return Sinv, det.value
 
 
-def particle_update(h, Sinv3, detS, lam, z_uv, found, prune_threshold, prob, use_ref=False):
+def particle_update(h, Sinv3, detS, lam, z_uv, found, prune_threshold, prob):
     """N2.  -> survivors, prob (normalised), keep, cumulative, (mean, variance)."""
     h, hp = _f64(h)
     Sinv3, sp = _f64(Sinv3)
@@ -258,7 +258,7 @@ def particle_update(h, Sinv3, detS, lam, z_uv, found, prune_threshold, prob, use
     keep = np.zeros(K, np.uint8)
     cum = np.zeros(K)
     mv = np.zeros(2)
-    f = ref_models().ref_particle_update if use_ref else lib().orc_particle_update
+    f = lib().orc_particle_update
     f.restype = C.c_int32
     left = f(K, hp, sp, dp, lp, _p(z_uv, i32p), _p(found, u8p), C.c_double(prune_threshold), _p(prob, f64p),
              _p(keep, u8p), _p(cum, f64p), _p(mv, f64p))

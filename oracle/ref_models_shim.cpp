@@ -2,9 +2,7 @@
 // (MotionModel, Camera, FullFeatureModel), compiled unmodified from /root/reference/scenelib2 against the
 // arithmetic stand-in of oracle/stubs_arith (see its header for what is and is not pinned).  Signatures
 // mirror the oracle's orc_* functions so tests can compare the two directly.
-#include <cmath>
 #include <cstring>
-#include <vector>
 
 #include "camera.h"
 #include "feature_init_info.h"
@@ -109,72 +107,6 @@ void ref_particle_set_S(const double *S4, double *Sinv4, double *detS) {
   p.set_S(mat(S4, 2, 2));
   out(p.m_SInv_, Sinv4);
   *detS = p.m_detS_;
-}
-
-// One FeatureInitInfo through the particle branch of MonoSLAM::update_partially_initialised_feature_
-// probabilities (monoslam.cpp:1447-1493).  That loop lives in monoslam.cpp (not compilable here) and is
-// transcribed below; normalise_particle_vector_and_calculate_cumulative, prune_particle_vector and
-// calculate_mean_and_covariance are the reference's own feature_init_info.cpp.
-// Outputs are per INPUT particle: keep[k] = 0 for pruned ones.
-int ref_particle_update(int K, const double *h, const double *Sinv3, const double *detS, const double *lambda,
-                        const int *z_uv, const unsigned char *found, double prune_probability_threshold,
-                        double *prob, unsigned char *keep, double *cumulative, double *mean_var) {
-  FeatureInitInfo feat(nullptr, 1, 2);
-  for (int k = 0; k < K; ++k) {
-    Eigen::VectorXd l(1);
-    l(0) = lambda[k];
-    feat.add_particle(l, prob[k]);
-    Particle &p = feat.particle_vector_.back();
-    p.m_h_(0) = h[2 * k];
-    p.m_h_(1) = h[2 * k + 1];
-    p.m_SInv_(0, 0) = Sinv3[3 * k];
-    p.m_SInv_(0, 1) = p.m_SInv_(1, 0) = Sinv3[3 * k + 1];
-    p.m_SInv_(1, 1) = Sinv3[3 * k + 2];
-    p.m_detS_ = detS[k];
-    p.m_z_(0) = z_uv[2 * k];
-    p.m_z_(1) = z_uv[2 * k + 1];
-    p.m_successful_measurement_flag_ = found[k] != 0;
-    p.cumulative_probability_ = -(double)(k + 1);  // tag: survives erase(), identifies the input particle
-  }
-  for (vector<Particle>::iterator it = feat.particle_vector_.begin(); it != feat.particle_vector_.end(); ++it) {
-    double likelihood;
-    if (it->m_successful_measurement_flag_ == true) {
-      Eigen::VectorXd nu = it->m_z_ - it->m_h_;
-      Eigen::VectorXd SInv_times_nu = it->m_SInv_ * nu;
-      double nuT_Sinv_nu = nu.dot(SInv_times_nu);
-      double pux = (1.0 / (sqrt(2.0 * M_PI * it->m_detS_))) * exp(-0.5 * nuT_Sinv_nu);
-      likelihood = pux;
-    } else {
-      likelihood = 0.0;
-    }
-    it->probability_ = it->probability_ * likelihood;
-  }
-  for (int k = 0; k < K; ++k) {
-    keep[k] = 0;
-    cumulative[k] = 0.0;
-  }
-  mean_var[0] = mean_var[1] = 0.0;
-  // tags are overwritten by normalise...(); remember the input index in lambda order instead
-  std::vector<double> lam_in(lambda, lambda + K);
-  if (!feat.normalise_particle_vector_and_calculate_cumulative()) {
-    for (int k = 0; k < K; ++k) prob[k] = feat.particle_vector_[k].probability_;
-    return 0;
-  }
-  feat.prune_particle_vector(prune_probability_threshold);
-  feat.calculate_mean_and_covariance();
-  for (int k = 0; k < K; ++k) prob[k] = 0.0;
-  size_t j = 0;  // survivors keep their order: match them to the inputs by position of equal lambda
-  for (int k = 0; k < K && j < feat.particle_vector_.size(); ++k) {
-    if (feat.particle_vector_[j].lambda_(0) == lam_in[k]) {
-      keep[k] = 1;
-      prob[k] = feat.particle_vector_[j].probability_;
-      cumulative[k] = feat.particle_vector_[j].cumulative_probability_;
-      ++j;
-    }
-  }
-  mean_var[0] = feat.mean_(0);
-  mean_var[1] = feat.covariance_(0, 0);
-  return (int)feat.particle_vector_.size();
 }
 
 }  // extern "C"
