@@ -148,6 +148,26 @@ def dist_selftest(rank, world):
     dist.destroy_process_group()
 
 
+def reference_sources_rate(config, seconds=3.0):
+    """frames/s of the reference's own MonoSLAM::GoOneStep (oracle/_ref/libsl2refmodels.so), one thread."""
+    try:
+        import tempfile
+        from oracle import pyoracle as po
+        from scenelib2_b200 import synth
+        if po.ref_models() is None:
+            return None
+        sc = synth.make_scene(config, n_frames=4, override=False)
+        r = po.RefSlam(sc, tempfile.mkdtemp(prefix="sl2ref_"))
+        t0, n = time.time(), 0
+        while time.time() - t0 < seconds:
+            r.step(sc.frames[n % 4])
+            n += 1
+        return {"value": n / (time.time() - t0), "unit": UNIT, "cores": 1, "sample": "%d steps" % n,
+                "workload": "same scene, search ellipses from the EKF's own S_i"}
+    except Exception as e:  # informational only
+        return {"unavailable": str(e)[:120]}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -163,13 +183,19 @@ def run_reference(args, rank, world):
             break
     v = float(np.mean(vals))
     sample = "%d streams (1 per thread) x ~%.0f s of oracle steps per bench step" % (threads, budget)
+    ref_src = reference_sources_rate(args.config)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1e3 * threads / v,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": {"workload": WORKLOADS.get(args.config, WORKLOAD), "streams": threads,
                                         "note": "CPU oracle = port of the reference path (Eigen3/OpenCV absent: "
-                                                "the reference itself cannot be built); faithful block storage"},
+                                                "the reference binary cannot be built); faithful block storage",
+                                        # for information: the reference's OWN tracking sources compiled against
+                                        # stand-ins for Eigen/OpenCV/Pangolin (oracle/_ref/libsl2refmodels.so), one
+                                        # thread, ellipses from S_i (it has no fixed-ellipse switch).  Slower than the
+                                        # port (its matrix stand-in is not Eigen), so the port stays the baseline.
+                                        "reference_sources_with_standins": ref_src},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
