@@ -124,6 +124,17 @@ int sl2_measure_particles(sl2_ctx *ctx, int32_t stream_id, int32_t slot, int32_t
                           double prune_probability_threshold, double *prob, int32_t *z_uv, uint8_t *found,
                           uint8_t *keep, double *cumulative, double *mean_var);
 
+/* The same two entry points for a template that is not a map feature: `patch` is boxsize x boxsize u8, row-major
+ * (the reference keeps the template of a partially-initialised feature in Feature::patch_, feature.cpp:45-95,
+ * and hands it to SearchMultipleOverlappingEllipses, monoslam.cpp:1413). */
+int sl2_smoe_search_patch(sl2_ctx *ctx, int32_t stream_id, int32_t slot, const uint8_t *patch, int32_t K,
+                          const double *PuInv3 /* K x 3 */, const double *centres /* K x 2 */,
+                          int32_t *res_u, int32_t *res_v, uint8_t *res_flag);
+int sl2_measure_particles_patch(sl2_ctx *ctx, int32_t stream_id, int32_t slot, const uint8_t *patch, int32_t K,
+                                const double *h, const double *Sinv3, const double *detS, const double *lambda,
+                                double prune_probability_threshold, double *prob, int32_t *z_uv,
+                                uint8_t *found, uint8_t *keep, double *cumulative, double *mean_var);
+
 /* MonoSLAM::find_best_patch_inside_region + find_eigenvalues (monoslam.cpp:1070-1205): Shi-Tomasi
  * smallest-eigenvalue detector over n regions (ustart, vstart, ufinish, vfinish) of one stream's
  * frame.  evbest[i] is always written; ubest/vbest[i] only when a position with a positive score

@@ -248,7 +248,7 @@ int sl2_create(const sl2_config *cfg, sl2_ctx **out) {
   bool ok = true;
 #define ALLOC(ptr, count) ok = ok && (dev_alloc(c, &(ptr), (count)) == cudaSuccess)
   ALLOC(d.frames, (size_t)d.slots * B * d.H * d.pitch);
-  ALLOC(d.patches, B * N * d.box * 16);
+  ALLOC(d.patches, (B * N + 1) * d.box * 16);  // + one scratch template (the *_patch entry points)
   ALLOC(d.x, B * d.ld);
   ALLOC(d.P, B * d.ld * d.ld);
   ALLOC(d.G, B * d.mmax * d.ldg);
@@ -473,6 +473,21 @@ int sl2_delete_feature(sl2_ctx *c, int32_t s, int32_t index) {
 }
 
 // ---- patch search -----------------------------------------------------------------------------
+// A raw BOX x BOX template goes into the scratch slot behind the map templates; the search kernel addresses
+// templates as (stream * Nmax + feature), so relative to stream s the slot is feature (B - s) * Nmax.
+static int upload_scratch_patch(sl2_ctx *c, int32_t s, const uint8_t *patch, int32_t *feat_rel) {
+  const Sl2Dev &d = c->d;
+  const int box = d.box;
+  uint8_t rows[32 * 16];
+  memset(rows, 0, sizeof(rows));
+  for (int r = 0; r < box; ++r) memcpy(rows + r * 16, patch + (size_t)r * box, box);
+  CU_TRY(c, cudaMemcpyAsync(d.patches + (size_t)d.B * d.Nmax * box * 16, rows, (size_t)box * 16,
+                            cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));  // `rows` is on the stack
+  *feat_rel = (d.B - s) * d.Nmax;
+  return SL2_OK;
+}
+
 static int search_staged(sl2_ctx *c, int32_t s, int32_t slot, int32_t n, const int32_t *feat_index,
                          int32_t single_feat, const double *centre, const double *PuInv3,
                          int32_t *u, int32_t *v, uint8_t *found, double *best, int smoe) {
@@ -482,9 +497,11 @@ static int search_staged(sl2_ctx *c, int32_t s, int32_t slot, int32_t n, const i
   int nf = 0;
   int rc = device_nfeat(c, s, &nf);
   if (rc) return rc;
+  const int scratch = (c->d.B - s) * c->d.Nmax;  // see upload_scratch_patch
   for (int i = 0; i < n; ++i) {
     const int f = feat_index ? feat_index[i] : single_feat;
-    if (f < 0 || f >= nf) return fail(c, SL2_ERR_ARG, "patch search: feature index out of range");
+    if ((f < 0 || f >= nf) && !(f == scratch && !feat_index))
+      return fail(c, SL2_ERR_ARG, "patch search: feature index out of range");
   }
   // staging layout: centre(2n) puinv(3n) best(n) | feat(n) uv(2n) | found(n)
   const size_t o_c = 0, o_p = o_c + 16 * (size_t)n, o_b = o_p + 24 * (size_t)n,
@@ -541,18 +558,25 @@ int sl2_smoe_search(sl2_ctx *c, int32_t s, int32_t slot, int32_t feat_index, int
                        nullptr, 1);
 }
 
-int sl2_measure_particles(sl2_ctx *c, int32_t s, int32_t slot, int32_t feat_index, int32_t K,
-                          const double *h, const double *Sinv3, const double *detS, const double *lambda,
-                          double prune_probability_threshold, double *prob, int32_t *z_uv, uint8_t *found,
-                          uint8_t *keep, double *cumulative, double *mean_var) {
+static int measure_particles(sl2_ctx *c, int32_t s, int32_t slot, int32_t feat_index, const uint8_t *patch,
+                             int32_t K, const double *h, const double *Sinv3, const double *detS,
+                             const double *lambda, double prune_probability_threshold, double *prob,
+                             int32_t *z_uv, uint8_t *found, uint8_t *keep, double *cumulative,
+                             double *mean_var) {
   if (bad_stream(c, s) || bad_slot(c, slot) || K < 0 || (K && (!h || !Sinv3 || !detS || !lambda || !prob)))
     return fail(c, SL2_ERR_ARG, "sl2_measure_particles: bad argument");
   if (K == 0) return 0;
-  int nf = 0;
-  int rc = device_nfeat(c, s, &nf);
-  if (rc) return rc;
-  if (feat_index < 0 || feat_index >= nf)
-    return fail(c, SL2_ERR_ARG, "sl2_measure_particles: feature index out of range");
+  int rc;
+  if (patch) {
+    rc = upload_scratch_patch(c, s, patch, &feat_index);
+    if (rc) return rc;
+  } else {
+    int nf = 0;
+    rc = device_nfeat(c, s, &nf);
+    if (rc) return rc;
+    if (feat_index < 0 || feat_index >= nf)
+      return fail(c, SL2_ERR_ARG, "sl2_measure_particles: feature index out of range");
+  }
   // staging: h(2K) Sinv3(3K) detS(K) lambda(K) prob(K) | cum(K) mean_var(2) | feat(K) uv(2K) left(1+pad) |
   //          found(K) keep(K)
   const size_t n = (size_t)K;
@@ -606,6 +630,33 @@ int sl2_measure_particles(sl2_ctx *c, int32_t s, int32_t slot, int32_t feat_inde
   int left = 0;
   memcpy(&left, hp + o_left, sizeof(int));
   return left;
+}
+
+int sl2_measure_particles(sl2_ctx *c, int32_t s, int32_t slot, int32_t feat_index, int32_t K,
+                          const double *h, const double *Sinv3, const double *detS, const double *lambda,
+                          double prune_probability_threshold, double *prob, int32_t *z_uv, uint8_t *found,
+                          uint8_t *keep, double *cumulative, double *mean_var) {
+  return measure_particles(c, s, slot, feat_index, nullptr, K, h, Sinv3, detS, lambda,
+                           prune_probability_threshold, prob, z_uv, found, keep, cumulative, mean_var);
+}
+
+int sl2_measure_particles_patch(sl2_ctx *c, int32_t s, int32_t slot, const uint8_t *patch, int32_t K,
+                                const double *h, const double *Sinv3, const double *detS, const double *lambda,
+                                double prune_probability_threshold, double *prob, int32_t *z_uv,
+                                uint8_t *found, uint8_t *keep, double *cumulative, double *mean_var) {
+  if (!patch) return fail(c, SL2_ERR_ARG, "sl2_measure_particles_patch: patch is null");
+  return measure_particles(c, s, slot, -1, patch, K, h, Sinv3, detS, lambda, prune_probability_threshold,
+                           prob, z_uv, found, keep, cumulative, mean_var);
+}
+
+int sl2_smoe_search_patch(sl2_ctx *c, int32_t s, int32_t slot, const uint8_t *patch, int32_t K,
+                          const double *PuInv3, const double *centres, int32_t *res_u, int32_t *res_v,
+                          uint8_t *res_flag) {
+  if (bad_stream(c, s) || !patch) return fail(c, SL2_ERR_ARG, "sl2_smoe_search_patch: bad argument");
+  int32_t feat = -1;
+  const int rc = upload_scratch_patch(c, s, patch, &feat);
+  if (rc) return rc;
+  return search_staged(c, s, slot, K, nullptr, feat, centres, PuInv3, res_u, res_v, res_flag, nullptr, 1);
 }
 
 int sl2_score_map(sl2_ctx *c, int32_t s, int32_t slot, int32_t feat, const double *centre,

@@ -43,7 +43,8 @@ EXPORTS = [
     "sl2_patch_search", "sl2_score_map", "sl2_smoe_search", "sl2_find_best_patch", "sl2_ekf_predict",
     "sl2_predict_measurements", "sl2_make_measurements", "sl2_ekf_update",
     "sl2_ekf_update_measured", "sl2_normalise_state", "sl2_step", "sl2_step_host",
-    "sl2_step_host_async", "sl2_wait_slot", "sl2_set_step_groups", "sl2_join", "sl2_measure_particles",
+    "sl2_step_host_async", "sl2_wait_slot", "sl2_set_step_groups", "sl2_join", "sl2_measure_particles", "sl2_measure_particles_patch",
+    "sl2_smoe_search_patch",
     "sl2_get_features", "sl2_get_feature_jacobians", "sl2_enable_timing", "sl2_last_step_times", "sl2_launch_count",
 ]
 
@@ -81,6 +82,10 @@ def load():
         L.sl2_join.argtypes = [C.c_void_p]
         L.sl2_measure_particles.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, f64p, f64p,
                                             f64p, f64p, C.c_double, f64p, i32p, u8p, u8p, f64p, f64p]
+        L.sl2_measure_particles_patch.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, f64p,
+                                                  f64p, f64p, f64p, C.c_double, f64p, i32p, u8p, u8p, f64p, f64p]
+        L.sl2_smoe_search_patch.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, f64p, f64p,
+                                            i32p, i32p, u8p]
         L.sl2_sync.argtypes = [C.c_void_p]
         L.sl2_score_map.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, f64p, f64p, i32p,
                                     f64p, f64p, u8p, C.c_size_t]
@@ -219,9 +224,23 @@ class Context:
                                         _p(ru, i32p), _p(rv, i32p), _p(rf, u8p)))
         return ru, rv, rf
 
-    def measure_particles(self, stream_id, slot, feat_index, h, Sinv3, detS, lam, prune_threshold, prob):
+    def smoe_search_patch(self, stream_id, slot, patch, puinv3, centres):
+        """SMOE search with a raw template (not a map feature)."""
+        patch = np.ascontiguousarray(patch, np.uint8)
+        assert patch.shape == (self.cfg.boxsize, self.cfg.boxsize)
+        puinv3, qp = _f64(puinv3)
+        centres, cp = _f64(centres)
+        K = puinv3.shape[0]
+        ru, rv, rf = np.zeros(K, np.int32), np.zeros(K, np.int32), np.zeros(K, np.uint8)
+        self._ck(self.L.sl2_smoe_search_patch(self.h, stream_id, slot, patch.ctypes.data, K, qp, cp, _p(ru, i32p),
+                                              _p(rv, i32p), _p(rf, u8p)))
+        return ru, rv, rf
+
+    def measure_particles(self, stream_id, slot, feat_index, h, Sinv3, detS, lam, prune_threshold, prob,
+                          patch=None):
         """N2: SMOE search + particle re-weighting of one partially-initialised feature ->
-        survivors, prob, z_uv (K,2), found, keep, cumulative, (mean, variance)."""
+        survivors, prob, z_uv (K,2), found, keep, cumulative, (mean, variance).  With `patch` (B x B u8) the
+        template is given directly instead of naming map feature `feat_index`."""
         h, hp = _f64(h)
         Sinv3, sp = _f64(Sinv3)
         detS, dp = _f64(detS)
@@ -233,9 +252,14 @@ class Context:
         keep = np.zeros(K, np.uint8)
         cum = np.zeros(K)
         mv = np.zeros(2)
-        left = self._ck(self.L.sl2_measure_particles(self.h, stream_id, slot, feat_index, K, hp, sp, dp, lp,
-                                                     float(prune_threshold), _p(prob, f64p), _p(z, i32p),
-                                                     _p(found, u8p), _p(keep, u8p), _p(cum, f64p), _p(mv, f64p)))
+        args = (K, hp, sp, dp, lp, float(prune_threshold), _p(prob, f64p), _p(z, i32p), _p(found, u8p),
+                _p(keep, u8p), _p(cum, f64p), _p(mv, f64p))
+        if patch is None:
+            left = self._ck(self.L.sl2_measure_particles(self.h, stream_id, slot, feat_index, *args))
+        else:
+            patch = np.ascontiguousarray(patch, np.uint8)
+            assert patch.shape == (self.cfg.boxsize, self.cfg.boxsize)
+            left = self._ck(self.L.sl2_measure_particles_patch(self.h, stream_id, slot, patch.ctypes.data, *args))
         return left, prob, z, found, keep, cum, mv
 
     def find_best_patch(self, stream_id, slot, regions, ubest=-1, vbest=-1):

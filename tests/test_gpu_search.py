@@ -206,3 +206,36 @@ def test_particle_measurement_and_reweighting_matches_oracle(oracle):
                                                                 np.full(K, 1.0 / K))
     assert left == 0 and not found.any() and not keep.any() and (prob == 0).all()
     ctx.close()
+
+
+def test_raw_template_variants_of_smoe_and_particles(oracle):
+    """sl2_smoe_search_patch / sl2_measure_particles_patch: the template of a partially-initialised feature is not
+    a map feature (the reference hands Feature::patch_ to the SMOE search, monoslam.cpp:1413).  Same results as
+    the oracle, and as the feat_index variants when the same template is registered as a map feature; the map
+    templates are untouched by the scratch slot."""
+    k = np.load(os.path.join(G, "a11_ref_kat.npz"))
+    img, patch = k["image"], k["patch"]
+    other = np.ascontiguousarray(img[20:31, 30:41])                       # the only map template: a different patch
+    ctx = ctx_for_image(img, other[None], radius=20)
+    ru, rv, rf = ctx.smoe_search_patch(0, 0, patch, k["puinv3"], k["centres"])
+    assert (ru == k["res_u"]).all() and (rv == k["res_v"]).all() and (rf == k["res_flag"]).all()
+    rng = np.random.default_rng(77)
+    hit = int(np.flatnonzero(k["res_flag"])[0])
+    K = 60
+    h = np.column_stack([k["res_u"][hit] + rng.normal(0, 6, K), k["res_v"][hit] + rng.normal(0, 6, K)])
+    pu = random_puinv(rng, K, 4, 12, iso_fraction=0.3)
+    det = 1.0 / (pu[:, 0] * pu[:, 2] - pu[:, 1] ** 2)
+    lam = np.linspace(0.5, 4.5, K)
+    p0 = np.full(K, 1.0 / K)
+    left, prob, z, found, keep, cum, mv = ctx.measure_particles(0, 0, -1, h, pu, det, lam, 0.05, p0, patch=patch)
+    ou, ov, of, _ = oracle.smoe_search(img, patch, pu, h)
+    oleft, oprob, okeep, ocum, omv = oracle.particle_update(h, pu, det, lam, np.column_stack([ou, ov]), of, 0.05, p0)
+    assert (found == of).all() and (z[of > 0, 0] == ou[of > 0]).all() and (z[of > 0, 1] == ov[of > 0]).all()
+    assert left == oleft and left > 0 and (keep == okeep).all()
+    np.testing.assert_allclose(prob, oprob, rtol=1e-13, atol=1e-300)
+    np.testing.assert_allclose(mv, omv, rtol=1e-12, atol=1e-15)
+    # the map feature still carries its own template
+    ou2, ov2, of2, _ = oracle.smoe_search(img, other, pu[:8], np.tile([35.3, 25.4], (8, 1)))
+    ru2, rv2, rf2 = ctx.smoe_search(0, 0, 0, pu[:8], np.tile([35.3, 25.4], (8, 1)))
+    assert (rf2 == of2).all() and (ru2[of2 > 0] == ou2[of2 > 0]).all() and (rv2[of2 > 0] == ov2[of2 > 0]).all()
+    ctx.close()

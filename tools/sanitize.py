@@ -29,6 +29,9 @@ K = 12
 pu = random_puinv(rng, K, 4, 10, 0.5)
 ctx.measure_particles(0, 0, 1, np.tile(sc.pix[1].astype(float), (K, 1)) + rng.normal(0, 3, (K, 2)), pu,
                       1.0 / (pu[:, 0] * pu[:, 2] - pu[:, 1] ** 2), np.linspace(0.5, 4.5, K), 0.05, np.full(K, 1.0 / K))
+ctx.measure_particles(0, 0, -1, np.tile(sc.pix[1].astype(float), (K, 1)), pu, 1.0 / (pu[:, 0] * pu[:, 2] - pu[:, 1] ** 2),
+                      np.linspace(0.5, 4.5, K), 0.05, np.full(K, 1.0 / K), patch=sc.patches[2])
+ctx.smoe_search_patch(0, 0, sc.patches[3], pu[:4], np.tile(sc.pix[3].astype(float), (4, 1)))
 ctx.delete_feature(1, 5)
 ctx.ekf_predict(0); ctx.predict_measurements(0); ctx.make_measurements(0, 0); ctx.ekf_update_measured(0)
 sc3 = synth.make_scene("C3", n_frames=1, n_features=9)
