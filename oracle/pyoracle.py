@@ -36,8 +36,22 @@ class OrcConfig(C.Structure):
 
 def build(force=False):
     """Compile liboracle.so (and _ref when /root/reference exists).  Building is not using."""
-    if force or not os.path.exists(_LIB) or (
-            os.path.isdir("/root/reference/scenelib2/improc") and not os.path.exists(_REF)):
+    have_ref = os.path.isdir("/root/reference/scenelib2/improc")
+    refm = os.path.join(_HERE, "_ref", "libsl2refmodels.so")
+    libs = [_LIB] + ([_REF, refm] if have_ref else [])
+    stale = force or any(not os.path.exists(p) for p in libs)
+    if not stale:
+        newest_src = 0.0
+        for root, _dirs, files in os.walk(_HERE):
+            if os.sep + "_ref" in root or "__pycache__" in root:
+                continue
+            for f in files:
+                if f.endswith((".cpp", ".hpp", ".h")) or f in ("Makefile", "Eigen", "StdVector"):
+                    newest_src = max(newest_src, os.path.getmtime(os.path.join(root, f)))
+        stale = newest_src > min(os.path.getmtime(p) for p in libs)
+    if stale:
+        if not force and os.path.exists(_LIB):
+            os.utime(os.path.join(_HERE, "capi.cpp"))  # make only tracks liboracle.so's own sources
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _LIB
 
