@@ -276,19 +276,14 @@ def run_ours(args, rank, local_rank, world):
     # ---- per-kernel durations (CUDA events on the launching stream, one sync per step) ----------
     ctx.enable_timing(True)
     kt = np.zeros(4)
+    ku = np.zeros(4)
     for k in range(args.steps):
         ctx.step(k % R)
         kt += ctx.last_step_times()
+        ku += ctx.last_update_times()
     kt /= args.steps
+    ku /= args.steps
     ctx.enable_timing(False)
-    if os.environ.get("SL2_PHASES"):
-        import ctypes
-        buf = (ctypes.c_longlong * 64)()
-        ctx.L.sl2_debug_phase_cycles(ctx.h, buf)
-        st = [buf[i] for i in range(8)]
-        print("update phase cycles (CTA 0):", [st[i + 1] - st[i] for i in range(7)],
-              "panel sub-phases (mult, mma, wait, apply):", [buf[i] for i in range(16, 21)], file=sys.stderr)
-
     # ---- end-to-end leg: host frames in, camera states out, through the C ABI -----------------
     # every step: pinned host frames -> H2D -> GoOneStep of all streams -> D2H of the camera states;
     # the copy of step t+1 overlaps the kernels of step t (frame ring); the region ends when the
@@ -367,7 +362,9 @@ def run_ours(args, rank, local_rank, world):
                                       "algorithmic_bytes_per_launch": search_bytes, "kernel_ms": float(kt[1]),
                                       "note": "integer / FP64 issue bound, not HBM bound: see DESIGN.md 3.1"},
             "kernel_ms": {"predict_select": float(kt[0]), "patch_search": float(kt[1]),
-                          "ekf_update": float(kt[2]), "cull": float(kt[3])},
+                          "ekf_update": float(kt[2]), "cull": float(kt[3]),
+                          "ekf_update_kernels": {"factor": float(ku[0]), "solve": float(ku[1]),
+                                                 "syrk": float(ku[2]), "finish": float(ku[3])}},
         }
         if not args.no_cpu_baseline and world == 1:
             fps, threads, steps, t = cpu_run(scenes, args.cpu_seconds, args.cpu_threads or None)

@@ -158,7 +158,8 @@ int sl2_make_measurements(sl2_ctx *ctx, int32_t stream_id, int32_t slot);
 /* Kalman::KalmanFilterUpdate (kalman.cpp:72-119) with host-supplied measurement rows, in the
  * order of construct_total_measurement_stuff (monoslam.cpp:548-572): row pair k belongs to
  * feature feat_index[k]; H_xv is (2k_meas) x 13 row-major, H_y (2k_meas) x 3 row-major,
- * R k_meas x (2x2 col-major), nu 2k_meas.  m = 2 * k_meas. */
+ * R k_meas x (2x2 col-major, symmetric: SL2_ERR_ARG otherwise; the full block enters S), nu 2k_meas.
+ * m = 2 * k_meas. */
 int sl2_ekf_update(sl2_ctx *ctx, int32_t stream_id, int32_t m, const int32_t *feat_index,
                    const double *H_xv, const double *H_y, const double *R, const double *nu);
 /* same, using the device-resident predictions/measurements of the two calls above */
@@ -203,6 +204,10 @@ int sl2_get_feature_jacobians(sl2_ctx *ctx, int32_t stream_id, double *dh_by_dxv
  * [2] EKF update, [3] cull.  Valid after sl2_enable_timing(ctx, 1). */
 int sl2_enable_timing(sl2_ctx *ctx, int32_t on);
 int sl2_last_step_times(sl2_ctx *ctx, float *ms4);
+/* the four kernels of the EKF update of the last sl2_step (ms): [0] factor (H P, S, Cholesky of S),
+ * [1] solve (Y = U^-T [H P | nu]), [2] syrk (P -= Y^T Y, x += Y^T w), [3] finish (normalise, symmetrise,
+ * counters).  Their sum is sl2_last_step_times()[2]. */
+int sl2_last_update_times(sl2_ctx *ctx, float *ms4);
 /* kernels launched by this context since creation */
 int64_t sl2_launch_count(const sl2_ctx *ctx);
 

@@ -3,7 +3,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["csrc/api.cu", "csrc/search.cu", "csrc/ekf.cu", "csrc/detect.cu", "csrc/particles.cu"]
+SOURCES = ["csrc/api.cu", "csrc/search.cu", "csrc/ekf.cu", "csrc/update.cu", "csrc/detect.cu", "csrc/particles.cu"]
 HEADERS = ["csrc/sl2_common.cuh", "../include/sl2b200.h", "host/scenelib2_b200.cpp",
            "host/scenelib2_b200.h", "host/sl2_compat.h", "host/sl2_headless.cpp"]
 LIB = os.path.join(HERE, "libsl2b200.so")
@@ -26,8 +26,6 @@ def build(force=False, verbose=False):
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
-    if os.environ.get("SL2_PHASE_STAMPS"):  # profiling builds only: per-phase clock64 stamps
-        cmd.insert(1, "-DSL2_PHASE_STAMPS")
     if os.environ.get("SL2_EXTRA_NVCC"):  # experiments only
         cmd[1:1] = os.environ["SL2_EXTRA_NVCC"].split()
     subprocess.check_call(cmd, cwd=HERE)

@@ -29,7 +29,9 @@ struct sl2_ctx {
   uint8_t *stg_host = nullptr;  // pinned
   int64_t launches = 0;
   bool timing = false;
+  // timing mode: ev[0..4] bracket predict / search / update / cull, evu[0..4] the four update kernels
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t evu[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   // asynchronous end-to-end path: frames of step t+1 are copied while step t computes
   cudaStream_t copy_stream = nullptr;  // H2D of the frames
   cudaStream_t out_stream = nullptr;   // D2H of the results (own stream: must not block the next H2D)
@@ -272,7 +274,8 @@ int sl2_create(const sl2_config *cfg, sl2_ctx **out) {
   ALLOC(d.nvisible, B);
   ALLOC(d.nmeas, B);
   ALLOC(d.ncull, B);
-  ALLOC(d.dbg, 64);
+  ALLOC(d.upd_m, B);
+  ALLOC(d.Wp, B * SL2_MAX_PANELS * 256);
   ALLOC(c->xv_stage, (size_t)d.slots * B * SL2_NXV);
 #undef ALLOC
   if (!ok) {
@@ -286,7 +289,8 @@ int sl2_create(const sl2_config *cfg, sl2_ctx **out) {
   if (rc == SL2_OK) rc = stage_reserve(c, 1 << 20);
   if (rc == SL2_OK) {
     for (int i = 0; i < 5 && rc == SL2_OK; ++i)
-      if (cudaEventCreate(&c->ev[i]) != cudaSuccess) rc = SL2_ERR_CUDA;
+      if (cudaEventCreate(&c->ev[i]) != cudaSuccess || cudaEventCreate(&c->evu[i]) != cudaSuccess)
+        rc = SL2_ERR_CUDA;
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) rc = SL2_ERR_CUDA;
     if (cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking) != cudaSuccess) rc = SL2_ERR_CUDA;
     if (cudaStreamCreateWithFlags(&c->stream_b, cudaStreamNonBlocking) != cudaSuccess) rc = SL2_ERR_CUDA;
@@ -341,6 +345,8 @@ void sl2_destroy(sl2_ctx *c) {
   if (c->stg_dev) cudaFree(c->stg_dev);
   if (c->stg_host) cudaFreeHost(c->stg_host);
   for (auto &e : c->ev)
+    if (e) cudaEventDestroy(e);
+  for (auto &e : c->evu)
     if (e) cudaEventDestroy(e);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -767,11 +773,18 @@ int sl2_make_measurements(sl2_ctx *c, int32_t s, int32_t slot) {
   L.scatter_to_features = 1;
   CU_TRY(c, sl2_launch_search(d, c->tmap, L, c->stream));
   ++c->launches;
+  // successful measurements of THIS step only: found[] keeps the flag of features that were not
+  // selected this frame (Feature::successful_measurement_flag_), so count over the job list
   std::vector<uint8_t> f(d.Nmax);
+  std::vector<int> jf(d.Nmax);
+  int nsel = 0;
   CU_TRY(c, cudaMemcpyAsync(f.data(), d.found + fb, d.Nmax, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(jf.data(), d.job_feat + fb, sizeof(int) * d.Nmax, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(&nsel, d.nsel + s, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(c, cudaStreamSynchronize(c->stream));
   int cnt = 0;
-  for (uint8_t b : f) cnt += b ? 1 : 0;
+  for (int r = 0; r < nsel && r < d.Nmax; ++r)
+    if (jf[r] >= 0 && jf[r] < d.Nmax && f[jf[r]]) ++cnt;
   return cnt;
 }
 
@@ -785,8 +798,11 @@ int sl2_ekf_update(sl2_ctx *c, int32_t s, int32_t m, const int32_t *feat_index, 
   int nf = 0;
   int rc = device_nfeat(c, s, &nf);
   if (rc) return rc;
-  for (int k = 0; k < K; ++k)
+  for (int k = 0; k < K; ++k) {
     if (feat_index[k] < 0 || feat_index[k] >= nf) return fail(c, SL2_ERR_ARG, "sl2_ekf_update: bad feature index");
+    // the full 2x2 block R_k enters S (kalman.cpp:101); a covariance block has to be symmetric
+    if (R[k * 4 + 1] != R[k * 4 + 2]) return fail(c, SL2_ERR_ARG, "sl2_ekf_update: R block is not symmetric");
+  }
   const size_t o_hx = 0, o_hy = o_hx + 8 * 26 * (size_t)K, o_r = o_hy + 8 * 6 * (size_t)K,
                o_nu = o_r + 8 * 4 * (size_t)K, o_f = o_nu + 8 * 2 * (size_t)K,
                total = o_f + 4 * (size_t)K + 64;
@@ -794,6 +810,7 @@ int sl2_ekf_update(sl2_ctx *c, int32_t s, int32_t m, const int32_t *feat_index, 
   if (rc) return rc;
   CU_TRY(c, cudaStreamSynchronize(c->stream));
   uint8_t *hp = c->stg_host;
+  int nl = 0;
   memcpy(hp + o_hx, H_xv, 8 * 26 * (size_t)K);
   memcpy(hp + o_hy, H_y, 8 * 6 * (size_t)K);
   memcpy(hp + o_r, R, 8 * 4 * (size_t)K);
@@ -804,24 +821,26 @@ int sl2_ekf_update(sl2_ctx *c, int32_t s, int32_t m, const int32_t *feat_index, 
                               reinterpret_cast<const double *>(c->stg_dev + o_hx),
                               reinterpret_cast<const double *>(c->stg_dev + o_hy),
                               reinterpret_cast<const double *>(c->stg_dev + o_r),
-                              reinterpret_cast<const double *>(c->stg_dev + o_nu), 0, c->stream));
-  ++c->launches;
+                              reinterpret_cast<const double *>(c->stg_dev + o_nu), 0, c->stream, nullptr, &nl));
+  c->launches += nl;
   CU_TRY(c, cudaStreamSynchronize(c->stream));
   return SL2_OK;
 }
 
 int sl2_ekf_update_measured(sl2_ctx *c, int32_t s) {
   if (bad_stream(c, s)) return fail(c, SL2_ERR_ARG, "bad stream");
-  CU_TRY(c, sl2_launch_update(c->d, s, 1, -1, nullptr, nullptr, nullptr, nullptr, nullptr, 0, c->stream));
-  ++c->launches;
+  int nl = 0;
+  CU_TRY(c, sl2_launch_update(c->d, s, 1, -1, nullptr, nullptr, nullptr, nullptr, nullptr, 0, c->stream, nullptr, &nl));
+  c->launches += nl;
   CU_TRY(c, cudaStreamSynchronize(c->stream));
   return SL2_OK;
 }
 
 int sl2_normalise_state(sl2_ctx *c, int32_t s) {
   if (bad_stream(c, s)) return fail(c, SL2_ERR_ARG, "bad stream");
-  CU_TRY(c, sl2_launch_update(c->d, s, 1, -1, nullptr, nullptr, nullptr, nullptr, nullptr, 1, c->stream));
-  ++c->launches;
+  int nl = 0;
+  CU_TRY(c, sl2_launch_update(c->d, s, 1, -1, nullptr, nullptr, nullptr, nullptr, nullptr, 1, c->stream, nullptr, &nl));
+  c->launches += nl;
   CU_TRY(c, cudaStreamSynchronize(c->stream));
   return SL2_OK;
 }
@@ -846,11 +865,13 @@ static int step_group(sl2_ctx *c, int32_t slot, int lo, int cnt, cudaStream_t st
   CU_TRY(c, sl2_launch_search(d, c->tmap, L, st));
   if (t) CU_TRY(c, cudaEventRecord(c->ev[2], st));
   if (after_search) CU_TRY(c, cudaEventRecord(after_search, st));
-  CU_TRY(c, sl2_launch_update(d, lo, cnt, -1, nullptr, nullptr, nullptr, nullptr, nullptr, 0, st));
+  int nl = 3;
+  CU_TRY(c, sl2_launch_update(d, lo, cnt, -1, nullptr, nullptr, nullptr, nullptr, nullptr, 0, st,
+                              t ? c->evu : nullptr, &nl));
   if (t) CU_TRY(c, cudaEventRecord(c->ev[3], st));
   CU_TRY(c, sl2_launch_cull(d, lo, cnt, -1, st));
   if (t) CU_TRY(c, cudaEventRecord(c->ev[4], st));
-  c->launches += 4;
+  c->launches += nl;
   return SL2_OK;
 }
 
@@ -907,7 +928,10 @@ int sl2_step_host_async(sl2_ctx *c, int32_t slot, const uint8_t *gray, double *x
   if (!c || bad_slot(c, slot) || !gray) return fail(c, SL2_ERR_ARG, "sl2_step_host_async: bad argument");
   const Sl2Dev &d = c->d;
   cudaStream_t cs = c->copy_stream;
-  // the frame slot may still be read by the step that used it last (either stream group)
+  // the frame slot may still be read by work queued earlier: the step that used it last (either stream
+  // group) or any other entry point (sl2_step, sl2_set_frames, staged searches) that ran on `stream`
+  CU_TRY(c, cudaEventRecord(c->ev_main, c->stream));
+  CU_TRY(c, cudaStreamWaitEvent(cs, c->ev_main, 0));
   CU_TRY(c, cudaStreamWaitEvent(cs, c->ev_cmp[slot], 0));
   CU_TRY(c, cudaStreamWaitEvent(cs, c->ev_cmp_b[slot], 0));
   uint8_t *dst = d.frames + (size_t)slot * d.B * d.H * d.pitch;
@@ -1009,11 +1033,12 @@ int sl2_get_feature_jacobians(sl2_ctx *c, int32_t s, double *dh_by_dxv, double *
   return nf;
 }
 
-// debug only (not part of the public header): clock64 stamps of the update kernel's phases
-int sl2_debug_phase_cycles(sl2_ctx *c, long long *out64) {
-  if (!c || !out64) return SL2_ERR_ARG;
-  CU_TRY(c, cudaMemcpyAsync(out64, c->d.dbg, 64 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
-  CU_TRY(c, cudaStreamSynchronize(c->stream));
+int sl2_last_update_times(sl2_ctx *c, float *ms4) {
+  enter(c);
+  if (!c || !ms4) return SL2_ERR_ARG;
+  if (!c->timing) return fail(c, SL2_ERR_STATE, "timing not enabled");
+  CU_TRY(c, cudaEventSynchronize(c->evu[4]));
+  for (int i = 0; i < 4; ++i) CU_TRY(c, cudaEventElapsedTime(&ms4[i], c->evu[i], c->evu[i + 1]));
   return SL2_OK;
 }
 

@@ -54,9 +54,13 @@ struct Sl2Dev {
   int *nsel;           // [B]
   int *nvisible;       // [B]
   int *nmeas;          // [B]  successful measurements of the last step
-  int *ncull;          // [B]  features the next cull would delete (set by update_kernel)
-  long long *dbg;      // [64] phase cycle stamps of CTA 0 of the update kernel (debug)
+  int *ncull;          // [B]  features the next cull would delete (set by the update's finish kernel)
+  // EKF update pipeline (update.cu): factor -> solve -> syrk -> finish
+  int *upd_m;          // [B]  measurement rows m of the running update (0: nothing to do)
+  double *Wp;          // [B][SL2_MAX_PANELS][16*16]  W_pp = U_pp^-T of every 16-row Cholesky panel
 };
+
+#define SL2_MAX_PANELS 16  // 16-row panels of S: m <= 2 * SL2_MAX_FEATURES = 256
 
 // ---- correctly-rounded, never-fused FP64 helpers: the oracle is built with
 // -ffp-contract=off, so every bit-critical expression must avoid FMA contraction.
@@ -66,7 +70,20 @@ __device__ __forceinline__ double sub_(double a, double b) { return __dsub_rn(a,
 __device__ __forceinline__ double div_(double a, double b) { return __ddiv_rn(a, b); }
 __device__ __forceinline__ double sqrt_(double a) { return __dsqrt_rn(a); }
 
-// launchers (defined in search.cu / ekf.cu), called from api.cu
+// never-fused FP64 scalar with natural operator syntax (bit-critical prologue math)
+struct rd {
+  double v;
+  __device__ __forceinline__ rd() : v(0.0) {}
+  __device__ __forceinline__ rd(double x) : v(x) {}
+};
+__device__ __forceinline__ rd operator+(rd a, rd b) { return rd(__dadd_rn(a.v, b.v)); }
+__device__ __forceinline__ rd operator-(rd a, rd b) { return rd(__dsub_rn(a.v, b.v)); }
+__device__ __forceinline__ rd operator*(rd a, rd b) { return rd(__dmul_rn(a.v, b.v)); }
+__device__ __forceinline__ rd operator/(rd a, rd b) { return rd(__ddiv_rn(a.v, b.v)); }
+__device__ __forceinline__ rd operator-(rd a) { return rd(-a.v); }
+__device__ __forceinline__ rd rsqrt_(rd a) { return rd(__dsqrt_rn(a.v)); }
+
+// launchers (defined in search.cu / ekf.cu / update.cu), called from api.cu
 struct SearchLaunch {
   // job arrays may be the context's own (fused step) or temporaries (staged API)
   const int *job_feat;       // [njobs_per_stream * B] or [n]
@@ -90,10 +107,11 @@ cudaError_t sl2_launch_score_map(const Sl2Dev &d, const CUtensorMap &tmap, int s
                                  cudaStream_t st);
 cudaError_t sl2_launch_predict(const Sl2Dev &d, int stream_lo, int stream_cnt, const double *u3_dev,
                                int do_predict, int do_measure, cudaStream_t st);
+// EKF update = 4 kernels (factor, solve, syrk, finish); ev5 (optional) = 5 events recorded around them
 cudaError_t sl2_launch_update(const Sl2Dev &d, int stream_lo, int stream_cnt, int staged_m,
                               const int *st_feat, const double *st_Hxv, const double *st_Hy,
                               const double *st_R, const double *st_nu, int only_normalise,
-                              cudaStream_t st);
+                              cudaStream_t st, cudaEvent_t *ev5 = nullptr, int *launches = nullptr);
 cudaError_t sl2_launch_cull(const Sl2Dev &d, int stream_lo, int stream_cnt, int force_index,
                             cudaStream_t st);
 size_t sl2_update_smem_bytes(const Sl2Dev &d);

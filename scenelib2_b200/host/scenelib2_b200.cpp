@@ -472,16 +472,18 @@ bool MonoSLAM::GoOneStep(cv::Mat frame, bool save_trajectory, bool enable_mappin
   kalman_->KalmanFilterPredict(this, u);
   number_of_visible_features_ = auto_select_n_features(kNumberOfFeaturesToSelect_);
   successful_measurement_vector_size_ = 0;
-  if (number_of_visible_features_ > 0) {
-    make_measurements(frame);
-    // (Kalman update + normalise_state + symmetrise are one device call; it is a no-op on the
-    // state when nothing was measured, and it books the attempt counters either way)
-    kalman_->KalmanFilterUpdate(this);
-  }
+  if (number_of_visible_features_ > 0) make_measurements(frame);
+  // Kalman update + normalise_state + symmetrise are one device call.  It runs on EVERY frame: with nothing
+  // selected or matched it leaves the state alone but still applies P = 0.5 P + 0.5 P^T, which the reference
+  // does unconditionally at the end of GoOneStep (monoslam.cpp:143-150), and books the attempt counters.
+  kalman_->KalmanFilterUpdate(this);
   SyncFromDevice();
+  const size_t features_before = feature_list_.size();
   delete_bad_features();
-  if (feature_list_.size() * 3 + 13 != (size_t)total_state_size_) total_state_size_ = 13 + 3 * (int)feature_list_.size();
-  SyncFromDevice();
+  if (feature_list_.size() != features_before) {  // the map shrank: mirror the compacted device state again
+    total_state_size_ = 13 + 3 * (int)feature_list_.size();
+    SyncFromDevice();
+  }
   motion_model_->func_xp(xv_);
   if (save_trajectory) {
     trajectory_store_.push_back(motion_model_->rRES_);

@@ -45,7 +45,7 @@ EXPORTS = [
     "sl2_ekf_update_measured", "sl2_normalise_state", "sl2_step", "sl2_step_host",
     "sl2_step_host_async", "sl2_wait_slot", "sl2_set_step_groups", "sl2_join", "sl2_measure_particles", "sl2_measure_particles_patch",
     "sl2_smoe_search_patch",
-    "sl2_get_features", "sl2_get_feature_jacobians", "sl2_enable_timing", "sl2_last_step_times", "sl2_launch_count",
+    "sl2_get_features", "sl2_get_feature_jacobians", "sl2_enable_timing", "sl2_last_step_times", "sl2_last_update_times", "sl2_launch_count",
 ]
 
 _lib = None
@@ -331,6 +331,12 @@ class Context:
     def last_step_times(self):
         ms = np.zeros(4, np.float32)
         self._ck(self.L.sl2_last_step_times(self.h, _p(ms, f32p)))
+        return ms
+
+    def last_update_times(self):
+        """ms of the four EKF update kernels of the last step: factor, solve, syrk, finish"""
+        ms = np.zeros(4, np.float32)
+        self._ck(self.L.sl2_last_update_times(self.h, _p(ms, f32p)))
         return ms
 
     def launch_count(self):
