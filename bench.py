@@ -276,7 +276,7 @@ def run_ours(args, rank, local_rank, world):
     # ---- per-kernel durations (CUDA events on the launching stream, one sync per step) ----------
     ctx.enable_timing(True)
     kt = np.zeros(4)
-    ku = np.zeros(4)
+    ku = np.zeros(5)
     for k in range(args.steps):
         ctx.step(k % R)
         kt += ctx.last_step_times()
@@ -363,8 +363,8 @@ def run_ours(args, rank, local_rank, world):
                                       "note": "integer / FP64 issue bound, not HBM bound: see DESIGN.md 3.1"},
             "kernel_ms": {"predict_select": float(kt[0]), "patch_search": float(kt[1]),
                           "ekf_update": float(kt[2]), "cull": float(kt[3]),
-                          "ekf_update_kernels": {"factor": float(ku[0]), "solve": float(ku[1]),
-                                                 "syrk": float(ku[2]), "finish": float(ku[3])}},
+                          "ekf_update_kernels": {"hp": float(ku[0]), "chol": float(ku[1]), "solve": float(ku[2]),
+                                                 "syrk": float(ku[3]), "finish": float(ku[4])}},
         }
         if not args.no_cpu_baseline and world == 1:
             fps, threads, steps, t = cpu_run(scenes, args.cpu_seconds, args.cpu_threads or None)

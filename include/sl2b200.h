@@ -204,10 +204,10 @@ int sl2_get_feature_jacobians(sl2_ctx *ctx, int32_t stream_id, double *dh_by_dxv
  * [2] EKF update, [3] cull.  Valid after sl2_enable_timing(ctx, 1). */
 int sl2_enable_timing(sl2_ctx *ctx, int32_t on);
 int sl2_last_step_times(sl2_ctx *ctx, float *ms4);
-/* the four kernels of the EKF update of the last sl2_step (ms): [0] factor (H P, S, Cholesky of S),
- * [1] solve (Y = U^-T [H P | nu]), [2] syrk (P -= Y^T Y, x += Y^T w), [3] finish (normalise, symmetrise,
- * counters).  Their sum is sl2_last_step_times()[2]. */
-int sl2_last_update_times(sl2_ctx *ctx, float *ms4);
+/* the five kernels of the EKF update of the last sl2_step (ms): [0] hp (measurement list, H P, S = H P H^T + R),
+ * [1] chol (Cholesky of S), [2] solve (Y = U^-T [H P | nu]), [3] syrk (P -= Y^T Y, x += Y^T w), [4] finish
+ * (normalise, symmetrise, counters).  Their sum is sl2_last_step_times()[2]. */
+int sl2_last_update_times(sl2_ctx *ctx, float *ms5);
 /* kernels launched by this context since creation */
 int64_t sl2_launch_count(const sl2_ctx *ctx);
 

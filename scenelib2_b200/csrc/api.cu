@@ -29,9 +29,9 @@ struct sl2_ctx {
   uint8_t *stg_host = nullptr;  // pinned
   int64_t launches = 0;
   bool timing = false;
-  // timing mode: ev[0..4] bracket predict / search / update / cull, evu[0..4] the four update kernels
+  // timing mode: ev[0..4] bracket predict / search / update / cull, evu[0..5] the five update kernels
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t evu[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t evu[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // asynchronous end-to-end path: frames of step t+1 are copied while step t computes
   cudaStream_t copy_stream = nullptr;  // H2D of the frames
   cudaStream_t out_stream = nullptr;   // D2H of the results (own stream: must not block the next H2D)
@@ -289,8 +289,9 @@ int sl2_create(const sl2_config *cfg, sl2_ctx **out) {
   if (rc == SL2_OK) rc = stage_reserve(c, 1 << 20);
   if (rc == SL2_OK) {
     for (int i = 0; i < 5 && rc == SL2_OK; ++i)
-      if (cudaEventCreate(&c->ev[i]) != cudaSuccess || cudaEventCreate(&c->evu[i]) != cudaSuccess)
-        rc = SL2_ERR_CUDA;
+      if (cudaEventCreate(&c->ev[i]) != cudaSuccess) rc = SL2_ERR_CUDA;
+    for (int i = 0; i < 6 && rc == SL2_OK; ++i)
+      if (cudaEventCreate(&c->evu[i]) != cudaSuccess) rc = SL2_ERR_CUDA;
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) rc = SL2_ERR_CUDA;
     if (cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking) != cudaSuccess) rc = SL2_ERR_CUDA;
     if (cudaStreamCreateWithFlags(&c->stream_b, cudaStreamNonBlocking) != cudaSuccess) rc = SL2_ERR_CUDA;
@@ -369,6 +370,7 @@ int sl2_set_frame(sl2_ctx *c, int32_t s, int32_t slot, const uint8_t *gray, size
   const Sl2Dev &d = c->d;
   uint8_t *dst = d.frames + ((size_t)slot * d.B + s) * d.H * d.pitch;
   CU_TRY(c, cudaMemcpy2DAsync(dst, d.pitch, gray, stride, d.W, d.H, cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaEventRecord(c->ev_cmp[slot], c->stream));  // slot busy until the copy has landed
   return SL2_OK;
 }
 
@@ -382,6 +384,7 @@ static int set_frames_any(sl2_ctx *c, int32_t slot, const uint8_t *gray, cudaMem
   } else {
     CU_TRY(c, cudaMemcpy2DAsync(dst, d.pitch, gray, d.W, d.W, (size_t)d.B * d.H, kind, c->stream));
   }
+  CU_TRY(c, cudaEventRecord(c->ev_cmp[slot], c->stream));  // slot busy until the copy has landed
   return SL2_OK;
 }
 int sl2_set_frames(sl2_ctx *c, int32_t slot, const uint8_t *gray) {
@@ -902,10 +905,18 @@ static int step_enqueue(sl2_ctx *c, int32_t slot, bool serial = false) {
   return SL2_OK;
 }
 
+// the slot's frames are busy until everything queued so far on the step stream(s) has run
+static int mark_slot_busy(sl2_ctx *c, int32_t slot) {
+  CU_TRY(c, cudaEventRecord(c->ev_cmp[slot], c->stream));
+  if (c->b_pending) CU_TRY(c, cudaEventRecord(c->ev_cmp_b[slot], c->stream_b));
+  return SL2_OK;
+}
+
 int sl2_step(sl2_ctx *c, int32_t slot) {
   enter(c, false);
   if (!c || bad_slot(c, slot)) return fail(c, SL2_ERR_ARG, "sl2_step: bad slot");
-  return step_enqueue(c, slot);
+  const int rc = step_enqueue(c, slot);
+  return rc ? rc : mark_slot_busy(c, slot);
 }
 
 int sl2_step_host(sl2_ctx *c, int32_t slot, const uint8_t *gray, double *xv_out) {
@@ -928,10 +939,10 @@ int sl2_step_host_async(sl2_ctx *c, int32_t slot, const uint8_t *gray, double *x
   if (!c || bad_slot(c, slot) || !gray) return fail(c, SL2_ERR_ARG, "sl2_step_host_async: bad argument");
   const Sl2Dev &d = c->d;
   cudaStream_t cs = c->copy_stream;
-  // the frame slot may still be read by work queued earlier: the step that used it last (either stream
-  // group) or any other entry point (sl2_step, sl2_set_frames, staged searches) that ran on `stream`
-  CU_TRY(c, cudaEventRecord(c->ev_main, c->stream));
-  CU_TRY(c, cudaStreamWaitEvent(cs, c->ev_main, 0));
+  // the frame slot may still be in use by work queued earlier on it: ev_cmp[slot] / ev_cmp_b[slot] are recorded
+  // behind EVERY operation that reads or writes the slot (fused steps of either stream group, sl2_set_frame(s));
+  // the remaining slot users (staged searches, detector, particles) synchronise the stream before they return.
+  // Work on OTHER slots is not waited for: the copy of frame t+1 overlaps the kernels of frame t.
   CU_TRY(c, cudaStreamWaitEvent(cs, c->ev_cmp[slot], 0));
   CU_TRY(c, cudaStreamWaitEvent(cs, c->ev_cmp_b[slot], 0));
   uint8_t *dst = d.frames + (size_t)slot * d.B * d.H * d.pitch;
@@ -1033,12 +1044,12 @@ int sl2_get_feature_jacobians(sl2_ctx *c, int32_t s, double *dh_by_dxv, double *
   return nf;
 }
 
-int sl2_last_update_times(sl2_ctx *c, float *ms4) {
+int sl2_last_update_times(sl2_ctx *c, float *ms5) {
   enter(c);
-  if (!c || !ms4) return SL2_ERR_ARG;
+  if (!c || !ms5) return SL2_ERR_ARG;
   if (!c->timing) return fail(c, SL2_ERR_STATE, "timing not enabled");
-  CU_TRY(c, cudaEventSynchronize(c->evu[4]));
-  for (int i = 0; i < 4; ++i) CU_TRY(c, cudaEventElapsedTime(&ms4[i], c->evu[i], c->evu[i + 1]));
+  CU_TRY(c, cudaEventSynchronize(c->evu[5]));
+  for (int i = 0; i < 5; ++i) CU_TRY(c, cudaEventElapsedTime(&ms5[i], c->evu[i], c->evu[i + 1]));
   return SL2_OK;
 }
 

@@ -35,23 +35,17 @@
 namespace {
 
 struct UpdSmem {
-  // carved from dynamic shared memory; sizes depend on Nmax
-  double *wv;    // [mmax]  nu (copied into the last column of G)
-  int *mfeat;    // [K]
-  double *Rv;    // [K][3]  R_k = (R00, R01, R11)
-  double *mult;  // [mmax][UPD_MS] (negated) multipliers of the current panel; phases 1a/1b: H*P(:, 0:13)
+  // upd_chol_global: carved from dynamic shared memory; sizes depend on Nmax
+  double *mult;  // [mmax][UPD_MS] (negated) multipliers of the current panel
   double *dg;    // [NB][UPD_DS] diagonal block of the current panel (factor scratch)
   double *Wm;    // [NB][UPD_WS]  W = U_pp^-T of the current panel
-  double *pan;   // phase 1: HxT / Hy (aliased); phase 2: panel buffer [NB][panw]
-  double *HxT;   // = pan          [16][hms]  Hx transposed, k-major, zero padded (cols 13..15, rows >= m)
-  double *Hy;    // = pan + 16*hms [K][2][3]
-  int panw, hms;
+  double *pan;   // panel buffer [NB][panw]
+  int panw;
 };
 
 constexpr int UPD_THREADS = 256;
 constexpr int UPD_NB = 16;   // Cholesky row-panel height (two DMMA M-tiles)
 constexpr int UPD_WS = 20;   // row stride of the W table
-constexpr int UPD_HXS = 14;  // row stride of the H*P(:, 0:13) table phase 1a leaves in sm.mult for phase 1b
 constexpr int UPD_DS = 20;   // row stride of the diagonal-block scratch (conflict-free fragments)
 constexpr int UPD_MS = 20;   // row stride of the multiplier table: 32 B (mod 128) => conflict-free A fragments
 constexpr int UPD_KC = 32;   // k-chunk of the Y^T Y tiles
@@ -65,32 +59,17 @@ __host__ __device__ inline int upd_panw(int Nmax) {
   // C fragment hit distinct banks
   return ((2 * upd_keven(Nmax) + 15) & ~15) + 2;
 }
-__host__ __device__ inline int upd_hms(int Nmax) {
-  // k-major Hx table: row stride = 4 (mod 16) doubles => the 4 k-rows of a fragment are 32 B apart
-  return ((2 * upd_keven(Nmax) + 15) & ~15) + 4;
-}
-__host__ __device__ inline size_t upd_pan_doubles(int Nmax) {
-  size_t a = (size_t)UPD_NB * upd_panw(Nmax);
-  const size_t h = (size_t)16 * upd_hms(Nmax) + (size_t)upd_keven(Nmax) * 6;
-  if (h > a) a = h;
-  return (a + 1) & ~(size_t)1;
-}
+__host__ __device__ inline size_t upd_pan_doubles(int Nmax) { return (size_t)UPD_NB * upd_panw(Nmax); }
 
 __device__ __forceinline__ UpdSmem carve(uint8_t *base, int Nmax) {
   UpdSmem u;
   const int K = upd_keven(Nmax), mmax = 2 * K;  // even counts keep every section 16 B aligned
   double *p = reinterpret_cast<double *>(base);
-  u.wv = p;  p += mmax;
-  u.Rv = p;  p += (size_t)K * 3 + (K & 1);
   u.mult = p;  p += (size_t)mmax * UPD_MS;
   u.dg = p;  p += UPD_NB * UPD_DS;
   u.Wm = p;  p += UPD_NB * UPD_WS;
-  u.pan = p;  p += upd_pan_doubles(Nmax);
+  u.pan = p;
   u.panw = upd_panw(Nmax);
-  u.hms = upd_hms(Nmax);
-  u.HxT = u.pan;
-  u.Hy = u.pan + (size_t)16 * u.hms;
-  u.mfeat = reinterpret_cast<int *>(p);
   return u;
 }
 
@@ -110,6 +89,67 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// wait until at most n groups are pending; n folds to a constant in unrolled loops
+__device__ __forceinline__ void cp_async_wait_n(int n) {
+  switch (n) {
+    case 0: cp_async_wait<0>(); break;
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    case 3: cp_async_wait<3>(); break;
+    case 4: cp_async_wait<4>(); break;
+    case 5: cp_async_wait<5>(); break;
+    case 6: cp_async_wait<6>(); break;
+    case 7: cp_async_wait<7>(); break;
+    case 8: cp_async_wait<8>(); break;
+    case 9: cp_async_wait<9>(); break;
+    case 10: cp_async_wait<10>(); break;
+    case 11: cp_async_wait<11>(); break;
+    case 12: cp_async_wait<12>(); break;
+    case 13: cp_async_wait<13>(); break;
+    case 14: cp_async_wait<14>(); break;
+    default: cp_async_wait<15>(); break;
+  }
+}
+
+// ---- mbarrier + bulk copy (cp.async.bulk: the TMA engine moves a contiguous run of bytes global -> shared and
+//      reports completion as transaction bytes on an mbarrier; one instruction per row, no per-chunk index math,
+//      and the consumers wait on the mbarrier instead of a CTA-wide barrier) ------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t phase) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(phase)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
+  while (!mbar_try_wait(bar, phase)) {
+  }
+}
+// bytes: multiple of 16; dst / src 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(bar)
+               : "memory");
 }
 
 // 1/sqrt(d) for a positive pivot: MUFU seed + two Newton steps (about 1 ulp); a handful of FP64
@@ -170,88 +210,147 @@ __device__ __forceinline__ void chol8_inv(double *dg, double *Wm, int o, int lan
 }
 
 // =============================================================================================
-// kernel 1: upd_factor — G = [ S | H P | nu ], Cholesky of S, W_pp per panel
+// kernel 0: upd_hp — measurement list, G = [ S | H P | nu ]: one CTA per HP_ROWS measurement rows per stream
 // =============================================================================================
-__global__ void __launch_bounds__(UPD_THREADS, 2) upd_factor_kernel(
+// H P: the dense part H_xv (rows x 16, zero padded) * P(0:16, :) runs on DMMA tiles with H_xv k-major in shared
+// memory; the 3 structural dh/dy columns of a row are added per element from P(:, pos_i + c) (16-byte loads,
+// contiguous along the state index because P is symmetric).  The 13 dense columns of the CTA's rows of H P stay
+// in shared memory for S = (H P) H^T + R (upper triangle): one warp per row, lane = measured feature (two columns
+// of S), dense part from shared memory, structural part from the row of H P just written (L1/L2).
+// The 7 CTAs of a stream (m = 200) share nothing but P; the measurement list is rebuilt by each of them with
+// ballots (it is ~100 flag reads).
+constexpr int HP_THREADS = 256;
+constexpr int HP_ROWS = 32;   // measurement rows per CTA (4 DMMA M tiles)
+constexpr int HP_HXS = 14;    // row stride of the CTA's H*P(:, 0:13) table
+struct HpSmem {
+  double *HxT;   // [16][hms]  H_xv transposed, k-major, zero padded (columns 13..15, rows >= m)
+  double *Hy;    // [K][2][3]
+  double *Rv;    // [K][3]  (R00, R01, R11)
+  double *nu;    // [mmax]
+  double *hpx;   // [HP_ROWS][HP_HXS]
+  int *mfeat;    // [K]
+  int *wcount;   // [8]
+  int hms;
+};
+__host__ __device__ inline int hp_hms(int Nmax) {
+  // k-major Hx table: row stride = 4 (mod 16) doubles => the 4 k-rows of a fragment are 32 B apart
+  return ((2 * upd_keven(Nmax) + 15) & ~15) + 4;
+}
+__host__ __device__ inline size_t hp_smem_doubles(int Nmax) {
+  const size_t K = upd_keven(Nmax);
+  return (size_t)16 * hp_hms(Nmax) + K * 6 + K * 3 + (K & 1) + 2 * K + HP_ROWS * HP_HXS;
+}
+__device__ __forceinline__ HpSmem hp_carve(uint8_t *base, int Nmax) {
+  HpSmem u;
+  const int K = upd_keven(Nmax);
+  double *p = reinterpret_cast<double *>(base);
+  u.hms = hp_hms(Nmax);
+  u.HxT = p;  p += (size_t)16 * u.hms;
+  u.Hy = p;  p += (size_t)K * 6;
+  u.Rv = p;  p += (size_t)K * 3 + (K & 1);
+  u.nu = p;  p += 2 * K;
+  u.hpx = p;  p += HP_ROWS * HP_HXS;
+  u.mfeat = reinterpret_cast<int *>(p);
+  u.wcount = u.mfeat + K;
+  return u;
+}
+
+__global__ void __launch_bounds__(HP_THREADS, 2) upd_hp_kernel(
     const Sl2Dev d, int stream_lo, int staged_m, const int *st_feat, const double *st_Hxv,
     const double *st_Hy, const double *st_R, const double *st_nu) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  const UpdSmem sm = carve(smem_raw, d.Nmax);
-  const int s = stream_lo + blockIdx.x;
-  const int tid = threadIdx.x;
+  const HpSmem sm = hp_carve(smem_raw, d.Nmax);
+  const int s = stream_lo + blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lc = lane & 3;  // DMMA fragment coordinates
   const int nf = d.nfeat[s];
   const int n = SL2_NXV + 3 * nf;
   const int ld = d.ld, ldg = d.ldg;
   const double *__restrict__ P = d.P + (size_t)s * ld * ld;
   double *__restrict__ G = d.G + (size_t)s * d.mmax * ldg;
-  double *__restrict__ Wp = d.Wp + (size_t)s * SL2_MAX_PANELS * 256;
   const size_t fb = (size_t)s * d.Nmax;
-  const int warp = tid >> 5, lane = tid & 31;
-  const int lr = lane >> 2, lc = lane & 3;  // DMMA fragment coordinates
-  __shared__ int s_m, s_next;
-
-  // ---- phase 0: measurement list in selected order, successful only (monoslam.cpp:556-571) ---
-  if (tid == 0) {
-    int k = 0;
-    if (staged_m >= 0) {
-      k = staged_m / 2;
-    } else {
-      const int nsel = d.nsel[s];
-      for (int r = 0; r < nsel; ++r) {
-        const int i = d.job_feat[fb + r];
-        if (i >= 0 && d.found[fb + i]) sm.mfeat[k++] = i;
-      }
-      d.nmeas[s] = k;
-    }
-    s_m = 2 * k;
-    d.upd_m[s] = 2 * k;
-  }
-  __syncthreads();
-  const int m = s_m;
-  const int K = m / 2;
-  if (m == 0) return;
   const int HMS = sm.hms;
-  // HxT[c][i] = H_xv(i, c) (k-major, zero padded), Hy[k][r][c], Rv[k], wv = nu
-  for (int e = tid; e < 16 * HMS; e += UPD_THREADS) sm.HxT[e] = 0.0;
-  __syncthreads();
+
+  // ---- measurement list in selected order, successful only (monoslam.cpp:556-571) --------------
+  int K;
   if (staged_m >= 0) {
-    for (int k = tid; k < K; k += UPD_THREADS) {
-      sm.mfeat[k] = st_feat[k];
+    K = staged_m / 2;
+    for (int k = tid; k < K; k += HP_THREADS) sm.mfeat[k] = st_feat[k];
+  } else {
+    const int nsel = d.nsel[s];
+    int feat = -1;
+    if (tid < d.Nmax && tid < nsel) {
+      const int i = d.job_feat[fb + tid];
+      if (i >= 0 && d.found[fb + i]) feat = i;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, feat >= 0);
+    if (lane == 0) sm.wcount[warp] = __popc(bal);
+    __syncthreads();
+    int base = 0, total = 0;
+    for (int w = 0; w < (SL2_MAX_FEAT_SMEM + 31) / 32; ++w) {
+      if (w < warp) base += sm.wcount[w];
+      total += sm.wcount[w];
+    }
+    if (feat >= 0) sm.mfeat[base + __popc(bal & ((1u << lane) - 1u))] = feat;
+    K = total;
+  }
+  const int m = 2 * K;
+  if (blockIdx.x == 0 && tid == 0) {
+    d.upd_m[s] = m;
+    if (staged_m < 0) d.nmeas[s] = K;
+  }
+  if (HP_ROWS * (int)blockIdx.x >= m) return;
+  for (int e = tid; e < 16 * HMS; e += HP_THREADS) sm.HxT[e] = 0.0;
+  __syncthreads();
+  // ---- H rows, R, nu of every measurement (flat loops: every CTA of the stream pays this prologue) -------
+  if (staged_m >= 0) {
+    for (int e = tid; e < m * 13; e += HP_THREADS) {
+      const int i = e / 13, c = e - i * 13;
+      sm.HxT[c * HMS + i] = st_Hxv[e];
+    }
+    for (int e = tid; e < K * 6; e += HP_THREADS) sm.Hy[e] = st_Hy[e];
+    for (int e = tid; e < m; e += HP_THREADS) sm.nu[e] = st_nu[e];
+    for (int k = tid; k < K; k += HP_THREADS) {
       // R_k 2x2 column-major (symmetric; the host entry point rejects R01 != R10)
       sm.Rv[k * 3 + 0] = st_R[k * 4 + 0];
       sm.Rv[k * 3 + 1] = st_R[k * 4 + 2];
       sm.Rv[k * 3 + 2] = st_R[k * 4 + 3];
-      sm.wv[2 * k] = st_nu[2 * k];
-      sm.wv[2 * k + 1] = st_nu[2 * k + 1];
     }
-    for (int e = tid; e < m * 13; e += UPD_THREADS) {
-      const int i = e / 13, c = e - i * 13;
-      sm.HxT[c * HMS + i] = st_Hxv[e];
-    }
-    for (int e = tid; e < K * 6; e += UPD_THREADS) sm.Hy[e] = st_Hy[e];
   } else {
-    for (int k = tid; k < K; k += UPD_THREADS) {
-      const int i = sm.mfeat[k];
-      sm.Rv[k * 3 + 0] = d.Rvar[fb + i];  // R_i = var * I (camera.cpp:294-299)
-      sm.Rv[k * 3 + 1] = 0.0;
-      sm.Rv[k * 3 + 2] = d.Rvar[fb + i];
+    for (int e = tid; e < K * 14; e += HP_THREADS) {  // dh/dxv = [dh/dxp | 0] (motion_model.cpp:224-235)
+      const int k = e / 14, q = e - k * 14, r = q >= 7;
+      sm.HxT[(q - 7 * r) * HMS + 2 * k + r] = d.dh_dxp[(fb + sm.mfeat[k]) * 14 + q];
+    }
+    for (int e = tid; e < K * 6; e += HP_THREADS) {
+      const int k = e / 6;
+      sm.Hy[e] = d.dh_dy[(fb + sm.mfeat[k]) * 6 + (e - k * 6)];
+    }
+    for (int e = tid; e < m; e += HP_THREADS) {
+      const size_t f = fb + sm.mfeat[e >> 1];
       // nu = z - h (full_feature_model.cpp:197-200), z = (double)(u,v) (monoslam.cpp:382-383)
-      sm.wv[2 * k] = (rd((double)d.z_uv[(fb + i) * 2]) - rd(d.h[(fb + i) * 2])).v;
-      sm.wv[2 * k + 1] = (rd((double)d.z_uv[(fb + i) * 2 + 1]) - rd(d.h[(fb + i) * 2 + 1])).v;
-      for (int r = 0; r < 2; ++r) {
-        for (int c = 0; c < 7; ++c) sm.HxT[c * HMS + 2 * k + r] = d.dh_dxp[(fb + i) * 14 + r * 7 + c];
-        for (int c = 0; c < 3; ++c) sm.Hy[k * 6 + r * 3 + c] = d.dh_dy[(fb + i) * 6 + r * 3 + c];
-      }
+      sm.nu[e] = (rd((double)d.z_uv[f * 2 + (e & 1)]) - rd(d.h[f * 2 + (e & 1)])).v;
+    }
+    for (int k = tid; k < K; k += HP_THREADS) {
+      const double var = d.Rvar[fb + sm.mfeat[k]];  // R_i = var * I (camera.cpp:294-299)
+      sm.Rv[k * 3 + 0] = var;
+      sm.Rv[k * 3 + 1] = 0.0;
+      sm.Rv[k * 3 + 2] = var;
     }
   }
   __syncthreads();
 
-  // ---- phase 1a: H*P.  Dense part H_xv (m x 16) * P(0:16, :) on DMMA tiles; the 3 structural
-  //      columns of dh/dy are added per element; nu goes into the last column.
+  // row blocks blockIdx.x, blockIdx.x + gridDim.x, ...: the measurement list and the H tables are built once
+  for (int rb = blockIdx.x; HP_ROWS * rb < m; rb += gridDim.x) {
+  const int row0 = HP_ROWS * rb, rows = min(HP_ROWS, m - row0);
+  // ---- H*P for the CTA's rows -------------------------------------------------------------------------
   {
-    constexpr int QB = 4;  // column groups per warp pass
-    const int mtiles = (m + 7) >> 3, ngrp = (n + 7) >> 3;
-    for (int gq = warp * QB; gq < ngrp; gq += (UPD_THREADS / 32) * QB) {
+    constexpr int QB = 4;  // column groups per work item
+    const int mt0 = row0 >> 3, mtiles = (rows + 7) >> 3, ngrp = (n + 7) >> 3;
+    // work item = (QB column groups, a quarter of the M tiles): n = 313 gives 10 x 4 items = 5 per warp (items of
+    // whole column passes left two warps with twice the work of the others: 21 % of the kernel at the barrier)
+    const int npass = (ngrp + QB - 1) / QB, nq = min(4, mtiles), mtq = (mtiles + nq - 1) / nq;
+    for (int item = warp; item < npass * nq; item += HP_THREADS / 32) {
+      const int gq = (item / nq) * QB, mtlo = (item % nq) * mtq, mthi = min(mtiles, mtlo + mtq);
       double b[QB][4];
       int j0[QB];  // first of the two columns of this lane's C elements, per group (-1: none)
 #pragma unroll
@@ -263,8 +362,8 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) upd_factor_kernel(
         j0[q] = (gq + q) * 8 + 2 * lc;
         if (gq + q >= ngrp || j0[q] >= n) j0[q] = -1;
       }
-      for (int mt = 0; mt < mtiles; ++mt) {
-        const int i = mt * 8 + lr;
+      for (int mt = mtlo; mt < mthi; ++mt) {
+        const int i = (mt0 + mt) * 8 + lr;
         const bool rv = i < m;
         const int k = rv ? (i >> 1) : 0;
         const int pos = SL2_NXV + 3 * sm.mfeat[k];
@@ -285,7 +384,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) upd_factor_kernel(
           }
         double a[4];
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) a[ks] = sm.HxT[(4 * ks + lc) * HMS + mt * 8 + lr];
+        for (int ks = 0; ks < 4; ++ks) a[ks] = sm.HxT[(4 * ks + lc) * HMS + (mt0 + mt) * 8 + lr];
 #pragma unroll
         for (int q = 0; q < QB; ++q) {
           double c0 = 0.0, c1 = 0.0;
@@ -301,25 +400,22 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) upd_factor_kernel(
             double *dst = G + (size_t)i * ldg + m + j0[q];
             if (j0[q] + 1 < n) *reinterpret_cast<double2 *>(dst) = make_double2(c0, c1);
             else *dst = c0;
-            if (j0[q] < SL2_NXV) {  // dense 13 columns of H*P: kept in shared memory for phase 1b
-              sm.mult[i * UPD_HXS + j0[q]] = c0;
-              if (j0[q] + 1 < SL2_NXV) sm.mult[i * UPD_HXS + j0[q] + 1] = c1;
+            if (j0[q] < SL2_NXV) {  // dense 13 columns of H*P: kept in shared memory for S
+              sm.hpx[(i - row0) * HP_HXS + j0[q]] = c0;
+              if (j0[q] + 1 < SL2_NXV) sm.hpx[(i - row0) * HP_HXS + j0[q] + 1] = c1;
             }
           }
         }
       }
     }
   }
-  for (int i = tid; i < m; i += UPD_THREADS) G[(size_t)i * ldg + m + n] = sm.wv[i];
+  for (int i = tid; i < rows; i += HP_THREADS) G[(size_t)(row0 + i) * ldg + m + n] = sm.nu[row0 + i];
   __syncthreads();
-  // ---- phase 1b: S = (H P) H^T + R, upper triangle, one warp per row.  The dense 13 columns of
-  //      the row of H*P come from shared memory (written by phase 1a; broadcast reads), lane = measured feature
-  //      (two columns of S); the 3 structural dh/dy columns and R are added per element.
+  // ---- S = (H P) H^T + R for the CTA's rows, columns from the row's own feature on --------------------
   {
-    constexpr int HXS = UPD_HXS;  // H*P(:, 0:13), left in sm.mult by phase 1a
-    const double *hpx = sm.mult;
     constexpr int SCH = 4;  // feature chunks of 32 per pass (covers K <= 128 in one pass)
-    for (int i = warp; i < m; i += UPD_THREADS / 32) {
+    for (int il = warp; il < rows; il += HP_THREADS / 32) {
+      const int i = row0 + il;
       const double *grow = G + (size_t)i * ldg + m;
       const int k0 = i >> 1;
       for (int kb = k0; kb < K; kb += 32 * SCH) {
@@ -339,7 +435,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) upd_factor_kernel(
             double s0 = 0.0, s1 = 0.0;
 #pragma unroll
             for (int c = 0; c < 13; ++c) {
-              const double hx = hpx[i * HXS + c];
+              const double hx = sm.hpx[il * HP_HXS + c];
               const double2 hv = *reinterpret_cast<const double2 *>(sm.HxT + c * HMS + 2 * kk);
               s0 += hx * hv.x;
               s1 += hx * hv.y;
@@ -361,7 +457,31 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) upd_factor_kernel(
       }
     }
   }
-  __syncthreads();
+  __syncthreads();  // hpx of this row block is rewritten by the next one
+  }  // row blocks
+}
+
+// =============================================================================================
+// kernel 1: upd_chol — Cholesky of S, finished rows of U in G (L2), two streams per SM
+// =============================================================================================
+// This kernel is a serial chain: 13 diagonal blocks per stream (m = 200), each factored by ONE warp (~7 k cycles:
+// two 8x8 register/shuffle factorizations joined by 8x8 DMMA products), and nothing in the update can start
+// before it ends.  What hides it is other streams on the same SM, so it is kept small enough for two CTAs per SM
+// (all 296 streams of the benchmark resident at once).  Measured alternative: S / U resident in shared memory
+// (193 KB, one CTA per SM, two waves) made every panel 1.7x faster and the kernel 17 % slower (0.159 vs 0.136 ms).
+__global__ void __launch_bounds__(UPD_THREADS, 2) upd_chol_kernel(const Sl2Dev d, int stream_lo) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const UpdSmem sm = carve(smem_raw, d.Nmax);
+  const int s = stream_lo + blockIdx.x;
+  const int tid = threadIdx.x;
+  const int ldg = d.ldg;
+  double *__restrict__ G = d.G + (size_t)s * d.mmax * ldg;
+  double *__restrict__ Wp = d.Wp + (size_t)s * SL2_MAX_PANELS * 256;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int lr = lane >> 2, lc = lane & 3;  // DMMA fragment coordinates
+  __shared__ int s_next;
+  const int m = d.upd_m[s];
+  if (m == 0) return;
 
   // ---- phase 2: left-looking Cholesky by row panels of 16 on the S part of G ------------------
   // Trailing update of a panel = C(16 x cols) - A(16 x i0) * B(i0 x cols) with A(r,k) = U(k,i0+r)
@@ -579,87 +699,159 @@ __device__ __forceinline__ double c_to_b(const double (&c)[2][2], int ks, int la
 
 // NP = number of 16-row panels the instantiation covers (m <= 16 NP).  Column c of the slab space is
 // column m + c of G: c < n is H P, c == n is nu.
+//
+// Right-looking, everything in registers: the warp holds all rows of its 8 columns as DMMA ACCUMULATORS
+// (C layout: tile j = rows 8j..8j+7).  Per panel p: Y_p = W_pp C_p (8 DMMAs, C_p moved to the B layout by
+// shuffles), the finished rows go straight to G as 16-byte stores, and every later row tile j gets
+// acc_j -= U(panel, tile j)^T Y_p: 4 DMMAs per tile (k-step outer, tile inner: consecutive DMMAs never share an
+// accumulator), A from the panel's rows of U in shared memory, B = Y_p from registers.
+// Staging: ALL panels of U (the part right of the diagonal blocks, <= 166 KB at m = 208) and all W_pp are
+// requested up front by warp 0 as bulk copies (one instruction per 16-row x row-segment / per W row, completion
+// counted in bytes on one mbarrier per panel), so the only latency the kernel ever waits for is the first
+// panel's, nobody computes a staging address, and there is NO CTA-wide barrier in the panel loop: a warp waits
+// on the mbarrier of the panel it needs and otherwise runs at its own pace.  (Measured before: a 2-deep cp.async
+// ring left the late, small panels bound by the L2 round trip of their own staging, and staging everything with
+// per-thread cp.async cost 22 % of the kernel in index arithmetic.)  NP = 16 does not fit one SM that way: its
+// panels >= SPLIT are requested at panel REUSE into the space of panels 0..REUSE-1 (one CTA barrier).
+template <int NP> struct SolveLayout {
+  static constexpr int SPLIT = NP > 13 ? 6 : NP;   // panels >= SPLIT are staged late (second generation)
+  static constexpr int REUSE = NP > 13 ? 4 : NP;   // ... once panels < REUSE have been consumed
+  __host__ __device__ static constexpr int pw(int p) { return 16 * (NP - 1 - p) + 4; }  // row stride (= 4 mod 16)
+  __host__ __device__ static constexpr int off_lin(int p0, int p) {  // doubles before panel p when packing starts at p0
+    int o = 0;
+    for (int q = p0; q < p; ++q) o += 16 * pw(q);
+    return o;
+  }
+  __host__ __device__ static constexpr int off(int p) { return p < SPLIT ? off_lin(0, p) : off_lin(SPLIT, p); }
+  static constexpr int PAN_DOUBLES = off_lin(0, SPLIT < NP - 1 ? SPLIT : NP - 1);
+  static constexpr int SMEM_DOUBLES = PAN_DOUBLES + NP * 16 * UPD_WS + NP + (NP & 1) +  // one mbarrier per panel
+                                      2 * SOLVE_MAX_WARPS * 2 * 32 * 2;     // C-tile exchange of the warp pairs
+  static_assert(SPLIT == NP || off_lin(SPLIT, NP - 1) <= off_lin(0, REUSE), "second generation must fit");
+};
+
+// Two warps share a group of 8 columns: warp (g, rho) owns the row tiles j = 2t + rho, so a thread keeps NP
+// tiles (not 2 NP) and 16 warps fit one SM -- 4 per scheduler instead of 2, which is what hides the shared-memory
+// latency in front of every DMMA (measured: 8 warps x 228 registers ran the FP64 pipe at 40 %).  Per panel the
+// two warps swap their C tile through shared memory (one named barrier of 64 threads), both form Y_p = W_pp C_p
+// (8 DMMAs, 4 of them redundant), each stores and keeps its own M tile.
 template <int NP>
-__global__ void __launch_bounds__(32 * SOLVE_MAX_WARPS, 1) upd_solve_kernel(const Sl2Dev d, int stream_lo) {
+__global__ void __launch_bounds__(64 * SOLVE_MAX_WARPS, 1) upd_solve_kernel(const Sl2Dev d, int stream_lo) {
+  using L = SolveLayout<NP>;
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  constexpr int MROWS = 16 * (NP - 1) > 0 ? 16 * (NP - 1) : 16;  // multiplier rows of the last panel
-  double *mult = reinterpret_cast<double *>(smem_raw);           // [2][MROWS][UPD_MS]
-  double *Wm = mult + 2 * (size_t)MROWS * UPD_MS;                // [2][16][UPD_WS]
+  double *pan = reinterpret_cast<double *>(smem_raw);  // panel p at L::off(p): [16][L::pw(p)]  U(16p + r, 16p + 16 + c)
+  double *Wm = pan + L::PAN_DOUBLES;                   // [NP][16][UPD_WS]
+  const uint32_t bars = smem_u32(Wm + NP * 16 * UPD_WS);  // [NP] mbarriers
+  double2 *xbuf = reinterpret_cast<double2 *>(Wm + NP * 16 * UPD_WS + NP + (NP & 1));  // [2][groups][2][32]
   const int s = stream_lo + blockIdx.y;
   const int m = d.upd_m[s];
   if (m == 0) return;
   const int tid = threadIdx.x, nthr = blockDim.x;
+  const int ngrp = nthr >> 6;  // column groups of this CTA
   const int warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
+  const int g = warp % ngrp, rho = warp / ngrp;
   const int n = SL2_NXV + 3 * d.nfeat[s];
   const int ncols = n + 1;
-  const int c0 = (blockIdx.x * (nthr >> 5) + warp) * 8;  // first column of this warp
-  if (blockIdx.x * (nthr >> 5) * 8 >= ncols) return;     // whole CTA beyond the last column
+  if (blockIdx.x * ngrp * 8 >= ncols) return;  // whole CTA beyond the last column
   const int ldg = d.ldg;
   double *__restrict__ G = d.G + (size_t)s * d.mmax * ldg;
   const double *__restrict__ Wp = d.Wp + (size_t)s * SL2_MAX_PANELS * 256;
-  const bool wact = c0 < ncols;  // warps past the last column only help staging
-  const bool colv = c0 + lr < ncols;
-  double *gcol = G + m + c0 + lr;
+  const int m8 = (m + 7) & ~7;
 
-  // stage the multipliers U(0:16p, 16p:16p+16) and W_pp of panel p into buffer `buf`
-  auto stage = [&](int p, int buf) {
-    const int i0 = 16 * p, nbp = min(16, m - i0);
-    double *mb = mult + (size_t)buf * MROWS * UPD_MS;
-    double *wb = Wm + (size_t)buf * 16 * UPD_WS;
-    const int nchunk = 8 * i0 + 128;
-    for (int e = tid; e < nchunk; e += nthr) {
-      if (e < 8 * i0) {
-        const int k = e >> 3, ch = (e & 7) * 2;
-        cp_async16(mb + k * UPD_MS + ch, G + (size_t)k * ldg + i0 + (ch < nbp ? ch : 0), ch < nbp ? 16 : 0);
+  if (tid == 0) {
+    for (int p = 0; p < NP; ++p) mbar_init(bars + 8 * p, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  // the columns m .. m8-1 of a staged panel are read (rows of the last tile that do not exist) but not copied
+  auto zero_pads = [&](int plo, int phi) {
+    for (int e = tid; e < (phi - plo) * 16; e += nthr) {
+      const int p = plo + (e >> 4), r = e & 15;
+      const int cfirst = 16 * p + 16;
+      if (16 * p < m)
+        for (int c = max(m, cfirst); c < m8; ++c) pan[L::off(p) + r * L::pw(p) + (c - cfirst)] = 0.0;
+    }
+  };
+  zero_pads(0, L::SPLIT);
+  __syncthreads();
+  // warp 0: lane r < 16 requests row r of U(panel p) right of the diagonal block, lane 16 + r row r of W_pp
+  auto request = [&](int p) {
+    if (16 * p < m) {
+      const int cfirst = 16 * p + 16;
+      const int nrow = min(16, m - 16 * p);
+      const uint32_t ubytes = m > cfirst ? (uint32_t)(m - cfirst) * 8u : 0u;
+      const uint32_t bar = bars + 8 * p;
+      if (lane == 0) mbar_expect_tx(bar, (uint32_t)nrow * ubytes + 16u * 128u);
+      __syncwarp();
+      if (lane < 16) {
+        if (lane < nrow && ubytes)
+          bulk_g2s(pan + L::off(p) + lane * L::pw(p), G + (size_t)(16 * p + lane) * ldg + cfirst, ubytes, bar);
       } else {
-        const int q = e - 8 * i0, r = q >> 3, ch = (q & 7) * 2;
-        cp_async16(wb + r * UPD_WS + ch, Wp + (size_t)p * 256 + r * 16 + ch, 16);
+        bulk_g2s(Wm + ((size_t)p * 16 + (lane - 16)) * UPD_WS, Wp + (size_t)p * 256 + (lane - 16) * 16, 128u, bar);
       }
     }
-    cp_async_commit();
   };
-  stage(0, 0);
+  if (warp == 0) {
+#pragma unroll 1
+    for (int p = 0; p < L::SPLIT; ++p) request(p);
+  }
 
-  // all rows of this warp's 8 columns, B-fragment layout: Y[s] = X(4 s + lc, c0 + lr)
-  double Y[4 * NP];
+  // The warp pair walks the column groups g, g + gridDim.x * ngrp, ...: with one CTA per stream (the batched
+  // launch) U is staged ONCE for all of the stream's columns and the pairs drift apart, so one pair's reload of
+  // its accumulators hides behind the other pairs' DMMAs; nothing below synchronises the CTA (NP <= 13).
+  int xpar = 0;
+  for (int grp = blockIdx.x * ngrp + g; L::SPLIT < NP ? grp == (int)(blockIdx.x * ngrp + g) : 8 * grp < ncols;
+       grp += gridDim.x * ngrp) {
+  const int c0 = 8 * grp;        // first column of this warp pair
+  const bool wact = c0 < ncols;  // warp pairs past the last column have nothing to do
+  const int cc = c0 + 2 * lc;    // this lane's two columns (C layout)
+  const int cval = wact ? min(2, ncols - cc) : 0;  // how many of them exist (<= 0: none)
+  double *gcol = G + m + cc;
+  double acc[NP][2];  // tile j = 2 t + rho: rows 8 j + lr, columns cc, cc + 1
 #pragma unroll
-  for (int q = 0; q < 4 * NP; ++q) {
-    const int row = 4 * q + lc;
-    Y[q] = (colv && row < m) ? gcol[(size_t)row * ldg] : 0.0;
+  for (int t = 0; t < NP; ++t) {
+    const int row = 8 * (2 * t + rho) + lr;
+    acc[t][0] = acc[t][1] = 0.0;
+    if (row < m) {
+      if (cval >= 2) {
+        const double2 v = *reinterpret_cast<const double2 *>(gcol + (size_t)row * ldg);
+        acc[t][0] = v.x;
+        acc[t][1] = v.y;
+      } else if (cval == 1) {
+        acc[t][0] = gcol[(size_t)row * ldg];
+      }
+    }
   }
 
 #pragma unroll
   for (int p = 0; p < NP; ++p) {
     if (16 * p < m) {  // uniform over the CTA
-      cp_async_wait<0>();
-      __syncthreads();  // panel p staged; every warp is done with the buffer panel p + 1 goes into
-      if (16 * (p + 1) < m) stage(p + 1, (p + 1) & 1);
+      if (L::SPLIT < NP && p == L::REUSE) {
+        __syncthreads();  // every warp is done with panels < REUSE: their space takes the second generation
+        zero_pads(L::SPLIT, NP);
+        __syncthreads();
+        if (warp == 0) {
+          fence_proxy_async();  // generic-proxy reads of the old panels are ordered before the bulk writes
+#pragma unroll 1
+          for (int q = L::SPLIT; q < NP; ++q) request(q);
+        }
+      }
       if (!wact) continue;
-      const double *mb = mult + (size_t)(p & 1) * MROWS * UPD_MS;
-      const double *wb = Wm + (size_t)(p & 1) * 16 * UPD_WS;
-      // T = A^T-product over the finished rows: T(r, c) = sum_k U(k, i0 + r) Y(k, c)
-      double t[2][2][2];  // [k parity][M tile][element]: two independent chains per M tile
-#pragma unroll
-      for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) t[h][mt][0] = t[h][mt][1] = 0.0;
-#pragma unroll
-      for (int q = 0; q < 4 * p; ++q) {
-        const double a0 = mb[(4 * q + lc) * UPD_MS + lr];
-        const double a1 = mb[(4 * q + lc) * UPD_MS + 8 + lr];
-        dmma884(t[q & 1][0][0], t[q & 1][0][1], a0, Y[q]);
-        dmma884(t[q & 1][1][0], t[q & 1][1][1], a1, Y[q]);
-      }
-      double tc[2][2];
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        tc[mt][0] = t[0][mt][0] + t[1][mt][0];
-        tc[mt][1] = t[0][mt][1] + t[1][mt][1];
-      }
-      // C = (H P)_panel - T in B layout, then Y_panel = W_pp * C
+      // swap the C tiles of panel p with the partner warp
+      xpar ^= 1;  // alternates over every panel this pair executes (also across column groups)
+      double2 *xb = xbuf + ((size_t)(xpar * ngrp + g) * 2) * 32;
+      xb[rho * 32 + lane] = make_double2(acc[p][0], acc[p][1]);
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + g) : "memory");
+      const double2 other = xb[(rho ^ 1) * 32 + lane];
+      const double cp2[2][2] = {{rho ? other.x : acc[p][0], rho ? other.y : acc[p][1]},
+                                {rho ? acc[p][0] : other.x, rho ? acc[p][1] : other.y}};
+      mbar_wait(bars + 8 * p, 0);
+      const double *pb = pan + L::off(p);
+      const int PW = L::pw(p);
+      const double *wb = Wm + (size_t)p * 16 * UPD_WS;
+      // Y_p = W_pp * C_p
       double cb[4];
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) cb[ks] = Y[4 * p + ks] - (p > 0 ? c_to_b(tc, ks, lane) : 0.0);
+      for (int ks = 0; ks < 4; ++ks) cb[ks] = c_to_b(cp2, ks, lane);
       double dd[2][2];
       dd[0][0] = dd[0][1] = dd[1][0] = dd[1][1] = 0.0;
 #pragma unroll
@@ -667,15 +859,31 @@ __global__ void __launch_bounds__(32 * SOLVE_MAX_WARPS, 1) upd_solve_kernel(cons
         dmma884(dd[0][0], dd[0][1], wb[lr * UPD_WS + 4 * ks + lc], cb[ks]);
         dmma884(dd[1][0], dd[1][1], wb[(8 + lr) * UPD_WS + 4 * ks + lc], cb[ks]);
       }
+      // this warp's finished M tile: 16-byte stores from the C fragments
+      {
+        const int row = 16 * p + 8 * rho + lr;
+        const double v0 = rho ? dd[1][0] : dd[0][0], v1 = rho ? dd[1][1] : dd[0][1];
+        if (row < m) {
+          if (cval >= 2) *reinterpret_cast<double2 *>(gcol + (size_t)row * ldg) = make_double2(v0, v1);
+          else if (cval == 1) gcol[(size_t)row * ldg] = v0;
+        }
+      }
+      // this warp's later row tiles: acc_j -= U(panel, tile j)^T Y_p
+      double yb[4];
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) Y[4 * p + ks] = c_to_b(dd, ks, lane);
+      for (int ks = 0; ks < 4; ++ks) yb[ks] = -c_to_b(dd, ks, lane);
+      const double *pbr = pb + 8 * rho + lr;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+        for (int t = p + 1; t < NP; ++t) {
+          if (8 * (2 * t + rho) < m)  // warp-uniform; a tile past m is never touched (its columns are not staged)
+            dmma884(acc[t][0], acc[t][1], pbr[(4 * ks + lc) * PW + 16 * (t - p - 1)], yb[ks]);
+        }
+      }
     }
   }
-#pragma unroll
-  for (int q = 0; q < 4 * NP; ++q) {
-    const int row = 4 * q + lc;
-    if (colv && row < m) gcol[(size_t)row * ldg] = Y[q];
-  }
+  }  // column groups of this warp pair
 }
 
 // =============================================================================================
@@ -900,8 +1108,13 @@ inline int solve_np(int Nmax) {  // instantiation that covers the capacity
   return p <= 4 ? 4 : (p <= 7 ? 7 : (p <= 10 ? 10 : (p <= 13 ? 13 : 16)));
 }
 inline size_t solve_smem(int np) {
-  const size_t mrows = np > 1 ? 16 * (np - 1) : 16;
-  return (2 * mrows * UPD_MS + 2 * 16 * UPD_WS) * sizeof(double);
+  switch (np) {
+    case 4: return SolveLayout<4>::SMEM_DOUBLES * sizeof(double);
+    case 7: return SolveLayout<7>::SMEM_DOUBLES * sizeof(double);
+    case 10: return SolveLayout<10>::SMEM_DOUBLES * sizeof(double);
+    case 13: return SolveLayout<13>::SMEM_DOUBLES * sizeof(double);
+    default: return SolveLayout<16>::SMEM_DOUBLES * sizeof(double);
+  }
 }
 inline void solve_shape(int Nmax, int &nslab, int &warps) {
   const int ngroups = (SL2_NXV + 3 * Nmax + 1 + 7) / 8;
@@ -912,16 +1125,21 @@ constexpr size_t SYRK_SMEM = (size_t)2 * 2 * UPD_KC * UPD_YS * sizeof(double);
 
 }  // namespace
 
-size_t sl2_update_smem_bytes(const Sl2Dev &d) {
+size_t sl2_update_smem_bytes(const Sl2Dev &d) {  // upd_chol
   const size_t K = upd_keven(d.Nmax), mmax = 2 * K;
-  const size_t doubles = mmax + (K * 3 + (K & 1)) + mmax * UPD_MS + UPD_NB * UPD_DS + UPD_NB * UPD_WS +
-                         upd_pan_doubles(d.Nmax);
-  return doubles * 8 + K * 4 + 16;
+  return (mmax * UPD_MS + UPD_NB * UPD_DS + UPD_NB * UPD_WS + upd_pan_doubles(d.Nmax)) * sizeof(double);
+}
+
+static size_t hp_smem_bytes(const Sl2Dev &d) {
+  return hp_smem_doubles(d.Nmax) * sizeof(double) + (upd_keven(d.Nmax) + 8) * sizeof(int);
 }
 
 cudaError_t sl2_configure_update(const Sl2Dev &d) {
-  cudaError_t e = cudaFuncSetAttribute(upd_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sl2_update_smem_bytes(d));
+  cudaError_t e = cudaFuncSetAttribute(upd_hp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)hp_smem_bytes(d));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(upd_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)sl2_update_smem_bytes(d));
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(upd_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM);
   if (e != cudaSuccess) return e;
@@ -936,26 +1154,41 @@ cudaError_t sl2_configure_update(const Sl2Dev &d) {
   }
 }
 
+// ev6 (optional): 6 events recorded around the 5 kernels (hp, chol, solve, syrk, finish)
 cudaError_t sl2_launch_update(const Sl2Dev &d, int stream_lo, int stream_cnt, int staged_m,
                               const int *st_feat, const double *st_Hxv, const double *st_Hy,
                               const double *st_R, const double *st_nu, int only_normalise,
-                              cudaStream_t st, cudaEvent_t *ev5, int *launches) {
+                              cudaStream_t st, cudaEvent_t *ev6, int *launches) {
   if (stream_cnt <= 0) return cudaSuccess;
   cudaError_t e;
   int nl = 0;
-  if (ev5 && (e = cudaEventRecord(ev5[0], st)) != cudaSuccess) return e;
+  auto mark = [&](int i) { return ev6 ? cudaEventRecord(ev6[i], st) : cudaSuccess; };
+  if ((e = mark(0)) != cudaSuccess) return e;
+  // row blocks of H P / S per stream: spread over CTAs unless the batch already fills the GPU (measured at 296
+  // streams: 1 CTA per stream 0.156 ms, 2: 0.167, 7: 0.200 -- every CTA rebuilds the measurement list and H tables)
+  const int hp_all = (2 * upd_keven(d.Nmax) + HP_ROWS - 1) / HP_ROWS;
+  const int hp_blocks = stream_cnt >= 2 * 148 ? 1 : hp_all;
   if (!only_normalise) {
-    upd_factor_kernel<<<stream_cnt, UPD_THREADS, sl2_update_smem_bytes(d), st>>>(
-        d, stream_lo, staged_m, st_feat, st_Hxv, st_Hy, st_R, st_nu);
+    upd_hp_kernel<<<dim3(hp_blocks, stream_cnt), HP_THREADS, hp_smem_bytes(d), st>>>(d, stream_lo, staged_m, st_feat,
+                                                                                st_Hxv, st_Hy, st_R, st_nu);
     ++nl;
   }
-  if (ev5 && (e = cudaEventRecord(ev5[1], st)) != cudaSuccess) return e;
+  if ((e = mark(1)) != cudaSuccess) return e;
+  if (!only_normalise) {
+    upd_chol_kernel<<<stream_cnt, UPD_THREADS, sl2_update_smem_bytes(d), st>>>(d, stream_lo);
+    ++nl;
+  }
+  if ((e = mark(2)) != cudaSuccess) return e;
   if (!only_normalise) {
     int nslab, warps;
     solve_shape(d.Nmax, nslab, warps);
     const int np = solve_np(d.Nmax);
     const size_t smem = solve_smem(np);
-    const dim3 grid(nslab, stream_cnt), block(32 * warps);
+    // two warps per 8-column group; a batch that fills the GPU runs one CTA per stream (U staged once per
+    // stream, groups walked inside), a small one spreads a stream over nslab CTAs (latency)
+    const bool walk = np <= 13 && stream_cnt >= 148;  // measured at 296 streams: 0.219 ms against 0.270 ms
+    if (walk) warps = SOLVE_MAX_WARPS;
+    const dim3 grid(walk ? 1 : nslab, stream_cnt), block(64 * warps);
     switch (np) {
       case 4: upd_solve_kernel<4><<<grid, block, smem, st>>>(d, stream_lo); break;
       case 7: upd_solve_kernel<7><<<grid, block, smem, st>>>(d, stream_lo); break;
@@ -965,16 +1198,18 @@ cudaError_t sl2_launch_update(const Sl2Dev &d, int stream_lo, int stream_cnt, in
     }
     ++nl;
   }
-  if (ev5 && (e = cudaEventRecord(ev5[2], st)) != cudaSuccess) return e;
+  if ((e = mark(3)) != cudaSuccess) return e;
   if (!only_normalise) {
+    // one 64x64 tile per CTA (measured: CTAs that walk several tiles with cross-tile prefetch were slower, 0.29-0.31
+    // against 0.264 ms, because they cost the third resident CTA per SM)
     const int nt = (SL2_NXV + 3 * d.Nmax + 1 + 63) / 64;
     upd_syrk_kernel<<<dim3(nt * (nt + 1) / 2, stream_cnt), UPD_THREADS, SYRK_SMEM, st>>>(d, stream_lo);
     ++nl;
   }
-  if (ev5 && (e = cudaEventRecord(ev5[3], st)) != cudaSuccess) return e;
+  if ((e = mark(4)) != cudaSuccess) return e;
   upd_finish_kernel<<<stream_cnt, UPD_THREADS, 0, st>>>(d, stream_lo, staged_m >= 0, only_normalise);
   ++nl;
-  if (ev5 && (e = cudaEventRecord(ev5[4], st)) != cudaSuccess) return e;
+  if ((e = mark(5)) != cudaSuccess) return e;
   if (launches) *launches += nl;
   return cudaGetLastError();
 }

@@ -334,13 +334,21 @@ class Context:
         return ms
 
     def last_update_times(self):
-        """ms of the four EKF update kernels of the last step: factor, solve, syrk, finish"""
-        ms = np.zeros(4, np.float32)
+        """ms of the five EKF update kernels of the last step: hp, chol, solve, syrk, finish"""
+        ms = np.zeros(5, np.float32)
         self._ck(self.L.sl2_last_update_times(self.h, _p(ms, f32p)))
         return ms
 
     def launch_count(self):
         return int(self.L.sl2_launch_count(self.h))
+
+    def feature_jacobians(self, stream_id):
+        """Feature::dh_by_dxv_ (nf,26), dh_by_dy_ (nf,6), R_ (nf,4), nu_ (nf,2), column-major like the Eigen members"""
+        N = self.cfg.max_features
+        J, Jy, R, nu = np.zeros((N, 26)), np.zeros((N, 6)), np.zeros((N, 4)), np.zeros((N, 2))
+        nf = self._ck(self.L.sl2_get_feature_jacobians(self.h, stream_id, _p(J, f64p), _p(Jy, f64p), _p(R, f64p),
+                                                       _p(nu, f64p)))
+        return J[:nf], Jy[:nf], R[:nf], nu[:nf]
 
     def features(self, stream_id):
         N = self.cfg.max_features

@@ -130,3 +130,80 @@ def test_delete_feature(oracle):
                                   np.array([[0.0225, 0, 0.0225]]))
     assert f[0] == 1 and (u[0], v[0]) == tuple(sc.pix[4])
     ctx.close()
+
+
+def test_update_honours_full_2x2_R_and_rejects_asymmetric(oracle):
+    """kalman.cpp:101 adds the whole block-diagonal R; the ABI takes R as K x (2x2 column-major)."""
+    nf, K = 24, 10
+    sc = synth.make_scene("C4", n_frames=1, n_features=nf)
+    ctx = ctx_from_scenes([sc])
+    rng = np.random.default_rng(77)
+    n = sc.n
+    feats, Hxv, Hy, R, nu, H, _ = _random_measurements(rng, n, nf, K)
+    Hxv[:, 7:] = rng.standard_normal((2 * K, 6)) * 20      # all 13 dh/dxv columns, not only [dh/dxp | 0]
+    H[:, :13] = Hxv
+    for k in range(K):                                     # anisotropic, correlated measurement noise
+        a = rng.standard_normal((2, 2))
+        R[k] = a @ a.T + 0.5 * np.eye(2)
+    Rfull = np.zeros((2 * K, 2 * K))
+    for k in range(K):
+        Rfull[2 * k:2 * k + 2, 2 * k:2 * k + 2] = R[k]
+    ctx.ekf_update(0, feats, Hxv, Hy, R, nu)
+    xg, Pg = ctx.get_state(0)
+    xo, Po = oracle.kalman_update_dense(sc.x0, sc.P0, H, Rfull, nu)
+    J = np.eye(n)
+    J[:13, :13] = oracle.dxvnorm_by_dxv(xo[:13])
+    Po = J @ Po @ J.T
+    Po = 0.5 * (Po + Po.T)
+    assert_state_close(xg, Pg, xo, Po)
+    bad = R.copy()
+    bad[3, 0, 1] += 1e-3                                   # R01 != R10: not a covariance block
+    with pytest.raises(Exception) as e:
+        ctx.ekf_update(0, feats, Hxv, Hy, bad, nu)
+    assert "symmetric" in str(e.value)
+    ctx.close()
+
+
+def test_make_measurements_counts_only_this_frames_selection(oracle):
+    """found[] keeps the flag of features that are not selected this frame (like
+    Feature::successful_measurement_flag_); the returned count must cover the selected ones only
+    (monoslam.cpp:336-359).  n_select = 4 of 20 and a camera that turns: the selection changes."""
+    sc = synth.make_scene("C2", n_frames=6, n_features=20, override=False)
+    sc.n_select = 4
+    ctx = ctx_from_scenes([sc])
+    o = oracle_slam_from_scene(oracle, sc)
+    sels = []
+    for t in range(6):
+        ctx.set_frame(0, 0, sc.frames[t])
+        ctx.ekf_predict(0)
+        ctx.predict_measurements(0)
+        cnt = ctx.make_measurements(0, 0)
+        ctx.ekf_update_measured(0)
+        o.predict()
+        o.select()
+        assert cnt == o.measure(sc.frames[t]), t
+        o.update()
+        o.normalise()
+        o.finish()
+        fg = ctx.features(0)
+        sel = fg["select_rank"] >= 0
+        assert cnt == int(((fg["flags"] & 2) > 0)[sel].sum()) and cnt <= 4
+        sels.append(tuple(np.nonzero(sel)[0]))
+    assert len(set(sels)) > 1, "the scenario must change the selection between frames"
+    ctx.close()
+
+
+def test_delete_feature_moves_jacobians_with_the_feature(oracle):
+    """ADVICE r1: Feature::dh_by_dxv_ / dh_by_dy_ / R_ belong to the Feature object (feature.h:104-112);
+    after a deletion the records of the later features must move down with them."""
+    sc = synth.make_scene("C2", n_frames=1, n_features=12, override=False)
+    ctx = ctx_from_scenes([sc])
+    ctx.ekf_predict(0)
+    ctx.predict_measurements(0)
+    J0, Jy0, R0, _ = ctx.feature_jacobians(0)
+    ctx.delete_feature(0, 4)
+    J1, Jy1, R1, _ = ctx.feature_jacobians(0)
+    keep = [i for i in range(12) if i != 4]
+    assert J1.shape[0] == 11
+    assert (J1 == J0[keep]).all() and (Jy1 == Jy0[keep]).all() and (R1 == R0[keep]).all()
+    ctx.close()
