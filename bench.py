@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dist-selftest", action="store_true", help="CPU/gloo check of the N>1 plumbing")
     ap.add_argument("--cpu-threads", type=int, default=0, help="host threads of the CPU legs (0 = all)")
+    ap.add_argument("--only-main", action="store_true", help="skip the legs of the other configs / single stream")
     ap.add_argument("--step-groups", type=int, default=1, choices=[1, 2],
                     help="staggered stream groups of the fused step (1 = serial kernel order)")
     return ap.parse_args()
@@ -116,18 +117,46 @@ def oracle_slams(po, scenes, count):
     return slams
 
 
-def cpu_run(scenes, seconds, threads=None):
-    """Oracle (CPU port of the reference path) timed on the host cores over a bounded sample."""
+def cpu_run(scenes, seconds, threads=None, pin=True):
+    """Oracle (CPU port of the reference path) timed on the host cores over a bounded sample: one independent
+    camera stream per thread, each thread pinned to its own usable CPU (affinity mask capped by the cgroup quota)."""
     from oracle import pyoracle as po
     po.build()
-    threads = threads or po.hardware_threads() or os.cpu_count() or 1
+    threads = threads or po.usable_cpus() or 1
     slams = oracle_slams(po, scenes, threads)
     frames = [scenes[i % len(scenes)].frames for i in range(threads)]
-    t1 = po.run_slams(slams, frames, 1, threads)            # calibration (also warms caches)
+    t1, _ = po.run_slams_pinned(slams, frames, 1, threads, pin)   # calibration (also warms caches)
     steps = max(2, int(seconds / max(t1, 1e-3)))
-    t = po.run_slams(slams, frames, steps, threads)
+    t, gs = po.run_slams_pinned(slams, frames, steps, threads, pin)
     fps = threads * steps / t
-    return fps, threads, steps, t
+    # "dense-resident" variant of SURVEY 8(d): the same run without the reference's 4 gather / scatter passes per
+    # frame (monoslam.cpp:518-614), whose time the oracle measures per stream; gs is summed over the streams
+    gs_share = gs / max(threads * t, 1e-12)
+    return {"fps": fps, "threads": threads, "steps": steps, "seconds": t, "gather_scatter_share": gs_share,
+            "fps_dense_resident": fps / max(1e-9, 1.0 - gs_share)}
+
+
+def cpu_baseline_block(scenes, seconds, threads=None):
+    """cpu_baseline object: all usable cores (the headline), plus 1 and 8 threads of the same sample."""
+    from oracle import pyoracle as po
+    po.build()
+    usable = threads or po.usable_cpus() or 1
+    legs = {}
+    for nt, share in ((1, 0.2), (min(8, usable), 0.25), (usable, 0.55)):
+        if nt in legs:
+            continue
+        legs[nt] = cpu_run(scenes, seconds * share, nt)
+    full = legs[usable]
+    return {"value": full["fps"], "unit": UNIT, "cores": usable, "kind": "port",
+            "sample": "%d streams (1 per pinned thread) x %d oracle steps (%.1f s)" % (usable, full["steps"], full["seconds"]),
+            "frames_per_s_per_core": full["fps"] / usable,
+            "by_threads": {str(k): round(v["fps"], 2) for k, v in sorted(legs.items())},
+            "hardware_threads_of_the_box": po.hardware_threads(),
+            "cores_how": "min(sched_getaffinity, cgroup cpu.max quota)",
+            "storage": "faithful (per-feature heap blocks + 4 gather/scatter passes per frame, like the reference)",
+            "gather_scatter_share": round(full["gather_scatter_share"], 4),
+            "dense_resident_value": full["fps_dense_resident"],
+            "dense_resident_how": "same run minus the measured time of the gather/scatter passes (monoslam.cpp:518-614)"}
 
 
 def dist_selftest(rank, world):
@@ -171,19 +200,22 @@ def reference_sources_rate(config, seconds=3.0):
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    from oracle import pyoracle as po
+    po.build()
     scenes = make_scenes(args.config, min(args.unique, 8), args.ring)
     budget = args.cpu_seconds if args.cpu_seconds < 12.0 else max(2.0, min(40.0, 120.0 / max(1, args.steps + args.warmup)))
-    vals = []
-    threads = None
+    vals, last = [], None
+    threads = args.cpu_threads or po.usable_cpus() or 1
     for k in range(args.warmup + args.steps):
-        fps, threads, steps, t = cpu_run(scenes, budget, args.cpu_threads or None)
+        last = cpu_run(scenes, budget, threads)
         if k >= args.warmup:
-            vals.append(fps)
-        if sum(1 for _ in vals) >= 3 and time.time() - T0 > 240:
+            vals.append(last["fps"])
+        if len(vals) >= 3 and time.time() - T0 > 240:
             break
     v = float(np.mean(vals))
-    sample = "%d streams (1 per thread) x ~%.0f s of oracle steps per bench step" % (threads, budget)
+    sample = "%d streams (1 per pinned thread) x ~%.0f s of oracle steps per bench step" % (threads, budget)
     ref_src = reference_sources_rate(args.config)
+    one = cpu_run(scenes, min(3.0, budget), 1)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1e3 * threads / v,
@@ -196,41 +228,50 @@ def run_reference(args, rank, world):
                                         # thread, ellipses from S_i (it has no fixed-ellipse switch).  Slower than the
                                         # port (its matrix stand-in is not Eigen), so the port stays the baseline.
                                         "reference_sources_with_standins": ref_src},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "frames_per_s_per_core": v / threads, "one_thread_value": one["fps"],
+                         "hardware_threads_of_the_box": po.hardware_threads(),
+                         "cores_how": "min(sched_getaffinity, cgroup cpu.max quota), one pinned thread per core",
+                         "gather_scatter_share": round(last["gather_scatter_share"], 4),
+                         "dense_resident_value": v / max(1e-9, 1.0 - last["gather_scatter_share"])},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
-def run_ours(args, rank, local_rank, world):
+def _traffic(config, kernel, B):
+    """dram__bytes_read + write per launch of `kernel`, from the ncu capture of THIS config (per stream x B), or None
+    when no capture of that config is committed (profiles/r02_dram_bytes.json, written by tools/ncu_traffic.py)."""
+    fp = os.path.join(ROOT, "profiles", "r02_dram_bytes.json")
+    if not os.path.exists(fp):
+        return None
+    try:
+        v = json.load(open(fp)).get(config, {}).get(kernel)
+        return None if v is None else v["bytes_per_stream"] * B
+    except Exception:
+        return None
+
+
+def measure_config(args, config, B, steps, warmup, rank, local_rank, world, stream, dev, e2e=True, clocks=False):
+    """One workload (BASELINE config) on this rank's GPU: device-resident throughput, end-to-end throughput through
+    the C ABI with host frames, per-kernel times.  Returns a dict (times already MAX-reduced over ranks)."""
     import torch
     import torch.distributed as dist
     import scenelib2_b200 as sl2
     from scenelib2_b200 import synth
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    B, R = args.streams, args.ring
-    scenes = make_scenes(args.config, min(args.unique, B), R, base_stream=rank * 1000)
+    R = args.ring
+    scenes = make_scenes(config, min(args.unique, B), R, base_stream=rank * 1000)
     sc0 = scenes[0]
     N, n, H, W = sc0.n_features, sc0.n, sc0.height, sc0.width
-    # a dedicated (non-default) torch stream: the library launches on it, torch events time it
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
     cfg = sl2.config_for_scene(sc0, num_streams=B, frame_slots=R, device=local_rank,
                                cuda_stream=stream.cuda_stream)
     ctx = sl2.Context(cfg)
     ctx.set_step_groups(args.step_groups)
     for s in range(B):
         sl2.load_scene(ctx, s, scenes[s % len(scenes)])
-    # host frame ring in pinned memory: [R][B][H][W]
-    host = torch.empty((R, B, H, W), dtype=torch.uint8, pin_memory=True)
+    host = torch.empty((R, B, H, W), dtype=torch.uint8, pin_memory=True)   # pinned host frame ring
     hv = host.numpy()
     for s in range(B):
         hv[:, s] = scenes[s % len(scenes)].frames
@@ -244,11 +285,11 @@ def run_ours(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, post=None):
+    def timed(fn, nsteps, post=None):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record(stream)
-        for k in range(steps):
+        for k in range(nsteps):
             fn(k)
         if post:
             post()
@@ -261,117 +302,191 @@ def run_ours(args, rank, local_rank, world):
             ms = float(t.item())
         return ms
 
+    out = {"config": config, "workload": WORKLOADS.get(config, config), "streams_per_gpu": B, "state_dim": n,
+           "features": N, "frame": [W, H]}
     # ---- device-resident leg (`value`) ----------------------------------------------------------
-    for k in range(args.warmup):
+    for k in range(warmup):
         ctx.step(k % R)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler = None
+    if clocks:
+        sampler = ClockSampler(local_rank)
+        sampler.start()
     l0 = ctx.launch_count()
-    ms = timed(lambda k: ctx.step(k % R), args.steps, post=ctx.join)
-    launches = ctx.launch_count() - l0
-    sampler.stop_flag.set()
-    sampler.join(timeout=2)
-    value = world * B * args.steps / (ms * 1e-3)
+    ms = timed(lambda k: ctx.step(k % R), steps, post=ctx.join)
+    out["gpu_launches"] = int(ctx.launch_count() - l0)
+    if sampler:
+        sampler.stop_flag.set()
+        sampler.join(timeout=2)
+        out["clocks"] = sampler.summary()
+    out["ms_per_step"] = ms / steps
+    out["value"] = world * B * steps / (ms * 1e-3)
 
     # ---- per-kernel durations (CUDA events on the launching stream, one sync per step) ----------
     ctx.enable_timing(True)
-    kt = np.zeros(4)
-    ku = np.zeros(5)
-    for k in range(args.steps):
+    kt, ku = np.zeros(4), np.zeros(5)
+    for k in range(steps):
         ctx.step(k % R)
         kt += ctx.last_step_times()
         ku += ctx.last_update_times()
-    kt /= args.steps
-    ku /= args.steps
+    kt /= steps
+    ku /= steps
     ctx.enable_timing(False)
+    out["kernel_ms"] = {"predict_select": float(kt[0]), "patch_search": float(kt[1]), "ekf_update": float(kt[2]),
+                        "cull": float(kt[3]),
+                        "ekf_update_kernels": {"hp": float(ku[0]), "chol": float(ku[1]), "solve": float(ku[2]),
+                                               "syrk": float(ku[3]), "finish": float(ku[4])}}
+
     # ---- end-to-end leg: host frames in, camera states out, through the C ABI -----------------
     # every step: pinned host frames -> H2D -> GoOneStep of all streams -> D2H of the camera states;
     # the copy of step t+1 overlaps the kernels of step t (frame ring); the region ends when the
     # last result has landed in host memory (ctx.sync).
-    def e2e_step(k):
-        ctx.step_host_async(k % R, host[k % R].data_ptr(), xv_out[k % R].data_ptr())
-    for k in range(min(3, args.warmup)):
-        e2e_step(k)
-    ctx.sync()
-    ms_e2e = timed(e2e_step, args.steps, post=ctx.sync)
-    e2e = world * B * args.steps / (ms_e2e * 1e-3)
-    ms_sync = timed(lambda k: ctx.step_host(k % R, host[k % R].data_ptr(), xv_out[k % R].data_ptr()),
-                    max(3, args.steps // 4))
-    e2e_sync = world * B * max(3, args.steps // 4) / (ms_sync * 1e-3)
+    if e2e:
+        def e2e_step(k):
+            ctx.step_host_async(k % R, host[k % R].data_ptr(), xv_out[k % R].data_ptr())
+        for k in range(min(3, warmup)):
+            e2e_step(k)
+        ctx.sync()
+        ms_e2e = timed(e2e_step, steps, post=ctx.sync)
+        ms_sync = timed(lambda k: ctx.step_host(k % R, host[k % R].data_ptr(), xv_out[k % R].data_ptr()),
+                        max(3, steps // 4))
+        out["e2e"] = {"value": world * B * steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": world * B * H * W,
+                      "d2h_bytes_per_step": world * B * 13 * 8, "ms_per_step": ms_e2e / steps,
+                      "api": "sl2_step_host_async over a ring of %d pinned frame sets" % R,
+                      "blocking_call_value": world * B * max(3, steps // 4) / (ms_sync * 1e-3)}
+    out["matched_fraction"] = float(np.mean([(ctx.features(s)["flags"] & 2).astype(bool).mean()
+                                             for s in sorted({0, B // 2, B - 1})]))
+    out["features_left_stream0"] = ctx.num_features(0)
 
-    matched = float(np.mean([(ctx.features(s)["flags"] & 2).astype(bool).mean() for s in (0, B // 2, B - 1)]))
-    nfeat_end = ctx.num_features(0)
+    # ---- rooflines ------------------------------------------------------------------------------
+    pk, pk_kind = peaks()
+    rad = sc0.meta["config"]["radius"] or 20   # C1: ellipses come from S_i; 20 px = the tile radius
+    nsel = min(sc0.n_select, N)
+    search_bytes = B * nsel * synth.algorithmic_search_bytes(sc0.boxsize, rad)   # per launch
+    ach = search_bytes / (kt[1] * 1e-3) / 1e9
+    m = 2 * nsel
+    flops = synth.ekf_structured_flops(n, m) * B
+    fp64_peak, fp64_kind = 37.0, "nominal"
+    fp = os.path.join(ROOT, "profiles", "fp64_peak_measured.json")
+    if os.path.exists(fp):
+        fp64_peak, fp64_kind = json.load(open(fp))["fp64_tflops"], "measured (tools/fp64_pipes.cu)"
+    upd_tr = [_traffic(config, k, B) for k in ("upd_hp", "upd_chol", "upd_solve", "upd_syrk", "upd_finish")]
+    out["roofline"] = {
+        "kernel": "EKF update = upd_hp + upd_chol + upd_solve + upd_syrk + upd_finish (%.0f %% of the step)"
+                  % (100 * kt[2] / kt.sum()),
+        "bound": "tensor", "achieved": flops / (kt[2] * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+        "frac": flops / (kt[2] * 1e-3) / 1e12 / fp64_peak,
+        "traffic": None if any(v is None for v in upd_tr) else float(sum(upd_tr)), "peak_kind": fp64_kind,
+        "algorithmic_flops_per_launch": flops, "kernel_ms": float(kt[2]),
+        "note": "FP64 DMMA m8n8k4 (tcgen05 has no FP64 kind); structured-minimum FLOPs of SURVEY 8(d) over the "
+                "summed duration of the five update kernels"}
+    out["roofline_patch_search"] = {
+        "kernel": "search_kernel (patch search)", "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"],
+        "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": _traffic(config, "search", B), "peak_kind": pk_kind,
+        "algorithmic_bytes_per_launch": search_bytes, "kernel_ms": float(kt[1]),
+        "note": "integer / FP64 issue bound, not HBM bound: see DESIGN.md 3.1"}
+    ctx.close()
+    return out, scenes
+
+
+def shim_rate(config, repeat=60):
+    """frames/s a SceneLib2 CALLER sees: the reference-shaped C++ class surface (scenelib2_b200/host) driven like
+    examples/MonoSlamSceneLib1.cpp by sl2_headless -- ONE camera stream, GoOneStep per frame with the frame upload
+    and the refresh of every host mirror (Feature::y_/Pxy_/Pyy_/matrix_block_list_) inside the timed region."""
+    import tempfile
+    from scenelib2_b200 import synth
+    exe = os.path.join(ROOT, "scenelib2_b200", "host", "sl2_headless")
+    if not os.path.exists(exe):
+        return {"unavailable": "sl2_headless not built"}
+    try:
+        kw = {}
+        if config == "C1":
+            kp = os.path.join(ROOT, "tests", "golden", "known_patches.npy")
+            if os.path.exists(kp):
+                kw["known_patches"] = np.load(kp)
+        sc = synth.make_scene(config, n_frames=4, **kw)
+        d = tempfile.mkdtemp(prefix="sl2shim_")
+        Pxx = np.diag([4e-4] * 3 + [2e-5] * 4 + [1e-3] * 3 + [1e-3] * 3)   # cf. data/SceneLib2.cfg:85-115
+        cfg = synth.write_reference_case(d, sc, Pxx)
+        env = dict(os.environ, SL2_HEADLESS_REPEAT=str(repeat))
+        r = subprocess.run([exe, cfg, os.path.join(d, "frames.raw"), str(sc.width), str(sc.height), "4"],
+                           capture_output=True, text=True, env=env, timeout=120)
+        for ln in r.stdout.splitlines():
+            if ln.startswith("shim_frames_per_s"):
+                t = ln.split()
+                return {"value": float(t[1]), "unit": UNIT, "streams": 1, "features": int(t[5]),
+                        "api": "SceneLib2::MonoSLAM::GoOneStep of the host shim (full host mirrors per frame)"}
+        return {"unavailable": (r.stderr or r.stdout)[-160:]}
+    except Exception as e:   # informational leg
+        return {"unavailable": str(e)[:160]}
+
+
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    # a dedicated (non-default) torch stream: the library launches on it, torch events time it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+
+    B = args.streams
+    main, scenes = measure_config(args, args.config, B, args.steps, args.warmup, rank, local_rank, world, stream, dev,
+                                  clocks=True)
+    # the other BASELINE configs (north star: N in {20, 50, 100}; C3 on 8 GPUs = C5) and the single-stream latency
+    extra = {}
+    if not args.only_main:
+        short = max(5, min(args.steps, 20))
+        for cname in ("C1", "C2", "C3", "C4"):
+            if cname == args.config:
+                continue
+            r, _ = measure_config(args, cname, B, short, 3, rank, local_rank, world, stream, dev)
+            key = "C5" if (cname == "C3" and world == 8) else cname
+            if key == "C5":
+                r["workload"] = "C5: 8 independent synthetic 640x480 stream sets, 100 features each, one set per GPU"
+            extra[key] = {k: r[k] for k in ("workload", "streams_per_gpu", "state_dim", "value", "ms_per_step", "e2e",
+                                            "kernel_ms", "roofline", "roofline_patch_search", "matched_fraction",
+                                            "gpu_launches")}
+        one, _ = measure_config(args, args.config, 1, short, 3, rank, local_rank, world, stream, dev, e2e=False)
+        extra["single_stream"] = {"workload": one["workload"] + ", ONE camera stream per GPU (latency)",
+                                  "ms_per_frame": one["ms_per_step"], "value": one["value"],
+                                  "kernel_ms": one["kernel_ms"]}
+        if rank == 0:
+            extra["shim_single_stream"] = {c: shim_rate(c) for c in ("C1", "C4")}
 
     if rank == 0:
-        pk, pk_kind = peaks()
-        rad = sc0.meta["config"]["radius"] or 20   # C1: ellipses come from S_i; 20 px = the tile radius
-        bytes_per_feature = synth.algorithmic_search_bytes(sc0.boxsize, rad)
-        search_bytes = B * N * bytes_per_feature                      # per launch
-        ach = search_bytes / (kt[1] * 1e-3) / 1e9
-        m = 2 * N
-        flops = synth.ekf_structured_flops(n, m) * B
-        fp64_peak, fp64_kind = 37.0, "nominal"
-        fp = os.path.join(ROOT, "profiles", "fp64_peak_measured.json")
-        if os.path.exists(fp):
-            fp64_peak, fp64_kind = json.load(open(fp))["fp64_tflops"], "measured (tools/fp64_pipes.cu)"
-        upd_traffic = None
-        up = os.path.join(ROOT, "profiles", "update_dram_bytes_per_launch.json")
-        if os.path.exists(up):
-            upd_traffic = json.load(open(up)).get("dram_bytes_per_launch_per_stream", 0) * B or None
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "search_dram_bytes_per_launch.json")
-        if os.path.exists(tp):
-            try:
-                tj = json.load(open(tp))
-                traffic = tj.get("dram_bytes_per_launch_per_stream", 0) * B or None
-            except Exception:
-                traffic = None
+        sc0 = scenes[0]
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64 (EKF, scores) + u8/int32 (correlation sums)",
             "data": "synthetic",
-            "config": {"workload": WORKLOADS.get(args.config, WORKLOAD), "streams_per_gpu": B, "frames_per_step": B * world,
-                       "state_dim": n, "measurements": m, "parallelism": "replicas x%d (no collective)" % world,
+            "config": {"workload": main["workload"], "streams_per_gpu": B, "frames_per_step": B * world,
+                       "state_dim": main["state_dim"], "measurements": 2 * min(sc0.n_select, sc0.n_features),
+                       "parallelism": "replicas x%d (no collective)" % world,
                        "l2": "per-step working set %.0f MB (P + scratch + frames of %d streams) exceeds the 126 MB L2"
-                             % ((B * (cfg.max_features * 3 + 13) ** 2 * 8 * 2.1) / 1e6, B),
-                       "matched_fraction": matched, "features_left_stream0": nfeat_end,
+                             % ((B * (sc0.n_features * 3 + 13) ** 2 * 8 * 2.1) / 1e6, B),
+                       "matched_fraction": main["matched_fraction"], "features_left_stream0": main["features_left_stream0"],
                        "step_groups": args.step_groups,
                        "kernel_timing": "kernel_ms / roofline: separate pass in serial kernel order (whole batch per "
-                                        "launch, CUDA events between launches); in the timed `value` and `e2e` "
-                                        "regions the step runs as %d staggered stream group(s) whose kernels overlap"
-                                        % args.step_groups},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": world * B * H * W,
-                    "d2h_bytes_per_step": world * B * 13 * 8, "ms_per_step": ms_e2e / args.steps,
-                    "api": "sl2_step_host_async over a ring of %d pinned frame sets" % R,
-                    "blocking_call_value": e2e_sync},
-            "gpu_launches": int(launches),
-            "clocks": sampler.summary(),
-            # dominant kernel of the step = EKF update on the FP64 tensor path (DMMA); MEASURED_PEAKS.json
+                                        "launch, CUDA events between launches); the timed `value` and `e2e` regions "
+                                        "launch back to back"},
+            "e2e": main["e2e"], "gpu_launches": main["gpu_launches"], "clocks": main.get("clocks"),
+            # the step's dominant stage = the EKF update (five kernels on the FP64 tensor path); MEASURED_PEAKS.json
             # has no FP64 entry, so the peak is the DMMA rate measured on this pool by tools/fp64_pipes.cu
-            "roofline": {"kernel": "update_kernel (EKF update, %.0f %% of the step)" % (100 * kt[2] / kt.sum()),
-                         "bound": "tensor", "achieved": flops / (kt[2] * 1e-3) / 1e12, "peak": fp64_peak,
-                         "unit": "TFLOP/s", "frac": flops / (kt[2] * 1e-3) / 1e12 / fp64_peak,
-                         "traffic": upd_traffic, "peak_kind": fp64_kind,
-                         "algorithmic_flops_per_launch": flops, "kernel_ms": float(kt[2]),
-                         "note": "FP64 DMMA m8n8k4 (tcgen05 has no FP64 kind); structured-minimum FLOPs of SURVEY 8(d)"},
+            "roofline": main["roofline"],
             # the metric also asks for the patch search against the HBM roofline
-            "roofline_patch_search": {"kernel": "search_kernel (patch search)", "bound": "hbm",
-                                      "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                                      "frac": ach / pk["hbm_gbs"], "traffic": traffic, "peak_kind": pk_kind,
-                                      "algorithmic_bytes_per_launch": search_bytes, "kernel_ms": float(kt[1]),
-                                      "note": "integer / FP64 issue bound, not HBM bound: see DESIGN.md 3.1"},
-            "kernel_ms": {"predict_select": float(kt[0]), "patch_search": float(kt[1]),
-                          "ekf_update": float(kt[2]), "cull": float(kt[3]),
-                          "ekf_update_kernels": {"hp": float(ku[0]), "chol": float(ku[1]), "solve": float(ku[2]),
-                                                 "syrk": float(ku[3]), "finish": float(ku[4])}},
+            "roofline_patch_search": main["roofline_patch_search"],
+            "kernel_ms": main["kernel_ms"],
+            "configs": extra,
         }
         if not args.no_cpu_baseline and world == 1:
-            fps, threads, steps, t = cpu_run(scenes, args.cpu_seconds, args.cpu_threads or None)
-            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": "%d streams x %d oracle steps (%.1f s)" % (threads, steps, t)}
+            line["cpu_baseline"] = cpu_baseline_block(scenes, args.cpu_seconds, args.cpu_threads or None)
         print(json.dumps(line))
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -84,6 +84,17 @@ int sl2_get_state(sl2_ctx *ctx, int32_t stream_id, double *x, double *P);
 /* MonoSLAM::delete_feature (monoslam.cpp:770-812): drop feature `index` and its rows/cols of P */
 int sl2_delete_feature(sl2_ctx *ctx, int32_t stream_id, int32_t index);
 
+/* MonoSLAM::AddNewKnownFeature (monoslam.cpp:1278-1289, Feature ctor feature.cpp:108-149): append ONE feature to the
+ * map on the device -- y (3), xp_org (7: camera position state the feature was acquired from), patch (boxsize x
+ * boxsize u8, row-major).  Pcol = NULL: Pxy_, Pyy_ and every matrix_block_list_ entry of the new feature are zero,
+ * like the reference's known features; otherwise Pcol is the new feature's covariance column block, column-major
+ * (n + 3) x 3 with n the state size before the call (rows 0..n-1: P_{x,y_new} / P_{y_j,y_new}, rows n..n+2: Pyy_,
+ * whose upper triangle is taken) -- what the conversion of a partially-initialised feature produces
+ * (monoslam.cpp:1262, feature.cpp:45-95).  Nothing else of the map moves (the mirror of sl2_delete_feature).
+ * Returns the index of the new feature (>= 0), SL2_ERR_STATE when the map already holds max_features. */
+int sl2_append_feature(sl2_ctx *ctx, int32_t stream_id, const double *y, const double *xp_org,
+                       const uint8_t *patch, const double *Pcol);
+
 /* ---- patch search --------------------------------------------------------------------------- */
 /* MonoSLAM::elliptical_search (monoslam.cpp:401-477) o correlate2_warning (improc/improc.cpp:
  * 55-134), batched over n features of one stream.  feat_index[i] selects the stored template;

@@ -1,5 +1,10 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see dense.hpp header).  extern "C" surface of liboracle.so.
 #include <chrono>
+#include <pthread.h>
+#include <sched.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <thread>
 
 #include "sl2_oracle.h"
@@ -273,11 +278,52 @@ void orc_slam_get_features(const orc_slam *s, int32_t *label, double *h, double 
     select_rank[s->s.selected_feature_list[r]->position_in_list] = (int32_t)r;
 }
 
-double orc_slam_run(orc_slam **slams, int32_t nslam, const uint8_t *const *frames, int32_t nframes,
-                    int32_t nsteps, int32_t nthreads) {
+// CPUs this process may really use: the scheduler affinity mask capped by the cgroup CPU quota
+// (std::thread::hardware_concurrency() reports the machine, not the container: round 1's "128 cores").
+static std::vector<int> usable_cpu_list() {
+  std::vector<int> cpus;
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  if (sched_getaffinity(0, sizeof(set), &set) == 0)
+    for (int c = 0; c < CPU_SETSIZE; ++c)
+      if (CPU_ISSET(c, &set)) cpus.push_back(c);
+  if (cpus.empty()) cpus.push_back(0);
+  double quota = -1.0;
+  if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {  // cgroup v2: "<quota|max> <period>"
+    char q[64];
+    long long period = 0;
+    if (fscanf(f, "%63s %lld", q, &period) == 2 && strcmp(q, "max") != 0 && period > 0) quota = atof(q) / (double)period;
+    fclose(f);
+  } else if (FILE *g = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r")) {  // cgroup v1
+    long long qv = -1, pv = 0;
+    if (fscanf(g, "%lld", &qv) != 1) qv = -1;
+    fclose(g);
+    if (FILE *h = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r")) {
+      if (fscanf(h, "%lld", &pv) != 1) pv = 0;
+      fclose(h);
+    }
+    if (qv > 0 && pv > 0) quota = (double)qv / (double)pv;
+  }
+  if (quota > 0.0) {
+    const size_t cap = (size_t)(quota + 0.999);
+    if (cap >= 1 && cap < cpus.size()) cpus.resize(cap);
+  }
+  return cpus;
+}
+
+double orc_slam_run_pinned(orc_slam **slams, int32_t nslam, const uint8_t *const *frames, int32_t nframes,
+                           int32_t nsteps, int32_t nthreads, int32_t pin, double *gather_scatter_seconds) {
   if (nthreads < 1) nthreads = 1;
   if (nthreads > nslam) nthreads = nslam;
+  const std::vector<int> cpus = usable_cpu_list();
+  for (int i = 0; i < nslam; ++i) slams[i]->s.gather_scatter_seconds = 0.0;
   auto worker = [&](int t) {
+    if (pin) {  // one stream per core: thread t stays on the t-th usable CPU
+      cpu_set_t set;
+      CPU_ZERO(&set);
+      CPU_SET(cpus[(size_t)t % cpus.size()], &set);
+      pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+    }
     for (int i = t; i < nslam; i += nthreads) {
       Slam &s = slams[i]->s;
       const size_t fsz = (size_t)s.cfg.width * s.cfg.height;
@@ -287,12 +333,28 @@ double orc_slam_run(orc_slam **slams, int32_t nslam, const uint8_t *const *frame
   const auto t0 = std::chrono::steady_clock::now();
   std::vector<std::thread> th;
   for (int t = 1; t < nthreads; ++t) th.emplace_back(worker, t);
-  worker(0);
+  {  // the calling thread works too, and gets its affinity back afterwards
+    cpu_set_t old;
+    const bool have = pin && pthread_getaffinity_np(pthread_self(), sizeof(old), &old) == 0;
+    worker(0);
+    if (have) pthread_setaffinity_np(pthread_self(), sizeof(old), &old);
+  }
   for (auto &x : th) x.join();
   const auto t1 = std::chrono::steady_clock::now();
+  if (gather_scatter_seconds) {
+    double g = 0.0;
+    for (int i = 0; i < nslam; ++i) g += slams[i]->s.gather_scatter_seconds;
+    *gather_scatter_seconds = g;  // summed over streams (= over threads when one stream runs per thread)
+  }
   return std::chrono::duration<double>(t1 - t0).count();
 }
 
+double orc_slam_run(orc_slam **slams, int32_t nslam, const uint8_t *const *frames, int32_t nframes,
+                    int32_t nsteps, int32_t nthreads) {
+  return orc_slam_run_pinned(slams, nslam, frames, nframes, nsteps, nthreads, 0, nullptr);
+}
+
 int32_t orc_hardware_threads(void) { return (int32_t)std::thread::hardware_concurrency(); }
+int32_t orc_usable_cpus(void) { return (int32_t)usable_cpu_list().size(); }
 
 }  // extern "C"

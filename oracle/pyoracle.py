@@ -82,6 +82,7 @@ def lib():
         L.orc_correlate2_warning.restype = C.c_double
         L.orc_slam_create.restype = C.c_void_p
         L.orc_slam_run.restype = C.c_double
+        L.orc_slam_run_pinned.restype = C.c_double
         for name in ("orc_slam_destroy", "orc_slam_add_feature", "orc_slam_set_state",
                      "orc_slam_get_state", "orc_slam_step", "orc_slam_predict",
                      "orc_slam_update", "orc_slam_normalise", "orc_slam_finish",
@@ -546,5 +547,22 @@ def run_slams(slams, frames, nsteps, nthreads):
     return lib().orc_slam_run(handles, n, ptrs, nframes, nsteps, nthreads)
 
 
+def run_slams_pinned(slams, frames, nsteps, nthreads, pin=True):
+    """Like run_slams with one thread pinned per usable CPU; returns (wall seconds, gather/scatter seconds summed
+    over the streams)."""
+    n = len(slams)
+    handles = (C.c_void_p * n)(*[s.h for s in slams])
+    keep = [np.ascontiguousarray(f, np.uint8) for f in frames]
+    ptrs = (u8p * n)(*[_p(f, u8p) for f in keep])
+    gs = C.c_double(0.0)
+    t = lib().orc_slam_run_pinned(handles, n, ptrs, keep[0].shape[0], nsteps, nthreads, 1 if pin else 0, C.byref(gs))
+    return t, gs.value
+
+
 def hardware_threads():
     return lib().orc_hardware_threads()
+
+
+def usable_cpus():
+    """CPUs this process may use: scheduler affinity capped by the cgroup CPU quota."""
+    return lib().orc_usable_cpus()

@@ -106,6 +106,12 @@ void orc_slam_get_features(const orc_slam *s, int32_t *label, double *h, double 
 double orc_slam_run(orc_slam **slams, int32_t nslam, const uint8_t *const *frames, int32_t nframes,
                     int32_t nsteps, int32_t nthreads);
 int32_t orc_hardware_threads(void);
+/* the same with one thread pinned per usable CPU (pin != 0) and the seconds the streams spent in the reference's
+ * gather / scatter passes (monoslam.cpp:518-614), summed over streams (may be NULL) */
+double orc_slam_run_pinned(orc_slam **slams, int32_t nslam, const uint8_t *const *frames, int32_t nframes,
+                           int32_t nsteps, int32_t nthreads, int32_t pin, double *gather_scatter_seconds);
+/* CPUs this process can really use: affinity mask capped by the cgroup CPU quota */
+int32_t orc_usable_cpus(void);
 
 #ifdef __cplusplus
 }

@@ -19,6 +19,7 @@
 // 1 000-step trajectory; state / covariance agree to ~1e-13.  PARITY UNPINNED only at the last ulp
 // (Eigen's own product order cannot be reproduced without Eigen), see dense.hpp.
 #pragma once
+#include <chrono>
 #include <memory>
 
 #include "improc.hpp"
@@ -69,6 +70,15 @@ struct Slam {
   int next_free_label = 0;
   int successful_measurement_vector_size = 0;
   int number_of_visible_features = 0;
+  // benchmark bookkeeping only: seconds spent in the 4 gather / scatter passes per frame (monoslam.cpp:518-614
+  // around the update and the symmetrisation); "dense-resident" CPU figure = run time minus this
+  double gather_scatter_seconds = 0.0;
+  struct GsTimer {
+    double &acc;
+    std::chrono::steady_clock::time_point t0;
+    explicit GsTimer(double &a) : acc(a), t0(std::chrono::steady_clock::now()) {}
+    ~GsTimer() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+  };
 
   explicit Slam(const SlamConfig &c) : cfg(c), Pxx(13, 13) {
     cam.width = c.width;
@@ -285,14 +295,20 @@ struct Slam {
     const int size2 = total_state_size;
     Vec x((size_t)size2, 0.0);
     Mat P(size2, size2);
-    construct_total_state(x);
-    construct_total_covariance(P);
+    {
+      GsTimer tm(gather_scatter_seconds);
+      construct_total_state(x);
+      construct_total_covariance(P);
+    }
     Vec nu_tot((size_t)size, 0.0);
     Mat H(size, size2), R_tot(size, size);
     construct_total_measurement_stuff(nu_tot, H, R_tot);
     kalman_update_dense(x, P, H, R_tot, nu_tot);
-    fill_states(x);
-    fill_covariances(P);
+    {
+      GsTimer tm(gather_scatter_seconds);
+      fill_states(x);
+      fill_covariances(P);
+    }
   }
 
   // ---- monoslam.cpp:616-637 --------------------------------------------------------------
@@ -351,10 +367,16 @@ struct Slam {
     }
     delete_bad_features();
     Mat P(total_state_size, total_state_size);
-    construct_total_covariance(P);
+    {
+      GsTimer tm(gather_scatter_seconds);
+      construct_total_covariance(P);
+    }
     const Mat PT = transpose(P);
     for (size_t i = 0; i < P.a.size(); ++i) P.a[i] = P.a[i] * 0.5 + PT.a[i] * 0.5;
-    fill_covariances(P);
+    {
+      GsTimer tm(gather_scatter_seconds);
+      fill_covariances(P);
+    }
   }
 };
 

@@ -481,6 +481,34 @@ int sl2_delete_feature(sl2_ctx *c, int32_t s, int32_t index) {
   return SL2_OK;
 }
 
+int sl2_append_feature(sl2_ctx *c, int32_t s, const double *y, const double *xp_org, const uint8_t *patch,
+                       const double *Pcol) {
+  if (bad_stream(c, s) || !y || !xp_org || !patch) return fail(c, SL2_ERR_ARG, "sl2_append_feature: bad argument");
+  const int nf = sl2_num_features(c, s);
+  if (nf < 0) return nf;
+  if (nf >= c->cfg.max_features) return fail(c, SL2_ERR_STATE, "sl2_append_feature: the map is full (max_features)");
+  const Sl2Dev &d = c->d;
+  const int box = d.box, n3 = SL2_NXV + 3 * nf + 3;
+  // staging: y(3) xp(7) Pcol(3 * n3) | patch rows (box x 16)
+  const size_t o_xp = 24, o_p = 80, o_patch = o_p + 8 * 3 * (size_t)n3, total = o_patch + (size_t)box * 16 + 64;
+  int rc = stage_reserve(c, total);
+  if (rc) return rc;
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  uint8_t *hp = c->stg_host;
+  memset(hp, 0, total);
+  memcpy(hp, y, 24);
+  memcpy(hp + o_xp, xp_org, 56);
+  if (Pcol) memcpy(hp + o_p, Pcol, 8 * 3 * (size_t)n3);
+  for (int r = 0; r < box; ++r) memcpy(hp + o_patch + (size_t)r * 16, patch + (size_t)r * box, box);
+  CU_TRY(c, cudaMemcpyAsync(c->stg_dev, hp, total - 64, cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, sl2_launch_append(d, s, reinterpret_cast<const double *>(c->stg_dev),
+                              reinterpret_cast<const double *>(c->stg_dev + o_xp), c->stg_dev + o_patch,
+                              Pcol ? reinterpret_cast<const double *>(c->stg_dev + o_p) : nullptr, c->stream));
+  ++c->launches;
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return nf;  // index of the new feature
+}
+
 // ---- patch search -----------------------------------------------------------------------------
 // A raw BOX x BOX template goes into the scratch slot behind the map templates; the search kernel addresses
 // templates as (stream * Nmax + feature), so relative to stream s the slot is feature (B - s) * Nmax.

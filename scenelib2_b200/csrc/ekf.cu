@@ -613,7 +613,61 @@ __global__ void __launch_bounds__(256) cull_kernel(const Sl2Dev d, int stream_lo
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// kernel 4: append one fully-initialised feature (monoslam.cpp:1278-1289, feature.cpp:108-149): the mirror of
+// cull_kernel -- x grows by y, P by three rows / columns (zero like the reference's Pxy_ / Pyy_ /
+// matrix_block_list_, or the caller's (n + 3) x 3 block), the per-feature records start like Feature::Initialise.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) append_kernel(const Sl2Dev d, int s, const double *y3, const double *xp7,
+                                                     const uint8_t *patch_rows16, const double *Pcol) {
+  const int tid = threadIdx.x;
+  const int nf = d.nfeat[s];
+  const int n = SL2_NXV + 3 * nf, ld = d.ld;
+  double *P = d.P + (size_t)s * ld * ld;
+  double *x = d.x + (size_t)s * ld;
+  const size_t f = (size_t)s * d.Nmax + nf;
+  for (int e = tid; e < 3 * (n + 3); e += blockDim.x) {
+    const int c = e / (n + 3), r = e - c * (n + 3);
+    const double v = Pcol ? Pcol[e] : 0.0;  // column-major (n + 3) x 3
+    P[r + (size_t)ld * (n + c)] = v;
+    if (r < n) P[(n + c) + (size_t)ld * r] = v;  // mirrored: both triangles stay consistent
+  }
+  if (Pcol) {
+    // the 3x3 diagonal block must be exactly symmetric: take the upper triangle of the caller's block
+    __syncthreads();
+    if (tid < 9) {
+      const int r = tid % 3, c = tid / 3;
+      if (r > c) P[(n + r) + (size_t)ld * (n + c)] = P[(n + c) + (size_t)ld * (n + r)];
+    }
+  }
+  if (tid < 3) x[n + tid] = y3[tid];
+  if (tid < 7) d.xp_org[f * 7 + tid] = xp7[tid];
+  const int box16 = d.box * 16;
+  for (int e = tid; e < box16; e += blockDim.x) d.patches[f * box16 + e] = patch_rows16[e];
+  if (tid == 0) {
+    d.attempted[f] = 0;
+    d.successful[f] = 0;
+    d.sel_rank[f] = -1;
+    d.found[f] = 0;
+    d.best[f] = 0.0;
+    d.h[f * 2] = d.h[f * 2 + 1] = 0.0;
+    d.z_uv[f * 2] = d.z_uv[f * 2 + 1] = 0;
+    for (int e = 0; e < 4; ++e) d.S[f * 4 + e] = 0.0;
+    for (int e = 0; e < 14; ++e) d.dh_dxp[f * 14 + e] = 0.0;
+    for (int e = 0; e < 6; ++e) d.dh_dy[f * 6 + e] = 0.0;
+    d.Rvar[f] = 0.0;
+  }
+  __syncthreads();
+  if (tid == 0) d.nfeat[s] = nf + 1;
+}
+
 }  // namespace
+
+cudaError_t sl2_launch_append(const Sl2Dev &d, int s, const double *y3_dev, const double *xp7_dev,
+                              const uint8_t *patch_rows16_dev, const double *Pcol_dev, cudaStream_t st) {
+  append_kernel<<<1, 256, 0, st>>>(d, s, y3_dev, xp7_dev, patch_rows16_dev, Pcol_dev);
+  return cudaGetLastError();
+}
 
 cudaError_t sl2_launch_predict(const Sl2Dev &d, int stream_lo, int stream_cnt, const double *u3_dev,
                                int do_predict, int do_measure, cudaStream_t st) {

@@ -122,6 +122,14 @@ MonoSLAM::~MonoSLAM() {
   delete camera_;
   delete motion_model_;
   delete kalman_;
+  delete frame_grabber_;
+  delete graphic_tool_;
+}
+
+void GraphicTool::Draw3dScene(const bool &, const bool &, const bool &) { ++draw_calls_; }
+void GraphicTool::DrawAR(cv::Mat, const bool &, const bool &, const bool &, const bool &, const bool &,
+                         const bool &, const bool &) {
+  ++draw_calls_;
 }
 
 // monoslam.cpp:1574-1969, minus GUI / grabber / particle parameters
@@ -151,7 +159,7 @@ void MonoSLAM::Init(const std::string &config_path) {
     }
   const size_t slash = config_path.find_last_of('/');
   const std::string dir = slash == std::string::npos ? "" : config_path.substr(0, slash + 1);
-  for (int fidx = 1; fidx <= 64; ++fidx) {
+  for (int fidx = 1; fidx <= SL2_MAX_FEATURES; ++fidx) {
     std::ostringstream p;
     p << "f" << fidx << ".";
     auto it = kv.find(p.str() + "identifier");
@@ -170,6 +178,14 @@ void MonoSLAM::Init(const std::string &config_path) {
   }
   CreateDevice((int)num(kv, "device.max_features", 100), (int)num(kv, "device.ordinal", 0));
   UploadMap();
+  // monoslam.cpp:1959-1963: GUI tool and frame source (file mode only; input.mode = true is the USB camera)
+  graphic_tool_ = new GraphicTool(this);
+  frame_grabber_ = new FrameGrabber();
+  const auto in = kv.find("input.name");
+  if (in != kv.end() && in->second != "empty" && num(kv, "input.mode", 0) == 0) {
+    const std::string name = in->second;
+    frame_grabber_->Init((name.size() && name[0] == '/') ? name : dir + name, false);
+  }
 }
 
 void MonoSLAM::CreateDevice(int max_features, int device) {
@@ -220,7 +236,16 @@ void MonoSLAM::AddNewKnownFeature(const Eigen::VectorXd &y, const Eigen::VectorX
   feature_list_.push_back(nf);
   total_state_size_ += 3;
   ++next_free_label_;
-  map_dirty_ = true;
+  if (ctx_ && !map_dirty_) {
+    // the device already holds the map: grow it in place (rows / columns of P appended on the device, nothing
+    // re-uploaded) -- the mirror of delete_feature
+    if (patch.rows != kBoxSize_ || patch.cols != kBoxSize_) throw std::runtime_error("feature patch must be BOXSIZE x BOXSIZE");
+    std::vector<uint8_t> pt((size_t)kBoxSize_ * kBoxSize_);
+    for (int r = 0; r < kBoxSize_; ++r) std::memcpy(&pt[(size_t)r * kBoxSize_], patch.data + r * patch.step, kBoxSize_);
+    check(ctx_, sl2_append_feature(ctx_, 0, y.data(), xp.data(), pt.data(), nullptr), "sl2_append_feature");
+  } else {
+    map_dirty_ = true;
+  }
 }
 void MonoSLAM::AddNewKnownFeature(const Eigen::VectorXd &y, const Eigen::VectorXd &xp,
                                   const std::string &identifier) {
@@ -490,6 +515,44 @@ bool MonoSLAM::GoOneStep(cv::Mat frame, bool save_trajectory, bool enable_mappin
     if (trajectory_store_.size() > 1000) trajectory_store_.erase(trajectory_store_.begin());
   }
   return true;
+}
+
+// monoslam.cpp:1495-1541 (caller side): the template under the selected location becomes a pending feature
+void MonoSLAM::InitialiseFeature(cv::Mat frame) {
+  if (!location_selected_flag_ || frame.empty()) return;
+  const int half = (kBoxSize_ - 1) / 2;
+  if (uu_ - half < 0 || vv_ - half < 0 || uu_ + half >= frame.cols || vv_ + half >= frame.rows) return;
+  PendingFeature p;
+  p.patch = cv::Mat(kBoxSize_, kBoxSize_, CV_8UC1);
+  for (int r = 0; r < kBoxSize_; ++r)
+    std::memcpy(p.patch.data + r * p.patch.step, frame.data + (size_t)(vv_ - half + r) * frame.step + (uu_ - half),
+                kBoxSize_);
+  p.u = uu_;
+  p.v = vv_;
+  pending_features_.push_back(p);
+  location_selected_flag_ = false;
+}
+
+void MonoSLAM::InitialiseAutoFeature(cv::Mat frame) {  // monoslam.cpp:1535-1541 -> AutoInitialiseFeature
+  if (frame.empty() || !ctx_) return;
+  // the reference searches an 80 x 60 box placed by the predicted motion (monoslam.cpp:823-1032); without a
+  // motion prior the shim takes the central box
+  const int bw = 80, bh = 60;
+  const int us = (frame.cols - bw) / 2, vs = (frame.rows - bh) / 2;
+  if (set_image_selection_automatically(frame, us, vs, us + bw, vs + bh) > 0.0) InitialiseFeature(frame);
+}
+
+bool MonoSLAM::SavePatch() {  // monoslam.cpp:1551-1572 (patch.png through cv::imwrite there; PGM here)
+  if (marked_feature_label_ == -1) return false;
+  for (Feature *f : feature_list_) {
+    if (f->label_ != marked_feature_label_) continue;
+    std::ofstream o("patch.pgm", std::ios::binary);
+    if (!o) return false;
+    o << "P5\n" << f->patch_.cols << " " << f->patch_.rows << "\n255\n";
+    for (int r = 0; r < f->patch_.rows; ++r) o.write((const char *)f->patch_.data + r * f->patch_.step, f->patch_.cols);
+    return true;
+  }
+  return false;
 }
 
 void MonoSLAM::print_robot_state() {  // monoslam.cpp:1543-1549

@@ -110,7 +110,30 @@ class FrameGrabber {
   int handed_out_ = 0;
 };
 
-class MonoSLAM {  // monoslam.h:73-218 (hot-path subset)
+// graphic/graphictool.h: the two entry points the main loop calls (examples/MonoSlamSceneLib1.cpp:124-126,
+// 144-151).  The GUI bodies are out of scope: headless no-ops that count their calls.
+class GraphicTool {
+ public:
+  explicit GraphicTool(MonoSLAM *monoslam) : monoslam_(monoslam) {}
+  void Draw3dScene(const bool &chk_display_trajectory, const bool &chk_display_3d_features,
+                   const bool &chk_display_3d_uncertainties);
+  void DrawAR(cv::Mat frame, const bool &chk_rectify_image_display, const bool &chk_display_trajectory,
+              const bool &chk_display_3d_features, const bool &chk_display_3d_uncertainties,
+              const bool &chk_display_2d_descriptors, const bool &chk_display_2d_search_regions,
+              const bool &chk_display_initialisation);
+  MonoSLAM *monoslam_;
+  long draw_calls_ = 0;
+};
+
+// a feature the user (InitialiseFeature) or the detector (InitialiseAutoFeature) has asked for: template and
+// pixel are kept; turning it into a map feature needs the depth particles of the partially-initialised
+// machinery (monoslam.cpp:1262, feature_init_info.cpp), whose measurement step is sl2_measure_particles_patch
+struct PendingFeature {
+  cv::Mat patch;
+  int u, v;
+};
+
+class MonoSLAM {  // monoslam.h:73-218 (hot-path subset + the calls of examples/MonoSlamSceneLib1.cpp)
  public:
   MonoSLAM();
   ~MonoSLAM();
@@ -118,6 +141,10 @@ class MonoSLAM {  // monoslam.h:73-218 (hot-path subset)
   void Init(const std::string &config_path);
   bool GoOneStep(cv::Mat frame, bool save_trajectory, bool enable_mapping);
   void print_robot_state();
+  // monoslam.h:79-81,142: caller-side surface of the example's buttons
+  void InitialiseFeature(cv::Mat frame);      // template at the selected image location (uu_, vv_)
+  void InitialiseAutoFeature(cv::Mat frame);  // Shi-Tomasi best patch of the central region, then the above
+  bool SavePatch();                           // template of the marked feature -> patch.pgm
 
   int auto_select_n_features(int n);
   int make_measurements(cv::Mat image);
@@ -145,6 +172,9 @@ class MonoSLAM {  // monoslam.h:73-218 (hot-path subset)
   Camera *camera_ = nullptr;
   MotionModel *motion_model_ = nullptr;
   Kalman *kalman_ = nullptr;
+  FrameGrabber *frame_grabber_ = nullptr;  // monoslam.h:163; created by Init() when the cfg names an input
+  GraphicTool *graphic_tool_ = nullptr;    // monoslam.h:164
+  std::vector<PendingFeature> pending_features_;
 
   Eigen::VectorXd xv_;
   Eigen::MatrixXd Pxx_;
@@ -167,7 +197,7 @@ class MonoSLAM {  // monoslam.h:73-218 (hot-path subset)
   // Creates the GPU context; called by Init(), or directly when the map is built in code.
   // max_features bounds the map size; device = CUDA ordinal.  Throws std::runtime_error on failure.
   void CreateDevice(int max_features = 100, int device = 0);
-  void UploadMap();    // host y_/xp_org_/patch_/xv_/P blocks -> device (after AddNewKnownFeature)
+  void UploadMap();    // host y_/xp_org_/patch_/xv_/P blocks -> device (whole map; first upload)
   void SyncFromDevice();  // device state + per-feature results -> host mirrors
   sl2_ctx *ctx_ = nullptr;
 

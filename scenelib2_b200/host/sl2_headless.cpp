@@ -6,6 +6,7 @@
 // FrameGrabber / FileGrabber pair like the reference's file mode (sorted file names, reader thread,
 // bounded queue).  Prints the camera state per frame and optionally writes the final total state and
 // covariance for comparison.
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -56,10 +57,26 @@ int main(int argc, char **argv) {
         std::fprintf(stderr, "cannot read %s\n", argv[2]);
         return 2;
       }
-      for (int t = 0; t < T; ++t) {
-        cv::Mat frame(H, W, CV_8UC1, buf.data() + (size_t)t * W * H);
-        g_monoslam->GoOneStep(frame, true, false);
-        report(g_monoslam, t);
+      // SL2_HEADLESS_REPEAT=k: benchmark mode -- the frames are replayed k times without per-frame output and the
+      // rate a SceneLib2 caller sees is printed: GoOneStep with the frame upload and BOTH host-mirror refreshes
+      // (every Feature's y_/Pxy_/Pyy_/matrix_block_list_, monoslam.cpp:574-614) inside the timed region
+      const char *rep = std::getenv("SL2_HEADLESS_REPEAT");
+      const int repeat = rep ? std::max(1, std::atoi(rep)) : 1;
+      if (rep) {
+        cv::Mat warm(H, W, CV_8UC1, buf.data());
+        g_monoslam->GoOneStep(warm, false, false);
+      }
+      const auto t0 = std::chrono::steady_clock::now();
+      for (int k = 0; k < repeat; ++k)
+        for (int t = 0; t < T; ++t) {
+          cv::Mat frame(H, W, CV_8UC1, buf.data() + (size_t)t * W * H);
+          g_monoslam->GoOneStep(frame, true, false);
+          if (!rep) report(g_monoslam, t);
+        }
+      if (rep) {
+        const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        std::printf("shim_frames_per_s %.3f frames %d features %zu measured %d\n", repeat * T / sec, repeat * T,
+                    g_monoslam->feature_list_.size(), g_monoslam->successful_measurement_vector_size_ / 2);
       }
     }
     g_monoslam->print_robot_state();

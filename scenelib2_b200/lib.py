@@ -39,7 +39,7 @@ class Sl2Config(C.Structure):
 EXPORTS = [
     "sl2_default_config", "sl2_create", "sl2_destroy", "sl2_last_error", "sl2_sync", "sl2_version",
     "sl2_set_frame", "sl2_set_frames", "sl2_set_frames_dev", "sl2_set_features",
-    "sl2_num_features", "sl2_state_size", "sl2_set_state", "sl2_get_state", "sl2_delete_feature",
+    "sl2_num_features", "sl2_state_size", "sl2_set_state", "sl2_get_state", "sl2_delete_feature", "sl2_append_feature",
     "sl2_patch_search", "sl2_score_map", "sl2_smoe_search", "sl2_find_best_patch", "sl2_ekf_predict",
     "sl2_predict_measurements", "sl2_make_measurements", "sl2_ekf_update",
     "sl2_ekf_update_measured", "sl2_normalise_state", "sl2_step", "sl2_step_host",
@@ -182,6 +182,17 @@ class Context:
         P = np.zeros((n, n), order="F")
         self._ck(self.L.sl2_get_state(self.h, stream_id, _p(x, f64p), _p(P, f64p)))
         return x, P
+
+    def append_feature(self, stream_id, y, xp_org, patch, Pcol=None):
+        """MonoSLAM::AddNewKnownFeature on the device; Pcol (n+3, 3) column block or None (zeros). Returns the index."""
+        y, yp = _f64(y)
+        xp, xpp = _f64(xp_org)
+        patch = np.ascontiguousarray(patch, np.uint8)
+        pc = None
+        if Pcol is not None:
+            Pcol = np.asfortranarray(Pcol, dtype=np.float64)   # column-major (n + 3) x 3
+            pc = Pcol.ctypes.data_as(f64p)
+        return self._ck(self.L.sl2_append_feature(self.h, stream_id, yp, xpp, _p(patch, u8p), pc))
 
     def delete_feature(self, stream_id, index):
         self._ck(self.L.sl2_delete_feature(self.h, stream_id, index))

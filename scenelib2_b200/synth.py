@@ -220,3 +220,37 @@ def ekf_structured_flops(n, m):
     nz = 10
     return (2 * m * nz * n + 2 * m * nz * m + m ** 3 / 3.0 + 2 * m * m * n + n * n * m
             + 2 * n * m + 2 * m * m)
+
+
+def write_reference_case(directory, sc, Pxx):
+    """A scene in the reference's own input format: `key = value;` cfg (data/SceneLib2.cfg), one PGM template per
+    known feature (feature.cpp:119 reads them with cv::imread) and the frames as raw 8-bit gray.  Returns the cfg path."""
+    import os
+    lines = ["cam.width = %d;" % sc.width, "cam.height = %d;" % sc.height,
+             "cam.fku = %d;" % sc.cam8[2], "cam.fkv = %d;" % sc.cam8[3], "cam.u0 = %d;" % sc.cam8[4],
+             "cam.v0 = %d;" % sc.cam8[5], "cam.kd1 = %r;" % float(sc.cam8[6]), "cam.sd = 1;",
+             "params.delta_t = %r;   # frame period" % sc.delta_t,
+             "params.number_of_features_to_select = %d;" % sc.n_select,
+             "params.number_of_features_to_keep_visible = 12;"]
+    names = ["rw_x", "rw_y", "rw_z", "qwr_w", "qwr_x", "qwr_y", "qwr_z", "vw_x", "vw_y", "vw_z",
+             "ww_x", "ww_y", "ww_z"]
+    for k, nm in enumerate(names):
+        lines.append("state.%s = %r;" % (nm, float(sc.x0[k])))
+    for i in range(13):
+        for j in range(13):
+            lines.append("state.pxx%d_%d = %r;" % (i, j, float(Pxx[i, j])))
+    for i in range(sc.n_features):
+        p = "f%d" % (i + 1)
+        y = sc.x0[13 + 3 * i:16 + 3 * i]
+        lines += ["%s.yi_x = %r;" % (p, float(y[0])), "%s.yi_y = %r;" % (p, float(y[1])),
+                  "%s.yi_z = %r;" % (p, float(y[2]))]
+        for k in range(7):
+            lines.append("%s.xp_org_%d = %r;" % (p, k, float(sc.xp_org[i, k])))
+        lines.append("%s.identifier = patch%d.pgm;" % (p, i))
+        with open(os.path.join(directory, "patch%d.pgm" % i), "wb") as f:
+            f.write(b"P5\n%d %d\n255\n" % (sc.boxsize, sc.boxsize) + sc.patches[i].tobytes())
+    lines.append("device.max_features = %d;" % max(sc.n_features, 4))
+    cfg = os.path.join(directory, "case.cfg")
+    open(cfg, "w").write("\n".join(lines) + "\n")
+    sc.frames.tofile(os.path.join(directory, "frames.raw"))
+    return cfg

@@ -207,3 +207,46 @@ def test_delete_feature_moves_jacobians_with_the_feature(oracle):
     assert J1.shape[0] == 11
     assert (J1 == J0[keep]).all() and (Jy1 == Jy0[keep]).all() and (R1 == R0[keep]).all()
     ctx.close()
+
+
+def test_append_feature_grows_the_map_in_place(oracle):
+    """MonoSLAM::AddNewKnownFeature on the device (monoslam.cpp:1278-1289, feature.cpp:108-149): x and P grow by the
+    new feature (zero covariance blocks for a known feature, or the caller's column block), nothing else moves, and a
+    fused step on the grown map equals a step on a map that was uploaded whole."""
+    import scenelib2_b200 as sl2
+    full = synth.make_scene("C2", n_frames=2, n_features=12, override=False)
+    n10 = 13 + 3 * 10
+    # context A: 10 features uploaded, 2 appended; context B: the 12-feature map uploaded whole
+    cfg = sl2.config_for_scene(full, num_streams=1, frame_slots=1, max_features=12)
+    a, b = sl2.Context(cfg), sl2.Context(cfg)
+    a.set_features(0, full.x0[13:n10].reshape(10, 3), full.xp_org[:10], full.patches[:10])
+    a.set_state(0, full.x0[:n10], full.P0[:n10, :n10])
+    Pcol10 = np.asfortranarray(full.P0[:n10 + 3, n10:n10 + 3])
+    assert a.append_feature(0, full.x0[n10:n10 + 3], full.xp_org[10], full.patches[10], Pcol10) == 10
+    n11 = n10 + 3
+    assert a.append_feature(0, full.x0[n11:n11 + 3], full.xp_org[11], full.patches[11],
+                            full.P0[:n11 + 3, n11:n11 + 3]) == 11
+    with pytest.raises(Exception):                       # the map is full
+        a.append_feature(0, full.x0[n11:n11 + 3], full.xp_org[11], full.patches[11])
+    sl2.load_scene(b, 0, full)
+    xa, Pa = a.get_state(0)
+    xb, Pb = b.get_state(0)
+    assert a.num_features(0) == 12 and (xa == xb).all() and (Pa == Pb).all()
+    for t in range(2):
+        for c in (a, b):
+            c.set_frames(0, full.frames[t][None])
+            c.step(0)
+        (xa, Pa), (xb, Pb) = a.get_state(0), b.get_state(0)
+        assert (xa == xb).all() and (Pa == Pb).all()
+        fa, fb = a.features(0), b.features(0)
+        assert all((fa[k] == fb[k]).all() for k in ("z", "flags", "attempted", "successful", "select_rank"))
+    # a known feature (Pcol = NULL): zero blocks like Feature::Pxy_ / Pyy_ / matrix_block_list_ of the reference
+    c = sl2.Context(cfg)
+    c.set_features(0, full.x0[13:n10].reshape(10, 3), full.xp_org[:10], full.patches[:10])
+    c.set_state(0, full.x0[:n10], full.P0[:n10, :n10])
+    c.append_feature(0, full.x0[n10:n10 + 3], full.xp_org[10], full.patches[10])
+    xc, Pc = c.get_state(0)
+    assert Pc.shape == (n10 + 3, n10 + 3) and (Pc[:n10, :n10] == full.P0[:n10, :n10]).all()
+    assert (Pc[n10:, :] == 0).all() and (Pc[:, n10:] == 0).all() and (xc[n10:] == full.x0[n10:n10 + 3]).all()
+    for ctx in (a, b, c):
+        ctx.close()

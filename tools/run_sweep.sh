@@ -1,6 +1,12 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -x -q -s 2>&1 | grep -E "H2 |passed|failed|Error|error|assert" | tail -15 > gpurun_out/r2_t10.log; cat gpurun_out/r2_t10.log
-run() { env "$@" timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline $EXTRA > gpurun_out/r2_b10.json 2> gpurun_out/r2_b10.err; python -c "
-import json,sys; j=json.load(open('gpurun_out/r2_b10.json')); k=j['kernel_ms']; print(sys.argv[1:], round(j['value']), round(j['e2e']['value']), round(k['ekf_update'],4), {a:round(b,4) for a,b in k['ekf_update_kernels'].items()})" "$@"; }
-run A=1
-EXTRA="--step-groups 2" run A=2
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/r2_t11.log; cat gpurun_out/r2_t11.log
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_b11.json 2> gpurun_out/r2_b11.err; tail -3 gpurun_out/r2_b11.err
+python - <<'PY'
+import json
+j=json.load(open('gpurun_out/r2_b11.json'))
+print('value',round(j['value']),'e2e',round(j['e2e']['value']),'frac',round(j['roofline']['frac'],3), j['kernel_ms'])
+for k,v in j['configs'].items():
+    if 'value' in v: print(k, round(v['value']), round(v.get('e2e',{}).get('value',0)), v.get('kernel_ms') or v)
+    else: print(k, v)
+print(j.get('cpu_baseline'))
+PY
