@@ -351,15 +351,17 @@ __global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32, FILTER ? (BOX <= 11 ? 4
                         cap[j] = -3.0e38f;  // knife edge of sdimage >= 10: the exact chain decides
                       }
                     } else {
-                      const double Sg1d = (double)(int)a1[j], Sg1sqd = (double)(int)a2[j],
-                                   Sg0g1d = (double)(int)ax[j];
-                      const double V1 = fma(n, Sg1sqd, -(Sg1d * Sg1d));  // exact
-                      if (V1 > T100) {
-                        const double N01 = fma(n, Sg0g1d, -(Sg0d * Sg1d));  // exact
-                        const float rho = (float)N01 * rsqrtf((float)(V0d * V1));
+                      // n = 225: n Sxx, Sx^2 and both terms of n Sxy - Sx0 Sx1 still fit 32 unsigned bits
+                      // (225 * 225 * 255^2 < 2^32); only the last difference needs 64: exact in the integer pipe
+                      // (the FP64 pipe runs at half rate and every candidate paid 2 conversions + 2 DFMA + DSETP)
+                      constexpr uint32_t NN = BOX * BOX, T100u = 100u * NN * NN;
+                      const uint32_t V1u = NN * a2[j] - a1[j] * a1[j];
+                      if (V1u > T100u) {
+                        const long long N01 = (long long)NN * (long long)ax[j] - (long long)Sg0 * (long long)a1[j];
+                        const float rho = (float)N01 * rsqrtf(V0f * (float)V1u);
                         cap[j] = fmaf(-2.0f, rho, 2.0f);
                         lmin = fminf(lmin, cap[j]);
-                      } else if (V1 == T100) {
+                      } else if (V1u == T100u) {
                         cap[j] = -3.0e38f;  // knife edge of sdimage >= 10: the exact chain decides
                       }
                     }

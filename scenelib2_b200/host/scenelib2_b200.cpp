@@ -16,6 +16,7 @@
 #include <stdexcept>
 
 #include "../../include/sl2b200.h"
+#include "png_decode.h"
 
 namespace SceneLib2 {
 
@@ -54,42 +55,78 @@ double num(const std::map<std::string, std::string> &kv, const std::string &k, d
 // PGM decoder standing in for cv::imread(path, 0) (feature.cpp:119, filegrabber.cpp:106-109): binary P5
 // and ASCII P2, maxval <= 255, '#' comments in the header.  Returns an empty Mat for anything else
 // (cv::imread returns an empty Mat when it cannot decode).
-cv::Mat decode_pgm(const std::string &path) {
-  std::ifstream f(path, std::ios::binary);
-  if (!f) return cv::Mat();
-  std::string magic;
-  f >> magic;
-  if (magic != "P5" && magic != "P2") return cv::Mat();
-  int vals[3], got = 0;
-  while (got < 3) {
-    f >> std::ws;
-    if (f.peek() == '#') {
-      std::string c;
-      std::getline(f, c);
-      continue;
+cv::Mat decode_pgm_bytes(const std::vector<uint8_t> &b) {
+  // hand-rolled header parser (no formatted stream extraction: the library is also loaded into foreign processes)
+  size_t pos = 0;
+  auto skip = [&]() {
+    for (;;) {
+      while (pos < b.size() && (b[pos] == ' ' || b[pos] == '\t' || b[pos] == '\n' || b[pos] == '\r')) ++pos;
+      if (pos < b.size() && b[pos] == '#') {
+        while (pos < b.size() && b[pos] != '\n') ++pos;
+        continue;
+      }
+      return;
     }
-    if (!(f >> vals[got++])) return cv::Mat();
-  }
-  if (vals[0] <= 0 || vals[1] <= 0 || vals[2] <= 0 || vals[2] > 255) return cv::Mat();
+  };
+  auto number = [&](int &v) {
+    skip();
+    if (pos >= b.size() || b[pos] < '0' || b[pos] > '9') return false;
+    long t = 0;
+    while (pos < b.size() && b[pos] >= '0' && b[pos] <= '9' && t < 100000000) t = t * 10 + (b[pos++] - '0');
+    v = (int)t;
+    return true;
+  };
+  if (b.size() < 7 || b[0] != 'P' || (b[1] != '5' && b[1] != '2')) return cv::Mat();
+  const bool binary = b[1] == '5';
+  pos = 2;
+  int vals[3];
+  for (int k = 0; k < 3; ++k)
+    if (!number(vals[k])) return cv::Mat();
+  if (vals[0] <= 0 || vals[1] <= 0 || vals[2] <= 0 || vals[2] > 255 || vals[0] > 16384 || vals[1] > 16384) return cv::Mat();
   cv::Mat m(vals[1], vals[0], CV_8UC1);
   const size_t count = (size_t)vals[0] * vals[1];
-  if (magic == "P5") {
-    f.get();  // the single whitespace byte after maxval
-    f.read(reinterpret_cast<char *>(m.data), (std::streamsize)count);
-    if ((size_t)f.gcount() != count) return cv::Mat();
+  if (binary) {
+    ++pos;  // the single whitespace byte after maxval
+    if (pos + count > b.size()) return cv::Mat();
+    std::memcpy(m.data, b.data() + pos, count);
   } else {
     for (size_t i = 0; i < count; ++i) {
       int v;
-      if (!(f >> v)) return cv::Mat();
+      if (!number(v)) return cv::Mat();
       m.data[i] = (unsigned char)v;
     }
   }
   return m;
 }
 
+// cv::imread(path, 0) of the reference (filegrabber.cpp:106-109, feature.cpp:119): PGM or PNG -> 8-bit gray; an
+// unreadable / unsupported file gives an empty Mat like a failed imread
+cv::Mat decode_image(const std::string &path) {
+  std::vector<uint8_t> bytes;
+  if (FILE *f = std::fopen(path.c_str(), "rb")) {
+    std::fseek(f, 0, SEEK_END);
+    const long sz = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    if (sz > 0) {
+      bytes.resize((size_t)sz);
+      if (std::fread(bytes.data(), 1, bytes.size(), f) != bytes.size()) bytes.clear();
+    }
+    std::fclose(f);
+  }
+  if (bytes.size() >= 8 && bytes[0] == 0x89 && bytes[1] == 'P' && bytes[2] == 'N' && bytes[3] == 'G') {
+    std::vector<uint8_t> gray;
+    int w = 0, h = 0;
+    if (!sl2png::decode_gray(bytes.data(), bytes.size(), gray, w, h)) return cv::Mat();
+    cv::Mat m(h, w, CV_8UC1);
+    std::memcpy(m.data, gray.data(), gray.size());
+    return m;
+  }
+  return decode_pgm_bytes(bytes);
+}
+
 cv::Mat read_pgm(const std::string &path) {  // known-feature templates: a missing patch is an error
-  cv::Mat m = decode_pgm(path);
-  if (m.empty()) throw std::runtime_error("cannot read PGM patch " + path);
+  cv::Mat m = decode_image(path);
+  if (m.empty()) throw std::runtime_error("cannot read patch image " + path);
   return m;
 }
 
@@ -600,7 +637,7 @@ void FileGrabber::operator()() {  // filegrabber.cpp:85-104
   }
 }
 
-cv::Mat FileGrabber::GetImageFile(const std::string &file_full_path) { return decode_pgm(file_full_path); }
+cv::Mat FileGrabber::GetImageFile(const std::string &file_full_path) { return decode_image(file_full_path); }
 
 FrameGrabber::FrameGrabber() {}
 
@@ -640,3 +677,16 @@ bool FrameGrabber::Exhausted() {
 }
 
 }  // namespace SceneLib2
+
+
+// test hook (tests/test_host_shim.py): decode one image file the way FileGrabber does; returns 0 and fills w / h /
+// out (cap bytes) on success, -1 when the file is not an image the shim reads, -2 when out is too small
+extern "C" int sl2_host_decode_image(const char *path, unsigned char *out, int cap, int *w, int *h) {
+  const cv::Mat m = SceneLib2::decode_image(path);
+  if (m.empty()) return -1;
+  *w = m.cols;
+  *h = m.rows;
+  if (cap < m.cols * m.rows) return -2;
+  for (int r = 0; r < m.rows; ++r) std::memcpy(out + (size_t)r * m.cols, m.data + (size_t)r * m.step, m.cols);
+  return 0;
+}

@@ -155,3 +155,113 @@ def test_headless_directory_mode_equals_raw_mode(tmp_path):
     assert r2.returncode == 0, r2.stderr
     assert r.stdout == r2.stdout
     assert (np.loadtxt(str(a)) == np.loadtxt(str(b))).all()
+
+
+def _png_bytes(img, color_type=0, depth=8, filters=None, level=6, palette=None, idat_split=None):
+    """Minimal PNG writer (zlib from the standard library): img is (H, W[, C]) uint8/uint16 samples."""
+    import struct
+    import zlib
+    h, w = img.shape[:2]
+    ch = {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}[color_type]
+    a = img.reshape(h, w, ch).astype(np.uint16 if depth == 16 else np.uint8)
+    rows = []
+    for y in range(h):
+        if depth == 16:
+            line = a[y].astype(">u2").tobytes()
+        elif depth == 8:
+            line = a[y].tobytes()
+        else:
+            bits = "".join(format(int(v), "0%db" % depth) for v in a[y].ravel())
+            bits += "0" * (-len(bits) % 8)
+            line = bytes(int(bits[i:i + 8], 2) for i in range(0, len(bits), 8))
+        rows.append(np.frombuffer(line, np.uint8).astype(np.int32))
+    bpp = max(1, ch * depth // 8)
+    out, prev = bytearray(), np.zeros(len(rows[0]), np.int32)
+    for y, cur in enumerate(rows):
+        ft = 0 if filters is None else filters[y % len(filters)]
+        left = np.concatenate([np.zeros(bpp, np.int32), cur[:-bpp]])
+        ul = np.concatenate([np.zeros(bpp, np.int32), prev[:-bpp]])
+        if ft == 0:
+            pred = 0
+        elif ft == 1:
+            pred = left
+        elif ft == 2:
+            pred = prev
+        elif ft == 3:
+            pred = (left + prev) // 2
+        else:
+            p = left + prev - ul
+            pa, pb, pc = abs(p - left), abs(p - prev), abs(p - ul)
+            pred = np.where((pa <= pb) & (pa <= pc), left, np.where(pb <= pc, prev, ul))
+        out.append(ft)
+        out += ((cur - pred) & 255).astype(np.uint8).tobytes()
+        prev = cur
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xffffffff)
+    z = zlib.compress(bytes(out), level)
+    parts = [z] if not idat_split else [z[:idat_split], z[idat_split:]]
+    png = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, color_type, 0, 0, 0))
+    if palette is not None:
+        png += chunk(b"PLTE", np.asarray(palette, np.uint8).tobytes())
+    for p in parts:
+        png += chunk(b"IDAT", p)
+    return png + chunk(b"IEND", b"")
+
+
+def test_png_and_pgm_frames_decode_like_imread(tmp_path):
+    """FileGrabber::GetImageFile (filegrabber.cpp:106-109: cv::imread(path, 0)) on the shim: PGM and PNG -> 8-bit gray.
+    Every PNG filter type, stored / fixed / dynamic deflate blocks, split IDAT, gray 1-16 bit, RGB(A), gray+alpha and
+    palette images; the expected gray values are computed here with OpenCV's IMREAD_GRAYSCALE formula."""
+    import ctypes as C
+    import __graft_entry__ as g
+    g.build()
+    lib = C.CDLL(os.path.join(HOST, "libscenelib2_b200_host.so"))
+    rng = np.random.default_rng(5)
+
+    def decode(path):
+        buf = np.zeros(1 << 20, np.uint8)
+        w, h = C.c_int(0), C.c_int(0)
+        rc = lib.sl2_host_decode_image(str(path).encode(), buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(w),
+                                       C.byref(h))
+        return rc, buf[:w.value * h.value].reshape(h.value, w.value) if rc == 0 else None
+
+    def luma(rgb):
+        r, gr, b = [rgb[..., k].astype(np.int64) for k in range(3)]
+        return ((r * 4899 + gr * 9617 + b * 1868 + 8192) >> 14).astype(np.uint8)
+
+    H, W = 37, 53
+    smooth = (np.add.outer(np.arange(H) * 3, np.arange(W) * 2) % 256).astype(np.uint8)   # compressible: LZ77 matches
+    noise = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    cases = []
+    for name, img in (("smooth", smooth), ("noise", noise)):
+        for level in (0, 1, 9):                       # 0 = stored blocks, 1 = mostly fixed, 9 = dynamic Huffman
+            cases.append((name + "_l%d" % level, _png_bytes(img, filters=[0, 1, 2, 3, 4], level=level), img))
+    cases.append(("split_idat", _png_bytes(smooth, filters=[4], idat_split=40), smooth))
+    rgb = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    cases.append(("rgb", _png_bytes(rgb, color_type=2, filters=[1, 4, 3]), luma(rgb)))
+    rgba = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    cases.append(("rgba", _png_bytes(rgba, color_type=6, filters=[2, 3]), luma(rgba)))
+    ga = rng.integers(0, 256, (H, W, 2), dtype=np.uint8)
+    cases.append(("gray_alpha", _png_bytes(ga, color_type=4, filters=[4]), ga[..., 0]))
+    g16 = rng.integers(0, 65536, (H, W), dtype=np.uint16)
+    cases.append(("gray16", _png_bytes(g16, depth=16, filters=[1, 2]), (g16 >> 8).astype(np.uint8)))
+    for d in (1, 2, 4):
+        v = rng.integers(0, 1 << d, (H, W), dtype=np.uint8)
+        cases.append(("gray%d" % d, _png_bytes(v, depth=d), (v.astype(np.int32) * 255 // ((1 << d) - 1)).astype(np.uint8)))
+    pal = rng.integers(0, 256, (16, 3), dtype=np.uint8)
+    idx = rng.integers(0, 16, (H, W), dtype=np.uint8)
+    cases.append(("palette4", _png_bytes(idx, color_type=3, depth=4, palette=pal), luma(pal[idx])))
+    for name, data, want in cases:
+        p = tmp_path / (name + ".png")
+        p.write_bytes(data)
+        rc, got = decode(p)
+        assert rc == 0, name
+        assert got.shape == want.shape and (got == want).all(), name
+    # PGM as before; garbage and truncated files give "no image" like a failed imread
+    (tmp_path / "a.pgm").write_bytes(b"P5\n%d %d\n255\n" % (W, H) + noise.tobytes())
+    rc, got = decode(tmp_path / "a.pgm")
+    assert rc == 0 and (got == noise).all()
+    (tmp_path / "bad.png").write_bytes(cases[0][1][:60])
+    (tmp_path / "text.txt").write_bytes(b"not an image")
+    assert decode(tmp_path / "bad.png")[0] == -1 and decode(tmp_path / "text.txt")[0] == -1
