@@ -137,12 +137,13 @@ __global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32, FILTER ? (BOX <= 11 ? 4
   const int tile_bytes = ((TW * TH + 16 + 127) / 128) * 128;
   const int max_tasks = TCW * ((TCH + V - 1) / V);
   const int list_bytes = ((max_tasks * 4 + 15) / 16) * 16;
-  const int vtab_bytes = TCH * 16;  // per candidate row: (double)v and P11*v*v of the ellipse test
+  const int vtab_bytes = max(TCH * 16, ((TCW * 4 + 15) / 16) * 16);  // row table of the ellipse test | column intervals
   const int per_warp = ((tile_bytes + list_bytes + 16 + vtab_bytes + 127) / 128) * 128;  // TMA dst: 128 B aligned
   uint8_t *tile = smem + (size_t)warp * per_warp;
   uint32_t *list = reinterpret_cast<uint32_t *>(tile + tile_bytes);
   const uint32_t bar = smem_u32(tile + tile_bytes + list_bytes);
   double2 *vtab = reinterpret_cast<double2 *>(tile + tile_bytes + list_bytes + 16);
+  short2 *colrange = reinterpret_cast<short2 *>(vtab);  // FILTER path: per-column candidate interval (same bytes)
   const uint32_t tile_s = smem_u32(tile);
 
   if (lane == 0) {
@@ -228,13 +229,92 @@ __global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32, FILTER ? (BOX <= 11 ? 4
         // ---- task list while the TMA is in flight ------------------------------------------
         const int nstrips = (tch + V - 1) / V;
         const int ntask = tcw * nstrips;
+        int nlist = 0;
+        if constexpr (FILTER) {
+          // The candidates of a column form ONE interval of rows: q(v) = (a + b v) + (P11 v) v is a parabola whose
+          // values at consecutive integers differ by >= 2 P11 (>= 2e-4 for a box of <= 255 px) once they are 1.5
+          // away from the vertex, eleven orders above the rounding error of the three operations, so the exact
+          // FP64 predicate (monoslam.cpp:453-454, same operations, same order) flips exactly once on each side.
+          // The ends come from a float estimate of the roots and are then MOVED BY THE EXACT PREDICATE until
+          // inside(lo), !inside(lo - 1), inside(hi), !inside(hi + 1) hold (an empty column is confirmed on the
+          // three rows around the vertex); a column that does not settle in a few moves is scanned row by row.
+          // ~5 exact evaluations per column instead of one per candidate.
+          const int vbase = vs + ty0;
+          for (int cu = lane; cu < tcw; cu += 32) {
+            const double du = (double)(us + tx0 + cu);
+            const double a = mul_(mul_(P00, du), du);
+            const double bcoef = mul_(twoP01, du);
+            auto inside = [&](int cv) {
+              const double dv = (double)(vbase + cv);
+              return add_(add_(a, mul_(bcoef, dv)), mul_(mul_(P11, dv), dv)) < 9.0;
+            };
+            int lo, hi;
+            bool scan = !(P11 > 1e-7) || !(P11 < 1e7);  // degenerate ellipse (or NaN): no shortcut
+            if (!scan) {
+              const double vx = -bcoef / (2.0 * P11);                   // vertex (approximate arithmetic from here)
+              const double disc = bcoef * bcoef - 4.0 * P11 * (a - 9.0);
+              const float r = disc > 0.0 ? __fsqrt_rn((float)disc) / (float)(2.0 * P11) : 0.0f;
+              const float lo_f = fminf(fmaxf(ceilf((float)vx - r) - (float)vbase, -1.0f), (float)tch);
+              const float hi_f = fminf(fmaxf(floorf((float)vx + r) - (float)vbase, -1.0f), (float)tch);
+              lo = max(0, min(tch - 1, (int)lo_f));
+              hi = max(0, min(tch - 1, (int)hi_f));
+              if (hi < lo) hi = lo;
+              int it = 0;
+              while (lo > 0 && it < 16 && inside(lo - 1)) { --lo; ++it; }
+              while (lo <= hi && it < 16 && !inside(lo)) { ++lo; ++it; }
+              if (it >= 16) {
+                scan = true;
+              } else if (lo > hi) {  // nothing found from the estimate: the rows around the vertex decide
+                const int v0 = max(0, min(tch - 1, __float2int_rn((float)vx) - vbase));
+                const int c0 = max(0, v0 - 1), c1 = min(tch - 1, v0 + 1);
+                for (int cv = c0; cv <= c1; ++cv)
+                  if (inside(cv)) scan = true;  // (never seen: the estimate is good to a fraction of a row)
+              } else {
+                while (hi < tch - 1 && it < 16 && inside(hi + 1)) { ++hi; ++it; }
+                while (hi > lo && it < 16 && !inside(hi)) { --hi; ++it; }
+                if (it >= 16) scan = true;
+              }
+            }
+            if (scan) {
+              lo = tch;
+              hi = -1;
+              for (int cv = 0; cv < tch; ++cv)
+                if (inside(cv)) {
+                  lo = min(lo, cv);
+                  hi = cv;
+                }
+            }
+            colrange[cu] = make_short2((short)lo, (short)hi);
+          }
+          __syncwarp();
+          // task list, strip-major and centre-out (the match is expected near the predicted position, so the running
+          // minimum of the filter is tight from the first round on; the arg-min carries its scan index, so the
+          // visiting order is free); the lanes of a round read consecutive columns of the same image rows
+          for (int sk = 0; sk < nstrips; ++sk) {
+            const int st = (sk & 1) ? (nstrips - 1) / 2 + (sk + 1) / 2 : (nstrips - 1) / 2 - sk / 2;
+            for (int cu0 = 0; cu0 < tcw; cu0 += 32) {
+              const int cu = cu0 + lane;
+              uint32_t entry = 0;
+              if (cu < tcw) {
+                const short2 rg = colrange[cu];
+                const int jlo = max((int)rg.x - st * V, 0), jhi = min(min((int)rg.y - st * V, V - 1), tch - 1 - st * V);
+                if (jlo <= jhi) {
+                  const uint32_t mask = ((1u << (jhi + 1)) - 1u) & ~((1u << jlo) - 1u);
+                  entry = (uint32_t)cu | ((uint32_t)st << 8) | (mask << 16);
+                }
+              }
+              const uint32_t bal = __ballot_sync(0xffffffffu, entry != 0);
+              if (entry) list[nlist + __popc(bal & ((1u << lane) - 1u))] = entry;
+              nlist += __popc(bal);
+            }
+          }
+        } else {
         // the v-only term of the ellipse test, once per candidate row instead of once per candidate
         for (int cv = lane; cv < tch; cv += 32) {
           const double dv = (double)(vs + ty0 + cv);
           vtab[cv] = make_double2(dv, mul_(mul_(P11, dv), dv));
         }
         __syncwarp();
-        int nlist = 0;
         for (int t0 = 0; t0 < ntask; t0 += 32) {
           const int t = t0 + lane;
           uint32_t entry = 0;
@@ -266,6 +346,7 @@ __global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32, FILTER ? (BOX <= 11 ? 4
           const uint32_t bal = __ballot_sync(0xffffffffu, entry != 0);
           if (entry) list[nlist + __popc(bal & ((1u << lane) - 1u))] = entry;
           nlist += __popc(bal);
+        }
         }
         __syncwarp();
         while (!mbar_try_wait(bar, phase)) {
@@ -455,7 +536,8 @@ size_t search_smem_bytes(const Sl2Dev &d) {
   const int tile_bytes = ((d.tile_w * d.tile_h + 16 + 127) / 128) * 128;
   const int max_tasks = TCW * ((TCH + SL2_STRIP - 1) / SL2_STRIP);
   const int list_bytes = ((max_tasks * 4 + 15) / 16) * 16;
-  return (size_t)SL2_SEARCH_WARPS * (((tile_bytes + list_bytes + 16 + TCH * 16 + 127) / 128) * 128);
+  const int vtab_bytes = TCH * 16 > ((TCW * 4 + 15) / 16) * 16 ? TCH * 16 : ((TCW * 4 + 15) / 16) * 16;
+  return (size_t)SL2_SEARCH_WARPS * (((tile_bytes + list_bytes + 16 + vtab_bytes + 127) / 128) * 128);
 }
 
 template <int BOX, bool FILTER>
