@@ -37,5 +37,20 @@ ctx.ekf_predict(0); ctx.predict_measurements(0); ctx.make_measurements(0, 0); ct
 sc3 = synth.make_scene("C3", n_frames=1, n_features=9)
 c3 = ctx_from_scenes([sc3])
 c3.set_frames(0, sc3.frames[:1]); c3.step(0); c3.sync()
+# round 2: full-size map (13 Cholesky panels, the register-resident solve with bulk copies + mbarriers + warp-pair
+# barriers, 15 syrk tiles), 3 streams so that streams differ; ragged m (one template spoiled -> one match fails)
+big = [synth.make_scene("C4", stream_id=s, n_frames=2) for s in range(3)]
+big[1].patches = big[1].patches.copy()
+big[1].patches[7] = rng.integers(0, 256, big[1].patches[7].shape, dtype=np.uint8)
+cb = ctx_from_scenes(big, frame_slots=1)
+for t in range(2):
+    cb.set_frames(0, np.stack([sc_.frames[t] for sc_ in big])); cb.step(0)
+cb.sync()
+# device-side map growth
+n10 = 13 + 3 * 10
+ca = ctx_from_scenes([synth.make_scene("C2", n_frames=1, n_features=10)], max_features=12)
+ca.append_feature(0, np.array([0.1, 0.2, 1.5]), scenes[0].xp_org[0], scenes[0].patches[0])
+ca.append_feature(0, np.array([0.0, 0.1, 1.2]), scenes[0].xp_org[1], scenes[0].patches[1], np.zeros((n10 + 6, 3)))
+print("big state finite:", bool(np.isfinite(cb.get_state(1)[1]).all()), "appended:", ca.num_features(0))
 print("found", int(f.sum()), "of", n, "| state finite:", bool(np.isfinite(ctx.get_state(0)[1]).all()),
       bool(np.isfinite(c3.get_state(0)[1]).all()))
