@@ -1,4 +1,4 @@
-// update.cu — EKF update on sm_100a as a pipeline of four kernels (all streams of a context per launch).
+// update.cu — EKF update on sm_100a as a pipeline of five kernels (all streams of a context per launch).
 //
 // Replaces, per camera stream:
 //   Kalman::KalmanFilterUpdate             kalman.cpp:72-119  (+ gather/scatter monoslam.cpp:501-614)
@@ -10,47 +10,38 @@
 // H is structurally sparse (7 + 3 non-zero columns per row) and is never formed.
 //
 //   kernel           grid                      work per CTA
-//   upd_factor       streams                   G = [ S | H P | nu ] (m x (m+n+1), row-major scratch); blocked
-//                                              Cholesky of the S part only (16-row panels) -> U in place, and
+//   upd_hp           streams                   measurement list; G = [ S | H P | nu ] (m x (m+n+1), row-major scratch):
+//                                              a stream over P, thread = state column, 16 rows of H P per block,
+//                                              S = (H P) H^T + R from the block's rows in shared memory.
+//   upd_chol         streams                   blocked Cholesky of the S part only (16-row panels, left-looking with
+//                                              a look-ahead for the next diagonal block) -> U in place, and
 //                                              W_pp = U_pp^-T of every panel.  The serial chain of the update
 //                                              lives here and touches 200 x 200 numbers, not 200 x 514.
-//   upd_solve        column slabs x streams    Y = U^-T [H P | nu]: each WARP owns 8 columns and keeps all m rows
-//                                              of them in REGISTERS (DMMA B-fragment layout); per panel the
-//                                              multipliers U(0:i0, panel) are staged once per CTA (cp.async) and
-//                                              the product runs on the FP64 tensor path with B from registers.
-//                                              No inter-warp or inter-CTA dependency: column slabs are independent.
+//   upd_solve        streams (x column slabs)  Y = U^-T [H P | nu]: a warp pair owns 8 columns and keeps all m rows
+//                                              of them in REGISTERS (DMMA fragment layout); U and the W_pp arrive
+//                                              by bulk copies on mbarriers, once per CTA; the product runs on the
+//                                              FP64 tensor path.  Column groups are independent.
 //   upd_syrk         64x64 tiles x streams     P -= Y^T Y (upper tiles computed, lower mirrored; sub-tiles of a
 //                                              diagonal tile below the diagonal are skipped); the nu column rides
 //                                              along as column n of Y, so the tile row that holds it yields
 //                                              x += Y^T w in its epilogue.
 //   upd_finish       streams                   normalise_state, symmetrise, counters.
 //
-// Every re-read of the old single-kernel design (finished rows of G gathered from L2/HBM by every panel, Y slabs
-// re-staged per tile by a CTA that owns the whole stream) is gone: G is written once and read once by upd_solve
-// (registers), Y is written once and read by the tiles of the same stream, which run at the same time on
-// neighbouring SMs (L2 hits).  The dense O(n^2 m) parts use ordinary FP64 FMAs / DMMA (tolerance 1e-5 relative,
-// north star); nothing in this file decides which pixels are searched.
+// Every re-read of the round-1 single-kernel design (finished rows of G gathered from L2/HBM by every panel over
+// all 514 columns, Y slabs re-staged per tile by a CTA that owns the whole stream) is gone: G is written once and
+// read once by upd_solve (registers), Y is written once and read by the tiles of the same stream, which run at the
+// same time on neighbouring SMs (L2 hits).  The dense O(n^2 m) parts use ordinary FP64 FMAs / DMMA (tolerance
+// 1e-5 relative, north star); nothing in this file decides which pixels are searched.
 #include "sl2_common.cuh"
 
 namespace {
-
-struct UpdSmem {
-  // upd_chol_global: carved from dynamic shared memory; sizes depend on Nmax
-  double *mult;  // [mmax][UPD_MS] (negated) multipliers of the current panel
-  double *dg;    // [NB][UPD_DS] diagonal block of the current panel (factor scratch)
-  double *Wm;    // [NB][UPD_WS]  W = U_pp^-T of the current panel
-  double *pan;   // panel buffer [NB][panw]
-  int panw;
-};
 
 constexpr int UPD_THREADS = 256;
 constexpr int UPD_NB = 16;   // Cholesky row-panel height (two DMMA M-tiles)
 constexpr int UPD_WS = 20;   // row stride of the W table
 constexpr int UPD_DS = 20;   // row stride of the diagonal-block scratch (conflict-free fragments)
 constexpr int UPD_MS = 20;   // row stride of the multiplier table: 32 B (mod 128) => conflict-free A fragments
-constexpr int UPD_KC = 32;   // k-chunk of the Y^T Y tiles
 constexpr int UPD_YS = 68;   // padded row stride of a staged Y slab (doubles): conflict-free DMMA reads
-constexpr int UPD_GB = 4;    // 8-column groups per warp iteration in the panel update
 constexpr int SOLVE_MAX_WARPS = 8;   // warps (8-column groups) per upd_solve CTA: 2 per SM sub-partition, <= 255 registers
 
 __host__ __device__ inline int upd_keven(int Nmax) { return (Nmax + 1) & ~1; }
@@ -60,18 +51,6 @@ __host__ __device__ inline int upd_panw(int Nmax) {
   return ((2 * upd_keven(Nmax) + 15) & ~15) + 2;
 }
 __host__ __device__ inline size_t upd_pan_doubles(int Nmax) { return (size_t)UPD_NB * upd_panw(Nmax); }
-
-__device__ __forceinline__ UpdSmem carve(uint8_t *base, int Nmax) {
-  UpdSmem u;
-  const int K = upd_keven(Nmax), mmax = 2 * K;  // even counts keep every section 16 B aligned
-  double *p = reinterpret_cast<double *>(base);
-  u.mult = p;  p += (size_t)mmax * UPD_MS;
-  u.dg = p;  p += UPD_NB * UPD_DS;
-  u.Wm = p;  p += UPD_NB * UPD_WS;
-  u.pan = p;
-  u.panw = upd_panw(Nmax);
-  return u;
-}
 
 // D(8x8) = A(8x4) * B(4x8) + C on the FP64 tensor path: lane holds A(lane/4, lane%4),
 // B(lane%4, lane/4) and C(lane/4, 2*(lane%4) + {0,1}).
@@ -90,28 +69,6 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
-// wait until at most n groups are pending; n folds to a constant in unrolled loops
-__device__ __forceinline__ void cp_async_wait_n(int n) {
-  switch (n) {
-    case 0: cp_async_wait<0>(); break;
-    case 1: cp_async_wait<1>(); break;
-    case 2: cp_async_wait<2>(); break;
-    case 3: cp_async_wait<3>(); break;
-    case 4: cp_async_wait<4>(); break;
-    case 5: cp_async_wait<5>(); break;
-    case 6: cp_async_wait<6>(); break;
-    case 7: cp_async_wait<7>(); break;
-    case 8: cp_async_wait<8>(); break;
-    case 9: cp_async_wait<9>(); break;
-    case 10: cp_async_wait<10>(); break;
-    case 11: cp_async_wait<11>(); break;
-    case 12: cp_async_wait<12>(); break;
-    case 13: cp_async_wait<13>(); break;
-    case 14: cp_async_wait<14>(); break;
-    default: cp_async_wait<15>(); break;
-  }
-}
-
 // ---- mbarrier + bulk copy (cp.async.bulk: the TMA engine moves a contiguous run of bytes global -> shared and
 //      reports completion as transaction bytes on an mbarrier; one instruction per row, no per-chunk index math,
 //      and the consumers wait on the mbarrier instead of a CTA-wide barrier) ------------------------------------
@@ -123,9 +80,6 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t phase) {
   uint32_t ok;
@@ -166,38 +120,32 @@ __device__ __forceinline__ double pivot_rsqrt(double dv) {
 }
 
 // One warp: Cholesky of the 8x8 block at (o, o) of dg (upper triangle, U^T U = A) and W = U^-T into
-// the same block of Wm.  Lane j (mod 8) holds column j in registers; pivots and multipliers travel
-// by shuffles.  All 32 lanes must call.
+// the same block of Wm.  Lane j (mod 8) holds column j of A and column j of W in registers.  Per pivot r:
+// the pivot travels by one shuffle, 1/u_rr is computed by every lane (uniform), row r of U is a[r] / u_rr,
+// and each multiplier U(r, i) (one more shuffle) updates a[i] AND w[i]: W is the forward elimination of the
+// identity with the same multipliers (row_i -= U(r,i) * row_r), so it costs no shuffles and no serial tail.
+// All 32 lanes must call.
 __device__ __forceinline__ void chol8_inv(double *dg, double *Wm, int o, int lane) {
   const int j = lane & 7;
   double a[8], w[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) a[i] = (i <= j) ? dg[(o + i) * UPD_DS + o + j] : 0.0;
-  double iud = 0.0;
+  for (int i = 0; i < 8; ++i) {
+    a[i] = (i <= j) ? dg[(o + i) * UPD_DS + o + j] : 0.0;
+    w[i] = (i == j) ? 1.0 : 0.0;
+  }
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     const double dv = __shfl_sync(0xffffffffu, a[r], r);
     const double iu = pivot_rsqrt(dv);
-    const double urj = (j == r) ? dv * iu : a[r] * iu;
+    const double urj = a[r] * iu;  // lane r: d / sqrt(d) = u_rr
     a[r] = urj;
-    if (j == r) iud = iu;
+    w[r] *= iu;
 #pragma unroll
     for (int i = r + 1; i < 8; ++i) {
       const double uri = __shfl_sync(0xffffffffu, urj, i);
       a[i] -= uri * urj;
+      w[i] -= uri * w[r];
     }
-  }
-  // column j of W = U^-T (lower triangular): U^T W = I by forward substitution
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const double iui = __shfl_sync(0xffffffffu, iud, i);
-    double sacc = 0.0;
-#pragma unroll
-    for (int t = 0; t < i; ++t) {
-      const double u = __shfl_sync(0xffffffffu, a[t], i);  // U(t, i), t < i
-      sacc += u * w[t];
-    }
-    w[i] = (i == j) ? iui : ((i > j) ? -sacc * iui : 0.0);
   }
   __syncwarp();  // every lane has read its (mirrored) column before the block is overwritten
   if (lane < 8) {
@@ -210,66 +158,62 @@ __device__ __forceinline__ void chol8_inv(double *dg, double *Wm, int o, int lan
 }
 
 // =============================================================================================
-// kernel 0: upd_hp — measurement list, G = [ S | H P | nu ]: one CTA per HP_ROWS measurement rows per stream
+// kernel 0: upd_hp — measurement list, G = [ S | H P | nu ]: streams P once, one thread per state column
 // =============================================================================================
-// H P: the dense part H_xv (rows x 16, zero padded) * P(0:16, :) runs on DMMA tiles with H_xv k-major in shared
-// memory; the 3 structural dh/dy columns of a row are added per element from P(:, pos_i + c) (16-byte loads,
-// contiguous along the state index because P is symmetric).  The 13 dense columns of the CTA's rows of H P stay
-// in shared memory for S = (H P) H^T + R (upper triangle): one warp per row, lane = measured feature (two columns
-// of S), dense part from shared memory, structural part from the row of H P just written (L1/L2).
-// The 7 CTAs of a stream (m = 200) share nothing but P; the measurement list is rebuilt by each of them with
-// ballots (it is ~100 flag reads).
-constexpr int HP_THREADS = 256;
-constexpr int HP_ROWS = 32;   // measurement rows per CTA (4 DMMA M tiles)
-constexpr int HP_HXS = 14;    // row stride of the CTA's H*P(:, 0:13) table
+// H has 7 (fused step: dh/dxv = [dh/dxp | 0]) or 13 (staged API) dense columns and 3 structural dh/dy columns per
+// row, so   (H P)(i, j) = sum_k Hx(i, k) P(k, j) + sum_c Hy(i, c) P(pos_i + c, j):
+// for the two rows of one measured feature that is three rows of P (contiguous along j, P symmetric) read exactly
+// once, plus the 13 leading rows of P, which a thread keeps in registers for its column j.  The kernel is a stream
+// over P (0.75 MB in, 0.5 MB H P + S out per 100-feature stream) with ~16 FMAs per element, so it is laid out for
+// the memory system: thread = column (8 B x 32 lanes = whole lines), all 24 row loads of an 8-feature block in
+// flight before the first FMA, H rows broadcast from shared memory.  (The round-2 first version ran the 13 dense
+// columns on DMMA tiles and gathered P into fragments: 34 % of HBM peak, L1 request bound.  Measured on this
+// version: prefetch.global.L2 of the next block's rows before the S phase made it 4 % slower.)
+// The CTA's 16 rows of H P also stay in shared memory for S = (H P) H^T + R: thread = measurement column i',
+// H(i', :) in registers, dense part from broadcast reads, structural part gathered from the rows.
+constexpr int HP_THREADS = 320;
+constexpr int HP_ROWS = 16;   // measurement rows per block (8 features)
+constexpr int HP_HRS = 18;    // row stride of the H table: [13 dense | 3 dh/dy | 2 pad] doubles (16 B aligned rows)
 struct HpSmem {
-  double *HxT;   // [16][hms]  H_xv transposed, k-major, zero padded (columns 13..15, rows >= m)
-  double *Hy;    // [K][2][3]
+  double *Hrow;  // [mmax][HP_HRS]
   double *Rv;    // [K][3]  (R00, R01, R11)
   double *nu;    // [mmax]
-  double *hpx;   // [HP_ROWS][HP_HXS]
+  double *hprow; // [HP_ROWS][ld]  H P rows of the running block
   int *mfeat;    // [K]
-  int *wcount;   // [8]
-  int hms;
+  int *wcount;   // [16]
 };
-__host__ __device__ inline int hp_hms(int Nmax) {
-  // k-major Hx table: row stride = 4 (mod 16) doubles => the 4 k-rows of a fragment are 32 B apart
-  return ((2 * upd_keven(Nmax) + 15) & ~15) + 4;
-}
-__host__ __device__ inline size_t hp_smem_doubles(int Nmax) {
+__host__ __device__ inline size_t hp_smem_doubles(int Nmax, int ld) {
   const size_t K = upd_keven(Nmax);
-  return (size_t)16 * hp_hms(Nmax) + K * 6 + K * 3 + (K & 1) + 2 * K + HP_ROWS * HP_HXS;
+  return (size_t)2 * K * HP_HRS + K * 3 + (K & 1) + 2 * K + (size_t)HP_ROWS * ld;
 }
-__device__ __forceinline__ HpSmem hp_carve(uint8_t *base, int Nmax) {
+__device__ __forceinline__ HpSmem hp_carve(uint8_t *base, int Nmax, int ld) {
   HpSmem u;
   const int K = upd_keven(Nmax);
   double *p = reinterpret_cast<double *>(base);
-  u.hms = hp_hms(Nmax);
-  u.HxT = p;  p += (size_t)16 * u.hms;
-  u.Hy = p;  p += (size_t)K * 6;
+  u.Hrow = p;  p += (size_t)2 * K * HP_HRS;
   u.Rv = p;  p += (size_t)K * 3 + (K & 1);
   u.nu = p;  p += 2 * K;
-  u.hpx = p;  p += HP_ROWS * HP_HXS;
+  u.hprow = p;  p += (size_t)HP_ROWS * ld;
   u.mfeat = reinterpret_cast<int *>(p);
   u.wcount = u.mfeat + K;
   return u;
 }
 
+// KD = dense columns of H that can be nonzero (7: fused step, 13: staged)
+template <int KD>
 __global__ void __launch_bounds__(HP_THREADS, 2) upd_hp_kernel(
     const Sl2Dev d, int stream_lo, int staged_m, const int *st_feat, const double *st_Hxv,
     const double *st_Hy, const double *st_R, const double *st_nu) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  const HpSmem sm = hp_carve(smem_raw, d.Nmax);
+  const int ld = d.ld, ldg = d.ldg;
+  const HpSmem sm = hp_carve(smem_raw, d.Nmax, ld);
   const int s = stream_lo + blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int lr = lane >> 2, lc = lane & 3;  // DMMA fragment coordinates
   const int nf = d.nfeat[s];
   const int n = SL2_NXV + 3 * nf;
-  const int ld = d.ld, ldg = d.ldg;
   const double *__restrict__ P = d.P + (size_t)s * ld * ld;
   double *__restrict__ G = d.G + (size_t)s * d.mmax * ldg;
   const size_t fb = (size_t)s * d.Nmax;
-  const int HMS = sm.hms;
 
   // ---- measurement list in selected order, successful only (monoslam.cpp:556-571) --------------
   int K;
@@ -300,15 +244,18 @@ __global__ void __launch_bounds__(HP_THREADS, 2) upd_hp_kernel(
     if (staged_m < 0) d.nmeas[s] = K;
   }
   if (HP_ROWS * (int)blockIdx.x >= m) return;
-  for (int e = tid; e < 16 * HMS; e += HP_THREADS) sm.HxT[e] = 0.0;
+  for (int e = tid; e < m * HP_HRS; e += HP_THREADS) sm.Hrow[e] = 0.0;
   __syncthreads();
-  // ---- H rows, R, nu of every measurement (flat loops: every CTA of the stream pays this prologue) -------
+  // ---- H rows, R, nu of every measurement (every CTA of the stream pays this prologue) -------------------
   if (staged_m >= 0) {
     for (int e = tid; e < m * 13; e += HP_THREADS) {
       const int i = e / 13, c = e - i * 13;
-      sm.HxT[c * HMS + i] = st_Hxv[e];
+      sm.Hrow[i * HP_HRS + c] = st_Hxv[e];
     }
-    for (int e = tid; e < K * 6; e += HP_THREADS) sm.Hy[e] = st_Hy[e];
+    for (int e = tid; e < K * 6; e += HP_THREADS) {
+      const int i = e / 3, c = e - i * 3;
+      sm.Hrow[i * HP_HRS + 13 + c] = st_Hy[e];
+    }
     for (int e = tid; e < m; e += HP_THREADS) sm.nu[e] = st_nu[e];
     for (int k = tid; k < K; k += HP_THREADS) {
       // R_k 2x2 column-major (symmetric; the host entry point rejects R01 != R10)
@@ -319,11 +266,11 @@ __global__ void __launch_bounds__(HP_THREADS, 2) upd_hp_kernel(
   } else {
     for (int e = tid; e < K * 14; e += HP_THREADS) {  // dh/dxv = [dh/dxp | 0] (motion_model.cpp:224-235)
       const int k = e / 14, q = e - k * 14, r = q >= 7;
-      sm.HxT[(q - 7 * r) * HMS + 2 * k + r] = d.dh_dxp[(fb + sm.mfeat[k]) * 14 + q];
+      sm.Hrow[(2 * k + r) * HP_HRS + q - 7 * r] = d.dh_dxp[(fb + sm.mfeat[k]) * 14 + q];
     }
     for (int e = tid; e < K * 6; e += HP_THREADS) {
-      const int k = e / 6;
-      sm.Hy[e] = d.dh_dy[(fb + sm.mfeat[k]) * 6 + (e - k * 6)];
+      const int i = e / 3, c = e - i * 3;
+      sm.Hrow[i * HP_HRS + 13 + c] = d.dh_dy[(fb + sm.mfeat[i >> 1]) * 6 + (i & 1) * 3 + c];
     }
     for (int e = tid; e < m; e += HP_THREADS) {
       const size_t f = fb + sm.mfeat[e >> 1];
@@ -339,126 +286,96 @@ __global__ void __launch_bounds__(HP_THREADS, 2) upd_hp_kernel(
   }
   __syncthreads();
 
+  constexpr int FB = HP_ROWS / 2;            // features per block
+  const int nch = (n + HP_THREADS - 1) / HP_THREADS;  // column chunks (1 up to 102 features)
+  double Pd[KD];
+  auto load_dense = [&](int j) {
+#pragma unroll
+    for (int k = 0; k < KD; ++k) Pd[k] = j < n ? P[(size_t)k * ld + j] : 0.0;
+  };
+  if (nch == 1) load_dense(tid);
   // row blocks blockIdx.x, blockIdx.x + gridDim.x, ...: the measurement list and the H tables are built once
   for (int rb = blockIdx.x; HP_ROWS * rb < m; rb += gridDim.x) {
-  const int row0 = HP_ROWS * rb, rows = min(HP_ROWS, m - row0);
-  // ---- H*P for the CTA's rows -------------------------------------------------------------------------
-  {
-    constexpr int QB = 4;  // column groups per work item
-    const int mt0 = row0 >> 3, mtiles = (rows + 7) >> 3, ngrp = (n + 7) >> 3;
-    // work item = (QB column groups, a quarter of the M tiles): n = 313 gives 10 x 4 items = 5 per warp (items of
-    // whole column passes left two warps with twice the work of the others: 21 % of the kernel at the barrier)
-    const int npass = (ngrp + QB - 1) / QB, nq = min(4, mtiles), mtq = (mtiles + nq - 1) / nq;
-    for (int item = warp; item < npass * nq; item += HP_THREADS / 32) {
-      const int gq = (item / nq) * QB, mtlo = (item % nq) * mtq, mthi = min(mtiles, mtlo + mtq);
-      double b[QB][4];
-      int j0[QB];  // first of the two columns of this lane's C elements, per group (-1: none)
+    const int row0 = HP_ROWS * rb, rows = min(HP_ROWS, m - row0), k0 = row0 >> 1;
+    // ---- H*P for the block's rows ---------------------------------------------------------------------
+    for (int ch = 0; ch < nch; ++ch) {
+      const int j = ch * HP_THREADS + tid;
+      if (nch > 1) load_dense(j);
+      double pv[FB][3];
 #pragma unroll
-      for (int q = 0; q < QB; ++q) {
-        const int jb = (gq + q) * 8 + lr;  // column of this lane's B element
+      for (int f = 0; f < FB; ++f) {  // every structural row load of the block first
+        const int kk = k0 + f;
+        const int pos = SL2_NXV + 3 * sm.mfeat[kk < K ? kk : 0];
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          b[q][ks] = (gq + q < ngrp && jb < n) ? P[jb + (size_t)ld * (4 * ks + lc)] : 0.0;
-        j0[q] = (gq + q) * 8 + 2 * lc;
-        if (gq + q >= ngrp || j0[q] >= n) j0[q] = -1;
+        for (int c = 0; c < 3; ++c) pv[f][c] = (kk < K && j < n) ? P[(size_t)(pos + c) * ld + j] : 0.0;
       }
-      for (int mt = mtlo; mt < mthi; ++mt) {
-        const int i = (mt0 + mt) * 8 + lr;
-        const bool rv = i < m;
-        const int k = rv ? (i >> 1) : 0;
-        const int pos = SL2_NXV + 3 * sm.mfeat[k];
-        const double *hy = sm.Hy + k * 6 + (i & 1) * 3;
-        const double h0 = hy[0], h1 = hy[1], h2 = hy[2];
-        // structural dh/dy columns: all loads of the pass first (independent, 16 B each)
-        double2 pv[QB][3];
 #pragma unroll
-        for (int q = 0; q < QB; ++q)
+      for (int f = 0; f < FB; ++f) {
+        if (k0 + f < K) {  // CTA-uniform
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            pv[q][c] = make_double2(0.0, 0.0);
-            if (rv && j0[q] >= 0) {
-              const double *src = P + j0[q] + (size_t)ld * (pos + c);
-              if (j0[q] + 1 < n) pv[q][c] = *reinterpret_cast<const double2 *>(src);
-              else pv[q][c].x = *src;
+          for (int r = 0; r < 2; ++r) {
+            const int i = row0 + 2 * f + r;
+            const double2 *hr = reinterpret_cast<const double2 *>(sm.Hrow + (size_t)i * HP_HRS);
+            double acc = 0.0;
+#pragma unroll
+            for (int k2 = 0; k2 < (KD + 1) / 2; ++k2) {
+              const double2 hv = hr[k2];
+              acc += hv.x * Pd[2 * k2];
+              if (2 * k2 + 1 < KD) acc += hv.y * Pd[2 * k2 + 1];
             }
-          }
-        double a[4];
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) a[ks] = sm.HxT[(4 * ks + lc) * HMS + (mt0 + mt) * 8 + lr];
-#pragma unroll
-        for (int q = 0; q < QB; ++q) {
-          double c0 = 0.0, c1 = 0.0;
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) dmma884(c0, c1, a[ks], b[q][ks]);
-          c0 += h0 * pv[q][0].x;
-          c1 += h0 * pv[q][0].y;
-          c0 += h1 * pv[q][1].x;
-          c1 += h1 * pv[q][1].y;
-          c0 += h2 * pv[q][2].x;
-          c1 += h2 * pv[q][2].y;
-          if (rv && j0[q] >= 0) {
-            double *dst = G + (size_t)i * ldg + m + j0[q];
-            if (j0[q] + 1 < n) *reinterpret_cast<double2 *>(dst) = make_double2(c0, c1);
-            else *dst = c0;
-            if (j0[q] < SL2_NXV) {  // dense 13 columns of H*P: kept in shared memory for S
-              sm.hpx[(i - row0) * HP_HXS + j0[q]] = c0;
-              if (j0[q] + 1 < SL2_NXV) sm.hpx[(i - row0) * HP_HXS + j0[q] + 1] = c1;
+            const double2 hy0 = hr[6], hy1 = hr[7];  // columns 12..15: (dense 12 | dh/dy 0..2)
+            acc += hy0.y * pv[f][0];
+            acc += hy1.x * pv[f][1];
+            acc += hy1.y * pv[f][2];
+            if (j < n) {
+              G[(size_t)i * ldg + m + j] = acc;
+              sm.hprow[(size_t)(2 * f + r) * ld + j] = acc;
             }
           }
         }
       }
     }
-  }
-  for (int i = tid; i < rows; i += HP_THREADS) G[(size_t)(row0 + i) * ldg + m + n] = sm.nu[row0 + i];
-  __syncthreads();
-  // ---- S = (H P) H^T + R for the CTA's rows, columns from the row's own feature on --------------------
-  {
-    constexpr int SCH = 4;  // feature chunks of 32 per pass (covers K <= 128 in one pass)
-    for (int il = warp; il < rows; il += HP_THREADS / 32) {
-      const int i = row0 + il;
-      const double *grow = G + (size_t)i * ldg + m;
-      const int k0 = i >> 1;
-      for (int kb = k0; kb < K; kb += 32 * SCH) {
-        double hp[SCH][3];
+    if (tid < rows) G[(size_t)(row0 + tid) * ldg + m + n] = sm.nu[row0 + tid];
+    __syncthreads();
+    // ---- S = (H P) H^T + R for the block's rows, columns from the row's own feature on ------------------
+    for (int ip = tid; ip < m; ip += HP_THREADS) {
+      if (ip < row0) continue;
+      const int kp = ip >> 1, rp = ip & 1;
+      const double2 *hr = reinterpret_cast<const double2 *>(sm.Hrow + (size_t)ip * HP_HRS);
+      double hreg[16];
 #pragma unroll
-        for (int t = 0; t < SCH; ++t) {  // all scattered loads of the pass first
-          const int k = kb + 32 * t + lane;
-          const int pos = SL2_NXV + 3 * sm.mfeat[k < K ? k : 0];
+      for (int k2 = 0; k2 < 8; ++k2) {
+        const double2 hv = hr[k2];
+        hreg[2 * k2] = hv.x;
+        hreg[2 * k2 + 1] = hv.y;
+      }
+      const int pos = SL2_NXV + 3 * sm.mfeat[kp];
+      const double r_same = sm.Rv[kp * 3 + 2 * rp], r_cross = sm.Rv[kp * 3 + 1];
+      // four rows at a time: independent accumulation chains (a single chain is 10-16 dependent FMAs per entry)
+      for (int il0 = 0; il0 < rows; il0 += 4) {
+        double acc[4];
 #pragma unroll
-          for (int c = 0; c < 3; ++c) hp[t][c] = k < K ? grow[pos + c] : 0.0;
-        }
+        for (int q = 0; q < 4; ++q) acc[q] = 0.0;
 #pragma unroll
-        for (int t = 0; t < SCH; ++t) {
-          const int k = kb + 32 * t + lane;
-          if (kb + 32 * t < K) {  // warp-uniform
-            const int kk = k < K ? k : 0;
-            double s0 = 0.0, s1 = 0.0;
+        for (int c = 0; c < KD; ++c)
 #pragma unroll
-            for (int c = 0; c < 13; ++c) {
-              const double hx = sm.hpx[il * HP_HXS + c];
-              const double2 hv = *reinterpret_cast<const double2 *>(sm.HxT + c * HMS + 2 * kk);
-              s0 += hx * hv.x;
-              s1 += hx * hv.y;
-            }
-            const double *hy = sm.Hy + kk * 6;
+          for (int q = 0; q < 4; ++q) acc[q] += sm.hprow[(size_t)(il0 + q) * ld + c] * hreg[c];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              s0 += hp[t][c] * hy[c];
-              s1 += hp[t][c] * hy[3 + c];
-            }
-            if (i == 2 * kk) {
-              s0 += sm.Rv[kk * 3 + 0];
-              s1 += sm.Rv[kk * 3 + 1];
-            }
-            if (i == 2 * kk + 1) s1 += sm.Rv[kk * 3 + 2];
-            if (k < K) *reinterpret_cast<double2 *>(G + (size_t)i * ldg + 2 * k) = make_double2(s0, s1);
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[q] += sm.hprow[(size_t)(il0 + q) * ld + pos + c] * hreg[13 + c];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = row0 + il0 + q;
+          if (il0 + q < rows && ip >= (i & ~1)) {
+            if ((i >> 1) == kp) acc[q] += (i == ip) ? r_same : r_cross;
+            G[(size_t)i * ldg + ip] = acc[q];
           }
         }
       }
     }
+    __syncthreads();  // hprow of this block is rewritten by the next one
   }
-  __syncthreads();  // hpx of this row block is rewritten by the next one
-  }  // row blocks
 }
 
 // =============================================================================================
@@ -469,9 +386,51 @@ __global__ void __launch_bounds__(HP_THREADS, 2) upd_hp_kernel(
 // before it ends.  What hides it is other streams on the same SM, so it is kept small enough for two CTAs per SM
 // (all 296 streams of the benchmark resident at once).  Measured alternative: S / U resident in shared memory
 // (193 KB, one CTA per SM, two waves) made every panel 1.7x faster and the kernel 17 % slower (0.159 vs 0.136 ms).
+//
+// Left-looking by 16-row panels with a look-ahead, so that the only things between two block factorizations are
+// four DMMA k-steps from shared memory and the W * C product of the finished panel:
+//   pool of work items per panel p, handed out dynamically to the 8 warps:
+//     item 0  (warp 0)  diagonal block of p = pre-updated block (dpre, from the look-ahead of panel p-1) minus the
+//                       contribution of panel p-1's 16 rows (multipliers already in shared memory), then factor it
+//     item 1            look-ahead for panel p+1: its diagonal block minus the contributions of all rows < i0
+//                       (final), into dpre_next; the multipliers it reads on the way go to mult_next
+//     items 2..         trailing columns of panel p in batches of CH_GB 8-column groups (B fragments from L2,
+//                       software pipelined CH_D k-steps deep)
+//   finish (all warps)  U_panel = W * C_panel -> G; the 16 columns that are panel p+1's multipliers -> mult_next
+constexpr int CH_GB = 4;   // 8-column groups per batch item
+constexpr int CH_D = 4;    // k-steps of B fragments in flight per warp
+constexpr int CH_DPS = 18; // row stride of the pre-updated diagonal block
+
+struct CholSmem {
+  double *mult;     // 2 x [mmax][UPD_MS] (negated) multipliers of the current / next panel
+  double *dpre;     // 2 x [NB][CH_DPS]  pre-updated diagonal block of the current / next panel
+  int msz;          // doubles per multiplier table
+  double *dg;       // [NB][UPD_DS]  diagonal block of the current panel (factor scratch)
+  double *Wm;       // [NB][UPD_WS]  W = U_pp^-T of the current panel
+  double *pan;      // panel buffer [NB][panw]
+  int panw;
+};
+__host__ __device__ inline size_t chol_smem_doubles(int Nmax) {
+  const size_t mmax = 2 * upd_keven(Nmax);
+  return 2 * mmax * UPD_MS + 2 * UPD_NB * CH_DPS + UPD_NB * UPD_DS + UPD_NB * UPD_WS + upd_pan_doubles(Nmax);
+}
+__device__ __forceinline__ CholSmem chol_carve(uint8_t *base, int Nmax) {
+  CholSmem u;
+  const int mmax = 2 * upd_keven(Nmax);
+  double *p = reinterpret_cast<double *>(base);
+  u.msz = mmax * UPD_MS;
+  u.mult = p;  p += (size_t)2 * u.msz;
+  u.dpre = p;  p += 2 * UPD_NB * CH_DPS;
+  u.dg = p;  p += UPD_NB * UPD_DS;
+  u.Wm = p;  p += UPD_NB * UPD_WS;
+  u.pan = p;
+  u.panw = upd_panw(Nmax);
+  return u;
+}
+
 __global__ void __launch_bounds__(UPD_THREADS, 2) upd_chol_kernel(const Sl2Dev d, int stream_lo) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  const UpdSmem sm = carve(smem_raw, d.Nmax);
+  const CholSmem sm = chol_carve(smem_raw, d.Nmax);
   const int s = stream_lo + blockIdx.x;
   const int tid = threadIdx.x;
   const int ldg = d.ldg;
@@ -482,105 +441,87 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) upd_chol_kernel(const Sl2Dev d
   __shared__ int s_next;
   const int m = d.upd_m[s];
   if (m == 0) return;
-
-  // ---- phase 2: left-looking Cholesky by row panels of 16 on the S part of G ------------------
-  // Trailing update of a panel = C(16 x cols) - A(16 x i0) * B(i0 x cols) with A(r,k) = U(k,i0+r)
-  // (multipliers, shared memory) and B = finished rows of U (global / L2): FP64 tensor-core
-  // tiles (DMMA m8n8k4, two M tiles per B fragment), each warp owning groups of 8 columns; the B
-  // fragments are software-pipelined three k-steps ahead.
   const int width = m;
   const int PW = sm.panw;
+  if (tid == 0) s_next = 1;  // item 0 is reserved for warp 0
+  __syncthreads();
+
   for (int i0 = 0, pidx = 0; i0 < m; i0 += UPD_NB, ++pidx) {
+    // (offsets from the carved bases, not a table of pointers: the accesses stay shared-memory instructions)
+    const int par = pidx & 1;
+    const double *__restrict__ mcur = sm.mult + par * sm.msz;
+    double *__restrict__ mnext = sm.mult + (par ^ 1) * sm.msz;
+    const double *__restrict__ dcur = sm.dpre + par * (UPD_NB * CH_DPS);
+    double *__restrict__ dnext = sm.dpre + (par ^ 1) * (UPD_NB * CH_DPS);
     const int nbp = min(UPD_NB, m - i0);
-    if (tid == 0) s_next = 1;  // batch 0 is reserved for warp 0
-    // multipliers, negated so that D = (-A) * B + C
-    for (int e = tid; e < i0 * UPD_NB; e += UPD_THREADS) {
-      const int k = e / UPD_NB, r = e - k * UPD_NB;
-      sm.mult[k * UPD_MS + r] = (r < nbp) ? -G[(size_t)k * ldg + i0 + r] : 0.0;
-    }
-    __syncthreads();
+    const int n0 = i0 + UPD_NB;                       // next panel
+    const int nbn = n0 < m ? min(UPD_NB, m - n0) : 0;
     const int ngroups = (width - i0 + 7) >> 3;
-    const int nk = i0 >> 2;  // k-steps of 4 rows; i0 is a multiple of 16 so nk % 4 == 0
-    const int nbatch = (ngroups + UPD_GB - 1) / UPD_GB;
-    // Batches of UPD_GB column groups are handed out dynamically.  Warp 0 takes batch 0 (it holds
-    // the 16 diagonal columns), factors the diagonal block straight away while the other warps
-    // keep multiplying, and only then joins the pool again.
+    const int nk = i0 >> 2;  // k-steps of 4 finished rows; i0 is a multiple of 16
+    const int nbatch = ngroups > 2 ? (ngroups - 2 + CH_GB - 1) / CH_GB : 0;
+    const int nitems = 2 + nbatch;
     bool first = true;
     for (;;) {
-      int bt;
+      int it;
       if (warp == 0 && first) {
-        bt = 0;
+        it = 0;
       } else {
-        if (lane == 0) bt = atomicAdd(&s_next, 1);
-        bt = __shfl_sync(0xffffffffu, bt, 0);
+        if (lane == 0) it = atomicAdd(&s_next, 1);
+        it = __shfl_sync(0xffffffffu, it, 0);
       }
-      if (bt >= nbatch) break;
-      const int g0 = bt * UPD_GB;
-      double c[UPD_GB][2][2];
-      int colb[UPD_GB];  // column of the B fragment element of this lane (-1: none)
+      if (it >= nitems) break;
+      if (it == 0) {
+        // ---- diagonal block of this panel: pre-updated block minus panel p-1's rows, then factor ----------
+        first = false;
+        double c[2][2][2];  // [column group q][M tile mt][element]
+        if (pidx == 0) {
 #pragma unroll
-      for (int q = 0; q < UPD_GB; ++q) {
-        const int cbase = i0 + (g0 + q) * 8;
-        colb[q] = (cbase + lr < width && g0 + q < ngroups) ? cbase + lr : -1;
-        const int cc = cbase + 2 * lc;  // C fragment: rows lr / lr+8, columns cc, cc+1
+          for (int q = 0; q < 2; ++q)
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          const int r = mt * 8 + lr;
-          const bool rv = r < nbp && (g0 + q) < ngroups;
-          c[q][mt][0] = (rv && cc < width) ? G[(size_t)(i0 + r) * ldg + cc] : 0.0;
-          c[q][mt][1] = (rv && cc + 1 < width) ? G[(size_t)(i0 + r) * ldg + cc + 1] : 0.0;
-        }
-      }
-      double b[4][UPD_GB];
-      auto loadb = [&](int step, double *dst) {
-        const double *gk = G + (size_t)(4 * step + lc) * ldg;
+            for (int mt = 0; mt < 2; ++mt) {
+              const int r = mt * 8 + lr, cc = 8 * q + 2 * lc;
+              c[q][mt][0] = (r < nbp && cc < width) ? G[(size_t)r * ldg + cc] : 0.0;
+              c[q][mt][1] = (r < nbp && cc + 1 < width) ? G[(size_t)r * ldg + cc + 1] : 0.0;
+            }
+        } else {
 #pragma unroll
-        for (int q = 0; q < UPD_GB; ++q) dst[q] = colb[q] >= 0 ? gk[colb[q]] : 0.0;
-      };
-      if (nk > 0) {
-        loadb(0, b[0]);
-        loadb(1, b[1]);
-        loadb(2, b[2]);
-      }
-      for (int kb = 0; kb < nk; kb += 4) {
+          for (int q = 0; q < 2; ++q)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int st = kb + u;
-          if (st + 3 < nk) loadb(st + 3, b[(u + 3) & 3]);
-          const double a0 = sm.mult[(4 * st + lc) * UPD_MS + lr];
-          const double a1 = sm.mult[(4 * st + lc) * UPD_MS + 8 + lr];
+            for (int mt = 0; mt < 2; ++mt) {
+              const double2 v = *reinterpret_cast<const double2 *>(dcur + (mt * 8 + lr) * CH_DPS + 8 * q + 2 * lc);
+              c[q][mt][0] = v.x;
+              c[q][mt][1] = v.y;
+            }
 #pragma unroll
-          for (int q = 0; q < UPD_GB; ++q) {
-            dmma884(c[q][0][0], c[q][0][1], a0, b[u][q]);
-            dmma884(c[q][1][0], c[q][1][1], a1, b[u][q]);
+          for (int u = 0; u < 4; ++u) {
+            const int st = nk - 4 + u;
+            const double a0 = mcur[(4 * st + lc) * UPD_MS + lr], a1 = mcur[(4 * st + lc) * UPD_MS + 8 + lr];
+            dmma884(c[0][0][0], c[0][0][1], a0, -a0);
+            dmma884(c[0][1][0], c[0][1][1], a1, -a0);
+            dmma884(c[1][0][0], c[1][0][1], a0, -a1);
+            dmma884(c[1][1][0], c[1][1][1], a1, -a1);
           }
         }
-      }
-#pragma unroll
-      for (int q = 0; q < UPD_GB; ++q) {
-        if (g0 + q < ngroups) {
-          const int pc = (g0 + q) * 8 + 2 * lc;
-#pragma unroll
-          for (int mt = 0; mt < 2; ++mt)
-            *reinterpret_cast<double2 *>(sm.pan + (size_t)(mt * 8 + lr) * PW + pc) =
-                make_double2(c[q][mt][0], c[q][mt][1]);
-        }
-      }
-      if (warp == 0 && first) {
-        first = false;
-        __syncwarp();
         // Factor the 16x16 diagonal block and form W = U_pp^-T (the panel is then finished with one
         // more DMMA product U_panel = W * C_panel).  This is the serial path of the panel, so it is
         // kept short: two 8x8 register/shuffle factorizations (chol8_inv) and 8x8 DMMA products
         //   U12 = W11 A12,  A22 -= U12^T U12,  W21 = -W22 (U12^T W11)
-        // on a private copy of the block (identity padding for the ragged last panel).
+        // on the block in its own scratch (identity padding for the ragged last panel).
         {
           double *dg = sm.dg;
-          for (int e = lane; e < UPD_NB * UPD_NB; e += 32) {
-            const int i = e >> 4, j = e & 15;
-            dg[i * UPD_DS + j] = (i < nbp && j < nbp) ? sm.pan[(size_t)i * PW + j] : (i == j ? 1.0 : 0.0);
-          }
-          for (int e = lane; e < UPD_NB * UPD_WS; e += 32) sm.Wm[e] = 0.0;
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+              const int r = mt * 8 + lr, cc = 8 * q + 2 * lc;
+              const bool rv = r < nbp;
+              *reinterpret_cast<double2 *>(dg + r * UPD_DS + cc) =
+                  make_double2((rv && cc < nbp) ? c[q][mt][0] : (r == cc ? 1.0 : 0.0),
+                               (rv && cc + 1 < nbp) ? c[q][mt][1] : (r == cc + 1 ? 1.0 : 0.0));
+            }
+          // W12 = 0 (the two diagonal blocks of W are written whole by chol8_inv, W21 by the glue below)
+          sm.Wm[(lane >> 3) * UPD_WS + 8 + (lane & 7)] = 0.0;
+          sm.Wm[(4 + (lane >> 3)) * UPD_WS + 8 + (lane & 7)] = 0.0;
           __syncwarp();
           chol8_inv(dg, sm.Wm, 0, lane);
           __syncwarp();
@@ -619,11 +560,107 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) upd_chol_kernel(const Sl2Dev d
             *reinterpret_cast<double2 *>(sm.Wm + (8 + lr) * UPD_WS + 2 * lc) = make_double2(w0, w1);
           }
           __syncwarp();
-          // U back into the panel (upper triangle); rows / columns of the padding carry no W
-          for (int e = lane; e < UPD_NB * UPD_NB; e += 32) {
-            const int i = e >> 4, j = e & 15;
-            if (i <= j && j < nbp) sm.pan[(size_t)i * PW + j] = dg[i * UPD_DS + j];
-            if (i >= nbp || j >= nbp) sm.Wm[i * UPD_WS + j] = 0.0;
+          if (nbp < UPD_NB)  // ragged last panel: rows / columns of the padding carry no W
+            for (int e = lane; e < UPD_NB * UPD_NB; e += 32) {
+              const int i = e >> 4, j = e & 15;
+              if (i >= nbp || j >= nbp) sm.Wm[i * UPD_WS + j] = 0.0;
+            }
+        }
+      } else if (it == 1) {
+        // ---- look-ahead: diagonal block of panel p+1 minus the contributions of rows < i0 -----------------
+        if (nbn == 0) continue;
+        double c[2][2][2];  // starts from the S entries of the block (their load overlaps the first B loads)
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            const int r = mt * 8 + lr, cc = 8 * q + 2 * lc;
+            c[q][mt][0] = (r < nbn && n0 + cc < width) ? G[(size_t)(n0 + r) * ldg + n0 + cc] : 0.0;
+            c[q][mt][1] = (r < nbn && n0 + cc + 1 < width) ? G[(size_t)(n0 + r) * ldg + n0 + cc + 1] : 0.0;
+          }
+        double v[CH_D][2];
+        auto loadv = [&](int st, double *dst) {  // negated multipliers U(k, n0 + r) of the next panel
+          const double *gk = G + (size_t)(4 * st + lc) * ldg + n0;
+          dst[0] = lr < nbn ? -gk[lr] : 0.0;
+          dst[1] = 8 + lr < nbn ? -gk[8 + lr] : 0.0;
+        };
+#pragma unroll
+        for (int u = 0; u < CH_D - 1; ++u)
+          if (u < nk) loadv(u, v[u]);
+        for (int kb = 0; kb < nk; kb += CH_D) {
+#pragma unroll
+          for (int u = 0; u < CH_D; ++u) {
+            const int st = kb + u;
+            if (st < nk) {  // warp-uniform
+              if (st + CH_D - 1 < nk) loadv(st + CH_D - 1, v[(u + CH_D - 1) % CH_D]);
+              const double a0 = v[u][0], a1 = v[u][1];
+              mnext[(4 * st + lc) * UPD_MS + lr] = a0;
+              mnext[(4 * st + lc) * UPD_MS + 8 + lr] = a1;
+              dmma884(c[0][0][0], c[0][0][1], a0, -a0);
+              dmma884(c[0][1][0], c[0][1][1], a1, -a0);
+              dmma884(c[1][0][0], c[1][0][1], a0, -a1);
+              dmma884(c[1][1][0], c[1][1][1], a1, -a1);
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+            *reinterpret_cast<double2 *>(dnext + (mt * 8 + lr) * CH_DPS + 8 * q + 2 * lc) =
+                make_double2(c[q][mt][0], c[q][mt][1]);
+      } else {
+        // ---- trailing columns of this panel: C(16 x cols) - A(16 x i0) * B(i0 x cols) ---------------------
+        // A(r,k) = U(k,i0+r) (negated multipliers, shared memory), B = finished rows of U (global / L2)
+        const int g0 = 2 + (it - 2) * CH_GB;
+        double c[CH_GB][2][2];
+        int colb[CH_GB];  // column of the B fragment element of this lane (-1: none)
+#pragma unroll
+        for (int q = 0; q < CH_GB; ++q) {
+          const int cbase = i0 + (g0 + q) * 8;
+          colb[q] = (cbase + lr < width && g0 + q < ngroups) ? cbase + lr : -1;
+          const int cc = cbase + 2 * lc;  // C fragment: rows lr / lr+8, columns cc, cc+1
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            const int r = mt * 8 + lr;
+            const bool rv = r < nbp && (g0 + q) < ngroups;
+            c[q][mt][0] = (rv && cc < width) ? G[(size_t)(i0 + r) * ldg + cc] : 0.0;
+            c[q][mt][1] = (rv && cc + 1 < width) ? G[(size_t)(i0 + r) * ldg + cc + 1] : 0.0;
+          }
+        }
+        double b[CH_D][CH_GB];
+        auto loadb = [&](int st, double *dst) {
+          const double *gk = G + (size_t)(4 * st + lc) * ldg;
+#pragma unroll
+          for (int q = 0; q < CH_GB; ++q) dst[q] = colb[q] >= 0 ? gk[colb[q]] : 0.0;
+        };
+#pragma unroll
+        for (int u = 0; u < CH_D - 1; ++u)
+          if (u < nk) loadb(u, b[u]);
+        for (int kb = 0; kb < nk; kb += CH_D) {
+#pragma unroll
+          for (int u = 0; u < CH_D; ++u) {
+            const int st = kb + u;
+            if (st < nk) {  // warp-uniform
+              if (st + CH_D - 1 < nk) loadb(st + CH_D - 1, b[(u + CH_D - 1) % CH_D]);
+              const double a0 = mcur[(4 * st + lc) * UPD_MS + lr];
+              const double a1 = mcur[(4 * st + lc) * UPD_MS + 8 + lr];
+#pragma unroll
+              for (int q = 0; q < CH_GB; ++q) {
+                dmma884(c[q][0][0], c[q][0][1], a0, b[u][q]);
+                dmma884(c[q][1][0], c[q][1][1], a1, b[u][q]);
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < CH_GB; ++q) {
+          if (g0 + q < ngroups) {
+            const int pc = (g0 + q) * 8 + 2 * lc;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+              *reinterpret_cast<double2 *>(sm.pan + (size_t)(mt * 8 + lr) * PW + pc) =
+                  make_double2(c[q][mt][0], c[q][mt][1]);
           }
         }
       }
@@ -631,19 +668,22 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) upd_chol_kernel(const Sl2Dev d
     __syncthreads();
     // finish the panel: rows of U for the 16 diagonal columns, U_panel = W * C_panel (DMMA) for
     // all other columns, written straight to G from the C fragments; W_pp goes to the solve kernel
+    const int ncol = width - i0;
     for (int e = tid; e < UPD_NB * UPD_NB; e += UPD_THREADS) {
       const int r = e / UPD_NB, cc = e - r * UPD_NB;
       if (r < nbp && cc < nbp && i0 + cc < width)
-        G[(size_t)(i0 + r) * ldg + i0 + cc] = (cc >= r) ? sm.pan[(size_t)r * PW + cc] : 0.0;
+        G[(size_t)(i0 + r) * ldg + i0 + cc] = (cc >= r) ? sm.dg[r * UPD_DS + cc] : 0.0;
       Wp[(size_t)pidx * 256 + e] = sm.Wm[r * UPD_WS + cc];
+      // multipliers of the next panel from this panel's rows: the entries the DMMA loop below does not write
+      if (r >= nbp || UPD_NB + cc >= ncol) mnext[(i0 + r) * UPD_MS + cc] = 0.0;
     }
+    if (tid == 0) s_next = 1;
     {
       double aw[2][4];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) aw[mt][ks] = sm.Wm[(mt * 8 + lr) * UPD_WS + 4 * ks + lc];
-      const int ncol = width - i0;
       // FG column groups per iteration: independent DMMA chains.  Only full panels reach this loop
       // with columns to do (a ragged last panel has ncol == nbp: nothing right of the diagonal block).
       constexpr int FG = 4;
@@ -667,7 +707,8 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) upd_chol_kernel(const Sl2Dev d
         }
 #pragma unroll
         for (int f = 0; f < FG; ++f) {
-          const int cc = (gb + f * (UPD_THREADS / 32)) * 8 + 2 * lc;
+          const int gq = gb + f * (UPD_THREADS / 32);
+          const int cc = gq * 8 + 2 * lc;
 #pragma unroll
           for (int mt = 0; mt < 2; ++mt) {
             const int r = mt * 8 + lr;
@@ -675,6 +716,10 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) upd_chol_kernel(const Sl2Dev d
               double *dst = G + (size_t)(i0 + r) * ldg + i0 + cc;
               if (cc + 1 < ncol) *reinterpret_cast<double2 *>(dst) = make_double2(c[f][mt][0], c[f][mt][1]);
               else *dst = c[f][mt][0];
+              if (gq < 4) {  // columns of the next panel's diagonal block: its multipliers for these rows
+                mnext[(i0 + r) * UPD_MS + cc - UPD_NB] = -c[f][mt][0];
+                if (cc + 1 < ncol) mnext[(i0 + r) * UPD_MS + cc + 1 - UPD_NB] = -c[f][mt][1];
+              }
             }
           }
         }
@@ -807,6 +852,16 @@ __global__ void __launch_bounds__(64 * SOLVE_MAX_WARPS, 1) upd_solve_kernel(cons
   const int cval = wact ? min(2, ncols - cc) : 0;  // how many of them exist (<= 0: none)
   double *gcol = G + m + cc;
   double acc[NP][2];  // tile j = 2 t + rho: rows 8 j + lr, columns cc, cc + 1
+  {  // the next group's tiles: towards L2 now (H P is larger than L2 at 296 streams; the registers are all taken)
+    const int ccn = cc + 8 * (int)(gridDim.x * ngrp);
+    if (L::SPLIT >= NP && ccn < ncols) {
+#pragma unroll
+      for (int t = 0; t < NP; ++t) {
+        const int row = 8 * (2 * t + rho) + lr;
+        if (row < m) asm volatile("prefetch.global.L2 [%0];" ::"l"(G + m + ccn + (size_t)row * ldg));
+      }
+    }
+  }
 #pragma unroll
   for (int t = 0; t < NP; ++t) {
     const int row = 8 * (2 * t + rho) + lr;
@@ -889,76 +944,20 @@ __global__ void __launch_bounds__(64 * SOLVE_MAX_WARPS, 1) upd_solve_kernel(cons
 // =============================================================================================
 // kernel 3: upd_syrk — P -= Y^T Y on 64x64 tiles, x += Y^T w from the column that carries nu
 // =============================================================================================
-// One 64x64 tile T = sum_{k < kr} A(k, :)^T B(k, :), A / B = 64-column slabs of the row-major matrix Gm (row
-// stride ldg) starting at columns colA / colB.  FP64 DMMA tiles; the slabs are staged by cp.async (LDGSTS)
-// into a double-buffered, conflict-free (stride UPD_YS) shared tile.  Warp w owns rows 16*(w%4).. and columns
-// 32*(w/4).. of the tile: acc[i][j][e] = T(16*(w%4) + 8*i + lane/4, 32*(w/4) + 8*j + 2*(lane%4) + e).
-// Columns >= lim and rows >= kr are zero-filled.  Warps with `skip` stage and synchronise but issue no DMMA.
-__device__ __forceinline__ void tile_product(double *stage_buf, const double *__restrict__ Gm, int ldg, int kr,
-                                             int colA, int colB, int lim, bool skip, double (&acc)[2][4][2]) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
-  const int wa = (warp & 3) * 16, wb = (warp >> 2) * 32;
-  const int nchunk = (kr + UPD_KC - 1) / UPD_KC;
-  const int cA = colA + 2 * lane, cB = colB + 2 * lane;
-  const int bytesA = cA + 1 < lim ? 16 : (cA < lim ? 8 : 0);
-  const int bytesB = cB + 1 < lim ? 16 : (cB < lim ? 8 : 0);
-  const double *srcA = Gm + (bytesA ? cA : 0);
-  const double *srcB = Gm + (bytesB ? cB : 0);
-  // stage loader: 2 slabs x KC rows x 64 columns; thread = (row warp + 8*j, 16-byte segment `lane`)
-  auto stage = [&](int chunk, int buf) {
-    double *dst = stage_buf + (size_t)buf * (2 * UPD_KC * UPD_YS) + 2 * lane;
-#pragma unroll
-    for (int j = 0; j < UPD_KC / 8; ++j) {
-      const int kk = warp + 8 * j;
-      const int k = chunk * UPD_KC + kk;
-      const bool kv = k < kr;
-      const size_t ro = (size_t)(kv ? k : 0) * ldg;
-      cp_async16(dst + kk * UPD_YS, srcA + ro, kv ? bytesA : 0);
-      cp_async16(dst + UPD_KC * UPD_YS + kk * UPD_YS, srcB + ro, kv ? bytesB : 0);
-    }
-    cp_async_commit();
-  };
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-  stage(0, 0);
-  for (int ch = 0; ch < nchunk; ++ch) {
-    if (ch + 1 < nchunk) {
-      stage(ch + 1, (ch + 1) & 1);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
-    if (!skip) {
-      const double *Ya = stage_buf + (size_t)(ch & 1) * (2 * UPD_KC * UPD_YS);
-      const double *Yb = Ya + UPD_KC * UPD_YS;
-      auto kstep = [&](int kk) {
-        double a[2], b[4];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) a[i] = Ya[(kk + lc) * UPD_YS + wa + i * 8 + lr];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = Yb[(kk + lc) * UPD_YS + wb + j * 8 + lr];
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-      };
-      const int krem = kr - ch * UPD_KC;  // rows of this chunk that exist (the rest is zero fill)
-      if (krem >= UPD_KC) {
-#pragma unroll
-        for (int kk = 0; kk < UPD_KC; kk += 4) kstep(kk);
-      } else {
-#pragma unroll 2
-        for (int kk = 0; kk < krem; kk += 4) kstep(kk);
-      }
-    }
-    __syncthreads();  // buffer (ch & 1) may be refilled by the stage issued in the next iteration
-  }
-}
-
+// One 64x64 tile T = sum_{k < m} A(k, :)^T B(k, :) per CTA, A / B = 64-column slabs of Y (rows of G, row stride
+// ldg) at columns m + 64 ta / m + 64 tb; a diagonal tile stages one slab and reads it twice.  FP64 DMMA tiles;
+// the slabs are staged by cp.async (LDGSTS) in chunks of KC rows into a ring of ST conflict-free (stride UPD_YS)
+// stages, one __syncthreads per chunk: the stage refilled after the barrier of chunk c is the one chunk c-1 was
+// read from.
+// Columns >= n + 1 and rows >= m are zero-filled.  Measured alternatives: skipping the 8x8 blocks below the
+// diagonal inside a diagonal tile as well (12 of 64 blocks fewer, a predicate per DMMA) was 4 % slower; the same ring filled by bulk copies
+// (cp.async.bulk, one 512-byte row per instruction, full/empty mbarriers, no CTA barrier) was 8 % slower (0.285 vs
+// 0.264 ms) with 2 x 32-row and with 4 x 16-row stages alike; 4 x 16 and 3 x 16 LDGSTS stages: 0.268-0.270 ms.
+// Warp w owns rows 16*(w%4).. and columns 32*(w/4).. of the tile:
+//   acc[i][j][e] = T(16*(w%4) + 8*i + lane/4, 32*(w/4) + 8*j + 2*(lane%4) + e).
+template <int KC, int ST>
 __global__ void __launch_bounds__(UPD_THREADS, 3) upd_syrk_kernel(const Sl2Dev d, int stream_lo) {
+  constexpr int STAGE = 2 * KC * UPD_YS;  // doubles per stage (A slab, B slab)
   extern __shared__ __align__(16) uint8_t smem_raw[];
   double *stage_buf = reinterpret_cast<double *>(smem_raw);
   const int s = stream_lo + blockIdx.y;
@@ -980,8 +979,73 @@ __global__ void __launch_bounds__(UPD_THREADS, 3) upd_syrk_kernel(const Sl2Dev d
   const bool diag = ta == tb;
   const bool skip = diag && wa >= wb + 32;      // sub-tile strictly below the diagonal: mirrored instead
   const bool mirror = !diag || wa + 16 <= wb;   // sub-tile strictly above the diagonal
+  // the tile of P this warp updates: into L2 while the products run (the epilogue reads it once)
+  if (!skip) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int a = ta * 64 + wa + i * 8, bq = tb * 64 + wb + lane;
+      if (a < n && bq < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(P + a + (size_t)ld * bq));
+    }
+  }
+  const int kr = m, lim = m + n + 1;
+  const int nchunk = (kr + KC - 1) / KC;
+  const int cA = m + ta * 64 + 2 * lane, cB = m + tb * 64 + 2 * lane;
+  const int bytesA = cA + 1 < lim ? 16 : (cA < lim ? 8 : 0);
+  const int bytesB = cB + 1 < lim ? 16 : (cB < lim ? 8 : 0);
+  const double *srcA = G + (bytesA ? cA : 0);
+  const double *srcB = G + (bytesB ? cB : 0);
+  // stage loader: 2 slabs x KC rows x 64 columns; thread = (row warp + 8*j, 16-byte segment `lane`)
+  auto stage = [&](int chunk) {
+    double *dst = stage_buf + (size_t)(chunk % ST) * STAGE + 2 * lane;
+#pragma unroll
+    for (int j = 0; j < KC / 8; ++j) {
+      const int kk = warp + 8 * j;
+      const int k = chunk * KC + kk;
+      const bool kv = k < kr;
+      const size_t ro = (size_t)(kv ? k : 0) * ldg;
+      cp_async16(dst + kk * UPD_YS, srcA + ro, kv ? bytesA : 0);
+      if (!diag) cp_async16(dst + KC * UPD_YS + kk * UPD_YS, srcB + ro, kv ? bytesB : 0);
+    }
+  };
   double acc[2][4][2];
-  tile_product(stage_buf, G, ldg, m, m + ta * 64, m + tb * 64, m + n + 1, skip, acc);
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+  for (int c = 0; c < ST - 1; ++c) {
+    if (c < nchunk) stage(c);
+    cp_async_commit();
+  }
+  for (int ch = 0; ch < nchunk; ++ch) {
+    cp_async_wait<ST - 2>();  // chunk ch has landed (one group is committed per iteration, empty or not)
+    __syncthreads();          // ... for every thread's part of it, and chunk ch-1 has been read by every warp
+    if (ch + ST - 1 < nchunk) stage(ch + ST - 1);
+    cp_async_commit();
+    if (!skip) {
+      const double *Ya = stage_buf + (size_t)(ch % ST) * STAGE;
+      const double *Yb = diag ? Ya : Ya + KC * UPD_YS;
+      auto kstep = [&](int kk) {
+        double a[2], b[4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) a[i] = Ya[(kk + lc) * UPD_YS + wa + i * 8 + lr];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = Yb[(kk + lc) * UPD_YS + wb + j * 8 + lr];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      };
+      const int krem = kr - ch * KC;  // rows of this chunk that exist (the rest is zero fill)
+      if (krem >= KC) {
+#pragma unroll
+        for (int kk = 0; kk < KC; kk += 4) kstep(kk);
+      } else {
+#pragma unroll 2
+        for (int kk = 0; kk < krem; kk += 4) kstep(kk);
+      }
+    }
+  }
   if (skip) return;
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
@@ -1121,27 +1185,28 @@ inline void solve_shape(int Nmax, int &nslab, int &warps) {
   nslab = (ngroups + SOLVE_MAX_WARPS - 1) / SOLVE_MAX_WARPS;
   warps = (ngroups + nslab - 1) / nslab;
 }
-constexpr size_t SYRK_SMEM = (size_t)2 * 2 * UPD_KC * UPD_YS * sizeof(double);
+constexpr size_t SYRK_SMEM = (size_t)4 * 2 * 16 * UPD_YS * sizeof(double);
 
 }  // namespace
 
 size_t sl2_update_smem_bytes(const Sl2Dev &d) {  // upd_chol
-  const size_t K = upd_keven(d.Nmax), mmax = 2 * K;
-  return (mmax * UPD_MS + UPD_NB * UPD_DS + UPD_NB * UPD_WS + upd_pan_doubles(d.Nmax)) * sizeof(double);
+  return chol_smem_doubles(d.Nmax) * sizeof(double);
 }
 
 static size_t hp_smem_bytes(const Sl2Dev &d) {
-  return hp_smem_doubles(d.Nmax) * sizeof(double) + (upd_keven(d.Nmax) + 8) * sizeof(int);
+  return hp_smem_doubles(d.Nmax, d.ld) * sizeof(double) + (upd_keven(d.Nmax) + 16) * sizeof(int);
 }
 
 cudaError_t sl2_configure_update(const Sl2Dev &d) {
-  cudaError_t e = cudaFuncSetAttribute(upd_hp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(upd_hp_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)hp_smem_bytes(d));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(upd_hp_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp_smem_bytes(d));
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(upd_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)sl2_update_smem_bytes(d));
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(upd_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM);
+  e = cudaFuncSetAttribute(upd_syrk_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM);
   if (e != cudaSuccess) return e;
   const int np = solve_np(d.Nmax);
   const int smem = (int)solve_smem(np);
@@ -1169,8 +1234,13 @@ cudaError_t sl2_launch_update(const Sl2Dev &d, int stream_lo, int stream_cnt, in
   const int hp_all = (2 * upd_keven(d.Nmax) + HP_ROWS - 1) / HP_ROWS;
   const int hp_blocks = stream_cnt >= 2 * 148 ? 1 : hp_all;
   if (!only_normalise) {
-    upd_hp_kernel<<<dim3(hp_blocks, stream_cnt), HP_THREADS, hp_smem_bytes(d), st>>>(d, stream_lo, staged_m, st_feat,
-                                                                                st_Hxv, st_Hy, st_R, st_nu);
+    const dim3 grid(hp_blocks, stream_cnt);
+    if (staged_m >= 0)
+      upd_hp_kernel<13><<<grid, HP_THREADS, hp_smem_bytes(d), st>>>(d, stream_lo, staged_m, st_feat, st_Hxv, st_Hy,
+                                                                     st_R, st_nu);
+    else
+      upd_hp_kernel<7><<<grid, HP_THREADS, hp_smem_bytes(d), st>>>(d, stream_lo, staged_m, st_feat, st_Hxv, st_Hy,
+                                                                    st_R, st_nu);
     ++nl;
   }
   if ((e = mark(1)) != cudaSuccess) return e;
@@ -1203,7 +1273,7 @@ cudaError_t sl2_launch_update(const Sl2Dev &d, int stream_lo, int stream_cnt, in
     // one 64x64 tile per CTA (measured: CTAs that walk several tiles with cross-tile prefetch were slower, 0.29-0.31
     // against 0.264 ms, because they cost the third resident CTA per SM)
     const int nt = (SL2_NXV + 3 * d.Nmax + 1 + 63) / 64;
-    upd_syrk_kernel<<<dim3(nt * (nt + 1) / 2, stream_cnt), UPD_THREADS, SYRK_SMEM, st>>>(d, stream_lo);
+    upd_syrk_kernel<32, 2><<<dim3(nt * (nt + 1) / 2, stream_cnt), UPD_THREADS, SYRK_SMEM, st>>>(d, stream_lo);
     ++nl;
   }
   if ((e = mark(4)) != cudaSuccess) return e;
