@@ -420,6 +420,54 @@ def shim_rate(config, repeat=60):
         return {"unavailable": str(e)[:160]}
 
 
+def aux_rates():
+    """Rows N2 / N3 of SURVEY 8(f) through the public API (host buffers in, results out, one call = one H2D, the
+    kernels, one D2H): the Shi-Tomasi detector over the reference's 80x60 initialisation window
+    (monoslam.cpp:947-948), batches of such windows and a whole frame, with the oracle port timed on the same input."""
+    import scenelib2_b200 as sl2
+    from scenelib2_b200 import synth
+    from oracle import pyoracle as po
+    out = {}
+    try:
+        rng = np.random.default_rng(5)
+        img = synth.make_texture(rng, 240, 320)
+        cfg = sl2.default_config()
+        cfg.width, cfg.height, cfg.boxsize, cfg.max_features = 320, 240, 11, 4
+        ctx = sl2.Context(cfg)
+        ctx.set_features(0, np.zeros((1, 3)), np.tile([0, 0, 0, 1, 0, 0, 0.0], (1, 1)), np.zeros((1, 11, 11), np.uint8))
+        ctx.set_frame(0, 0, img)
+
+        def rate(regions, reps=30):
+            for _ in range(3):
+                ctx.find_best_patch(0, 0, regions)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                ctx.find_best_patch(0, 0, regions)
+            return (time.perf_counter() - t0) / reps
+
+        one = np.array([[120, 90, 200, 150]], np.int32)
+        x0 = rng.integers(6, 234, 64)
+        y0 = rng.integers(6, 174, 64)
+        many = np.column_stack([x0, y0, x0 + 80, y0 + 60]).astype(np.int32)
+        full = np.array([[0, 0, 320, 240]], np.int32)
+        t1, t64, tf = rate(one), rate(many), rate(full)
+        c0 = time.perf_counter()
+        creps = 20
+        for _ in range(creps):
+            po.find_best_patch(img, 11, one[0])
+        tc = (time.perf_counter() - c0) / creps
+        out["N3_detector"] = {
+            "workload": "Shi-Tomasi best patch, 11x11 box, 320x240 frame; window = 80x60 (monoslam.cpp:947-948)",
+            "api": "sl2_find_best_patch (blocking: regions H2D, 2 kernels, results D2H)",
+            "us_per_call_1_window": t1 * 1e6, "us_per_call_64_windows": t64 * 1e6, "us_per_window_batched": t64 / 64 * 1e6,
+            "us_per_call_full_frame": tf * 1e6, "positions_per_s_batched": 64 * 80 * 60 / t64,
+            "cpu_port_us_per_window": tc * 1e6, "cpu_cores": 1}
+        ctx.close()
+    except Exception as e:   # informational leg
+        out["N3_detector"] = {"unavailable": str(e)[:160]}
+    return out
+
+
 def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -457,6 +505,7 @@ def run_ours(args, rank, local_rank, world):
                                   "kernel_ms": one["kernel_ms"]}
         if rank == 0:
             extra["shim_single_stream"] = {c: shim_rate(c) for c in ("C1", "C4")}
+            extra.update(aux_rates())
 
     if rank == 0:
         sc0 = scenes[0]

@@ -739,7 +739,8 @@ int sl2_find_best_patch(sl2_ctx *c, int32_t s, int32_t slot, int32_t n, const in
   if (bad_stream(c, s) || bad_slot(c, slot) || n < 0 || (n && (!regions || !evbest)))
     return fail(c, SL2_ERR_ARG, "sl2_find_best_patch: bad argument");
   if (n == 0) return SL2_OK;
-  const size_t o_uv = 16 * (size_t)n, o_ev = o_uv + 8 * (size_t)n, total = o_ev + 8 * (size_t)n + 64;
+  const size_t o_uv = 16 * (size_t)n, o_ev = o_uv + 8 * (size_t)n, o_sc = o_ev + 8 * (size_t)n,
+               total = o_sc + sl2_detect_scratch_bytes(c->d, n) + 64;
   int rc = stage_reserve(c, total);
   if (rc) return rc;
   CU_TRY(c, cudaStreamSynchronize(c->stream));
@@ -747,8 +748,8 @@ int sl2_find_best_patch(sl2_ctx *c, int32_t s, int32_t slot, int32_t n, const in
   CU_TRY(c, cudaMemcpyAsync(c->stg_dev, c->stg_host, 16 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
   CU_TRY(c, sl2_launch_detect(c->d, s, slot, n, reinterpret_cast<const int *>(c->stg_dev),
                               reinterpret_cast<int *>(c->stg_dev + o_uv),
-                              reinterpret_cast<double *>(c->stg_dev + o_ev), c->stream));
-  ++c->launches;
+                              reinterpret_cast<double *>(c->stg_dev + o_ev), c->stg_dev + o_sc, c->stream));
+  c->launches += 2;
   CU_TRY(c, cudaMemcpyAsync(c->stg_host + o_uv, c->stg_dev + o_uv, 16 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(c, cudaStreamSynchronize(c->stream));
   const int *uv = reinterpret_cast<const int *>(c->stg_host + o_uv);

@@ -182,7 +182,6 @@ __global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32, FILTER ? (BOX <= 11 ? 4
   const double Sg0x2 = mul_(Sg0d, 2.0);        // Sg0doub * 2.0
   // exact integers (< 2^53, so FP64 holds them exactly): n^2 * var = n*Sxx - Sx^2
   const double V0d = fma(n, Sg0sqd, -(Sg0d * Sg0d));
-  const double T100 = 100.0 * n * n;           // sigma >= 10  <=>  n^2 var >= 100 n^2
   const float V0f = (float)V0d;
   const bool patch_ok = !(sigmag0 < 10.0);     // kCorrelationSigmaThreshold_ gate on the template
   float bmin = 3.0e38f;                        // running minimum of the approximate score

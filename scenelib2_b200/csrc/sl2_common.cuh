@@ -123,5 +123,6 @@ cudaError_t sl2_launch_particles(int K, const double *h, const double *sinv3, co
                                  const double *lambda, const int *z_uv, const uint8_t *found,
                                  double prune_threshold, double *prob, uint8_t *keep, double *cumulative,
                                  double *mean_var, int *left_out, cudaStream_t st);
+size_t sl2_detect_scratch_bytes(const Sl2Dev &d, int n);
 cudaError_t sl2_launch_detect(const Sl2Dev &d, int stream, int slot, int n, const int *regions_dev,
-                              int *out_uv_dev, double *out_ev_dev, cudaStream_t st);
+                              int *out_uv_dev, double *out_ev_dev, void *scratch_dev, cudaStream_t st);

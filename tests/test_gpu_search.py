@@ -141,6 +141,37 @@ def test_shi_tomasi_best_patch_bit_exact(oracle, B):
     ctx.close()
 
 
+@pytest.mark.parametrize("B", [11, 15])
+def test_shi_tomasi_many_regions_and_ties_across_tiles(oracle, B):
+    """N3, batched: 48 regions of a 320x240 frame in one call (the kernel works on 32x32 tiles of positions and
+    reduces across tiles), and a periodic image whose maxima repeat every 32 / 40 pixels, so that equal eigenvalues
+    meet in different tiles: the first in (v, u) scan order must win, like the reference's strict `>`."""
+    rng = np.random.default_rng(80 + B)
+    img = synth.make_texture(rng, 240, 320)
+    patches = np.zeros((1, B, B), np.uint8)
+    ctx = ctx_for_image(img, patches)
+    x0 = rng.integers(-10, 300, 48)
+    y0 = rng.integers(-10, 220, 48)
+    regions = np.column_stack([x0, y0, x0 + rng.integers(1, 130, 48), y0 + rng.integers(1, 100, 48)]).astype(np.int32)
+    regions[0] = [0, 0, 320, 240]
+    u, v, ev = ctx.find_best_patch(0, 0, regions, ubest=-1, vbest=-1)
+    for i, reg in enumerate(regions):
+        ou, ov, oev = oracle.find_best_patch(img, B, reg, ubest=-1, vbest=-1)
+        assert (u[i], v[i]) == (ou, ov), (i, reg)
+        assert np.float64(ev[i]).tobytes() == np.float64(oev).tobytes(), (i, reg)
+    for period in (32, 40):
+        cell = synth.make_texture(rng, period, period)
+        per = np.tile(cell, (240 // period + 1, 320 // period + 1))[:240, :320].copy()
+        ctx.set_frame(0, 0, per)
+        regs = np.array([[20, 20, 300, 220], [0, 0, 320, 240], [33, 41, 200, 150]], np.int32)
+        u, v, ev = ctx.find_best_patch(0, 0, regs, ubest=-1, vbest=-1)
+        for i, reg in enumerate(regs):
+            ou, ov, oev = oracle.find_best_patch(per, B, reg, ubest=-1, vbest=-1)
+            assert (u[i], v[i]) == (ou, ov), (period, i)
+            assert np.float64(ev[i]).tobytes() == np.float64(oev).tobytes()
+    ctx.close()
+
+
 def test_odd_frame_size_pitch_padding(oracle):
     """Frame width not a multiple of 16 (device pitch != width): search, score map and detector."""
     rng = np.random.default_rng(12)
