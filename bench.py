@@ -423,7 +423,9 @@ def shim_rate(config, repeat=60):
 def aux_rates():
     """Rows N2 / N3 of SURVEY 8(f) through the public API (host buffers in, results out, one call = one H2D, the
     kernels, one D2H): the Shi-Tomasi detector over the reference's 80x60 initialisation window
-    (monoslam.cpp:947-948), batches of such windows and a whole frame, with the oracle port timed on the same input."""
+    (monoslam.cpp:947-948), batches of such windows and a whole frame; and the partially-initialised-feature cycle
+    (particle prediction, overlapping-ellipse search, re-weighting) for 1 and 8 features of 100 particles.  The
+    oracle port is timed on the same inputs (one host core)."""
     import scenelib2_b200 as sl2
     from scenelib2_b200 import synth
     from oracle import pyoracle as po
@@ -465,6 +467,62 @@ def aux_rates():
         ctx.close()
     except Exception as e:   # informational leg
         out["N3_detector"] = {"unavailable": str(e)[:160]}
+    try:
+        rng = np.random.default_rng(6)
+        img = synth.make_texture(rng, 240, 320)
+        cfg = sl2.default_config()
+        cfg.width, cfg.height, cfg.boxsize, cfg.max_features = 320, 240, 11, 4
+        ctx = sl2.Context(cfg)
+        ctx.set_features(0, np.zeros((1, 3)), np.tile([0, 0, 0, 1, 0, 0, 0.0], (1, 1)), np.zeros((1, 11, 11), np.uint8))
+        ctx.set_frame(0, 0, img)
+        cam8 = np.array([cfg.width, cfg.height, cfg.fku, cfg.fkv, cfg.u0, cfg.v0, cfg.kd1, cfg.sd], float)
+        xv = np.zeros(13)
+        xv[:3] = [0.06, -0.03, 0.01]
+        xv[3:7] = np.array([1.0, 0.01, -0.02, 0.015]) / np.linalg.norm([1.0, 0.01, -0.02, 0.015])
+        A = rng.normal(0, 1, (16, 16))
+        P = A @ A.T * 2e-6 + 1e-8 * np.eye(16)
+        ctx.set_state(0, np.concatenate([xv, [0.1, 0.1, 2.0]]), P)
+        F, K = 8, 100   # kNumberOfParticles-sized features (monoslam.cpp: 100 depth hypotheses 0.5 .. 5 m)
+        ypi, Pxy, Pyy = np.zeros((F, 6)), np.zeros((F, 13, 6)), np.zeros((F, 6, 6))
+        lam = np.tile(np.linspace(0.5, 5.0, K), (F, 1))
+        prob = np.full((F, K), 1.0 / K)
+        patches = np.zeros((F, 11, 11), np.uint8)
+        for f in range(F):
+            u, v = rng.uniform(60, 260), rng.uniform(50, 190)
+            hh = np.array([-(u - cfg.u0) / cfg.fku, -(v - cfg.v0) / cfg.fkv, 1.0])
+            ypi[f, 3:] = hh / np.linalg.norm(hh)
+            Af = rng.normal(0, 1, (19, 19))
+            Pf = Af @ Af.T * 2e-6 + 1e-8 * np.eye(19)
+            Pxy[f], Pyy[f] = Pf[:13, 13:], Pf[13:, 13:]
+            hm = po.predict_particles(cam8, xv, ypi[f], [2.0], P[:13, :13], Pxy[f], Pyy[f])[0][0]
+            cu, cv = int(round(hm[0])), int(round(hm[1]))
+            patches[f] = img[cv - 5:cv + 6, cu - 5:cu + 6]
+
+        def rate(nf, reps=30):
+            for _ in range(3):
+                ctx.measure_partial_features(0, 0, patches[:nf], ypi[:nf], Pxy[:nf], Pyy[:nf], lam[:nf], 0.05, prob[:nf])
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                ctx.measure_partial_features(0, 0, patches[:nf], ypi[:nf], Pxy[:nf], Pyy[:nf], lam[:nf], 0.05, prob[:nf])
+            return (time.perf_counter() - t0) / reps
+
+        t1, t8 = rate(1), rate(F)
+        c0 = time.perf_counter()
+        creps = 3
+        for _ in range(creps):
+            oh, _, osi, odet = po.predict_particles(cam8, xv, ypi[0], lam[0], P[:13, :13], Pxy[0], Pyy[0])
+            ou, ov, of, _ = po.smoe_search(img, patches[0], osi, oh)
+            po.particle_update(oh, osi, odet, lam[0], np.column_stack([ou, ov]), of, 0.05, prob[0])
+        tc = (time.perf_counter() - c0) / creps
+        out["N2_partial_features"] = {
+            "workload": "partially-initialised features, 100 depth particles each, 11x11 template, 320x240 frame: "
+                        "ellipse prediction + overlapping-ellipse search + particle re-weighting (monoslam.cpp:1347-1493)",
+            "api": "sl2_measure_partial_features (blocking: one H2D, 4 kernels, one D2H for all features of the call)",
+            "us_per_call_1_feature": t1 * 1e6, "us_per_call_8_features": t8 * 1e6, "us_per_feature_batched": t8 / F * 1e6,
+            "cpu_port_us_per_feature": tc * 1e6, "cpu_cores": 1}
+        ctx.close()
+    except Exception as e:   # informational leg
+        out["N2_partial_features"] = {"unavailable": str(e)[:160]}
     return out
 
 

@@ -124,7 +124,7 @@ int sl2_smoe_search(sl2_ctx *ctx, int32_t stream_id, int32_t slot, int32_t feat_
  * update_partially_initialised_feature_probabilities for that feature (monoslam.cpp:1447-1493):
  * prob_k *= N(z_k - h_k; S_k) (0 where the match failed), normalise_particle_vector_and_calculate_cumulative,
  * prune_particle_vector(prune_probability_threshold), calculate_mean_and_covariance (feature_init_info.cpp:
- * 95-172, scalar lambda).  Both kernels run back to back on the device.
+ * 95-172, scalar lambda).  The kernels run back to back on the device; K <= SL2_MAX_PARTICLES.
  * in: h (K x 2), Sinv3 (K x (S00,S01,S11)), detS (K), lambda (K); in/out: prob (K);
  * out (each may be NULL): z_uv (K x 2), found (K), keep (K; 1 = particle survives), cumulative (K; of the
  * survivors in order, 0 for pruned ones), mean_var (2).
@@ -145,6 +145,31 @@ int sl2_measure_particles_patch(sl2_ctx *ctx, int32_t stream_id, int32_t slot, c
                                 const double *h, const double *Sinv3, const double *detS, const double *lambda,
                                 double prune_probability_threshold, double *prob, int32_t *z_uv,
                                 uint8_t *found, uint8_t *keep, double *cumulative, double *mean_var);
+
+/* All partially-initialised features of one stream in ONE call (no host round trip between the stages):
+ *   MonoSLAM::predict_partially_initialised_feature_measurements   monoslam.cpp:1347-1400
+ *     per particle h_pi (PartFeatureModel::func_hpi_and_dhpi_by_dxp_and_dhpi_by_dyi, part_feature_model.cpp:
+ *     231-265), R_i, S_i (FeatureModel::func_Si, feature_model.cpp:99-116), S_i^-1 and det S_i (Particle::set_S,
+ *     feature_init_info.cpp:57-65), from the stream's CURRENT x_v / P_xx on the device;
+ *   MonoSLAM::measure_feature_with_multiple_priors                 monoslam.cpp:1408-1438
+ *     SearchMultipleOverlappingEllipses with the score of every image location computed once per feature;
+ *   MonoSLAM::update_partially_initialised_feature_probabilities   monoslam.cpp:1447-1493 (see above).
+ * F <= SL2_MAX_PARTIAL features, feature f uses K[f] <= Kmax <= SL2_MAX_PARTICLES particles; every per-particle
+ * array is F x Kmax (entries k >= K[f] are ignored / left alone).
+ * in : patches (F x boxsize x boxsize u8), ypi (F x 6: r, hhat), Pxy (F x 13x6 column-major: covariance between
+ *      x_v and the feature's 6 states), Pyy (F x 6x6 column-major), lambda (F x Kmax), prune threshold;
+ * in/out: prob (F x Kmax);
+ * out (each may be NULL): h (F x Kmax x 2), Sinv3 (F x Kmax x (S00,S01,S11)), detS (F x Kmax), z_uv (F x Kmax x 2),
+ *      found, keep (F x Kmax), cumulative (F x Kmax), mean_var (F x 2), left (F: survivors, 0 = the reference
+ *      deletes the feature). */
+#define SL2_MAX_PARTIAL 16
+#define SL2_MAX_PARTICLES 256
+int sl2_measure_partial_features(sl2_ctx *ctx, int32_t stream_id, int32_t slot, int32_t F, int32_t Kmax,
+                                 const int32_t *K, const uint8_t *patches, const double *ypi, const double *Pxy,
+                                 const double *Pyy, const double *lambda, double prune_probability_threshold,
+                                 double *prob, double *h, double *Sinv3, double *detS, int32_t *z_uv,
+                                 uint8_t *found, uint8_t *keep, double *cumulative, double *mean_var,
+                                 int32_t *left);
 
 /* MonoSLAM::find_best_patch_inside_region + find_eigenvalues (monoslam.cpp:1070-1205): Shi-Tomasi
  * smallest-eigenvalue detector over n regions (ustart, vstart, ufinish, vfinish) of one stream's

@@ -196,6 +196,24 @@ void orc_predict_feature(const double *cam8, const double *xv, const double *y, 
   std::memcpy(S, p.S.a.data(), sizeof(double) * 4);
 }
 
+void orc_predict_particles(const double *cam8, const double *xv, const double *ypi, int32_t K,
+                           const double *lambda, const double *Pxx, const double *Pxy, const double *Pyy,
+                           double *h, double *S4, double *Sinv3, double *detS) {
+  Camera cam = cam_from8(cam8);
+  const Mat mPxx = mat_from(Pxx, 13, 13), mPxy = mat_from(Pxy, 13, 6), mPyy = mat_from(Pyy, 6, 6);
+  for (int k = 0; k < K; ++k) {
+    ParticlePrediction p;
+    PartFeatureModel::predict_particle(cam, xv, ypi, lambda[k], mPxx, mPxy, mPyy, p);
+    h[2 * k] = p.h[0];
+    h[2 * k + 1] = p.h[1];
+    if (S4) std::memcpy(S4 + 4 * k, p.S.a.data(), sizeof(double) * 4);
+    Sinv3[3 * k] = p.Sinv[0];
+    Sinv3[3 * k + 1] = p.Sinv[1];
+    Sinv3[3 * k + 2] = p.Sinv[3];
+    detS[k] = p.detS;
+  }
+}
+
 int32_t orc_visibility_test(const double *cam8, const double *xp, const double *y,
                             const double *xp_org, const double *h) {
   const Camera cam = cam_from8(cam8);

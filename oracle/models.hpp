@@ -408,4 +408,107 @@ struct FullFeatureModel {
   }
 };
 
+// ---------------------------------------------------------------------------------------
+// Partially-initialised feature (a ray r + lambda * hhat) measured through one depth particle
+// (part_feature_model.cpp:80-143, 231-265; monoslam.cpp:1375-1392; feature_init_info.cpp:57-65)
+// ---------------------------------------------------------------------------------------
+struct ParticlePrediction {
+  double h[2];
+  Mat dh_by_dxp;  // 2x7
+  Mat dh_by_dy;   // 2x6
+  Mat S;          // 2x2
+  double var;     // R = var * I
+  double Sinv[4]; // Particle::m_SInv_ (column-major 2x2)
+  double detS;
+};
+
+struct PartFeatureModel {
+  // part_feature_model.cpp:80-143: yi = (ri, hhati) -> zeroedyi = (RRW (ri - r), RRW hhati) and its Jacobians
+  static void zeroedyi(const double yi[6], const double xp[7], double zeroed[6], Mat &dz_by_dxp,
+                       Mat &dz_by_dyi) {
+    const double d[3] = {yi[0] - xp[0], yi[1] - xp[1], yi[2] - xp[2]};
+    const double hh[3] = {yi[3], yi[4], yi[5]};
+    const Quat q = {xp[3], xp[4], xp[5], xp[6]};
+    const Quat qRW = quat_inverse(q);
+    double RRW[3][3];
+    quat_to_R(qRW, RRW);
+    for (int i = 0; i < 3; ++i) {
+      double s = 0.0, t = 0.0;
+      for (int k = 0; k < 3; ++k) {
+        s += RRW[i][k] * d[k];
+        t += RRW[i][k] * hh[k];
+      }
+      zeroed[i] = s;
+      zeroed[3 + i] = t;
+    }
+    Mat R(3, 3), Rneg(3, 3);
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        R(i, j) = RRW[i][j];
+        Rneg(i, j) = RRW[i][j] * -1.0;
+      }
+    Mat dqbar(4, 4);  // feature_model.cpp:152-162
+    dqbar(0, 0) = 1.0;
+    dqbar(1, 1) = -1.0;
+    dqbar(2, 2) = -1.0;
+    dqbar(3, 3) = -1.0;
+    dz_by_dxp = Mat(6, 7);
+    set_block(dz_by_dxp, 0, 0, Rneg);
+    set_block(dz_by_dxp, 0, 3, mul(FullFeatureModel::dRq_times_a_by_dq(qRW, d), dqbar));
+    set_block(dz_by_dxp, 3, 3, mul(FullFeatureModel::dRq_times_a_by_dq(qRW, hh), dqbar));
+    dz_by_dyi = Mat(6, 6);
+    set_block(dz_by_dyi, 0, 0, R);
+    set_block(dz_by_dyi, 3, 3, R);
+  }
+
+  // One particle of MonoSLAM::predict_partially_initialised_feature_measurements (monoslam.cpp:1375-1392):
+  // func_hpi_and_dhpi_by_dxp_and_dhpi_by_dyi (part_feature_model.cpp:231-265), func_Ri, func_Si
+  // (feature_model.cpp:99-116) with the 13x6 / 6x6 covariance blocks of the 6-dimensional feature state,
+  // Particle::set_S (feature_init_info.cpp:57-65; the L^-1 of the 2x2 factor in closed form like puinv_from_S).
+  static void predict_particle(Camera &cam, const double xv[13], const double ypi[6], double lambda,
+                               const Mat &Pxx, const Mat &Pxy, const Mat &Pyy, ParticlePrediction &out) {
+    double z[6];
+    Mat dz_by_dxp, dz_by_dyi;
+    zeroedyi(ypi, xv, z, dz_by_dxp, dz_by_dyi);  // xp = xv[0..6]
+    const double hLR[3] = {z[0] + lambda * z[3], z[1] + lambda * z[4], z[2] + lambda * z[5]};
+    cam.project(hLR, out.h);
+    const Mat J = cam.projection_jacobian();
+    Mat D(3, 6);  // dhLRi_by_dzeroedyi
+    for (int i = 0; i < 3; ++i) {
+      D(i, i) = 1.0;
+      D(i, 3 + i) = lambda;
+    }
+    const Mat M1 = mul(J, D);
+    out.dh_by_dxp = mul(M1, dz_by_dxp);
+    out.dh_by_dy = mul(M1, dz_by_dyi);
+    Mat dxp_by_dxv(7, 13);  // motion_model.cpp:224-235
+    for (int i = 0; i < 7; ++i) dxp_by_dxv(i, i) = 1.0;
+    const Mat dh_by_dxv = mul(out.dh_by_dxp, dxp_by_dxv);
+    out.var = cam.measurement_noise_variance(out.h);
+    Mat R(2, 2);
+    R(0, 0) = 1.0 * out.var;
+    R(1, 1) = 1.0 * out.var;
+    Mat S(2, 2);
+    add_inplace(S, mul_nt(mul(dh_by_dxv, Pxx), dh_by_dxv));
+    const Mat T1 = mul_nt(mul(dh_by_dxv, Pxy), out.dh_by_dy);
+    add_inplace(S, T1);
+    add_inplace(S, transpose(T1));
+    add_inplace(S, mul_nt(mul(out.dh_by_dy, Pyy), out.dh_by_dy));
+    add_inplace(S, R);
+    out.S = S;
+    const double s00 = S(0, 0), s10 = S(1, 0), s11 = S(1, 1);
+    const double l00 = std::sqrt(s00);
+    const double l10 = s10 / l00;
+    const double l11 = std::sqrt(s11 - l10 * l10);
+    const double x00 = 1.0 / l00;
+    const double x10 = (0.0 - l10 * x00) / l11;
+    const double x11 = 1.0 / l11;
+    out.Sinv[0] = x00 * x00 + x10 * x10;
+    out.Sinv[1] = x10 * x11;
+    out.Sinv[2] = x10 * x11;
+    out.Sinv[3] = x11 * x11;
+    out.detS = S(0, 0) * S(1, 1) - S(0, 1) * S(1, 0);
+  }
+};
+
 }  // namespace sl2o

@@ -325,6 +325,34 @@ def predict_feature(cam8, xv, y, Pxx, Pxy, Pyy, use_ref=False):
     return h, dxv, dy, R, S
 
 
+def predict_particles(cam8, xv, ypi, lam, Pxx, Pxy, Pyy, use_ref=False):
+    """N2 prediction (monoslam.cpp:1347-1400, one feature): K particles -> h (K,2), S (K,2,2), Sinv3 (K,3), detS (K)."""
+    cam8, cp = _f64(cam8)
+    xv, xp = _f64(xv)
+    ypi, yp = _f64(ypi)
+    lam = np.ascontiguousarray(lam, np.float64).ravel()
+    Pxx, a = _colmajor(Pxx)
+    Pxy, b = _colmajor(Pxy)
+    Pyy, c = _colmajor(Pyy)
+    K = lam.size
+    h = np.zeros((K, 2))
+    S = np.zeros((K, 4))
+    Sinv3 = np.zeros((K, 3))
+    det = np.zeros(K)
+    if use_ref:
+        f = ref_models().ref_predict_particle
+        f.restype = None
+        for k in range(K):
+            hk, Sk, Sik, dk = np.zeros(2), np.zeros(4), np.zeros(4), C.c_double(0.0)
+            f(cp, xp, yp, C.c_double(lam[k]), a, b, c, _p(hk, f64p), _p(Sk, f64p), _p(Sik, f64p), C.byref(dk))
+            h[k], S[k], Sinv3[k], det[k] = hk, Sk, (Sik[0], Sik[2], Sik[3]), dk.value
+    else:
+        f = lib().orc_predict_particles
+        f.restype = None
+        f(cp, xp, yp, C.c_int32(K), _p(lam, f64p), a, b, c, _p(h, f64p), _p(S, f64p), _p(Sinv3, f64p), _p(det, f64p))
+    return h, S.reshape(K, 2, 2).transpose(0, 2, 1), Sinv3, det
+
+
 def visibility_test(cam8, xp, y, xp_org, h, use_ref=False):
     cam8, cp = _f64(cam8)
     xp, a = _f64(xp)

@@ -8,6 +8,7 @@
 #include "feature_init_info.h"
 #include "full_feature_model.h"
 #include "motion_model.h"
+#include "part_feature_model.h"
 
 using namespace SceneLib2;
 
@@ -105,6 +106,35 @@ void ref_particle_set_S(const double *S4, double *Sinv4, double *detS) {
   Eigen::VectorXd l(1);
   Particle p(l, 1.0, 2);
   p.set_S(mat(S4, 2, 2));
+  out(p.m_SInv_, Sinv4);
+  *detS = p.m_detS_;
+}
+
+// one particle of MonoSLAM::predict_partially_initialised_feature_measurements (monoslam.cpp:1375-1392) on the
+// reference's own PartFeatureModel / Particle objects: h_pi, S_i, S_i^-1, det S_i
+void ref_predict_particle(const double *cam8, const double *xv, const double *ypi, double lambda,
+                          const double *Pxx, const double *Pxy, const double *Pyy, double *h, double *S4,
+                          double *Sinv4, double *detS) {
+  Camera cam;
+  set_camera(cam, cam8);
+  MotionModel mm;
+  PartFeatureModel pm(2, 6, 6, &cam, &mm, 3);
+  const Eigen::VectorXd x = vec(xv, 13);
+  mm.func_xp(x);
+  const Eigen::VectorXd local_xp = mm.xpRES_;
+  mm.func_dxp_by_dxv(x);
+  const Eigen::MatrixXd local_dxp_by_dxv = mm.dxp_by_dxvRES_;
+  Eigen::VectorXd lam(1);
+  lam(0) = lambda;
+  pm.func_hpi_and_dhpi_by_dxp_and_dhpi_by_dyi(vec(ypi, 6), local_xp, lam);
+  const Eigen::VectorXd m_h = pm.hpiRES_;
+  pm.func_Ri(m_h);
+  pm.func_Si(mat(Pxx, 13, 13), mat(Pxy, 13, 6), mat(Pyy, 6, 6), pm.dhpi_by_dxpRES_ * local_dxp_by_dxv,
+             pm.dhpi_by_dyiRES_, pm.RiRES_);
+  Particle p(lam, 1.0, 2);
+  p.set_S(pm.SiRES_);
+  out(m_h, h);
+  out(pm.SiRES_, S4);
   out(p.m_SInv_, Sinv4);
   *detS = p.m_detS_;
 }

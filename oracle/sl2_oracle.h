@@ -68,6 +68,14 @@ void orc_motion(const double *xv, const double *u, double delta_t, double *fv, d
 /* A8  motion_model.cpp:237-263 ; J 13x13 */
 void orc_dxvnorm_by_dxv(const double *xv, double *J);
 /* N1  monoslam.cpp:289-308 ; cam8 = (width,height,fku,fkv,u0,v0,kd1,sd) */
+/* N2 prediction: the K depth particles of one partially-initialised feature (ypi = (r, hhat), 6 numbers),
+ * MonoSLAM::predict_partially_initialised_feature_measurements (monoslam.cpp:1347-1400, body per particle):
+ * h (K x 2), S (K x 2x2 col-major, may be NULL), Sinv3 (K x (00, 01, 11)), detS (K).
+ * Pxx 13x13, Pxy 13x6, Pyy 6x6 column-major. */
+void orc_predict_particles(const double *cam8, const double *xv, const double *ypi, int32_t K,
+                           const double *lambda, const double *Pxx, const double *Pxy, const double *Pyy,
+                           double *h, double *S4, double *Sinv3, double *detS);
+
 void orc_predict_feature(const double *cam8, const double *xv, const double *y, const double *Pxx,
                          const double *Pxy, const double *Pyy, double *h, double *dh_by_dxv,
                          double *dh_by_dy, double *R, double *S);

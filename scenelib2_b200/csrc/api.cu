@@ -27,6 +27,8 @@ struct sl2_ctx {
   uint8_t *stg_dev = nullptr;   // device scratch for staged API calls
   size_t stg_bytes = 0;
   uint8_t *stg_host = nullptr;  // pinned
+  double *smoe_map = nullptr;   // [features of the call][W][H] score cache of the SMOE kernels (lazily sized)
+  size_t smoe_map_bytes = 0;
   int64_t launches = 0;
   bool timing = false;
   // timing mode: ev[0..4] bracket predict / search / update / cull, evu[0..5] the five update kernels
@@ -250,7 +252,7 @@ int sl2_create(const sl2_config *cfg, sl2_ctx **out) {
   bool ok = true;
 #define ALLOC(ptr, count) ok = ok && (dev_alloc(c, &(ptr), (count)) == cudaSuccess)
   ALLOC(d.frames, (size_t)d.slots * B * d.H * d.pitch);
-  ALLOC(d.patches, (B * N + 1) * d.box * 16);  // + one scratch template (the *_patch entry points)
+  ALLOC(d.patches, (B * N + SL2_MAX_PARTIAL) * d.box * 16);  // + scratch templates (partially-initialised features)
   ALLOC(d.x, B * d.ld);
   ALLOC(d.P, B * d.ld * d.ld);
   ALLOC(d.G, B * d.mmax * d.ldg);
@@ -344,6 +346,7 @@ void sl2_destroy(sl2_ctx *c) {
     if (e) cudaEventDestroy(e);
   for (void *p : c->allocs) cudaFree(p);
   if (c->stg_dev) cudaFree(c->stg_dev);
+  if (c->smoe_map) cudaFree(c->smoe_map);
   if (c->stg_host) cudaFreeHost(c->stg_host);
   for (auto &e : c->ev)
     if (e) cudaEventDestroy(e);
@@ -510,35 +513,18 @@ int sl2_append_feature(sl2_ctx *c, int32_t s, const double *y, const double *xp_
 }
 
 // ---- patch search -----------------------------------------------------------------------------
-// A raw BOX x BOX template goes into the scratch slot behind the map templates; the search kernel addresses
-// templates as (stream * Nmax + feature), so relative to stream s the slot is feature (B - s) * Nmax.
-static int upload_scratch_patch(sl2_ctx *c, int32_t s, const uint8_t *patch, int32_t *feat_rel) {
-  const Sl2Dev &d = c->d;
-  const int box = d.box;
-  uint8_t rows[32 * 16];
-  memset(rows, 0, sizeof(rows));
-  for (int r = 0; r < box; ++r) memcpy(rows + r * 16, patch + (size_t)r * box, box);
-  CU_TRY(c, cudaMemcpyAsync(d.patches + (size_t)d.B * d.Nmax * box * 16, rows, (size_t)box * 16,
-                            cudaMemcpyHostToDevice, c->stream));
-  CU_TRY(c, cudaStreamSynchronize(c->stream));  // `rows` is on the stack
-  *feat_rel = (d.B - s) * d.Nmax;
-  return SL2_OK;
-}
-
 static int search_staged(sl2_ctx *c, int32_t s, int32_t slot, int32_t n, const int32_t *feat_index,
                          int32_t single_feat, const double *centre, const double *PuInv3,
-                         int32_t *u, int32_t *v, uint8_t *found, double *best, int smoe) {
+                         int32_t *u, int32_t *v, uint8_t *found, double *best) {
   if (bad_stream(c, s) || bad_slot(c, slot) || n < 0 || !centre || !PuInv3)
     return fail(c, SL2_ERR_ARG, "patch search: bad argument");
   if (n == 0) return SL2_OK;
   int nf = 0;
   int rc = device_nfeat(c, s, &nf);
   if (rc) return rc;
-  const int scratch = (c->d.B - s) * c->d.Nmax;  // see upload_scratch_patch
   for (int i = 0; i < n; ++i) {
     const int f = feat_index ? feat_index[i] : single_feat;
-    if ((f < 0 || f >= nf) && !(f == scratch && !feat_index))
-      return fail(c, SL2_ERR_ARG, "patch search: feature index out of range");
+    if (f < 0 || f >= nf) return fail(c, SL2_ERR_ARG, "patch search: feature index out of range");
   }
   // staging layout: centre(2n) puinv(3n) best(n) | feat(n) uv(2n) | found(n)
   const size_t o_c = 0, o_p = o_c + 16 * (size_t)n, o_b = o_p + 24 * (size_t)n,
@@ -565,7 +551,6 @@ static int search_staged(sl2_ctx *c, int32_t s, int32_t slot, int32_t n, const i
   L.out_found = c->stg_dev + o_fd;
   L.out_best = reinterpret_cast<double *>(c->stg_dev + o_b);
   L.scatter_to_features = 0;
-  L.smoe_mode = smoe;
   CU_TRY(c, sl2_launch_search(c->d, c->tmap, L, c->stream));
   ++c->launches;
   CU_TRY(c, cudaMemcpyAsync(hp + o_b, c->stg_dev + o_b, total - 64 - o_b, cudaMemcpyDeviceToHost, c->stream));
@@ -585,95 +570,197 @@ int sl2_patch_search(sl2_ctx *c, int32_t s, int32_t slot, int32_t n, const int32
                      const double *centre, const double *PuInv3, int32_t *u, int32_t *v,
                      uint8_t *found, double *best) {
   if (n > 0 && !feat_index) return fail(c, SL2_ERR_ARG, "sl2_patch_search: feat_index is null");
-  return search_staged(c, s, slot, n, feat_index, 0, centre, PuInv3, u, v, found, best, 0);
+  return search_staged(c, s, slot, n, feat_index, 0, centre, PuInv3, u, v, found, best);
+}
+
+// ---- partially-initialised features: F features x Kmax particle slots in one pass ------------------------------
+// One H2D of everything, [particle_predict] -> smoe map -> smoe argmin -> [reweight], one D2H.
+//   feat_index / patches : templates, either map features or raw BOX x BOX templates (scratch slots behind the map)
+//   ypi != NULL          : predict h / Sinv3 / detS on the device (they are outputs), else they are inputs
+//   prob != NULL         : run the re-weighting (lambda, prob, prune threshold), else search only
+struct PartialIO {
+  int F, Kmax;
+  const int32_t *K;
+  const int32_t *feat_index;
+  const uint8_t *patches;
+  const double *ypi, *Pxy, *Pyy;
+  double *h, *Sinv3, *detS;
+  const double *lambda;
+  double prune;
+  double *prob;
+  int32_t *z_uv;
+  uint8_t *found, *keep;
+  double *cumulative, *mean_var;
+  int32_t *left;
+};
+
+static int partial_features(sl2_ctx *c, int32_t s, int32_t slot, const PartialIO &io, const char *who) {
+  const Sl2Dev &d = c->d;
+  const int F = io.F, Kmax = io.Kmax;
+  const bool predict = io.ypi != nullptr, reweight = io.prob != nullptr;
+  if (bad_stream(c, s) || bad_slot(c, slot) || F < 0 || F > SL2_MAX_PARTIAL || Kmax < 0 ||
+      Kmax > SL2_MAX_PARTICLES || (F && Kmax && (!io.K || (!io.feat_index && !io.patches) || !io.h || !io.Sinv3)) ||
+      (predict && (!io.Pxy || !io.Pyy || !io.lambda || !io.detS)) || (reweight && (!io.lambda || !io.detS)))
+    return fail(c, SL2_ERR_ARG, std::string(who) + ": bad argument");
+  if (F == 0 || Kmax == 0) return SL2_OK;
+  for (int f = 0; f < F; ++f)
+    if (io.K[f] < 0 || io.K[f] > Kmax) return fail(c, SL2_ERR_ARG, std::string(who) + ": particle count out of range");
+  if (io.feat_index) {
+    int nf = 0;
+    const int rc = device_nfeat(c, s, &nf);
+    if (rc) return rc;
+    for (int f = 0; f < F; ++f)
+      if (io.feat_index[f] < 0 || io.feat_index[f] >= nf)
+        return fail(c, SL2_ERR_ARG, std::string(who) + ": feature index out of range");
+  }
+  const size_t n = (size_t)F * Kmax, box = (size_t)d.box;
+  // staging, inputs first: K(F) feat(F) | ypi(6F) Pxy(78F) Pyy(36F) lambda(n) prob(n) h(2n) Sinv3(3n) detS(n) |
+  //          templates (F x box x 16)   then outputs: cum(n) mean_var(2F) uv(2n int) left(F int) found(n) keep(n)
+  size_t o = 0;
+  auto take = [&](size_t bytes) { const size_t at = o; o += (bytes + 15) & ~(size_t)15; return at; };
+  const size_t o_K = take(4 * F), o_ft = take(4 * F), o_y = take(48 * F), o_xy = take(8 * 78 * F),
+               o_yy = take(8 * 36 * F), o_l = take(8 * n), o_pr = take(8 * n), o_h = take(16 * n),
+               o_si = take(24 * n), o_dt = take(8 * n), o_tp = take((size_t)F * box * 16), o_in_end = o,
+               o_cu = take(8 * n), o_mv = take(16 * F), o_uv = take(8 * n), o_left = take(4 * F), o_fd = take(n),
+               o_kp = take(n), total = o + 64;
+  int rc = stage_reserve(c, total);
+  if (rc) return rc;
+  const size_t map_bytes = sl2_smoe_map_bytes(d, F);
+  if (map_bytes > c->smoe_map_bytes) {
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->smoe_map) cudaFree(c->smoe_map);
+    c->smoe_map = nullptr;
+    c->smoe_map_bytes = 0;
+    CU_TRY(c, cudaMalloc(&c->smoe_map, map_bytes));
+    c->smoe_map_bytes = map_bytes;
+  }
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  uint8_t *hp = c->stg_host;
+  memset(hp, 0, o_in_end);
+  memcpy(hp + o_K, io.K, 4 * (size_t)F);
+  int *hf = reinterpret_cast<int *>(hp + o_ft);
+  for (int f = 0; f < F; ++f) hf[f] = io.feat_index ? io.feat_index[f] : (d.B - s) * d.Nmax + f;
+  if (predict) {
+    memcpy(hp + o_y, io.ypi, 48 * (size_t)F);
+    memcpy(hp + o_xy, io.Pxy, 8 * 78 * (size_t)F);
+    memcpy(hp + o_yy, io.Pyy, 8 * 36 * (size_t)F);
+  } else {
+    memcpy(hp + o_h, io.h, 16 * n);
+    memcpy(hp + o_si, io.Sinv3, 24 * n);
+    if (io.detS) memcpy(hp + o_dt, io.detS, 8 * n);
+  }
+  if (io.lambda) memcpy(hp + o_l, io.lambda, 8 * n);
+  if (reweight) memcpy(hp + o_pr, io.prob, 8 * n);
+  if (io.patches)
+    for (int f = 0; f < F; ++f)
+      for (size_t r = 0; r < box; ++r)
+        memcpy(hp + o_tp + ((size_t)f * box + r) * 16, io.patches + ((size_t)f * box + r) * box, box);
+  CU_TRY(c, cudaMemcpyAsync(c->stg_dev, hp, o_in_end, cudaMemcpyHostToDevice, c->stream));
+  if (io.patches)  // raw templates -> the scratch slots behind the map templates
+    CU_TRY(c, cudaMemcpyAsync(d.patches + (size_t)d.B * d.Nmax * box * 16, c->stg_dev + o_tp, (size_t)F * box * 16,
+                              cudaMemcpyDeviceToDevice, c->stream));
+  uint8_t *dv = c->stg_dev;
+  const int *dK = reinterpret_cast<const int *>(dv + o_K);
+  double *dh = reinterpret_cast<double *>(dv + o_h), *dsi = reinterpret_cast<double *>(dv + o_si),
+         *ddt = reinterpret_cast<double *>(dv + o_dt), *dl = reinterpret_cast<double *>(dv + o_l);
+  if (predict) {
+    CU_TRY(c, sl2_launch_particle_predict(d, s, F, Kmax, dK, reinterpret_cast<const double *>(dv + o_y),
+                                          reinterpret_cast<const double *>(dv + o_xy),
+                                          reinterpret_cast<const double *>(dv + o_yy), dl, dh, dsi, ddt, c->stream));
+    ++c->launches;
+  }
+  // measure_feature_with_multiple_priors (monoslam.cpp:1408-1438): ellipses (SInv_k, h_k), one template per feature
+  CU_TRY(c, sl2_launch_smoe(d, s, slot, F, Kmax, dK, reinterpret_cast<const int *>(dv + o_ft), dh, dsi, c->smoe_map,
+                            reinterpret_cast<int *>(dv + o_uv), dv + o_fd, nullptr, c->stream));
+  c->launches += 2;
+  if (reweight) {
+    CU_TRY(c, sl2_launch_particles(F, Kmax, dK, dh, dsi, ddt, dl, reinterpret_cast<const int *>(dv + o_uv), dv + o_fd,
+                                   io.prune, reinterpret_cast<double *>(dv + o_pr), dv + o_kp,
+                                   reinterpret_cast<double *>(dv + o_cu), reinterpret_cast<double *>(dv + o_mv),
+                                   reinterpret_cast<int *>(dv + o_left), c->stream));
+    ++c->launches;
+  }
+  // results: prob .. detS (inputs region, rewritten on the device) and the output region
+  CU_TRY(c, cudaMemcpyAsync(hp + o_pr, dv + o_pr, o_tp - o_pr, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(hp + o_cu, dv + o_cu, total - 64 - o_cu, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  if (predict) {
+    memcpy(io.h, hp + o_h, 16 * n);
+    memcpy(io.Sinv3, hp + o_si, 24 * n);
+    memcpy(io.detS, hp + o_dt, 8 * n);
+  }
+  if (reweight) {
+    memcpy(io.prob, hp + o_pr, 8 * n);
+    if (io.cumulative) memcpy(io.cumulative, hp + o_cu, 8 * n);
+    if (io.mean_var) memcpy(io.mean_var, hp + o_mv, 16 * (size_t)F);
+    if (io.keep) memcpy(io.keep, hp + o_kp, n);
+    if (io.left) memcpy(io.left, hp + o_left, 4 * (size_t)F);
+  }
+  if (io.z_uv) memcpy(io.z_uv, hp + o_uv, 8 * n);
+  if (io.found) memcpy(io.found, hp + o_fd, n);
+  return SL2_OK;
+}
+
+static int smoe_one(sl2_ctx *c, int32_t s, int32_t slot, const int32_t *feat_index, const uint8_t *patch, int32_t K,
+                    const double *PuInv3, const double *centres, int32_t *res_u, int32_t *res_v, uint8_t *res_flag,
+                    const char *who) {
+  if (K < 0 || (K && (!PuInv3 || !centres))) return fail(c, SL2_ERR_ARG, std::string(who) + ": bad argument");
+  if (K == 0) return SL2_OK;
+  if (K > SL2_MAX_PARTICLES) return fail(c, SL2_ERR_ARG, std::string(who) + ": more than SL2_MAX_PARTICLES ellipses");
+  std::vector<int32_t> uv(2 * (size_t)K);
+  PartialIO io = {};
+  io.F = 1, io.Kmax = K, io.K = &K;
+  io.feat_index = feat_index, io.patches = patch;
+  io.h = const_cast<double *>(centres), io.Sinv3 = const_cast<double *>(PuInv3);  // inputs (no prediction)
+  io.z_uv = uv.data(), io.found = res_flag;
+  const int rc = partial_features(c, s, slot, io, who);
+  if (rc) return rc;
+  for (int i = 0; i < K; ++i) {
+    if (res_u) res_u[i] = uv[2 * i];
+    if (res_v) res_v[i] = uv[2 * i + 1];
+  }
+  return SL2_OK;
 }
 
 int sl2_smoe_search(sl2_ctx *c, int32_t s, int32_t slot, int32_t feat_index, int32_t K,
                     const double *PuInv3, const double *centres, int32_t *res_u, int32_t *res_v,
                     uint8_t *res_flag) {
-  return search_staged(c, s, slot, K, nullptr, feat_index, centres, PuInv3, res_u, res_v, res_flag,
-                       nullptr, 1);
+  return smoe_one(c, s, slot, &feat_index, nullptr, K, PuInv3, centres, res_u, res_v, res_flag, "sl2_smoe_search");
 }
 
-static int measure_particles(sl2_ctx *c, int32_t s, int32_t slot, int32_t feat_index, const uint8_t *patch,
+int sl2_smoe_search_patch(sl2_ctx *c, int32_t s, int32_t slot, const uint8_t *patch, int32_t K,
+                          const double *PuInv3, const double *centres, int32_t *res_u, int32_t *res_v,
+                          uint8_t *res_flag) {
+  if (!patch) return fail(c, SL2_ERR_ARG, "sl2_smoe_search_patch: patch is null");
+  return smoe_one(c, s, slot, nullptr, patch, K, PuInv3, centres, res_u, res_v, res_flag, "sl2_smoe_search_patch");
+}
+
+static int measure_particles(sl2_ctx *c, int32_t s, int32_t slot, const int32_t *feat_index, const uint8_t *patch,
                              int32_t K, const double *h, const double *Sinv3, const double *detS,
                              const double *lambda, double prune_probability_threshold, double *prob,
                              int32_t *z_uv, uint8_t *found, uint8_t *keep, double *cumulative,
                              double *mean_var) {
-  if (bad_stream(c, s) || bad_slot(c, slot) || K < 0 || (K && (!h || !Sinv3 || !detS || !lambda || !prob)))
+  if (K < 0 || (K && (!h || !Sinv3 || !detS || !lambda || !prob)))
     return fail(c, SL2_ERR_ARG, "sl2_measure_particles: bad argument");
   if (K == 0) return 0;
-  int rc;
-  if (patch) {
-    rc = upload_scratch_patch(c, s, patch, &feat_index);
-    if (rc) return rc;
-  } else {
-    int nf = 0;
-    rc = device_nfeat(c, s, &nf);
-    if (rc) return rc;
-    if (feat_index < 0 || feat_index >= nf)
-      return fail(c, SL2_ERR_ARG, "sl2_measure_particles: feature index out of range");
-  }
-  // staging: h(2K) Sinv3(3K) detS(K) lambda(K) prob(K) | cum(K) mean_var(2) | feat(K) uv(2K) left(1+pad) |
-  //          found(K) keep(K)
-  const size_t n = (size_t)K;
-  const size_t o_h = 0, o_p = o_h + 16 * n, o_d = o_p + 24 * n, o_l = o_d + 8 * n, o_pr = o_l + 8 * n,
-               o_cu = o_pr + 8 * n, o_mv = o_cu + 8 * n, o_f = o_mv + 16, o_uv = o_f + 4 * n,
-               o_left = o_uv + 8 * n, o_fd = o_left + 8, o_kp = o_fd + n, total = o_kp + n + 64;
-  rc = stage_reserve(c, total);
-  if (rc) return rc;
-  CU_TRY(c, cudaStreamSynchronize(c->stream));
-  uint8_t *hp = c->stg_host;
-  memcpy(hp + o_h, h, 16 * n);
-  memcpy(hp + o_p, Sinv3, 24 * n);
-  memcpy(hp + o_d, detS, 8 * n);
-  memcpy(hp + o_l, lambda, 8 * n);
-  memcpy(hp + o_pr, prob, 8 * n);
-  int *hf = reinterpret_cast<int *>(hp + o_f);
-  for (int i = 0; i < K; ++i) hf[i] = feat_index;
-  CU_TRY(c, cudaMemcpyAsync(c->stg_dev, hp, o_uv, cudaMemcpyHostToDevice, c->stream));
-  // measure_feature_with_multiple_priors (monoslam.cpp:1408-1438): ellipses (SInv_k, h_k), one template
-  SearchLaunch L = {};
-  L.job_centre = reinterpret_cast<const double *>(c->stg_dev + o_h);
-  L.job_puinv = reinterpret_cast<const double *>(c->stg_dev + o_p);
-  L.job_feat = reinterpret_cast<const int *>(c->stg_dev + o_f);
-  L.jobs_per_stream = K;
-  L.stream_lo = s;
-  L.stream_cnt = 1;
-  L.slot = slot;
-  L.out_uv = reinterpret_cast<int *>(c->stg_dev + o_uv);
-  L.out_found = c->stg_dev + o_fd;
-  L.scatter_to_features = 0;
-  L.smoe_mode = 1;
-  CU_TRY(c, sl2_launch_search(c->d, c->tmap, L, c->stream));
-  CU_TRY(c, sl2_launch_particles(K, reinterpret_cast<const double *>(c->stg_dev + o_h),
-                                 reinterpret_cast<const double *>(c->stg_dev + o_p),
-                                 reinterpret_cast<const double *>(c->stg_dev + o_d),
-                                 reinterpret_cast<const double *>(c->stg_dev + o_l),
-                                 reinterpret_cast<const int *>(c->stg_dev + o_uv), c->stg_dev + o_fd,
-                                 prune_probability_threshold, reinterpret_cast<double *>(c->stg_dev + o_pr),
-                                 c->stg_dev + o_kp, reinterpret_cast<double *>(c->stg_dev + o_cu),
-                                 reinterpret_cast<double *>(c->stg_dev + o_mv),
-                                 reinterpret_cast<int *>(c->stg_dev + o_left), c->stream));
-  c->launches += 2;
-  CU_TRY(c, cudaMemcpyAsync(hp + o_pr, c->stg_dev + o_pr, total - 64 - o_pr, cudaMemcpyDeviceToHost, c->stream));
-  CU_TRY(c, cudaStreamSynchronize(c->stream));
-  memcpy(prob, hp + o_pr, 8 * n);
-  if (cumulative) memcpy(cumulative, hp + o_cu, 8 * n);
-  if (mean_var) memcpy(mean_var, hp + o_mv, 16);
-  if (z_uv) memcpy(z_uv, hp + o_uv, 8 * n);
-  if (found) memcpy(found, hp + o_fd, n);
-  if (keep) memcpy(keep, hp + o_kp, n);
-  int left = 0;
-  memcpy(&left, hp + o_left, sizeof(int));
-  return left;
+  if (K > SL2_MAX_PARTICLES) return fail(c, SL2_ERR_ARG, "sl2_measure_particles: more than SL2_MAX_PARTICLES particles");
+  int32_t left = 0;
+  PartialIO io = {};
+  io.F = 1, io.Kmax = K, io.K = &K;
+  io.feat_index = feat_index, io.patches = patch;
+  io.h = const_cast<double *>(h), io.Sinv3 = const_cast<double *>(Sinv3), io.detS = const_cast<double *>(detS);
+  io.lambda = lambda, io.prune = prune_probability_threshold, io.prob = prob;
+  io.z_uv = z_uv, io.found = found, io.keep = keep, io.cumulative = cumulative, io.mean_var = mean_var;
+  io.left = &left;
+  const int rc = partial_features(c, s, slot, io, "sl2_measure_particles");
+  return rc ? rc : left;
 }
 
 int sl2_measure_particles(sl2_ctx *c, int32_t s, int32_t slot, int32_t feat_index, int32_t K,
                           const double *h, const double *Sinv3, const double *detS, const double *lambda,
                           double prune_probability_threshold, double *prob, int32_t *z_uv, uint8_t *found,
                           uint8_t *keep, double *cumulative, double *mean_var) {
-  return measure_particles(c, s, slot, feat_index, nullptr, K, h, Sinv3, detS, lambda,
+  return measure_particles(c, s, slot, &feat_index, nullptr, K, h, Sinv3, detS, lambda,
                            prune_probability_threshold, prob, z_uv, found, keep, cumulative, mean_var);
 }
 
@@ -682,18 +769,32 @@ int sl2_measure_particles_patch(sl2_ctx *c, int32_t s, int32_t slot, const uint8
                                 double prune_probability_threshold, double *prob, int32_t *z_uv,
                                 uint8_t *found, uint8_t *keep, double *cumulative, double *mean_var) {
   if (!patch) return fail(c, SL2_ERR_ARG, "sl2_measure_particles_patch: patch is null");
-  return measure_particles(c, s, slot, -1, patch, K, h, Sinv3, detS, lambda, prune_probability_threshold,
+  return measure_particles(c, s, slot, nullptr, patch, K, h, Sinv3, detS, lambda, prune_probability_threshold,
                            prob, z_uv, found, keep, cumulative, mean_var);
 }
 
-int sl2_smoe_search_patch(sl2_ctx *c, int32_t s, int32_t slot, const uint8_t *patch, int32_t K,
-                          const double *PuInv3, const double *centres, int32_t *res_u, int32_t *res_v,
-                          uint8_t *res_flag) {
-  if (bad_stream(c, s) || !patch) return fail(c, SL2_ERR_ARG, "sl2_smoe_search_patch: bad argument");
-  int32_t feat = -1;
-  const int rc = upload_scratch_patch(c, s, patch, &feat);
-  if (rc) return rc;
-  return search_staged(c, s, slot, K, nullptr, feat, centres, PuInv3, res_u, res_v, res_flag, nullptr, 1);
+int sl2_measure_partial_features(sl2_ctx *c, int32_t s, int32_t slot, int32_t F, int32_t Kmax, const int32_t *K,
+                                 const uint8_t *patches, const double *ypi, const double *Pxy, const double *Pyy,
+                                 const double *lambda, double prune_probability_threshold, double *prob,
+                                 double *h, double *Sinv3, double *detS, int32_t *z_uv, uint8_t *found,
+                                 uint8_t *keep, double *cumulative, double *mean_var, int32_t *left) {
+  if (F > 0 && Kmax > 0 && (!patches || !ypi || !prob))
+    return fail(c, SL2_ERR_ARG, "sl2_measure_partial_features: bad argument");
+  // h / Sinv3 / detS are outputs the caller may not want: they still travel through the staging buffer
+  std::vector<double> th, ts, td;
+  const size_t n = (size_t)std::max(F, 0) * std::max(Kmax, 0);
+  if (!h) th.resize(2 * n), h = th.data();
+  if (!Sinv3) ts.resize(3 * n), Sinv3 = ts.data();
+  if (!detS) td.resize(n), detS = td.data();
+  PartialIO io = {};
+  io.F = F, io.Kmax = Kmax, io.K = K;
+  io.patches = patches;
+  io.ypi = ypi, io.Pxy = Pxy, io.Pyy = Pyy;
+  io.h = h, io.Sinv3 = Sinv3, io.detS = detS;
+  io.lambda = lambda, io.prune = prune_probability_threshold, io.prob = prob;
+  io.z_uv = z_uv, io.found = found, io.keep = keep, io.cumulative = cumulative, io.mean_var = mean_var;
+  io.left = left;
+  return partial_features(c, s, slot, io, "sl2_measure_partial_features");
 }
 
 int sl2_score_map(sl2_ctx *c, int32_t s, int32_t slot, int32_t feat, const double *centre,

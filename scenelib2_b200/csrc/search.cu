@@ -1,8 +1,7 @@
 // search.cu — patch-correlation feature search on sm_100a.
 //
 // Replaces MonoSLAM::elliptical_search (monoslam.cpp:401-477) calling correlate2_warning
-// (improc/improc.cpp:55-134), and SearchMultipleOverlappingEllipses::search
-// (improc/search_multiple_overlapping_ellipses.cpp:106-196).
+// (improc/improc.cpp:55-134).  (SearchMultipleOverlappingEllipses::search lives in smoe.cu.)
 //
 // Design (one WARP per feature, SL2_SEARCH_WARPS features per CTA):
 //   * the feature's search window (bounding box of the 3-sigma ellipse + BOXSIZE-1) is staged
@@ -23,6 +22,7 @@
 //     urel-major / vrel-minor scan order wins) carried as (score, scan index) through a
 //     warp-shuffle reduction.
 #include "sl2_common.cuh"
+#include "sl2_score.cuh"
 
 namespace {
 
@@ -76,30 +76,6 @@ __device__ __forceinline__ void consider(Best &b, double corr, int idx) {
     b.corr = corr;
     b.idx = idx;
   }
-}
-
-// improc.cpp:99-133 op for op (never-fused, IEEE div/sqrt).  Deliberately NOT inlined: the
-// filtered kernel reaches it for a handful of candidates per warp, and eight inlined copies of the
-// div/sqrt sequences blew the kernel up to ~66 KB of SASS (instruction-cache misses were the top
-// stall reason, profiles/r01b).
-struct PatchConst {
-  double n, sigmag0, A0, g0s, Sg0x2;
-};
-__device__ __noinline__ double exact_score_fn(const PatchConst pc, double Sg1d, double Sg1sqd,
-                                              double Sg0g1d, double *sigma1_out) {
-  const double g1bar = div_(Sg1d, pc.n);
-  const double varg1 = sub_(div_(Sg1sqd, pc.n), mul_(g1bar, g1bar));
-  const double sigmag1 = sqrt_(varg1);
-  *sigma1_out = sigmag1;
-  if (pc.sigmag0 == 0.0) return (sigmag1 == 0.0) ? 0.0 : 1.0;
-  if (sigmag1 == 0.0) return 1.0;
-  const double k = sub_(pc.g0s, div_(g1bar, sigmag1));
-  double C = add_(pc.A0, div_(Sg1sqd, varg1));
-  C = add_(C, mul_(pc.n, mul_(k, k)));
-  C = sub_(C, div_(mul_(Sg0g1d, 2.0), mul_(pc.sigmag0, sigmag1)));
-  C = sub_(C, div_(mul_(pc.Sg0x2, k), pc.sigmag0));
-  C = add_(C, div_(mul_(mul_(Sg1d, 2.0), k), sigmag1));
-  return div_(C, pc.n);
 }
 
 struct DumpPtrs {
@@ -195,8 +171,8 @@ __global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32, FILTER ? (BOX <= 11 ? 4
       __double2int_rz(div_(3.0, sqrt_(sub_(P00, div_(mul_(P01, P01), P11)))));
   const int halfheight =
       __double2int_rz(div_(3.0, sqrt_(sub_(P11, div_(mul_(P01, P01), P00)))));
-  const int uc = L.smoe_mode ? __double2int_rz(cx) : __double2int_rz(add_(cx, 0.5));
-  const int vc = L.smoe_mode ? __double2int_rz(cy) : __double2int_rz(add_(cy, 0.5));
+  const int uc = __double2int_rz(add_(cx, 0.5));
+  const int vc = __double2int_rz(add_(cy, 0.5));
   int us = -halfwidth, uf = halfwidth, vs = -halfheight, vf = halfheight;
   if (uc + us - HALF < 0) us = HALF - uc;
   if (uc + uf - HALF > d.W - BOX) uf = d.W - BOX - uc + HALF;
@@ -465,15 +441,8 @@ __global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32, FILTER ? (BOX <= 11 ? 4
                     dump.sd[idx] = sigmag1;
                     dump.inside[idx] = inside ? 1 : 0;
                   }
-                  if (inside) {
-                    if (L.smoe_mode) {
-                      // smoe.cpp:173-184: penalise low image sigma, no patch-sigma gate
-                      if (sigmag1 < 10.0) corr = add_(corr, 5.0);
-                      if (corr <= 1000000.0) consider(best, corr, idx);
-                    } else if (corr <= 1000000.0 && !(sigmag0 < 10.0) && !(sigmag1 < 10.0)) {
-                      consider(best, corr, idx);  // monoslam.cpp:457-467
-                    }
-                  }
+                  if (inside && corr <= 1000000.0 && !(sigmag0 < 10.0) && !(sigmag1 < 10.0))
+                    consider(best, corr, idx);  // monoslam.cpp:457-467
                 }
               }
             }
@@ -508,7 +477,7 @@ __global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32, FILTER ? (BOX <= 11 ? 4
     consider(best, oc, oi);
   }
   if (lane == 0) {
-    int u = L.smoe_mode ? 0 : -1, v = L.smoe_mode ? 0 : -1;  // smoe.cpp:43-44 default (0,0)
+    int u = -1, v = -1;
     if (best.idx >= 0) {
       u = us + best.idx / CH + uc;
       v = vs + best.idx % CH + vc;
@@ -552,7 +521,7 @@ cudaError_t launch_t(const Sl2Dev &d, const CUtensorMap &tmap, const SearchLaunc
 
 cudaError_t launch_any(const Sl2Dev &d, const CUtensorMap &tmap, const SearchLaunch &L,
                        const DumpPtrs &dump, cudaStream_t st) {
-  const bool exact_all = L.smoe_mode || dump.corr;  // A11 semantics / score dump: no filter
+  const bool exact_all = dump.corr != nullptr;  // score dump: every candidate through the exact chain
   switch (d.box) {
     case 11:
       return exact_all ? launch_t<11, false>(d, tmap, L, dump, st) : launch_t<11, true>(d, tmap, L, dump, st);

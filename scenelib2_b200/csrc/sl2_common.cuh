@@ -96,7 +96,6 @@ struct SearchLaunch {
   uint8_t *out_found;        // by job
   double *out_best;          // by job
   int scatter_to_features;   // 1: also write d.z_uv/found/best indexed by feature
-  int smoe_mode;             // 1: A11 semantics (centre truncation, penalty, no patch gate)
 };
 
 cudaError_t sl2_launch_search(const Sl2Dev &d, const CUtensorMap &tmap, const SearchLaunch &L,
@@ -119,8 +118,17 @@ cudaError_t sl2_launch_append(const Sl2Dev &d, int s, const double *y3_dev, cons
 size_t sl2_update_smem_bytes(const Sl2Dev &d);
 cudaError_t sl2_configure_search(const Sl2Dev &d);  // per context: dynamic smem opt-in
 cudaError_t sl2_configure_update(const Sl2Dev &d);
-cudaError_t sl2_launch_particles(int K, const double *h, const double *sinv3, const double *detS,
-                                 const double *lambda, const int *z_uv, const uint8_t *found,
+// partially-initialised features (particles.cu, smoe.cu): F features x Kmax particle slots (K_dev[f] used)
+cudaError_t sl2_launch_particle_predict(const Sl2Dev &d, int s, int F, int Kmax, const int *K_dev,
+                                        const double *ypi, const double *Pxy, const double *Pyy,
+                                        const double *lambda, double *h, double *sinv3, double *detS,
+                                        cudaStream_t st);
+size_t sl2_smoe_map_bytes(const Sl2Dev &d, int F);
+cudaError_t sl2_launch_smoe(const Sl2Dev &d, int s, int slot, int F, int Kmax, const int *K_dev, const int *feat_dev,
+                            const double *centre_dev, const double *puinv_dev, double *map_dev, int *out_uv_dev,
+                            uint8_t *out_found_dev, double *out_best_dev, cudaStream_t st);
+cudaError_t sl2_launch_particles(int F, int Kmax, const int *K_dev, const double *h, const double *sinv3,
+                                 const double *detS, const double *lambda, const int *z_uv, const uint8_t *found,
                                  double prune_threshold, double *prob, uint8_t *keep, double *cumulative,
                                  double *mean_var, int *left_out, cudaStream_t st);
 size_t sl2_detect_scratch_bytes(const Sl2Dev &d, int n);

@@ -44,7 +44,7 @@ EXPORTS = [
     "sl2_predict_measurements", "sl2_make_measurements", "sl2_ekf_update",
     "sl2_ekf_update_measured", "sl2_normalise_state", "sl2_step", "sl2_step_host",
     "sl2_step_host_async", "sl2_wait_slot", "sl2_set_step_groups", "sl2_join", "sl2_measure_particles", "sl2_measure_particles_patch",
-    "sl2_smoe_search_patch",
+    "sl2_smoe_search_patch", "sl2_measure_partial_features",
     "sl2_get_features", "sl2_get_feature_jacobians", "sl2_enable_timing", "sl2_last_step_times", "sl2_last_update_times", "sl2_launch_count",
 ]
 
@@ -272,6 +272,32 @@ class Context:
             assert patch.shape == (self.cfg.boxsize, self.cfg.boxsize)
             left = self._ck(self.L.sl2_measure_particles_patch(self.h, stream_id, slot, patch.ctypes.data, *args))
         return left, prob, z, found, keep, cum, mv
+
+    def measure_partial_features(self, stream_id, slot, patches, ypi, Pxy, Pyy, lam, prune_threshold, prob, K=None):
+        """N2 for F partially-initialised features in one call: device prediction of every particle's ellipse
+        (monoslam.cpp:1347-1400), SMOE search with one score map per feature, particle re-weighting.
+        patches (F,B,B) u8; ypi (F,6); Pxy (F,13,6); Pyy (F,6,6); lam, prob (F,Kmax); K (F,) particle counts
+        (default Kmax).  Returns a dict of arrays."""
+        patches = np.ascontiguousarray(patches, np.uint8)
+        F = patches.shape[0]
+        ypi = np.ascontiguousarray(ypi, np.float64).reshape(F, 6)
+        Pxy = np.ascontiguousarray(np.asarray(Pxy, np.float64).reshape(F, 13, 6).transpose(0, 2, 1))  # column-major
+        Pyy = np.ascontiguousarray(np.asarray(Pyy, np.float64).reshape(F, 6, 6).transpose(0, 2, 1))
+        lam = np.ascontiguousarray(lam, np.float64).reshape(F, -1)
+        Kmax = lam.shape[1]
+        prob = np.array(prob, np.float64).reshape(F, Kmax)
+        K = np.full(F, Kmax, np.int32) if K is None else np.ascontiguousarray(K, np.int32)
+        out = {"h": np.zeros((F, Kmax, 2)), "Sinv3": np.zeros((F, Kmax, 3)), "detS": np.zeros((F, Kmax)),
+               "z": np.zeros((F, Kmax, 2), np.int32), "found": np.zeros((F, Kmax), np.uint8),
+               "keep": np.zeros((F, Kmax), np.uint8), "cumulative": np.zeros((F, Kmax)),
+               "mean_var": np.zeros((F, 2)), "left": np.zeros(F, np.int32)}
+        self._ck(self.L.sl2_measure_partial_features(
+            self.h, stream_id, slot, F, Kmax, _p(K, i32p), C.c_void_p(patches.ctypes.data), _p(ypi, f64p), _p(Pxy, f64p),
+            _p(Pyy, f64p), _p(lam, f64p), C.c_double(float(prune_threshold)), _p(prob, f64p), _p(out["h"], f64p),
+            _p(out["Sinv3"], f64p), _p(out["detS"], f64p), _p(out["z"], i32p), _p(out["found"], u8p),
+            _p(out["keep"], u8p), _p(out["cumulative"], f64p), _p(out["mean_var"], f64p), _p(out["left"], i32p)))
+        out["prob"] = prob
+        return out
 
     def find_best_patch(self, stream_id, slot, regions, ubest=-1, vbest=-1):
         """regions (n,4) = (ustart, vstart, ufinish, vfinish) -> u, v (kept at ubest/vbest where the

@@ -239,6 +239,77 @@ def test_particle_measurement_and_reweighting_matches_oracle(oracle):
     ctx.close()
 
 
+def test_partial_features_batched_prediction_search_reweighting(oracle):
+    """N2 in one call (sl2_measure_partial_features): device prediction of every particle's ellipse
+    (monoslam.cpp:1347-1400; bit-exact against the reference-pinned oracle: only IEEE + - * / sqrt are involved),
+    the shared-score-map SMOE search (positions / flags exact) and the re-weighting (1e-13), for three features
+    with different particle counts on one frame."""
+    rng = np.random.default_rng(77)
+    img = synth.make_texture(rng, 240, 320)
+    B = 11
+    ctx = ctx_for_image(img, np.zeros((1, B, B), np.uint8))
+    cfg = ctx.cfg
+    cam8 = np.array([cfg.width, cfg.height, cfg.fku, cfg.fkv, cfg.u0, cfg.v0, cfg.kd1, cfg.sd], float)
+    xv = np.zeros(13)
+    xv[:3] = [0.06, -0.03, 0.01]
+    q = np.array([1.0, 0.01, -0.02, 0.015])
+    xv[3:7] = q / np.linalg.norm(q)
+    A = rng.normal(0, 1, (16, 16))
+    P = A @ A.T * 2e-6 + 1e-8 * np.eye(16)
+    x = np.concatenate([xv, [0.1, 0.1, 2.0]])
+    ctx.set_state(0, x, P)
+    F, Kmax = 3, 60
+    K = np.array([Kmax, Kmax - 7, 1], np.int32)
+    pix = [(120.0, 100.0), (215.0, 150.0), (160.0, 60.0)]
+    ypi = np.zeros((F, 6))
+    Pxy = np.zeros((F, 13, 6))
+    Pyy = np.zeros((F, 6, 6))
+    lam = np.zeros((F, Kmax))
+    prob = np.zeros((F, Kmax))
+    patches = np.zeros((F, B, B), np.uint8)
+    for f, (u, v) in enumerate(pix):
+        hh = np.array([-(u - cfg.u0) / cfg.fku, -(v - cfg.v0) / cfg.fkv, 1.0])
+        ypi[f] = np.concatenate([[0.0, 0.0, 0.0], hh / np.linalg.norm(hh)])
+        Af = rng.normal(0, 1, (19, 19))
+        Pf = Af @ Af.T * 2e-6 + 1e-8 * np.eye(19)
+        Pf[:13, :13] = P[:13, :13]
+        Pxy[f], Pyy[f] = Pf[:13, 13:], Pf[13:, 13:]
+        lam[f] = np.linspace(0.4, 6.0, Kmax)
+        p0 = rng.uniform(0.2, 1.0, Kmax)
+        p0[K[f]:] = 0.0
+        prob[f] = p0 / p0.sum()
+    # templates: what the image shows where the middle particle of each feature projects
+    for f in range(F):
+        h_mid = oracle.predict_particles(cam8, xv, ypi[f], lam[f, :1] * 0 + lam[f, K[f] // 2], P[:13, :13], Pxy[f],
+                                         Pyy[f])[0][0]
+        cu, cv = int(round(h_mid[0])), int(round(h_mid[1]))
+        patches[f] = img[cv - 5:cv + 6, cu - 5:cu + 6]
+    out = ctx.measure_partial_features(0, 0, patches, ypi, Pxy, Pyy, lam, 0.05, prob, K=K)
+    any_found = False
+    for f in range(F):
+        k = K[f]
+        oh, oS, osi, odet = oracle.predict_particles(cam8, xv, ypi[f], lam[f, :k], P[:13, :13], Pxy[f], Pyy[f])
+        assert out["h"][f, :k].tobytes() == oh.tobytes(), f
+        assert out["Sinv3"][f, :k].tobytes() == osi.tobytes(), f
+        assert out["detS"][f, :k].tobytes() == odet.tobytes(), f
+        ou, ov, of, _ = oracle.smoe_search(img, patches[f], osi, oh)
+        assert (out["found"][f, :k] == of).all(), f
+        z = out["z"][f, :k]
+        assert (z[of > 0, 0] == ou[of > 0]).all() and (z[of > 0, 1] == ov[of > 0]).all(), f
+        any_found |= bool(of.any())
+        oleft, oprob, okeep, ocum, omv = oracle.particle_update(oh, osi, odet, lam[f, :k], np.column_stack([ou, ov]),
+                                                                of, 0.05, prob[f, :k])
+        assert out["left"][f] == oleft and (out["keep"][f, :k] == okeep).all(), f
+        np.testing.assert_allclose(out["prob"][f, :k], oprob, rtol=1e-13, atol=1e-300)
+        np.testing.assert_allclose(out["cumulative"][f, :k], ocum, rtol=1e-13, atol=1e-300)
+        np.testing.assert_allclose(out["mean_var"][f], omv, rtol=1e-12, atol=1e-15)
+    assert any_found
+    # argument checks
+    with pytest.raises(sl2.Sl2Error):
+        ctx.measure_partial_features(0, 0, patches, ypi, Pxy, Pyy, lam, 0.05, prob, K=np.array([Kmax + 1, 1, 1], np.int32))
+    ctx.close()
+
+
 def test_raw_template_variants_of_smoe_and_particles(oracle):
     """sl2_smoe_search_patch / sl2_measure_particles_patch: the template of a partially-initialised feature is not
     a map feature (the reference hands Feature::patch_ to the SMOE search, monoslam.cpp:1413).  Same results as
