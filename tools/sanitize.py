@@ -32,8 +32,23 @@ ctx.measure_particles(0, 0, 1, np.tile(sc.pix[1].astype(float), (K, 1)) + rng.no
 ctx.measure_particles(0, 0, -1, np.tile(sc.pix[1].astype(float), (K, 1)), pu, 1.0 / (pu[:, 0] * pu[:, 2] - pu[:, 1] ** 2),
                       np.linspace(0.5, 4.5, K), 0.05, np.full(K, 1.0 / K), patch=sc.patches[2])
 ctx.smoe_search_patch(0, 0, sc.patches[3], pu[:4], np.tile(sc.pix[3].astype(float), (4, 1)))
+# all partially-initialised features of a stream in one call: particle prediction, score maps, re-weighting
+Fp, Kp = 3, 20
+ypi = np.zeros((Fp, 6))
+ypi[:, 3:] = [[0.1, 0.05, 1.0], [-0.2, 0.1, 1.0], [0.05, -0.15, 1.0]]
+ypi[:, 3:] /= np.linalg.norm(ypi[:, 3:], axis=1)[:, None]
+Ap = rng.normal(0, 1, (Fp, 19, 19))
+Pp = Ap @ Ap.transpose(0, 2, 1) * 2e-6
+ctx.measure_partial_features(0, 0, sc.patches[:Fp], ypi, Pp[:, :13, 13:], Pp[:, 13:, 13:],
+                             np.tile(np.linspace(0.5, 5, Kp), (Fp, 1)), 0.05, np.full((Fp, Kp), 1.0 / Kp),
+                             K=np.array([Kp, Kp - 3, 1], np.int32))
 ctx.delete_feature(1, 5)
 ctx.ekf_predict(0); ctx.predict_measurements(0); ctx.make_measurements(0, 0); ctx.ekf_update_measured(0)
+# staged update with caller-supplied rows (13 dense columns of H: the other instantiation of upd_hp)
+ms = 6
+nf0 = ctx.num_features(0)
+ctx.ekf_update(0, np.array([0, 2, 4], np.int32), rng.normal(0, 1, (ms, 13)), rng.normal(0, 1, (ms, 3)),
+               np.tile(np.eye(2) * 4.0, (ms // 2, 1, 1)), rng.normal(0, 0.1, ms))
 sc3 = synth.make_scene("C3", n_frames=1, n_features=9)
 c3 = ctx_from_scenes([sc3])
 c3.set_frames(0, sc3.frames[:1]); c3.step(0); c3.sync()
