@@ -397,8 +397,14 @@ __global__ void __launch_bounds__(HP_THREADS, 2) upd_hp_kernel(
 //     items 2..         trailing columns of panel p in batches of CH_GB 8-column groups (B fragments from L2,
 //                       software pipelined CH_D k-steps deep)
 //   finish (all warps)  U_panel = W * C_panel -> G; the 16 columns that are panel p+1's multipliers -> mult_next
-constexpr int CH_GB = 4;   // 8-column groups per batch item
-constexpr int CH_D = 4;    // k-steps of B fragments in flight per warp
+#ifndef SL2_CH_GB
+#define SL2_CH_GB 4
+#endif
+#ifndef SL2_CH_D
+#define SL2_CH_D 4
+#endif
+constexpr int CH_GB = SL2_CH_GB;   // 8-column groups per batch item
+constexpr int CH_D = SL2_CH_D;     // k-steps of B fragments in flight per warp
 constexpr int CH_DPS = 18; // row stride of the pre-updated diagonal block
 
 struct CholSmem {
