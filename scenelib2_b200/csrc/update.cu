@@ -394,18 +394,79 @@ __global__ void __launch_bounds__(HP_THREADS, 2) upd_hp_kernel(
 //                       contribution of panel p-1's 16 rows (multipliers already in shared memory), then factor it
 //     item 1            look-ahead for panel p+1: its diagonal block minus the contributions of all rows < i0
 //                       (final), into dpre_next; the multipliers it reads on the way go to mult_next
-//     items 2..         trailing columns of panel p in batches of CH_GB 8-column groups (B fragments from L2,
-//                       software pipelined CH_D k-steps deep)
+//     items 2..         trailing columns of panel p in batches of 4 / 2 / 1 8-column groups (B fragments from L2,
+//                       software pipelined 4 / 8 / 16 k-steps deep: the fewer groups are left, the narrower and deeper)
 //   finish (all warps)  U_panel = W * C_panel -> G; the 16 columns that are panel p+1's multipliers -> mult_next
-#ifndef SL2_CH_GB
-#define SL2_CH_GB 4
-#endif
-#ifndef SL2_CH_D
-#define SL2_CH_D 4
-#endif
-constexpr int CH_GB = SL2_CH_GB;   // 8-column groups per batch item
-constexpr int CH_D = SL2_CH_D;     // k-steps of B fragments in flight per warp
+constexpr int CH_D = 4;    // k-steps in flight of the look-ahead item (2 loads per step)
 constexpr int CH_DPS = 18; // row stride of the pre-updated diagonal block
+
+// One batch item of the panel update: GB 8-column groups from group g0 on, C(16 x 8 GB) = S entries - A * B over the
+// nk finished k-steps (nk is a multiple of 4); A(r,k) = U(k,i0+r) (negated multipliers, shared memory), B = finished
+// rows of U (global / L2), D (4 or 8) k-steps of B fragments in flight.  The result goes to the panel buffer.
+// The k loop is kept to a pointer bump, GB loads, 2 shared loads and 2 GB DMMAs per step: columns past the width are
+// loaded like any other (they are columns of H P in the same row: valid memory, finite, and they only reach entries
+// of C that are never used), so there is no per-element predicate or index arithmetic in it.
+template <int GB, int D>
+__device__ __forceinline__ void chol_batch(const double *__restrict__ G, int ldg, const double *__restrict__ mcur,
+                                           double *__restrict__ pan, int PW, int i0, int nbp, int nk, int ngroups,
+                                           int width, int g0, int lr, int lc) {
+  static_assert(D == 4 || D == 8, "nk is a multiple of 4");
+  double c[GB][2][2];
+#pragma unroll
+  for (int q = 0; q < GB; ++q) {
+    const int cc = i0 + (g0 + q) * 8 + 2 * lc;  // C fragment: rows lr / lr+8, columns cc, cc+1
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int r = mt * 8 + lr;
+      const bool rv = r < nbp && (g0 + q) < ngroups;
+      c[q][mt][0] = (rv && cc < width) ? G[(size_t)(i0 + r) * ldg + cc] : 0.0;
+      c[q][mt][1] = (rv && cc + 1 < width) ? G[(size_t)(i0 + r) * ldg + cc + 1] : 0.0;
+    }
+  }
+  // B fragment of k-step st, group q: G[(4 st + lc) * ldg + i0 + 8 (g0 + q) + lr]
+  const size_t kstride = (size_t)4 * ldg;
+  const double *gpre = G + (size_t)lc * ldg + i0 + g0 * 8 + lr;  // next k-step to request
+  const double *ap = mcur + lc * UPD_MS + lr;                    // A fragments of the next k-step to use
+  double b[D][GB];
+  auto loadb = [&](double *dst) {
+#pragma unroll
+    for (int q = 0; q < GB; ++q) dst[q] = gpre[8 * q];
+    gpre += kstride;
+  };
+  auto step = [&](const double *bu) {
+    const double a0 = ap[0], a1 = ap[8];
+    ap += 4 * UPD_MS;
+#pragma unroll
+    for (int q = 0; q < GB; ++q) {
+      dmma884(c[q][0][0], c[q][0][1], a0, bu[q]);
+      dmma884(c[q][1][0], c[q][1][1], a1, bu[q]);
+    }
+  };
+#pragma unroll
+  for (int u = 0; u < D - 1; ++u)
+    if (u < nk) loadb(b[u]);
+  int kb = 0;
+  for (; kb + D <= nk; kb += D) {
+#pragma unroll
+    for (int u = 0; u < D; ++u) {
+      if (kb + u + D - 1 < nk) loadb(b[(u + D - 1) % D]);  // warp-uniform
+      step(b[u]);
+    }
+  }
+  if (D == 8 && kb < nk) {  // four steps left, their fragments are in flight or landed
+#pragma unroll
+    for (int u = 0; u < 4; ++u) step(b[u]);
+  }
+#pragma unroll
+  for (int q = 0; q < GB; ++q) {
+    if (g0 + q < ngroups) {
+      const int pc = (g0 + q) * 8 + 2 * lc;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+        *reinterpret_cast<double2 *>(pan + (size_t)(mt * 8 + lr) * PW + pc) = make_double2(c[q][mt][0], c[q][mt][1]);
+    }
+  }
+}
 
 struct CholSmem {
   double *mult;     // 2 x [mmax][UPD_MS] (negated) multipliers of the current / next panel
@@ -464,7 +525,9 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) upd_chol_kernel(const Sl2Dev d
     const int nbn = n0 < m ? min(UPD_NB, m - n0) : 0;
     const int ngroups = (width - i0 + 7) >> 3;
     const int nk = i0 >> 2;  // k-steps of 4 finished rows; i0 is a multiple of 16
-    const int nbatch = ngroups > 2 ? (ngroups - 2 + CH_GB - 1) / CH_GB : 0;
+    // 8-column groups per batch item: about one item per warp (7 warps besides the one that factors)
+    const int gb = 4;
+    const int nbatch = ngroups > 2 ? (ngroups - 2 + gb - 1) / gb : 0;
     const int nitems = 2 + nbatch;
     bool first = true;
     for (;;) {
@@ -585,29 +648,40 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) upd_chol_kernel(const Sl2Dev d
             c[q][mt][1] = (r < nbn && n0 + cc + 1 < width) ? G[(size_t)(n0 + r) * ldg + n0 + cc + 1] : 0.0;
           }
         double v[CH_D][2];
-        auto loadv = [&](int st, double *dst) {  // negated multipliers U(k, n0 + r) of the next panel
-          const double *gk = G + (size_t)(4 * st + lc) * ldg + n0;
-          dst[0] = lr < nbn ? -gk[lr] : 0.0;
-          dst[1] = 8 + lr < nbn ? -gk[8 + lr] : 0.0;
+        const size_t kstride = (size_t)4 * ldg;
+        const double *gpre = G + (size_t)lc * ldg + n0 + lr;  // next k-step to request
+        double *mp = mnext + lc * UPD_MS + lr;               // where the multipliers of the next k-step to use go
+        const bool v0 = lr < nbn, v1 = 8 + lr < nbn;         // rows of the (ragged) next panel
+        auto loadv = [&](double *dst) {  // negated multipliers U(k, n0 + r) of the next panel
+          const double x0 = gpre[0], x1 = gpre[8];
+          dst[0] = v0 ? -x0 : 0.0;
+          dst[1] = v1 ? -x1 : 0.0;
+          gpre += kstride;
+        };
+        auto step = [&](const double *vu) {
+          const double a0 = vu[0], a1 = vu[1];
+          mp[0] = a0;
+          mp[8] = a1;
+          mp += 4 * UPD_MS;
+          dmma884(c[0][0][0], c[0][0][1], a0, -a0);
+          dmma884(c[0][1][0], c[0][1][1], a1, -a0);
+          dmma884(c[1][0][0], c[1][0][1], a0, -a1);
+          dmma884(c[1][1][0], c[1][1][1], a1, -a1);
         };
 #pragma unroll
         for (int u = 0; u < CH_D - 1; ++u)
-          if (u < nk) loadv(u, v[u]);
-        for (int kb = 0; kb < nk; kb += CH_D) {
+          if (u < nk) loadv(v[u]);
+        int kb = 0;
+        for (; kb + CH_D <= nk; kb += CH_D) {
 #pragma unroll
           for (int u = 0; u < CH_D; ++u) {
-            const int st = kb + u;
-            if (st < nk) {  // warp-uniform
-              if (st + CH_D - 1 < nk) loadv(st + CH_D - 1, v[(u + CH_D - 1) % CH_D]);
-              const double a0 = v[u][0], a1 = v[u][1];
-              mnext[(4 * st + lc) * UPD_MS + lr] = a0;
-              mnext[(4 * st + lc) * UPD_MS + 8 + lr] = a1;
-              dmma884(c[0][0][0], c[0][0][1], a0, -a0);
-              dmma884(c[0][1][0], c[0][1][1], a1, -a0);
-              dmma884(c[1][0][0], c[1][0][1], a0, -a1);
-              dmma884(c[1][1][0], c[1][1][1], a1, -a1);
-            }
+            if (kb + u + CH_D - 1 < nk) loadv(v[(u + CH_D - 1) % CH_D]);  // warp-uniform
+            step(v[u]);
           }
+        }
+        if (CH_D == 8 && kb < nk) {  // nk is a multiple of 4: four steps left
+#pragma unroll
+          for (int u = 0; u < 4; ++u) step(v[u]);
         }
 #pragma unroll
         for (int q = 0; q < 2; ++q)
@@ -617,58 +691,12 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) upd_chol_kernel(const Sl2Dev d
                 make_double2(c[q][mt][0], c[q][mt][1]);
       } else {
         // ---- trailing columns of this panel: C(16 x cols) - A(16 x i0) * B(i0 x cols) ---------------------
-        // A(r,k) = U(k,i0+r) (negated multipliers, shared memory), B = finished rows of U (global / L2)
-        const int g0 = 2 + (it - 2) * CH_GB;
-        double c[CH_GB][2][2];
-        int colb[CH_GB];  // column of the B fragment element of this lane (-1: none)
-#pragma unroll
-        for (int q = 0; q < CH_GB; ++q) {
-          const int cbase = i0 + (g0 + q) * 8;
-          colb[q] = (cbase + lr < width && g0 + q < ngroups) ? cbase + lr : -1;
-          const int cc = cbase + 2 * lc;  // C fragment: rows lr / lr+8, columns cc, cc+1
-#pragma unroll
-          for (int mt = 0; mt < 2; ++mt) {
-            const int r = mt * 8 + lr;
-            const bool rv = r < nbp && (g0 + q) < ngroups;
-            c[q][mt][0] = (rv && cc < width) ? G[(size_t)(i0 + r) * ldg + cc] : 0.0;
-            c[q][mt][1] = (rv && cc + 1 < width) ? G[(size_t)(i0 + r) * ldg + cc + 1] : 0.0;
-          }
-        }
-        double b[CH_D][CH_GB];
-        auto loadb = [&](int st, double *dst) {
-          const double *gk = G + (size_t)(4 * st + lc) * ldg;
-#pragma unroll
-          for (int q = 0; q < CH_GB; ++q) dst[q] = colb[q] >= 0 ? gk[colb[q]] : 0.0;
-        };
-#pragma unroll
-        for (int u = 0; u < CH_D - 1; ++u)
-          if (u < nk) loadb(u, b[u]);
-        for (int kb = 0; kb < nk; kb += CH_D) {
-#pragma unroll
-          for (int u = 0; u < CH_D; ++u) {
-            const int st = kb + u;
-            if (st < nk) {  // warp-uniform
-              if (st + CH_D - 1 < nk) loadb(st + CH_D - 1, b[(u + CH_D - 1) % CH_D]);
-              const double a0 = mcur[(4 * st + lc) * UPD_MS + lr];
-              const double a1 = mcur[(4 * st + lc) * UPD_MS + 8 + lr];
-#pragma unroll
-              for (int q = 0; q < CH_GB; ++q) {
-                dmma884(c[q][0][0], c[q][0][1], a0, b[u][q]);
-                dmma884(c[q][1][0], c[q][1][1], a1, b[u][q]);
-              }
-            }
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < CH_GB; ++q) {
-          if (g0 + q < ngroups) {
-            const int pc = (g0 + q) * 8 + 2 * lc;
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-              *reinterpret_cast<double2 *>(sm.pan + (size_t)(mt * 8 + lr) * PW + pc) =
-                  make_double2(c[q][mt][0], c[q][mt][1]);
-          }
-        }
+        // few column groups left (late panels): narrow items with a deep B pipeline, so that every warp has an
+        // item and an item's nk dependent k-steps do not each wait for L2
+        const int bt = it - 2;
+        if (gb == 4) chol_batch<4, 4>(G, ldg, mcur, sm.pan, PW, i0, nbp, nk, ngroups, width, 2 + bt * 4, lr, lc);
+        else if (gb == 2) chol_batch<2, 8>(G, ldg, mcur, sm.pan, PW, i0, nbp, nk, ngroups, width, 2 + bt * 2, lr, lc);
+        else chol_batch<1, 8>(G, ldg, mcur, sm.pan, PW, i0, nbp, nk, ngroups, width, 2 + bt, lr, lc);
       }
     }
     __syncthreads();
