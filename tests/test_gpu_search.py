@@ -310,6 +310,71 @@ def test_partial_features_batched_prediction_search_reweighting(oracle):
     ctx.close()
 
 
+def test_partial_features_at_the_limits_640x480_box15(oracle):
+    """sl2_measure_partial_features at its limits: SL2_MAX_PARTIAL = 16 features x SL2_MAX_PARTICLES = 256 particle
+    slots on a 640x480 frame with 15x15 templates, particle counts from 0 to 256, rays that leave the image (ellipse
+    boxes clipped at the border, ellipses with no valid location)."""
+    rng = np.random.default_rng(91)
+    img = synth.make_texture(rng, 480, 640)
+    B = 15
+    ctx = ctx_for_image(img, np.zeros((1, B, B), np.uint8))
+    cfg = ctx.cfg
+    cam8 = np.array([cfg.width, cfg.height, cfg.fku, cfg.fkv, cfg.u0, cfg.v0, cfg.kd1, cfg.sd], float)
+    xv = np.zeros(13)
+    xv[:3] = [0.12, 0.05, -0.02]
+    q = np.array([1.0, -0.02, 0.03, 0.01])
+    xv[3:7] = q / np.linalg.norm(q)
+    A = rng.normal(0, 1, (16, 16))
+    P = A @ A.T * 4e-6 + 1e-8 * np.eye(16)
+    ctx.set_state(0, np.concatenate([xv, [0.1, 0.1, 2.0]]), P)
+    F, Kmax = 16, 256
+    K = rng.integers(1, Kmax + 1, F).astype(np.int32)
+    K[0], K[1], K[2] = Kmax, 0, 1
+    ypi = np.zeros((F, 6))
+    Pxy = np.zeros((F, 13, 6))
+    Pyy = np.zeros((F, 6, 6))
+    lam = np.tile(np.linspace(0.3, 8.0, Kmax), (F, 1))
+    prob = np.zeros((F, Kmax))
+    patches = rng.integers(0, 256, (F, B, B), dtype=np.uint8)
+    for f in range(F):
+        # pixel the ray points at from the origin; some of them close to / beyond the image border
+        u, v = rng.uniform(-20, cfg.width + 20), rng.uniform(-20, cfg.height + 20)
+        hh = np.array([-(u - cfg.u0) / cfg.fku, -(v - cfg.v0) / cfg.fkv, 1.0])
+        ypi[f, 3:] = hh / np.linalg.norm(hh)
+        Af = rng.normal(0, 1, (19, 19))
+        Pf = Af @ Af.T * 4e-6 + 1e-8 * np.eye(19)
+        Pxy[f], Pyy[f] = Pf[:13, 13:], Pf[13:, 13:]
+        if K[f]:
+            p0 = rng.uniform(0.2, 1.0, K[f])
+            prob[f, :K[f]] = p0 / p0.sum()
+    for f in (0, 3, 7):   # a real template where the ray's middle particle lands, when that is inside the image
+        hm = oracle.predict_particles(cam8, xv, ypi[f], [lam[f, K[f] // 2]], P[:13, :13], Pxy[f], Pyy[f])[0][0]
+        cu, cv = int(round(hm[0])), int(round(hm[1]))
+        if 7 <= cu < cfg.width - 8 and 7 <= cv < cfg.height - 8:
+            patches[f] = img[cv - 7:cv + 8, cu - 7:cu + 8]
+    before = prob.copy()
+    out = ctx.measure_partial_features(0, 0, patches, ypi, Pxy, Pyy, lam, 0.05, prob, K=K)
+    assert out["left"][1] == 0 and (out["prob"][1] == 0).all()          # no particles: nothing to do
+    for f in range(F):
+        k = K[f]
+        if k == 0:
+            continue
+        oh, oS, osi, odet = oracle.predict_particles(cam8, xv, ypi[f], lam[f, :k], P[:13, :13], Pxy[f], Pyy[f])
+        assert out["h"][f, :k].tobytes() == oh.tobytes() and out["Sinv3"][f, :k].tobytes() == osi.tobytes(), f
+        if f % 3 == 0 or k < 40:   # the CPU side of the search is the slow part of this test
+            ou, ov, of, _ = oracle.smoe_search(img, patches[f], osi, oh)
+            assert (out["found"][f, :k] == of).all(), f
+            assert (out["z"][f, :k, 0] == ou).all() and (out["z"][f, :k, 1] == ov).all(), f
+            oleft, oprob, okeep, ocum, omv = oracle.particle_update(oh, osi, odet, lam[f, :k],
+                                                                    np.column_stack([ou, ov]), of, 0.05, before[f, :k])
+            assert out["left"][f] == oleft and (out["keep"][f, :k] == okeep).all(), f
+            np.testing.assert_allclose(out["prob"][f, :k], oprob, rtol=1e-13, atol=1e-300)
+    with pytest.raises(sl2.Sl2Error):   # one feature too many
+        ctx.measure_partial_features(0, 0, np.zeros((17, B, B), np.uint8), np.zeros((17, 6)), np.zeros((17, 13, 6)),
+                                     np.zeros((17, 6, 6)), np.ones((17, 4)), 0.05, np.ones((17, 4)))
+    ctx.close()
+
+
 def test_raw_template_variants_of_smoe_and_particles(oracle):
     """sl2_smoe_search_patch / sl2_measure_particles_patch: the template of a partially-initialised feature is not
     a map feature (the reference hands Feature::patch_ to the SMOE search, monoslam.cpp:1413).  Same results as
