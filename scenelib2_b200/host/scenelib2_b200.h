@@ -7,7 +7,8 @@
 // matrix_block_list_, h_/z_/S_/flags/counters) are refreshed before GoOneStep / the Kalman calls
 // return, because the reference's GUI reads them on every redraw (graphic/graphictool.cpp:130-168).
 // Also here: the file-based FrameGrabber / FileGrabber (framegrabber/*.h).
-// Out of scope: GUI, USB camera grabber, feature initialisation, particle prediction.
+// Out of scope: GUI, USB camera grabber, creation / conversion of partially-initialised features
+// (their per-frame cycle is one C-ABI call, sl2_measure_partial_features; the shim keeps the pending templates).
 #pragma once
 #include <atomic>
 #include <mutex>
@@ -127,7 +128,7 @@ class GraphicTool {
 
 // a feature the user (InitialiseFeature) or the detector (InitialiseAutoFeature) has asked for: template and
 // pixel are kept; turning it into a map feature needs the depth particles of the partially-initialised
-// machinery (monoslam.cpp:1262, feature_init_info.cpp), whose measurement step is sl2_measure_particles_patch
+// machinery (monoslam.cpp:1262, feature_init_info.cpp), whose per-frame cycle is sl2_measure_partial_features
 struct PendingFeature {
   cv::Mat patch;
   int u, v;
