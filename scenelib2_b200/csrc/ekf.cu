@@ -339,6 +339,7 @@ __device__ int visibility_test(const double *cam, const double *xp, const rd yi[
 __global__ void __launch_bounds__(128) predict_kernel(const Sl2Dev d, int stream_lo,
                                                       const double *u3, int do_predict,
                                                       int do_measure) {
+  pdl_prologue();
   const int s = stream_lo + blockIdx.x;
   const int tid = threadIdx.x;
   const int nf = d.nfeat[s];
@@ -503,6 +504,7 @@ __global__ void __launch_bounds__(128) predict_kernel(const Sl2Dev d, int stream
 // removes the rows/columns of the culled features from x and P in place.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) cull_kernel(const Sl2Dev d, int stream_lo, int force_index) {
+  pdl_prologue();
   const int s = stream_lo + blockIdx.x;
   const int tid = threadIdx.x;
   const int nf = d.nfeat[s];
@@ -674,13 +676,13 @@ cudaError_t sl2_launch_predict(const Sl2Dev &d, int stream_lo, int stream_cnt, c
   if (stream_cnt <= 0) return cudaSuccess;
   // 128 threads = one per feature (SL2_MAX_FEATURES); the kernel needs ~255 registers per thread,
   // so 128-thread CTAs are what lets two streams share an SM
-  predict_kernel<<<stream_cnt, 128, 0, st>>>(d, stream_lo, u3_dev, do_predict, do_measure);
-  return cudaGetLastError();
+  return sl2_launch_kernel(predict_kernel, dim3(stream_cnt), dim3(128), 0, st, d.tune[SL2_TUNE_PDL] != 0, d,
+                           stream_lo, u3_dev, do_predict, do_measure);
 }
 
 cudaError_t sl2_launch_cull(const Sl2Dev &d, int stream_lo, int stream_cnt, int force_index,
                             cudaStream_t st) {
   if (stream_cnt <= 0) return cudaSuccess;
-  cull_kernel<<<stream_cnt, 256, 0, st>>>(d, stream_lo, force_index);
-  return cudaGetLastError();
+  return sl2_launch_kernel(cull_kernel, dim3(stream_cnt), dim3(256), 0, st, d.tune[SL2_TUNE_PDL] != 0, d,
+                           stream_lo, force_index);
 }

@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(SL2_SEARCH_WARPS * 32, FILTER ? (BOX <= 11 ? 4
   constexpr int V = SL2_STRIP;
   constexpr uint32_t LASTMASK = (BOX % 4 == 0) ? 0xffffffffu : ((1u << (8 * (BOX % 4))) - 1u);
   extern __shared__ __align__(128) uint8_t smem[];
+  pdl_prologue();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int groups = (L.jobs_per_stream + SL2_SEARCH_WARPS - 1) / SL2_SEARCH_WARPS;
@@ -515,8 +516,8 @@ cudaError_t launch_t(const Sl2Dev &d, const CUtensorMap &tmap, const SearchLaunc
   const int groups = (L.jobs_per_stream + SL2_SEARCH_WARPS - 1) / SL2_SEARCH_WARPS;
   const int grid = groups * L.stream_cnt;
   if (grid <= 0) return cudaSuccess;
-  search_kernel<BOX, FILTER><<<grid, SL2_SEARCH_WARPS * 32, smem, st>>>(tmap, d, L, dump);
-  return cudaGetLastError();
+  return sl2_launch_kernel(search_kernel<BOX, FILTER>, dim3(grid), dim3(SL2_SEARCH_WARPS * 32), smem, st,
+                           d.tune[SL2_TUNE_PDL] != 0, tmap, d, L, dump);
 }
 
 cudaError_t launch_any(const Sl2Dev &d, const CUtensorMap &tmap, const SearchLaunch &L,

@@ -10,6 +10,14 @@
 #define SL2_STRIP 8         // candidates per vertical strip task
 #define SL2_MAX_FEAT_SMEM 128  // == SL2_MAX_FEATURES (include/sl2b200.h)
 
+// keys of sl2_set_tuning (include/sl2b200.h: SL2_TUNE_*)
+#define SL2_TUNE_SYRK_STAGGER_NS 0  // first-wave CTAs of upd_syrk on one SM start this far apart
+#define SL2_TUNE_HP_STAGGER_NS 1    // the second upd_hp CTA of an SM starts this much later
+#define SL2_TUNE_PDL 2              // programmatic dependent launch between the kernels of the fused step
+#define SL2_TUNE_HP_PIPELINED 3     // upd_hp: 8-row blocks, S phase of block b under the loads of block b+1
+#define SL2_TUNE_SYRK_EPILOGUE 4    // upd_syrk: 1 = the 16 old entries of P per thread in one round of loads
+#define SL2_TUNE_COUNT 8
+
 // Device view of one context: everything the kernels need, passed by value.
 struct Sl2Dev {
   // geometry / constants
@@ -58,6 +66,10 @@ struct Sl2Dev {
   // EKF update pipeline (update.cu): factor -> solve -> syrk -> finish
   int *upd_m;          // [B]  measurement rows m of the running update (0: nothing to do)
   double *Wp;          // [B][SL2_MAX_PANELS][16*16]  W_pp = U_pp^-T of every 16-row Cholesky panel
+  // scheduling knobs (sl2_set_tuning; they never change a result, only when / where the work runs)
+  int tune[SL2_TUNE_COUNT];
+  int nsm;             // SMs of the device
+  unsigned *sm_ctr;    // [SL2_TUNE_COUNT][256] per-SM arrival counters of the staggered kernels
 };
 
 #define SL2_MAX_PANELS 16  // 16-row panels of S: m <= 2 * SL2_MAX_FEATURES = 256
@@ -82,6 +94,56 @@ __device__ __forceinline__ rd operator*(rd a, rd b) { return rd(__dmul_rn(a.v, b
 __device__ __forceinline__ rd operator/(rd a, rd b) { return rd(__ddiv_rn(a.v, b.v)); }
 __device__ __forceinline__ rd operator-(rd a) { return rd(-a.v); }
 __device__ __forceinline__ rd rsqrt_(rd a) { return rd(__dsqrt_rn(a.v)); }
+
+// ---- programmatic dependent launch (PDL): a kernel launched with the attribute may be scheduled while its
+// predecessor in the stream drains; griddepcontrol.wait returns once the predecessor has completed and its
+// writes are visible (without the attribute both instructions do nothing).  Every kernel of the fused step
+// executes the pair FIRST, so completion is transitive along the chain of launches.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ unsigned long long sl2_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// Stagger the CTAs that start together on one SM: CTAs of one kernel that share an SM run in lockstep
+// (same length, same start), so their prologues / epilogues / barrier phases coincide and the pipe they are bound
+// by idles in those phases.  The k-th CTA to arrive on an SM (k < ways, first wave only) waits k * ns; later waves
+// inherit the offset because every CTA takes the same time.  `slot` selects a counter row.
+__device__ __forceinline__ void sl2_stagger(const Sl2Dev &d, int slot, int ns, int ways, unsigned linear_cta) {
+  if (ns <= 0 || linear_cta >= (unsigned)(ways * d.nsm)) return;  // uniform over the CTA
+  if (threadIdx.x == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    const unsigned k = atomicAdd(d.sm_ctr + slot * 256 + (smid & 255), 1u) % (unsigned)ways;
+    if (k) {
+      const unsigned long long t0 = sl2_globaltimer(), dt = (unsigned long long)k * (unsigned)ns;
+      while (sl2_globaltimer() - t0 < dt) __nanosleep(256);
+    }
+  }
+  __syncthreads();
+}
+
+#ifdef __CUDACC__
+// one launch path for every kernel of the step: plain launch, or with the PDL attribute
+template <typename... KArgs, typename... Args>
+inline cudaError_t sl2_launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     bool pdl, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
 
 // launchers (defined in search.cu / ekf.cu / update.cu), called from api.cu
 struct SearchLaunch {

@@ -199,22 +199,14 @@ __device__ __forceinline__ HpSmem hp_carve(uint8_t *base, int Nmax, int ld) {
   return u;
 }
 
-// KD = dense columns of H that can be nonzero (7: fused step, 13: staged)
-template <int KD>
-__global__ void __launch_bounds__(HP_THREADS, 2) upd_hp_kernel(
-    const Sl2Dev d, int stream_lo, int staged_m, const int *st_feat, const double *st_Hxv,
-    const double *st_Hy, const double *st_R, const double *st_nu) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  const int ld = d.ld, ldg = d.ldg;
-  const HpSmem sm = hp_carve(smem_raw, d.Nmax, ld);
-  const int s = stream_lo + blockIdx.y;
+// Measurement list in selected order (successful only, monoslam.cpp:556-571) and the H rows, R, nu of every
+// measurement into shared memory; returns K (measured features) or -1 when this CTA has no row block (rows_per_block
+// rows per block, block index blockIdx.x).  Every CTA of the stream pays this prologue.  All threads must call.
+__device__ __forceinline__ int hp_tables(const Sl2Dev &d, const HpSmem &sm, int s, int rows_per_block, int staged_m,
+                                         const int *st_feat, const double *st_Hxv, const double *st_Hy,
+                                         const double *st_R, const double *st_nu) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nf = d.nfeat[s];
-  const int n = SL2_NXV + 3 * nf;
-  const double *__restrict__ P = d.P + (size_t)s * ld * ld;
-  double *__restrict__ G = d.G + (size_t)s * d.mmax * ldg;
   const size_t fb = (size_t)s * d.Nmax;
-
   // ---- measurement list in selected order, successful only (monoslam.cpp:556-571) --------------
   int K;
   if (staged_m >= 0) {
@@ -243,7 +235,7 @@ __global__ void __launch_bounds__(HP_THREADS, 2) upd_hp_kernel(
     d.upd_m[s] = m;
     if (staged_m < 0) d.nmeas[s] = K;
   }
-  if (HP_ROWS * (int)blockIdx.x >= m) return;
+  if (rows_per_block * (int)blockIdx.x >= m) return -1;
   for (int e = tid; e < m * HP_HRS; e += HP_THREADS) sm.Hrow[e] = 0.0;
   __syncthreads();
   // ---- H rows, R, nu of every measurement (every CTA of the stream pays this prologue) -------------------
@@ -285,6 +277,29 @@ __global__ void __launch_bounds__(HP_THREADS, 2) upd_hp_kernel(
     }
   }
   __syncthreads();
+
+  return K;
+}
+
+// KD = dense columns of H that can be nonzero (7: fused step, 13: staged)
+template <int KD>
+__global__ void __launch_bounds__(HP_THREADS, 2) upd_hp_kernel(
+    const Sl2Dev d, int stream_lo, int staged_m, const int *st_feat, const double *st_Hxv,
+    const double *st_Hy, const double *st_R, const double *st_nu) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  pdl_prologue();
+  sl2_stagger(d, SL2_TUNE_HP_STAGGER_NS, d.tune[SL2_TUNE_HP_STAGGER_NS], 2, blockIdx.y * gridDim.x + blockIdx.x);
+  const int ld = d.ld, ldg = d.ldg;
+  const HpSmem sm = hp_carve(smem_raw, d.Nmax, ld);
+  const int s = stream_lo + blockIdx.y;
+  const int tid = threadIdx.x;
+  const int nf = d.nfeat[s];
+  const int n = SL2_NXV + 3 * nf;
+  const double *__restrict__ P = d.P + (size_t)s * ld * ld;
+  double *__restrict__ G = d.G + (size_t)s * d.mmax * ldg;
+  const int K = hp_tables(d, sm, s, HP_ROWS, staged_m, st_feat, st_Hxv, st_Hy, st_R, st_nu);
+  if (K < 0) return;
+  const int m = 2 * K;
 
   constexpr int FB = HP_ROWS / 2;            // features per block
   const int nch = (n + HP_THREADS - 1) / HP_THREADS;  // column chunks (1 up to 102 features)
@@ -375,6 +390,150 @@ __global__ void __launch_bounds__(HP_THREADS, 2) upd_hp_kernel(
       }
     }
     __syncthreads();  // hprow of this block is rewritten by the next one
+  }
+}
+
+// upd_hp, software-pipelined (SL2_TUNE_HP_PIPELINED; maps of up to (HP_THREADS - 13) / 3 features): the same
+// stream over P in 8-row blocks (4 features) with the shared-memory rows of H P double-buffered, so that
+//   loads of block b+1 issued  ->  S = (H P) H^T + R of block b from shared memory  ->  FMAs / stores of block b+1
+// and the structural row loads (the HBM stream) are in flight WHILE the S phase runs instead of after it; one
+// __syncthreads per block.  Same arithmetic in the same order as upd_hp_kernel (identical results); the dense
+// columns of the S phase are read as 16-byte pairs.
+template <int KD>
+__global__ void __launch_bounds__(HP_THREADS, 2) upd_hp2_kernel(
+    const Sl2Dev d, int stream_lo, int staged_m, const int *st_feat, const double *st_Hxv,
+    const double *st_Hy, const double *st_R, const double *st_nu) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  pdl_prologue();
+  sl2_stagger(d, SL2_TUNE_HP_STAGGER_NS, d.tune[SL2_TUNE_HP_STAGGER_NS], 2, blockIdx.y * gridDim.x + blockIdx.x);
+  constexpr int R2 = 8, F2 = 4;  // rows / features per block
+  const int ld = d.ld, ldg = d.ldg;
+  const HpSmem sm = hp_carve(smem_raw, d.Nmax, ld);
+  const int s = stream_lo + blockIdx.y;
+  const int tid = threadIdx.x;
+  const int n = SL2_NXV + 3 * d.nfeat[s];
+  const double *__restrict__ P = d.P + (size_t)s * ld * ld;
+  double *__restrict__ G = d.G + (size_t)s * d.mmax * ldg;
+  const int K = hp_tables(d, sm, s, R2, staged_m, st_feat, st_Hxv, st_Hy, st_R, st_nu);
+  if (K < 0) return;
+  const int m = 2 * K;
+  const int j = tid;  // this thread's state column (n <= HP_THREADS: the launcher's condition)
+  const bool jv = j < n;
+  // the KD leading rows of P for this thread's column: parked in shared memory (own slot per thread, no barrier
+  // needed) so that they do not occupy registers during the S phase, when the 12 structural loads are in flight
+  double *const pdcol = reinterpret_cast<double *>(sm.wcount + 16) + tid;
+#pragma unroll
+  for (int k = 0; k < KD; ++k) pdcol[k * HP_THREADS] = jv ? P[(size_t)k * ld + j] : 0.0;
+  double pv[F2][3];
+  auto issue = [&](int rb) {  // the structural rows of block rb: 12 loads in flight per thread
+    const int k0 = F2 * rb;
+#pragma unroll
+    for (int f = 0; f < F2; ++f) {
+      const int kk = k0 + f;
+      const int pos = SL2_NXV + 3 * sm.mfeat[kk < K ? kk : 0];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) pv[f][c] = (kk < K && jv) ? P[(size_t)(pos + c) * ld + j] : 0.0;
+    }
+  };
+  auto consume = [&](int rb, double *__restrict__ buf) {  // H P of block rb -> G and the shared rows
+    const int row0 = R2 * rb, k0 = F2 * rb;
+    double Pd[KD];
+#pragma unroll
+    for (int k = 0; k < KD; ++k) Pd[k] = pdcol[k * HP_THREADS];
+#pragma unroll
+    for (int f = 0; f < F2; ++f) {
+      if (k0 + f < K) {  // CTA-uniform
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int i = row0 + 2 * f + r;
+          const double2 *hr = reinterpret_cast<const double2 *>(sm.Hrow + (size_t)i * HP_HRS);
+          double acc = 0.0;
+#pragma unroll
+          for (int k2 = 0; k2 < (KD + 1) / 2; ++k2) {
+            const double2 hv = hr[k2];
+            acc += hv.x * Pd[2 * k2];
+            if (2 * k2 + 1 < KD) acc += hv.y * Pd[2 * k2 + 1];
+          }
+          const double2 hy0 = hr[6], hy1 = hr[7];  // columns 12..15: (dense 12 | dh/dy 0..2)
+          acc += hy0.y * pv[f][0];
+          acc += hy1.x * pv[f][1];
+          acc += hy1.y * pv[f][2];
+          if (jv) {
+            G[(size_t)i * ldg + m + j] = acc;
+            buf[(size_t)(2 * f + r) * ld + j] = acc;
+          }
+        }
+      }
+    }
+    const int rows = min(R2, m - row0);
+    if (tid < rows) G[(size_t)(row0 + tid) * ldg + m + n] = sm.nu[row0 + tid];
+  };
+  auto sphase = [&](int rb, const double *__restrict__ buf) {  // S rows of block rb, columns from the row's feature on
+    const int row0 = R2 * rb, rows = min(R2, m - row0);
+    for (int ip = tid; ip < m; ip += HP_THREADS) {
+      if (ip < row0) continue;
+      const int kp = ip >> 1, rp = ip & 1;
+      const double2 *hr = reinterpret_cast<const double2 *>(sm.Hrow + (size_t)ip * HP_HRS);
+      double hd[KD + 1];
+#pragma unroll
+      for (int k2 = 0; k2 < (KD + 1) / 2; ++k2) {
+        const double2 hv = hr[k2];
+        hd[2 * k2] = hv.x;
+        hd[2 * k2 + 1] = hv.y;
+      }
+      const double2 hy0 = hr[6], hy1 = hr[7];
+      const double hys[3] = {hy0.y, hy1.x, hy1.y};
+      const int pos = SL2_NXV + 3 * sm.mfeat[kp];
+      const double r_same = sm.Rv[kp * 3 + 2 * rp], r_cross = sm.Rv[kp * 3 + 1];
+#pragma unroll
+      for (int il0 = 0; il0 < R2; il0 += 4) {
+        if (il0 < rows) {
+          double acc[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[q] = 0.0;
+#pragma unroll
+          for (int c2 = 0; c2 < KD / 2; ++c2)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const double2 v = *reinterpret_cast<const double2 *>(buf + (size_t)(il0 + q) * ld + 2 * c2);
+              acc[q] += v.x * hd[2 * c2];
+              acc[q] += v.y * hd[2 * c2 + 1];
+            }
+          if (KD & 1) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] += buf[(size_t)(il0 + q) * ld + KD - 1] * hd[KD - 1];
+          }
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] += buf[(size_t)(il0 + q) * ld + pos + c] * hys[c];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int i = row0 + il0 + q;
+            if (il0 + q < rows && ip >= (i & ~1)) {
+              if ((i >> 1) == kp) acc[q] += (i == ip) ? r_same : r_cross;
+              G[(size_t)i * ldg + ip] = acc[q];
+            }
+          }
+        }
+      }
+    }
+  };
+  int rb = blockIdx.x, par = 0;
+  double *const buf0 = sm.hprow, *const buf1 = sm.hprow + (size_t)R2 * ld;
+  issue(rb);
+  consume(rb, buf0);
+  __syncthreads();
+  for (;;) {
+    const int nb = rb + gridDim.x;
+    const bool more = R2 * nb < m;  // CTA-uniform
+    if (more) issue(nb);
+    sphase(rb, par ? buf1 : buf0);
+    if (!more) break;
+    consume(nb, par ? buf0 : buf1);
+    __syncthreads();  // block nb's rows are complete, and nobody still reads the buffer block nb + 1 will take
+    rb = nb;
+    par ^= 1;
   }
 }
 
@@ -497,6 +656,7 @@ __device__ __forceinline__ CholSmem chol_carve(uint8_t *base, int Nmax) {
 
 __global__ void __launch_bounds__(UPD_THREADS, 2) upd_chol_kernel(const Sl2Dev d, int stream_lo) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
+  pdl_prologue();
   const CholSmem sm = chol_carve(smem_raw, d.Nmax);
   const int s = stream_lo + blockIdx.x;
   const int tid = threadIdx.x;
@@ -817,6 +977,7 @@ template <int NP>
 __global__ void __launch_bounds__(64 * SOLVE_MAX_WARPS, 1) upd_solve_kernel(const Sl2Dev d, int stream_lo) {
   using L = SolveLayout<NP>;
   extern __shared__ __align__(16) uint8_t smem_raw[];
+  pdl_prologue();
   double *pan = reinterpret_cast<double *>(smem_raw);  // panel p at L::off(p): [16][L::pw(p)]  U(16p + r, 16p + 16 + c)
   double *Wm = pan + L::PAN_DOUBLES;                   // [NP][16][UPD_WS]
   const uint32_t bars = smem_u32(Wm + NP * 16 * UPD_WS);  // [NP] mbarriers
@@ -989,11 +1150,14 @@ __global__ void __launch_bounds__(64 * SOLVE_MAX_WARPS, 1) upd_solve_kernel(cons
 // 0.264 ms) with 2 x 32-row and with 4 x 16-row stages alike; 4 x 16 and 3 x 16 LDGSTS stages: 0.268-0.270 ms.
 // Warp w owns rows 16*(w%4).. and columns 32*(w/4).. of the tile:
 //   acc[i][j][e] = T(16*(w%4) + 8*i + lane/4, 32*(w/4) + 8*j + 2*(lane%4) + e).
-template <int KC, int ST>
+// EPI16: the epilogue loads the warp's 16 entries of P per thread at once (one L2 round trip, a few spills at the
+// 80-register limit of three CTAs per SM) instead of 8 + 8.
+template <int KC, int ST, bool EPI16>
 __global__ void __launch_bounds__(UPD_THREADS, 3) upd_syrk_kernel(const Sl2Dev d, int stream_lo) {
   constexpr int STAGE = 2 * KC * UPD_YS;  // doubles per stage (A slab, B slab)
   extern __shared__ __align__(16) uint8_t smem_raw[];
   double *stage_buf = reinterpret_cast<double *>(smem_raw);
+  pdl_prologue();
   const int s = stream_lo + blockIdx.y;
   const int m = d.upd_m[s];
   if (m == 0) return;
@@ -1004,6 +1168,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 3) upd_syrk_kernel(const Sl2Dev d
   while ((tb + 1) * (tb + 2) / 2 <= t) ++tb;
   const int ta = t - tb * (tb + 1) / 2;
   if (tb * 64 >= n + 1) return;  // this stream's map is smaller than the capacity the grid was sized for
+  sl2_stagger(d, SL2_TUNE_SYRK_STAGGER_NS, d.tune[SL2_TUNE_SYRK_STAGGER_NS], 3, blockIdx.y * gridDim.x + blockIdx.x);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
   const int wa = (warp & 3) * 16, wb = (warp >> 2) * 32;
   const int ld = d.ld, ldg = d.ldg;
@@ -1081,21 +1246,30 @@ __global__ void __launch_bounds__(UPD_THREADS, 3) upd_syrk_kernel(const Sl2Dev d
     }
   }
   if (skip) return;
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
+  // the warp's 16 x 32 entries of P: the loads of a thread first (independent), then the subtraction and the stores
+  double pold[2][4][2];
+  auto load_old = [&](int i) {
     const int a = ta * 64 + wa + i * 8 + lr;
-    double pold[4][2];  // the loads of one row group first (independent), then the subtraction
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int bq = tb * 64 + wb + j * 8 + 2 * lc + e;
-        pold[j][e] = (a < n && bq < n) ? P[a + (size_t)ld * bq] : 0.0;
+        pold[i][j][e] = (a < n && bq < n) ? P[a + (size_t)ld * bq] : 0.0;
       }
+  };
+  if (EPI16) {
+    load_old(0);
+    load_old(1);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int a = ta * 64 + wa + i * 8 + lr;
+    if (!EPI16) load_old(i);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int bq = tb * 64 + wb + j * 8 + 2 * lc;
-      const double v0 = pold[j][0] - acc[i][j][0], v1 = pold[j][1] - acc[i][j][1];
+      const double v0 = pold[i][j][0] - acc[i][j][0], v1 = pold[i][j][1] - acc[i][j][1];
       if (a < n && bq < n) {
         P[a + (size_t)ld * bq] = v0;
         if (bq + 1 < n) P[a + (size_t)ld * (bq + 1)] = v1;
@@ -1119,6 +1293,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 3) upd_syrk_kernel(const Sl2Dev d
 // =============================================================================================
 __global__ void __launch_bounds__(UPD_THREADS) upd_finish_kernel(const Sl2Dev d, int stream_lo, int staged,
                                                                   int only_normalise) {
+  pdl_prologue();
   const int s = stream_lo + blockIdx.x;
   const int tid = threadIdx.x;
   const int nf = d.nfeat[s];
@@ -1230,6 +1405,9 @@ size_t sl2_update_smem_bytes(const Sl2Dev &d) {  // upd_chol
 static size_t hp_smem_bytes(const Sl2Dev &d) {
   return hp_smem_doubles(d.Nmax, d.ld) * sizeof(double) + (upd_keven(d.Nmax) + 16) * sizeof(int);
 }
+static size_t hp2_smem_bytes(const Sl2Dev &d, int kd) {  // + the parked leading rows of P: [kd][HP_THREADS]
+  return hp_smem_bytes(d) + (size_t)kd * HP_THREADS * sizeof(double);
+}
 
 cudaError_t sl2_configure_update(const Sl2Dev &d) {
   cudaError_t e = cudaFuncSetAttribute(upd_hp_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1237,10 +1415,16 @@ cudaError_t sl2_configure_update(const Sl2Dev &d) {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(upd_hp_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp_smem_bytes(d));
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(upd_hp2_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp2_smem_bytes(d, 7));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(upd_hp2_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp2_smem_bytes(d, 13));
+  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(upd_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)sl2_update_smem_bytes(d));
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(upd_syrk_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM);
+  e = cudaFuncSetAttribute(upd_syrk_kernel<32, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(upd_syrk_kernel<32, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM);
   if (e != cudaSuccess) return e;
   const int np = solve_np(d.Nmax);
   const int smem = (int)solve_smem(np);
@@ -1267,19 +1451,24 @@ cudaError_t sl2_launch_update(const Sl2Dev &d, int stream_lo, int stream_cnt, in
   // streams: 1 CTA per stream 0.156 ms, 2: 0.167, 7: 0.200 -- every CTA rebuilds the measurement list and H tables)
   const int hp_all = (2 * upd_keven(d.Nmax) + HP_ROWS - 1) / HP_ROWS;
   const int hp_blocks = stream_cnt >= 2 * 148 ? 1 : hp_all;
+  const bool pdl = d.tune[SL2_TUNE_PDL] != 0;
   if (!only_normalise) {
     const dim3 grid(hp_blocks, stream_cnt);
-    if (staged_m >= 0)
-      upd_hp_kernel<13><<<grid, HP_THREADS, hp_smem_bytes(d), st>>>(d, stream_lo, staged_m, st_feat, st_Hxv, st_Hy,
-                                                                     st_R, st_nu);
-    else
-      upd_hp_kernel<7><<<grid, HP_THREADS, hp_smem_bytes(d), st>>>(d, stream_lo, staged_m, st_feat, st_Hxv, st_Hy,
-                                                                    st_R, st_nu);
+    // the software-pipelined form: one CTA per stream, one state column per thread
+    const bool piped = d.tune[SL2_TUNE_HP_PIPELINED] != 0 && hp_blocks == 1 && SL2_NXV + 3 * d.Nmax <= HP_THREADS;
+    auto *k13 = piped ? upd_hp2_kernel<13> : upd_hp_kernel<13>;
+    auto *k7 = piped ? upd_hp2_kernel<7> : upd_hp_kernel<7>;
+    const size_t smem = piped ? hp2_smem_bytes(d, staged_m >= 0 ? 13 : 7) : hp_smem_bytes(d);
+    e = sl2_launch_kernel(staged_m >= 0 ? k13 : k7, grid, dim3(HP_THREADS), smem, st, pdl, d, stream_lo, staged_m,
+                          st_feat, st_Hxv, st_Hy, st_R, st_nu);
+    if (e != cudaSuccess) return e;
     ++nl;
   }
   if ((e = mark(1)) != cudaSuccess) return e;
   if (!only_normalise) {
-    upd_chol_kernel<<<stream_cnt, UPD_THREADS, sl2_update_smem_bytes(d), st>>>(d, stream_lo);
+    e = sl2_launch_kernel(upd_chol_kernel, dim3(stream_cnt), dim3(UPD_THREADS), sl2_update_smem_bytes(d), st, pdl, d,
+                          stream_lo);
+    if (e != cudaSuccess) return e;
     ++nl;
   }
   if ((e = mark(2)) != cudaSuccess) return e;
@@ -1294,12 +1483,13 @@ cudaError_t sl2_launch_update(const Sl2Dev &d, int stream_lo, int stream_cnt, in
     if (walk) warps = SOLVE_MAX_WARPS;
     const dim3 grid(walk ? 1 : nslab, stream_cnt), block(64 * warps);
     switch (np) {
-      case 4: upd_solve_kernel<4><<<grid, block, smem, st>>>(d, stream_lo); break;
-      case 7: upd_solve_kernel<7><<<grid, block, smem, st>>>(d, stream_lo); break;
-      case 10: upd_solve_kernel<10><<<grid, block, smem, st>>>(d, stream_lo); break;
-      case 13: upd_solve_kernel<13><<<grid, block, smem, st>>>(d, stream_lo); break;
-      default: upd_solve_kernel<16><<<grid, block, smem, st>>>(d, stream_lo); break;
+      case 4: e = sl2_launch_kernel(upd_solve_kernel<4>, grid, block, smem, st, pdl, d, stream_lo); break;
+      case 7: e = sl2_launch_kernel(upd_solve_kernel<7>, grid, block, smem, st, pdl, d, stream_lo); break;
+      case 10: e = sl2_launch_kernel(upd_solve_kernel<10>, grid, block, smem, st, pdl, d, stream_lo); break;
+      case 13: e = sl2_launch_kernel(upd_solve_kernel<13>, grid, block, smem, st, pdl, d, stream_lo); break;
+      default: e = sl2_launch_kernel(upd_solve_kernel<16>, grid, block, smem, st, pdl, d, stream_lo); break;
     }
+    if (e != cudaSuccess) return e;
     ++nl;
   }
   if ((e = mark(3)) != cudaSuccess) return e;
@@ -1307,11 +1497,15 @@ cudaError_t sl2_launch_update(const Sl2Dev &d, int stream_lo, int stream_cnt, in
     // one 64x64 tile per CTA (measured: CTAs that walk several tiles with cross-tile prefetch were slower, 0.29-0.31
     // against 0.264 ms, because they cost the third resident CTA per SM)
     const int nt = (SL2_NXV + 3 * d.Nmax + 1 + 63) / 64;
-    upd_syrk_kernel<32, 2><<<dim3(nt * (nt + 1) / 2, stream_cnt), UPD_THREADS, SYRK_SMEM, st>>>(d, stream_lo);
+    e = sl2_launch_kernel(d.tune[SL2_TUNE_SYRK_EPILOGUE] ? upd_syrk_kernel<32, 2, true> : upd_syrk_kernel<32, 2, false>,
+                          dim3(nt * (nt + 1) / 2, stream_cnt), dim3(UPD_THREADS), SYRK_SMEM, st, pdl, d, stream_lo);
+    if (e != cudaSuccess) return e;
     ++nl;
   }
   if ((e = mark(4)) != cudaSuccess) return e;
-  upd_finish_kernel<<<stream_cnt, UPD_THREADS, 0, st>>>(d, stream_lo, staged_m >= 0, only_normalise);
+  e = sl2_launch_kernel(upd_finish_kernel, dim3(stream_cnt), dim3(UPD_THREADS), 0, st, pdl, d, stream_lo,
+                        (int)(staged_m >= 0), only_normalise);
+  if (e != cudaSuccess) return e;
   ++nl;
   if ((e = mark(5)) != cudaSuccess) return e;
   if (launches) *launches += nl;
