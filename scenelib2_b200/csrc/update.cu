@@ -964,7 +964,8 @@ template <int NP> struct SolveLayout {
   __host__ __device__ static constexpr int off(int p) { return p < SPLIT ? off_lin(0, p) : off_lin(SPLIT, p); }
   static constexpr int PAN_DOUBLES = off_lin(0, SPLIT < NP - 1 ? SPLIT : NP - 1);
   static constexpr int SMEM_DOUBLES = PAN_DOUBLES + NP * 16 * UPD_WS + NP + (NP & 1) +  // one mbarrier per panel
-                                      2 * SOLVE_MAX_WARPS * 2 * 32 * 2;     // C-tile exchange of the warp pairs
+                                      2 * SOLVE_MAX_WARPS * 2 * 32 * 2 +    // C-tile exchange of the warp pairs
+                                      SOLVE_MAX_WARPS * 128;                // Y_p exchange (DEDUP)
   static_assert(SPLIT == NP || off_lin(SPLIT, NP - 1) <= off_lin(0, REUSE), "second generation must fit");
 };
 
@@ -973,7 +974,11 @@ template <int NP> struct SolveLayout {
 // latency in front of every DMMA (measured: 8 warps x 228 registers ran the FP64 pipe at 40 %).  Per panel the
 // two warps swap their C tile through shared memory (one named barrier of 64 threads), both form Y_p = W_pp C_p
 // (8 DMMAs, 4 of them redundant), each stores and keeps its own M tile.
-template <int NP>
+//
+// DEDUP (SL2_TUNE_SOLVE_DEDUP): each warp of a pair forms only ITS M tile of Y_p (4 DMMAs instead of 8) and the pair
+// swaps the two tiles of Y_p through shared memory (one more 64-thread barrier, and the B fragments of Y_p are then
+// plain shared loads instead of 8 shuffles): 1/8 fewer DMMAs on a kernel that is bound by the DMMA pipe.
+template <int NP, bool DEDUP>
 __global__ void __launch_bounds__(64 * SOLVE_MAX_WARPS, 1) upd_solve_kernel(const Sl2Dev d, int stream_lo) {
   using L = SolveLayout<NP>;
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -982,6 +987,7 @@ __global__ void __launch_bounds__(64 * SOLVE_MAX_WARPS, 1) upd_solve_kernel(cons
   double *Wm = pan + L::PAN_DOUBLES;                   // [NP][16][UPD_WS]
   const uint32_t bars = smem_u32(Wm + NP * 16 * UPD_WS);  // [NP] mbarriers
   double2 *xbuf = reinterpret_cast<double2 *>(Wm + NP * 16 * UPD_WS + NP + (NP & 1));  // [2][groups][2][32]
+  double *ybuf = reinterpret_cast<double *>(xbuf + 2 * SOLVE_MAX_WARPS * 2 * 32);       // [groups][16][8]  Y_p (DEDUP)
   const int s = stream_lo + blockIdx.y;
   const int m = d.upd_m[s];
   if (m == 0) return;
@@ -1102,26 +1108,45 @@ __global__ void __launch_bounds__(64 * SOLVE_MAX_WARPS, 1) upd_solve_kernel(cons
       double cb[4];
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) cb[ks] = c_to_b(cp2, ks, lane);
-      double dd[2][2];
-      dd[0][0] = dd[0][1] = dd[1][0] = dd[1][1] = 0.0;
+      double yb[4];
+      if (DEDUP) {
+        // this warp's M tile only: rows 8 rho .. 8 rho + 7 of Y_p
+        double d0 = 0.0, d1 = 0.0;
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        dmma884(dd[0][0], dd[0][1], wb[lr * UPD_WS + 4 * ks + lc], cb[ks]);
-        dmma884(dd[1][0], dd[1][1], wb[(8 + lr) * UPD_WS + 4 * ks + lc], cb[ks]);
-      }
-      // this warp's finished M tile: 16-byte stores from the C fragments
-      {
+        for (int ks = 0; ks < 4; ++ks) dmma884(d0, d1, wb[(8 * rho + lr) * UPD_WS + 4 * ks + lc], cb[ks]);
         const int row = 16 * p + 8 * rho + lr;
-        const double v0 = rho ? dd[1][0] : dd[0][0], v1 = rho ? dd[1][1] : dd[0][1];
         if (row < m) {
-          if (cval >= 2) *reinterpret_cast<double2 *>(gcol + (size_t)row * ldg) = make_double2(v0, v1);
-          else if (cval == 1) gcol[(size_t)row * ldg] = v0;
+          if (cval >= 2) *reinterpret_cast<double2 *>(gcol + (size_t)row * ldg) = make_double2(d0, d1);
+          else if (cval == 1) gcol[(size_t)row * ldg] = d0;
         }
+        // both tiles through shared memory: row-major [16][8]; the B fragment of k-step ks is Y_p(4 ks + lc, lr).
+        // (No second buffer: the partner passes the C-tile barrier of the next panel only after these loads.)
+        double *yg = ybuf + (size_t)g * 128;
+        *reinterpret_cast<double2 *>(yg + (8 * rho + lr) * 8 + 2 * lc) = make_double2(d0, d1);
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + g) : "memory");
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) yb[ks] = -yg[(4 * ks + lc) * 8 + lr];
+      } else {
+        double dd[2][2];
+        dd[0][0] = dd[0][1] = dd[1][0] = dd[1][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          dmma884(dd[0][0], dd[0][1], wb[lr * UPD_WS + 4 * ks + lc], cb[ks]);
+          dmma884(dd[1][0], dd[1][1], wb[(8 + lr) * UPD_WS + 4 * ks + lc], cb[ks]);
+        }
+        // this warp's finished M tile: 16-byte stores from the C fragments
+        {
+          const int row = 16 * p + 8 * rho + lr;
+          const double v0 = rho ? dd[1][0] : dd[0][0], v1 = rho ? dd[1][1] : dd[0][1];
+          if (row < m) {
+            if (cval >= 2) *reinterpret_cast<double2 *>(gcol + (size_t)row * ldg) = make_double2(v0, v1);
+            else if (cval == 1) gcol[(size_t)row * ldg] = v0;
+          }
+        }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) yb[ks] = -c_to_b(dd, ks, lane);
       }
       // this warp's later row tiles: acc_j -= U(panel, tile j)^T Y_p
-      double yb[4];
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) yb[ks] = -c_to_b(dd, ks, lane);
       const double *pbr = pb + 8 * rho + lr;
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
@@ -1428,13 +1453,22 @@ cudaError_t sl2_configure_update(const Sl2Dev &d) {
   if (e != cudaSuccess) return e;
   const int np = solve_np(d.Nmax);
   const int smem = (int)solve_smem(np);
+#define SL2_SOLVE_ATTR(NPV)                                                                                        \
+  case NPV:                                                                                                        \
+    e = cudaFuncSetAttribute(upd_solve_kernel<NPV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);     \
+    if (e != cudaSuccess) return e;                                                                                \
+    return cudaFuncSetAttribute(upd_solve_kernel<NPV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   switch (np) {
-    case 4: return cudaFuncSetAttribute(upd_solve_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    case 7: return cudaFuncSetAttribute(upd_solve_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    case 10: return cudaFuncSetAttribute(upd_solve_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    case 13: return cudaFuncSetAttribute(upd_solve_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    default: return cudaFuncSetAttribute(upd_solve_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    SL2_SOLVE_ATTR(4)
+    SL2_SOLVE_ATTR(7)
+    SL2_SOLVE_ATTR(10)
+    SL2_SOLVE_ATTR(13)
+    default:
+      e = cudaFuncSetAttribute(upd_solve_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return e;
+      return cudaFuncSetAttribute(upd_solve_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   }
+#undef SL2_SOLVE_ATTR
 }
 
 // ev6 (optional): 6 events recorded around the 5 kernels (hp, chol, solve, syrk, finish)
@@ -1482,13 +1516,19 @@ cudaError_t sl2_launch_update(const Sl2Dev &d, int stream_lo, int stream_cnt, in
     const bool walk = np <= 13 && stream_cnt >= 148;  // measured at 296 streams: 0.219 ms against 0.270 ms
     if (walk) warps = SOLVE_MAX_WARPS;
     const dim3 grid(walk ? 1 : nslab, stream_cnt), block(64 * warps);
+    const bool dedup = d.tune[SL2_TUNE_SOLVE_DEDUP] != 0;
+#define SL2_SOLVE_LAUNCH(NPV)                                                                                   \
+  e = dedup ? sl2_launch_kernel(upd_solve_kernel<NPV, true>, grid, block, smem, st, pdl, d, stream_lo)          \
+            : sl2_launch_kernel(upd_solve_kernel<NPV, false>, grid, block, smem, st, pdl, d, stream_lo);        \
+  break;
     switch (np) {
-      case 4: e = sl2_launch_kernel(upd_solve_kernel<4>, grid, block, smem, st, pdl, d, stream_lo); break;
-      case 7: e = sl2_launch_kernel(upd_solve_kernel<7>, grid, block, smem, st, pdl, d, stream_lo); break;
-      case 10: e = sl2_launch_kernel(upd_solve_kernel<10>, grid, block, smem, st, pdl, d, stream_lo); break;
-      case 13: e = sl2_launch_kernel(upd_solve_kernel<13>, grid, block, smem, st, pdl, d, stream_lo); break;
-      default: e = sl2_launch_kernel(upd_solve_kernel<16>, grid, block, smem, st, pdl, d, stream_lo); break;
+      case 4: SL2_SOLVE_LAUNCH(4)
+      case 7: SL2_SOLVE_LAUNCH(7)
+      case 10: SL2_SOLVE_LAUNCH(10)
+      case 13: SL2_SOLVE_LAUNCH(13)
+      default: SL2_SOLVE_LAUNCH(16)
     }
+#undef SL2_SOLVE_LAUNCH
     if (e != cudaSuccess) return e;
     ++nl;
   }
