@@ -61,7 +61,6 @@ static void tune_defaults(Sl2Dev &d) {
   d.tune[SL2_TUNE_PDL] = 0;
   d.tune[SL2_TUNE_HP_PIPELINED] = 0;
   d.tune[SL2_TUNE_SYRK_EPILOGUE] = 0;
-  d.tune[SL2_TUNE_SOLVE_DEDUP] = 1;  // solve 0.213 -> 0.195 ms
   const char *e = getenv("SL2_TUNE");
   while (e && *e) {
     char *end = nullptr;

@@ -32,6 +32,8 @@
 // read once by upd_solve (registers), Y is written once and read by the tiles of the same stream, which run at the
 // same time on neighbouring SMs (L2 hits).  The dense O(n^2 m) parts use ordinary FP64 FMAs / DMMA (tolerance
 // 1e-5 relative, north star); nothing in this file decides which pixels are searched.
+#include <type_traits>
+
 #include "sl2_common.cuh"
 
 namespace {
@@ -965,20 +967,23 @@ template <int NP> struct SolveLayout {
   static constexpr int PAN_DOUBLES = off_lin(0, SPLIT < NP - 1 ? SPLIT : NP - 1);
   static constexpr int SMEM_DOUBLES = PAN_DOUBLES + NP * 16 * UPD_WS + NP + (NP & 1) +  // one mbarrier per panel
                                       2 * SOLVE_MAX_WARPS * 2 * 32 * 2 +    // C-tile exchange of the warp pairs
-                                      SOLVE_MAX_WARPS * 128;                // Y_p exchange (DEDUP)
+                                      SOLVE_MAX_WARPS * 128;                // Y_p exchange
   static_assert(SPLIT == NP || off_lin(SPLIT, NP - 1) <= off_lin(0, REUSE), "second generation must fit");
 };
 
 // Two warps share a group of 8 columns: warp (g, rho) owns the row tiles j = 2t + rho, so a thread keeps NP
 // tiles (not 2 NP) and 16 warps fit one SM -- 4 per scheduler instead of 2, which is what hides the shared-memory
 // latency in front of every DMMA (measured: 8 warps x 228 registers ran the FP64 pipe at 40 %).  Per panel the
-// two warps swap their C tile through shared memory (one named barrier of 64 threads), both form Y_p = W_pp C_p
-// (8 DMMAs, 4 of them redundant), each stores and keeps its own M tile.
+// two warps swap their C tile through shared memory (one named barrier of 64 threads), each forms ITS M tile of
+// Y_p = W_pp C_p (4 DMMAs), stores it, and the pair swaps the two tiles of Y_p through shared memory as well (a second
+// 64-thread barrier; the B fragments of Y_p are then plain shared loads).  (Until the middle of round 2 both warps
+// formed all of Y_p -- 8 DMMAs, 4 of them redundant, fragments moved by 8 shuffles: 0.213 ms against 0.195 ms.)
 //
-// DEDUP (SL2_TUNE_SOLVE_DEDUP): each warp of a pair forms only ITS M tile of Y_p (4 DMMAs instead of 8) and the pair
-// swaps the two tiles of Y_p through shared memory (one more 64-thread barrier, and the B fragments of Y_p are then
-// plain shared loads instead of 8 shuffles): 1/8 fewer DMMAs on a kernel that is bound by the DMMA pipe.
-template <int NP, bool DEDUP>
+// FULL: when the measurement rows reach into the last panel the instantiation covers (m > 16 NP - 16: the benchmark
+// shapes), every row tile of every panel exists except possibly the very last one, whose staged columns are zero-filled
+// instead -- so the trailing update needs NO per-tile predicate.  (With the predicate the compiler wraps every DMMA
+// in @P WARPSYNC / NOP / ISETP and keeps the predicates in a spilled mask: ~6 instructions per DMMA.)
+template <int NP>
 __global__ void __launch_bounds__(64 * SOLVE_MAX_WARPS, 1) upd_solve_kernel(const Sl2Dev d, int stream_lo) {
   using L = SolveLayout<NP>;
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -987,7 +992,7 @@ __global__ void __launch_bounds__(64 * SOLVE_MAX_WARPS, 1) upd_solve_kernel(cons
   double *Wm = pan + L::PAN_DOUBLES;                   // [NP][16][UPD_WS]
   const uint32_t bars = smem_u32(Wm + NP * 16 * UPD_WS);  // [NP] mbarriers
   double2 *xbuf = reinterpret_cast<double2 *>(Wm + NP * 16 * UPD_WS + NP + (NP & 1));  // [2][groups][2][32]
-  double *ybuf = reinterpret_cast<double *>(xbuf + 2 * SOLVE_MAX_WARPS * 2 * 32);       // [groups][16][8]  Y_p (DEDUP)
+  double *ybuf = reinterpret_cast<double *>(xbuf + 2 * SOLVE_MAX_WARPS * 2 * 32);       // [groups][16][8]  Y_p
   const int s = stream_lo + blockIdx.y;
   const int m = d.upd_m[s];
   if (m == 0) return;
@@ -1002,19 +1007,21 @@ __global__ void __launch_bounds__(64 * SOLVE_MAX_WARPS, 1) upd_solve_kernel(cons
   double *__restrict__ G = d.G + (size_t)s * d.mmax * ldg;
   const double *__restrict__ Wp = d.Wp + (size_t)s * SL2_MAX_PANELS * 256;
   const int m8 = (m + 7) & ~7;
+  const bool full = L::SPLIT == NP && m8 >= 16 * NP - 8;  // uniform over the CTA
+  const int zend = full ? 16 * NP : m8;
 
   if (tid == 0) {
     for (int p = 0; p < NP; ++p) mbar_init(bars + 8 * p, 1);
     fence_barrier_init();
     fence_proxy_async();
   }
-  // the columns m .. m8-1 of a staged panel are read (rows of the last tile that do not exist) but not copied
+  // the columns m .. zend-1 of a staged panel are read (rows of the last tile(s) that do not exist) but not copied
   auto zero_pads = [&](int plo, int phi) {
     for (int e = tid; e < (phi - plo) * 16; e += nthr) {
       const int p = plo + (e >> 4), r = e & 15;
       const int cfirst = 16 * p + 16;
       if (16 * p < m)
-        for (int c = max(m, cfirst); c < m8; ++c) pan[L::off(p) + r * L::pw(p) + (c - cfirst)] = 0.0;
+        for (int c = max(m, cfirst); c < zend; ++c) pan[L::off(p) + r * L::pw(p) + (c - cfirst)] = 0.0;
     }
   };
   zero_pads(0, L::SPLIT);
@@ -1041,124 +1048,113 @@ __global__ void __launch_bounds__(64 * SOLVE_MAX_WARPS, 1) upd_solve_kernel(cons
     for (int p = 0; p < L::SPLIT; ++p) request(p);
   }
 
-  // The warp pair walks the column groups g, g + gridDim.x * ngrp, ...: with one CTA per stream (the batched
-  // launch) U is staged ONCE for all of the stream's columns and the pairs drift apart, so one pair's reload of
-  // its accumulators hides behind the other pairs' DMMAs; nothing below synchronises the CTA (NP <= 13).
   int xpar = 0;
-  for (int grp = blockIdx.x * ngrp + g; L::SPLIT < NP ? grp == (int)(blockIdx.x * ngrp + g) : 8 * grp < ncols;
-       grp += gridDim.x * ngrp) {
-  const int c0 = 8 * grp;        // first column of this warp pair
-  const bool wact = c0 < ncols;  // warp pairs past the last column have nothing to do
-  const int cc = c0 + 2 * lc;    // this lane's two columns (C layout)
-  const int cval = wact ? min(2, ncols - cc) : 0;  // how many of them exist (<= 0: none)
-  double *gcol = G + m + cc;
-  double acc[NP][2];  // tile j = 2 t + rho: rows 8 j + lr, columns cc, cc + 1
-  {  // the next group's tiles: towards L2 now (H P is larger than L2 at 296 streams; the registers are all taken)
-    const int ccn = cc + 8 * (int)(gridDim.x * ngrp);
-    if (L::SPLIT >= NP && ccn < ncols) {
+  // one group of 8 columns through all panels; FULL (compile time): no tile / panel predicates
+  auto solve_group = [&](auto full_c, const int grp) {
+    constexpr bool FULL = decltype(full_c)::value;
+    const int c0 = 8 * grp;        // first column of this warp pair
+    const bool wact = c0 < ncols;  // warp pairs past the last column have nothing to do
+    const int cc = c0 + 2 * lc;    // this lane's two columns (C layout)
+    const int cval = wact ? min(2, ncols - cc) : 0;  // how many of them exist (<= 0: none)
+    double *gcol = G + m + cc;
+    double acc[NP][2];  // tile j = 2 t + rho: rows 8 j + lr, columns cc, cc + 1
+    {  // the next group's tiles: towards L2 now (H P is larger than L2 at 296 streams; the registers are all taken)
+      const int ccn = cc + 8 * (int)(gridDim.x * ngrp);
+      if (L::SPLIT >= NP && ccn < ncols) {
 #pragma unroll
-      for (int t = 0; t < NP; ++t) {
-        const int row = 8 * (2 * t + rho) + lr;
-        if (row < m) asm volatile("prefetch.global.L2 [%0];" ::"l"(G + m + ccn + (size_t)row * ldg));
-      }
-    }
-  }
-#pragma unroll
-  for (int t = 0; t < NP; ++t) {
-    const int row = 8 * (2 * t + rho) + lr;
-    acc[t][0] = acc[t][1] = 0.0;
-    if (row < m) {
-      if (cval >= 2) {
-        const double2 v = *reinterpret_cast<const double2 *>(gcol + (size_t)row * ldg);
-        acc[t][0] = v.x;
-        acc[t][1] = v.y;
-      } else if (cval == 1) {
-        acc[t][0] = gcol[(size_t)row * ldg];
-      }
-    }
-  }
-
-#pragma unroll
-  for (int p = 0; p < NP; ++p) {
-    if (16 * p < m) {  // uniform over the CTA
-      if (L::SPLIT < NP && p == L::REUSE) {
-        __syncthreads();  // every warp is done with panels < REUSE: their space takes the second generation
-        zero_pads(L::SPLIT, NP);
-        __syncthreads();
-        if (warp == 0) {
-          fence_proxy_async();  // generic-proxy reads of the old panels are ordered before the bulk writes
-#pragma unroll 1
-          for (int q = L::SPLIT; q < NP; ++q) request(q);
+        for (int t = 0; t < NP; ++t) {
+          const int row = 8 * (2 * t + rho) + lr;
+          if (row < m) asm volatile("prefetch.global.L2 [%0];" ::"l"(G + m + ccn + (size_t)row * ldg));
         }
       }
-      if (!wact) continue;
-      // swap the C tiles of panel p with the partner warp
-      xpar ^= 1;  // alternates over every panel this pair executes (also across column groups)
-      double2 *xb = xbuf + ((size_t)(xpar * ngrp + g) * 2) * 32;
-      xb[rho * 32 + lane] = make_double2(acc[p][0], acc[p][1]);
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + g) : "memory");
-      const double2 other = xb[(rho ^ 1) * 32 + lane];
-      const double cp2[2][2] = {{rho ? other.x : acc[p][0], rho ? other.y : acc[p][1]},
-                                {rho ? acc[p][0] : other.x, rho ? acc[p][1] : other.y}};
-      mbar_wait(bars + 8 * p, 0);
-      const double *pb = pan + L::off(p);
-      const int PW = L::pw(p);
-      const double *wb = Wm + (size_t)p * 16 * UPD_WS;
-      // Y_p = W_pp * C_p
-      double cb[4];
+    }
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) cb[ks] = c_to_b(cp2, ks, lane);
-      double yb[4];
-      if (DEDUP) {
-        // this warp's M tile only: rows 8 rho .. 8 rho + 7 of Y_p
+    for (int t = 0; t < NP; ++t) {
+      const int row = 8 * (2 * t + rho) + lr;
+      acc[t][0] = acc[t][1] = 0.0;
+      if (row < m) {
+        if (cval >= 2) {
+          const double2 v = *reinterpret_cast<const double2 *>(gcol + (size_t)row * ldg);
+          acc[t][0] = v.x;
+          acc[t][1] = v.y;
+        } else if (cval == 1) {
+          acc[t][0] = gcol[(size_t)row * ldg];
+        }
+      }
+    }
+
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      if (FULL || 16 * p < m) {  // uniform over the CTA
+        if (L::SPLIT < NP && p == L::REUSE) {
+          __syncthreads();  // every warp is done with panels < REUSE: their space takes the second generation
+          zero_pads(L::SPLIT, NP);
+          __syncthreads();
+          if (warp == 0) {
+            fence_proxy_async();  // generic-proxy reads of the old panels are ordered before the bulk writes
+#pragma unroll 1
+            for (int q = L::SPLIT; q < NP; ++q) request(q);
+          }
+        }
+        if (!wact) continue;
+        // swap the C tiles of panel p with the partner warp
+        xpar ^= 1;  // alternates over every panel this pair executes (also across column groups)
+        double2 *xb = xbuf + ((size_t)(xpar * ngrp + g) * 2) * 32;
+        xb[rho * 32 + lane] = make_double2(acc[p][0], acc[p][1]);
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + g) : "memory");
+        const double2 other = xb[(rho ^ 1) * 32 + lane];
+        const double cp2[2][2] = {{rho ? other.x : acc[p][0], rho ? other.y : acc[p][1]},
+                                  {rho ? acc[p][0] : other.x, rho ? acc[p][1] : other.y}};
+        mbar_wait(bars + 8 * p, 0);
+        const double *pb = pan + L::off(p);
+        const int PW = L::pw(p);
+        const double *wb = Wm + (size_t)p * 16 * UPD_WS;
+        // this warp's M tile of Y_p = W_pp * C_p: rows 8 rho .. 8 rho + 7
+        double cb[4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) cb[ks] = c_to_b(cp2, ks, lane);
         double d0 = 0.0, d1 = 0.0;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) dmma884(d0, d1, wb[(8 * rho + lr) * UPD_WS + 4 * ks + lc], cb[ks]);
-        const int row = 16 * p + 8 * rho + lr;
-        if (row < m) {
-          if (cval >= 2) *reinterpret_cast<double2 *>(gcol + (size_t)row * ldg) = make_double2(d0, d1);
-          else if (cval == 1) gcol[(size_t)row * ldg] = d0;
-        }
-        // both tiles through shared memory: row-major [16][8]; the B fragment of k-step ks is Y_p(4 ks + lc, lr).
-        // (No second buffer: the partner passes the C-tile barrier of the next panel only after these loads.)
-        double *yg = ybuf + (size_t)g * 128;
-        *reinterpret_cast<double2 *>(yg + (8 * rho + lr) * 8 + 2 * lc) = make_double2(d0, d1);
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + g) : "memory");
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) yb[ks] = -yg[(4 * ks + lc) * 8 + lr];
-      } else {
-        double dd[2][2];
-        dd[0][0] = dd[0][1] = dd[1][0] = dd[1][1] = 0.0;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          dmma884(dd[0][0], dd[0][1], wb[lr * UPD_WS + 4 * ks + lc], cb[ks]);
-          dmma884(dd[1][0], dd[1][1], wb[(8 + lr) * UPD_WS + 4 * ks + lc], cb[ks]);
-        }
-        // this warp's finished M tile: 16-byte stores from the C fragments
-        {
+        {  // the finished rows: 16-byte stores from the C fragments
           const int row = 16 * p + 8 * rho + lr;
-          const double v0 = rho ? dd[1][0] : dd[0][0], v1 = rho ? dd[1][1] : dd[0][1];
           if (row < m) {
-            if (cval >= 2) *reinterpret_cast<double2 *>(gcol + (size_t)row * ldg) = make_double2(v0, v1);
-            else if (cval == 1) gcol[(size_t)row * ldg] = v0;
+            if (cval >= 2) *reinterpret_cast<double2 *>(gcol + (size_t)row * ldg) = make_double2(d0, d1);
+            else if (cval == 1) gcol[(size_t)row * ldg] = d0;
           }
         }
+        if (p + 1 < NP) {
+          // both tiles through shared memory, row-major [16][8]: the B fragment of k-step ks is Y_p(4 ks + lc, lr).
+          // (No second buffer: the partner passes the C-tile barrier of the next panel only after these loads.)
+          double *yg = ybuf + (size_t)g * 128;
+          *reinterpret_cast<double2 *>(yg + (8 * rho + lr) * 8 + 2 * lc) = make_double2(d0, d1);
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + g) : "memory");
+          double yb[4];
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) yb[ks] = -c_to_b(dd, ks, lane);
-      }
-      // this warp's later row tiles: acc_j -= U(panel, tile j)^T Y_p
-      const double *pbr = pb + 8 * rho + lr;
+          for (int ks = 0; ks < 4; ++ks) yb[ks] = -yg[(4 * ks + lc) * 8 + lr];
+          // this warp's later row tiles: acc_j -= U(panel, tile j)^T Y_p
+          const double *pbr = pb + 8 * rho + lr;
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
+          for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
-        for (int t = p + 1; t < NP; ++t) {
-          if (8 * (2 * t + rho) < m)  // warp-uniform; a tile past m is never touched (its columns are not staged)
-            dmma884(acc[t][0], acc[t][1], pbr[(4 * ks + lc) * PW + 16 * (t - p - 1)], yb[ks]);
+            for (int t = p + 1; t < NP; ++t) {
+              // warp-uniform; without FULL a tile past m8 is never touched (its columns are not staged)
+              if (FULL || 8 * (2 * t + rho) < m)
+                dmma884(acc[t][0], acc[t][1], pbr[(4 * ks + lc) * PW + 16 * (t - p - 1)], yb[ks]);
+            }
+          }
         }
       }
     }
+  };
+  // The warp pair walks the column groups g, g + gridDim.x * ngrp, ...: with one CTA per stream (the batched
+  // launch) U is staged ONCE for all of the stream's columns and the pairs drift apart, so one pair's reload of
+  // its accumulators hides behind the other pairs' DMMAs; nothing below synchronises the CTA (NP <= 13).
+  for (int grp = blockIdx.x * ngrp + g; L::SPLIT < NP ? grp == (int)(blockIdx.x * ngrp + g) : 8 * grp < ncols;
+       grp += gridDim.x * ngrp) {
+    if (L::SPLIT == NP && full) solve_group(std::true_type{}, grp);
+    else solve_group(std::false_type{}, grp);
   }
-  }  // column groups of this warp pair
 }
 
 // =============================================================================================
@@ -1218,18 +1214,41 @@ __global__ void __launch_bounds__(UPD_THREADS, 3) upd_syrk_kernel(const Sl2Dev d
   const int bytesB = cB + 1 < lim ? 16 : (cB < lim ? 8 : 0);
   const double *srcA = G + (bytesA ? cA : 0);
   const double *srcB = G + (bytesB ? cB : 0);
-  // stage loader: 2 slabs x KC rows x 64 columns; thread = (row warp + 8*j, 16-byte segment `lane`)
+  // stage loader: 2 slabs x KC rows x 64 columns; thread = (row warp + 8*j, 16-byte segment `lane`).  Chunks are
+  // staged in increasing order, so the source pointers just advance; a full chunk costs the copies, two pointer
+  // bumps and nothing else (the first version recomputed row / validity / offsets per copy: ~125 instructions per
+  // chunk and thread, as many as the DMMA loop of the chunk itself; ncu: 10 % of the kernel's warp samples).
+  const double *pa = srcA + (size_t)warp * ldg, *pb = srcB + (size_t)warp * ldg;  // row `warp` of the next chunk
+  const uint32_t sdst = smem_u32(stage_buf + 2 * lane + warp * UPD_YS);
+  const size_t rstep = (size_t)8 * ldg;
   auto stage = [&](int chunk) {
-    double *dst = stage_buf + (size_t)(chunk % ST) * STAGE + 2 * lane;
+    const uint32_t dd = sdst + (uint32_t)(chunk % ST) * (STAGE * 8);
+    if ((chunk + 1) * KC <= kr) {  // every row of the chunk exists (CTA-uniform)
 #pragma unroll
-    for (int j = 0; j < KC / 8; ++j) {
-      const int kk = warp + 8 * j;
-      const int k = chunk * KC + kk;
-      const bool kv = k < kr;
-      const size_t ro = (size_t)(kv ? k : 0) * ldg;
-      cp_async16(dst + kk * UPD_YS, srcA + ro, kv ? bytesA : 0);
-      if (!diag) cp_async16(dst + KC * UPD_YS + kk * UPD_YS, srcB + ro, kv ? bytesB : 0);
+      for (int j = 0; j < KC / 8; ++j) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dd + j * 8 * UPD_YS * 8),
+                     "l"(pa + j * rstep), "r"(bytesA)
+                     : "memory");
+        if (!diag)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dd + (KC + j * 8) * UPD_YS * 8),
+                       "l"(pb + j * rstep), "r"(bytesB)
+                       : "memory");
+      }
+    } else {  // the ragged last chunk: rows past kr are zero-filled
+#pragma unroll
+      for (int j = 0; j < KC / 8; ++j) {
+        const bool kv = chunk * KC + warp + 8 * j < kr;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dd + j * 8 * UPD_YS * 8),
+                     "l"(kv ? pa + j * rstep : srcA), "r"(kv ? bytesA : 0)
+                     : "memory");
+        if (!diag)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dd + (KC + j * 8) * UPD_YS * 8),
+                       "l"(kv ? pb + j * rstep : srcB), "r"(kv ? bytesB : 0)
+                       : "memory");
+      }
     }
+    pa += (size_t)KC * ldg;
+    pb += (size_t)KC * ldg;
   };
   double acc[2][4][2];
 #pragma unroll
@@ -1453,22 +1472,13 @@ cudaError_t sl2_configure_update(const Sl2Dev &d) {
   if (e != cudaSuccess) return e;
   const int np = solve_np(d.Nmax);
   const int smem = (int)solve_smem(np);
-#define SL2_SOLVE_ATTR(NPV)                                                                                        \
-  case NPV:                                                                                                        \
-    e = cudaFuncSetAttribute(upd_solve_kernel<NPV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);     \
-    if (e != cudaSuccess) return e;                                                                                \
-    return cudaFuncSetAttribute(upd_solve_kernel<NPV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   switch (np) {
-    SL2_SOLVE_ATTR(4)
-    SL2_SOLVE_ATTR(7)
-    SL2_SOLVE_ATTR(10)
-    SL2_SOLVE_ATTR(13)
-    default:
-      e = cudaFuncSetAttribute(upd_solve_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      if (e != cudaSuccess) return e;
-      return cudaFuncSetAttribute(upd_solve_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    case 4: return cudaFuncSetAttribute(upd_solve_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    case 7: return cudaFuncSetAttribute(upd_solve_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    case 10: return cudaFuncSetAttribute(upd_solve_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    case 13: return cudaFuncSetAttribute(upd_solve_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    default: return cudaFuncSetAttribute(upd_solve_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   }
-#undef SL2_SOLVE_ATTR
 }
 
 // ev6 (optional): 6 events recorded around the 5 kernels (hp, chol, solve, syrk, finish)
@@ -1516,19 +1526,13 @@ cudaError_t sl2_launch_update(const Sl2Dev &d, int stream_lo, int stream_cnt, in
     const bool walk = np <= 13 && stream_cnt >= 148;  // measured at 296 streams: 0.219 ms against 0.270 ms
     if (walk) warps = SOLVE_MAX_WARPS;
     const dim3 grid(walk ? 1 : nslab, stream_cnt), block(64 * warps);
-    const bool dedup = d.tune[SL2_TUNE_SOLVE_DEDUP] != 0;
-#define SL2_SOLVE_LAUNCH(NPV)                                                                                   \
-  e = dedup ? sl2_launch_kernel(upd_solve_kernel<NPV, true>, grid, block, smem, st, pdl, d, stream_lo)          \
-            : sl2_launch_kernel(upd_solve_kernel<NPV, false>, grid, block, smem, st, pdl, d, stream_lo);        \
-  break;
     switch (np) {
-      case 4: SL2_SOLVE_LAUNCH(4)
-      case 7: SL2_SOLVE_LAUNCH(7)
-      case 10: SL2_SOLVE_LAUNCH(10)
-      case 13: SL2_SOLVE_LAUNCH(13)
-      default: SL2_SOLVE_LAUNCH(16)
+      case 4: e = sl2_launch_kernel(upd_solve_kernel<4>, grid, block, smem, st, pdl, d, stream_lo); break;
+      case 7: e = sl2_launch_kernel(upd_solve_kernel<7>, grid, block, smem, st, pdl, d, stream_lo); break;
+      case 10: e = sl2_launch_kernel(upd_solve_kernel<10>, grid, block, smem, st, pdl, d, stream_lo); break;
+      case 13: e = sl2_launch_kernel(upd_solve_kernel<13>, grid, block, smem, st, pdl, d, stream_lo); break;
+      default: e = sl2_launch_kernel(upd_solve_kernel<16>, grid, block, smem, st, pdl, d, stream_lo); break;
     }
-#undef SL2_SOLVE_LAUNCH
     if (e != cudaSuccess) return e;
     ++nl;
   }

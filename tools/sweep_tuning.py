@@ -51,10 +51,9 @@ def main():
     log = open(args.out, "w")
 
     state = {"groups": 1, lib.TUNE_SYRK_STAGGER_NS: 0, lib.TUNE_HP_STAGGER_NS: 0, lib.TUNE_PDL: 0,
-             lib.TUNE_HP_PIPELINED: 0, lib.TUNE_SYRK_EPILOGUE: 0, lib.TUNE_SOLVE_DEDUP: 0}
+             lib.TUNE_HP_PIPELINED: 0, lib.TUNE_SYRK_EPILOGUE: 0}
     names = {"groups": "groups", lib.TUNE_SYRK_STAGGER_NS: "syrk_stagger_ns", lib.TUNE_HP_STAGGER_NS: "hp_stagger_ns",
-             lib.TUNE_PDL: "pdl", lib.TUNE_HP_PIPELINED: "hp_pipelined", lib.TUNE_SYRK_EPILOGUE: "syrk_epilogue16",
-             lib.TUNE_SOLVE_DEDUP: "solve_dedup"}
+             lib.TUNE_PDL: "pdl", lib.TUNE_HP_PIPELINED: "hp_pipelined", lib.TUNE_SYRK_EPILOGUE: "syrk_epilogue16"}
 
     def apply(st):
         ctx.set_step_groups(st["groups"])
@@ -101,10 +100,9 @@ def main():
 
     base = measure(dict(state), "baseline")
     sweeps = [(lib.TUNE_HP_PIPELINED, [1]),
-              (lib.TUNE_HP_STAGGER_NS, [1500, 3000, 5000]),
-              (lib.TUNE_SOLVE_DEDUP, [1]),
+              (lib.TUNE_HP_STAGGER_NS, [2000]),
               (lib.TUNE_SYRK_EPILOGUE, [1]),
-              (lib.TUNE_SYRK_STAGGER_NS, [3000, 6000, 9000, 13000]),
+              (lib.TUNE_SYRK_STAGGER_NS, [5000]),
               (lib.TUNE_PDL, [1]),
               ("groups", [2])]
     for key, values in sweeps:
