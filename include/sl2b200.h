@@ -232,18 +232,16 @@ int sl2_join(sl2_ctx *ctx);
  *   SL2_TUNE_SYRK_STAGGER_NS  the CTAs of the covariance-update tiles that start together on one SM start this
  *                             many ns apart, so their staging / write-back phases do not coincide (0 = off)
  *   SL2_TUNE_HP_STAGGER_NS    the same for the two H*P CTAs of an SM
- *   SL2_TUNE_PDL              1: the kernels of a step are launched with programmatic dependent launch
- *                             (the next kernel's CTAs are scheduled while the previous one drains)
+ *   SL2_TUNE_PDL              the kernels of a step are launched with programmatic dependent launch (the next
+ *                             kernel's CTAs are scheduled while the previous one drains): 0 never, 1 always,
+ *                             2 (default) for launches that cover only a few camera streams (latency bound)
  *   SL2_TUNE_HP_PIPELINED     1: H*P in 8-row blocks with S of block b formed under the loads of block b+1
- *   SL2_TUNE_SYRK_EPILOGUE    1: the covariance tiles read their old entries of P in one round of loads
- *   SL2_TUNE_SYRK_MIX         1 / 2: the covariance-update CTAs take runs of 1,2,1,2.. / 1,2,3,1,2,3.. tiles instead of
- *                             one tile each, so that CTAs sharing an SM do not run in lockstep */
+ *   SL2_TUNE_SYRK_EPILOGUE    1: the covariance tiles read their old entries of P in one round of loads */
 #define SL2_TUNE_SYRK_STAGGER_NS 0
 #define SL2_TUNE_HP_STAGGER_NS 1
 #define SL2_TUNE_PDL 2
 #define SL2_TUNE_HP_PIPELINED 3
 #define SL2_TUNE_SYRK_EPILOGUE 4
-#define SL2_TUNE_SYRK_MIX 5
 int sl2_set_tuning(sl2_ctx *ctx, int32_t key, int32_t value);
 
 /* ---- read-back of per-feature results (Feature::h_/z_/S_/flags/counters, feature.h:96-140) */

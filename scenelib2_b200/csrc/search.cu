@@ -517,7 +517,7 @@ cudaError_t launch_t(const Sl2Dev &d, const CUtensorMap &tmap, const SearchLaunc
   const int grid = groups * L.stream_cnt;
   if (grid <= 0) return cudaSuccess;
   return sl2_launch_kernel(search_kernel<BOX, FILTER>, dim3(grid), dim3(SL2_SEARCH_WARPS * 32), smem, st,
-                           d.tune[SL2_TUNE_PDL] != 0, tmap, d, L, dump);
+                           sl2_use_pdl(d, L.stream_cnt), tmap, d, L, dump);
 }
 
 cudaError_t launch_any(const Sl2Dev &d, const CUtensorMap &tmap, const SearchLaunch &L,

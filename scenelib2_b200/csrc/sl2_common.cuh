@@ -16,7 +16,6 @@
 #define SL2_TUNE_PDL 2              // programmatic dependent launch between the kernels of the fused step
 #define SL2_TUNE_HP_PIPELINED 3     // upd_hp: 8-row blocks, S phase of block b under the loads of block b+1
 #define SL2_TUNE_SYRK_EPILOGUE 4    // upd_syrk: 1 = the 16 old entries of P per thread in one round of loads
-#define SL2_TUNE_SYRK_MIX 5         // upd_syrk: CTAs of unequal length (runs of 1,2 / 1,2,3 tiles) instead of one tile each
 #define SL2_TUNE_COUNT 8
 
 // Device view of one context: everything the kernels need, passed by value.
@@ -125,6 +124,16 @@ __device__ __forceinline__ void sl2_stagger(const Sl2Dev &d, int slot, int ns, i
     }
   }
   __syncthreads();
+}
+
+// SL2_TUNE_PDL: 0 never, 1 always, 2 (default) when the launch covers fewer camera streams than
+// SL2_PDL_AUTO_STREAMS: the kernels of a small batch last a few microseconds each and the step is bound by the
+// launch-to-launch latency, which PDL hides; a batch that fills the GPU measured SLOWER with it (1.057 -> 1.115 ms at
+// C4 x 296 streams: profiles/r02_tuning_sweep.txt).
+#define SL2_PDL_AUTO_STREAMS 32
+inline bool sl2_use_pdl(const Sl2Dev &d, int stream_cnt) {
+  const int mode = d.tune[SL2_TUNE_PDL];
+  return mode == 1 || (mode == 2 && stream_cnt < SL2_PDL_AUTO_STREAMS);
 }
 
 #ifdef __CUDACC__

@@ -1171,28 +1171,6 @@ __global__ void __launch_bounds__(64 * SOLVE_MAX_WARPS, 1) upd_solve_kernel(cons
 // 0.264 ms) with 2 x 32-row and with 4 x 16-row stages alike; 4 x 16 and 3 x 16 LDGSTS stages: 0.268-0.270 ms.
 // Warp w owns rows 16*(w%4).. and columns 32*(w/4).. of the tile:
 //   acc[i][j][e] = T(16*(w%4) + 8*i + lane/4, 32*(w/4) + 8*j + 2*(lane%4) + e).
-// tiles [t0, t1) of CTA c: mix 0 -> one tile per CTA; 1 -> runs of 1, 2, 1, 2, ...; 2 -> 1, 2, 3, 1, 2, 3, ...
-__host__ __device__ inline void syrk_tile_range(int mix, int c, int &t0, int &t1) {
-  if (mix == 1) {
-    t0 = 3 * (c >> 1) + (c & 1);
-    t1 = t0 + 1 + (c & 1);
-  } else if (mix == 2) {
-    const int q = c / 3, r = c - 3 * q;
-    t0 = 6 * q + (r == 0 ? 0 : (r == 1 ? 1 : 3));
-    t1 = t0 + 1 + r;
-  } else {
-    t0 = c;
-    t1 = c + 1;
-  }
-}
-inline int syrk_ctas(int mix, int ntiles) {  // CTAs that cover ntiles
-  int c = 0, t0 = 0, t1 = 0;
-  for (;; ++c) {
-    syrk_tile_range(mix, c, t0, t1);
-    if (t0 >= ntiles) return c;
-  }
-}
-
 // EPI16: the epilogue loads the warp's 16 entries of P per thread at once (one L2 round trip, a few spills at the
 // 80-register limit of three CTAs per SM) instead of 8 + 8.
 template <int KC, int ST, bool EPI16>
@@ -1205,6 +1183,12 @@ __global__ void __launch_bounds__(UPD_THREADS, 3) upd_syrk_kernel(const Sl2Dev d
   const int m = d.upd_m[s];
   if (m == 0) return;
   const int n = SL2_NXV + 3 * d.nfeat[s];
+  // tiles in (tb outer, ta <= tb inner) order
+  int tb = 0;
+  const int t = blockIdx.x;
+  while ((tb + 1) * (tb + 2) / 2 <= t) ++tb;
+  const int ta = t - tb * (tb + 1) / 2;
+  if (tb * 64 >= n + 1) return;  // this stream's map is smaller than the capacity the grid was sized for
   sl2_stagger(d, SL2_TUNE_SYRK_STAGGER_NS, d.tune[SL2_TUNE_SYRK_STAGGER_NS], 3, blockIdx.y * gridDim.x + blockIdx.x);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
   const int wa = (warp & 3) * 16, wb = (warp >> 2) * 32;
@@ -1212,18 +1196,6 @@ __global__ void __launch_bounds__(UPD_THREADS, 3) upd_syrk_kernel(const Sl2Dev d
   double *__restrict__ P = d.P + (size_t)s * ld * ld;
   double *__restrict__ x = d.x + (size_t)s * ld;
   const double *__restrict__ G = d.G + (size_t)s * d.mmax * ldg;
-  // The tiles of this CTA (SL2_TUNE_SYRK_MIX): one, or a run of 1 / 2 (/ 3) consecutive tiles -- CTAs of unequal
-  // length.  CTAs of EQUAL length that share an SM share the DMMA pipe equally and therefore start and end together,
-  // wave after wave (a CTA that starts late catches up while its neighbours are in their prologue), so their
-  // prologues / epilogues coincide and the pipe idles there; unequal lengths keep them out of phase.
-  int t0, t1;
-  syrk_tile_range(d.tune[SL2_TUNE_SYRK_MIX], blockIdx.x, t0, t1);
-  auto do_tile = [&](const int t) {
-  // tiles in (tb outer, ta <= tb inner) order
-  int tb = 0;
-  while ((tb + 1) * (tb + 2) / 2 <= t) ++tb;
-  const int ta = t - tb * (tb + 1) / 2;
-  if (tb * 64 >= n + 1) return;  // this stream's map is smaller than the capacity the grid was sized for
   const bool diag = ta == tb;
   const bool skip = diag && wa >= wb + 32;      // sub-tile strictly below the diagonal: mirrored instead
   const bool mirror = !diag || wa + 16 <= wb;   // sub-tile strictly above the diagonal
@@ -1357,11 +1329,6 @@ __global__ void __launch_bounds__(UPD_THREADS, 3) upd_syrk_kernel(const Sl2Dev d
         if (bq + 1 == n) x[a] += acc[i][j][1];
       }
     }
-  }
-  };  // do_tile
-  for (int t = t0; t < t1; ++t) {
-    if (t > t0) __syncthreads();  // the stage ring is free: every warp has read the last chunk of the tile before
-    do_tile(t);
   }
 }
 
@@ -1528,7 +1495,7 @@ cudaError_t sl2_launch_update(const Sl2Dev &d, int stream_lo, int stream_cnt, in
   // streams: 1 CTA per stream 0.156 ms, 2: 0.167, 7: 0.200 -- every CTA rebuilds the measurement list and H tables)
   const int hp_all = (2 * upd_keven(d.Nmax) + HP_ROWS - 1) / HP_ROWS;
   const int hp_blocks = stream_cnt >= 2 * 148 ? 1 : hp_all;
-  const bool pdl = d.tune[SL2_TUNE_PDL] != 0;
+  const bool pdl = sl2_use_pdl(d, stream_cnt);
   if (!only_normalise) {
     const dim3 grid(hp_blocks, stream_cnt);
     // the software-pipelined form: one CTA per stream, one state column per thread
@@ -1574,14 +1541,8 @@ cudaError_t sl2_launch_update(const Sl2Dev &d, int stream_lo, int stream_cnt, in
     // one 64x64 tile per CTA (measured: CTAs that walk several tiles with cross-tile prefetch were slower, 0.29-0.31
     // against 0.264 ms, because they cost the third resident CTA per SM)
     const int nt = (SL2_NXV + 3 * d.Nmax + 1 + 63) / 64;
-    // a batch that fills the GPU may run CTAs of unequal length (see the kernel); tiles past the last one of the
-    // stream's own map return at once
-    const int mix = stream_cnt >= 148 ? d.tune[SL2_TUNE_SYRK_MIX] : 0;
-    Sl2Dev dk = d;
-    dk.tune[SL2_TUNE_SYRK_MIX] = mix;
     e = sl2_launch_kernel(d.tune[SL2_TUNE_SYRK_EPILOGUE] ? upd_syrk_kernel<32, 2, true> : upd_syrk_kernel<32, 2, false>,
-                          dim3(syrk_ctas(mix, nt * (nt + 1) / 2), stream_cnt), dim3(UPD_THREADS), SYRK_SMEM, st, pdl,
-                          dk, stream_lo);
+                          dim3(nt * (nt + 1) / 2, stream_cnt), dim3(UPD_THREADS), SYRK_SMEM, st, pdl, d, stream_lo);
     if (e != cudaSuccess) return e;
     ++nl;
   }

@@ -51,9 +51,9 @@ def main():
     log = open(args.out, "w")
 
     state = {"groups": 1, lib.TUNE_SYRK_STAGGER_NS: 0, lib.TUNE_HP_STAGGER_NS: 0, lib.TUNE_PDL: 0,
-             lib.TUNE_HP_PIPELINED: 0, lib.TUNE_SYRK_EPILOGUE: 0, lib.TUNE_SYRK_MIX: 0}
+             lib.TUNE_HP_PIPELINED: 0, lib.TUNE_SYRK_EPILOGUE: 0}
     names = {"groups": "groups", lib.TUNE_SYRK_STAGGER_NS: "syrk_stagger_ns", lib.TUNE_HP_STAGGER_NS: "hp_stagger_ns",
-             lib.TUNE_PDL: "pdl", lib.TUNE_HP_PIPELINED: "hp_pipelined", lib.TUNE_SYRK_EPILOGUE: "syrk_epilogue16", lib.TUNE_SYRK_MIX: "syrk_mix"}
+             lib.TUNE_PDL: "pdl", lib.TUNE_HP_PIPELINED: "hp_pipelined", lib.TUNE_SYRK_EPILOGUE: "syrk_epilogue16"}
 
     def apply(st):
         ctx.set_step_groups(st["groups"])
@@ -99,8 +99,7 @@ def main():
         return best
 
     base = measure(dict(state), "baseline")
-    sweeps = [(lib.TUNE_SYRK_MIX, [1, 2]),
-              (lib.TUNE_HP_PIPELINED, [1]),
+    sweeps = [(lib.TUNE_HP_PIPELINED, [1]),
               (lib.TUNE_HP_STAGGER_NS, [2000]),
               (lib.TUNE_SYRK_EPILOGUE, [1]),
               (lib.TUNE_SYRK_STAGGER_NS, [5000]),
