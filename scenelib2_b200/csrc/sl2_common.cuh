@@ -127,10 +127,11 @@ __device__ __forceinline__ void sl2_stagger(const Sl2Dev &d, int slot, int ns, i
 }
 
 // SL2_TUNE_PDL: 0 never, 1 always, 2 (default) when the launch covers fewer camera streams than
-// SL2_PDL_AUTO_STREAMS: the kernels of a small batch last a few microseconds each and the step is bound by the
-// launch-to-launch latency, which PDL hides; a batch that fills the GPU measured SLOWER with it (1.057 -> 1.115 ms at
-// C4 x 296 streams: profiles/r02_tuning_sweep.txt).
-#define SL2_PDL_AUTO_STREAMS 32
+// SL2_PDL_AUTO_STREAMS.  Measured (profiles/r02_pdl_vs_batch.txt, C4): ONE stream 0.186 -> 0.183 ms per frame (the step
+// is a chain of 8 kernels of 7-70 us, bound by launch-to-launch latency: a step on an empty map goes 0.047 -> 0.032 ms),
+// but 4 streams 0.194 -> 0.212, 148 streams 0.633 -> 0.693, 296 streams 1.057 -> 1.115 ms: every kernel triggers its
+// dependents at its top, so the whole chain of the step becomes resident and waits on the SMs.
+#define SL2_PDL_AUTO_STREAMS 2
 inline bool sl2_use_pdl(const Sl2Dev &d, int stream_cnt) {
   const int mode = d.tune[SL2_TUNE_PDL];
   return mode == 1 || (mode == 2 && stream_cnt < SL2_PDL_AUTO_STREAMS);
