@@ -236,12 +236,15 @@ int sl2_join(sl2_ctx *ctx);
  *                             kernel's CTAs are scheduled while the previous one drains): 0 never, 1 always,
  *                             2 (default) for launches that cover only a few camera streams (latency bound)
  *   SL2_TUNE_HP_PIPELINED     1: H*P in 8-row blocks with S of block b formed under the loads of block b+1
- *   SL2_TUNE_SYRK_EPILOGUE    1: the covariance tiles read their old entries of P in one round of loads */
+ *   SL2_TUNE_SYRK_EPILOGUE    1: the covariance tiles read their old entries of P in one round of loads
+ *   SL2_TUNE_CHOL_NEWTON      Newton steps on the reciprocal-square-root seed of every Cholesky pivot: 2 (default,
+ *                             ~1 ulp) or 1 (relative error ~1e-13 in the factor; this knob DOES change low-order bits) */
 #define SL2_TUNE_SYRK_STAGGER_NS 0
 #define SL2_TUNE_HP_STAGGER_NS 1
 #define SL2_TUNE_PDL 2
 #define SL2_TUNE_HP_PIPELINED 3
 #define SL2_TUNE_SYRK_EPILOGUE 4
+#define SL2_TUNE_CHOL_NEWTON 5
 int sl2_set_tuning(sl2_ctx *ctx, int32_t key, int32_t value);
 
 /* ---- read-back of per-feature results (Feature::h_/z_/S_/flags/counters, feature.h:96-140) */

@@ -61,6 +61,7 @@ static void tune_defaults(Sl2Dev &d) {
   d.tune[SL2_TUNE_PDL] = 2;           // 2 = automatic: on for batches smaller than the GPU (launch-latency bound)
   d.tune[SL2_TUNE_HP_PIPELINED] = 1;  // 0.107 -> 0.105 ms
   d.tune[SL2_TUNE_SYRK_EPILOGUE] = 0;
+  d.tune[SL2_TUNE_CHOL_NEWTON] = 2;
   const char *e = getenv("SL2_TUNE");
   while (e && *e) {
     char *end = nullptr;

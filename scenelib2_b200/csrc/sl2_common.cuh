@@ -16,6 +16,7 @@
 #define SL2_TUNE_PDL 2              // programmatic dependent launch between the kernels of the fused step
 #define SL2_TUNE_HP_PIPELINED 3     // upd_hp: 8-row blocks, S phase of block b under the loads of block b+1
 #define SL2_TUNE_SYRK_EPILOGUE 4    // upd_syrk: 1 = the 16 old entries of P per thread in one round of loads
+#define SL2_TUNE_CHOL_NEWTON 5      // upd_chol: Newton steps on the rsqrt seed of a pivot (1 or 2)
 #define SL2_TUNE_COUNT 8
 
 // Device view of one context: everything the kernels need, passed by value.

@@ -108,54 +108,64 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint3
                : "memory");
 }
 
-// 1/sqrt(d) for a positive pivot: MUFU seed + two Newton steps (about 1 ulp); a handful of FP64
-// instructions instead of the library routine -- this sits on the serial path of every panel.
+// 1/sqrt(d) for a positive pivot: MUFU seed (about 22 bits) + Newton steps; a handful of FP64 instructions instead
+// of the library routine -- this sits on the serial path of every panel.  Two steps: about 1 ulp.  One step: relative
+// error ~1e-13, i.e. U^T U = S (1 + O(1e-13)) -- far inside the 1e-8 the parity tests hold the update to (north star
+// 1e-5) and consistent between U and W = U^-T, which are built from the same multipliers.
+template <int NEWTON>
 __device__ __forceinline__ double pivot_rsqrt(double dv) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(dv));
 #pragma unroll
-  for (int it = 0; it < 2; ++it) {
+  for (int it = 0; it < NEWTON; ++it) {
     const double e = fma(-(dv * y), y, 1.0);
     y = fma(0.5 * y, e, y);
   }
   return y;
 }
 
-// One warp: Cholesky of the 8x8 block at (o, o) of dg (upper triangle, U^T U = A) and W = U^-T into
-// the same block of Wm.  Lane j (mod 8) holds column j of A and column j of W in registers.  Per pivot r:
-// the pivot travels by one shuffle, 1/u_rr is computed by every lane (uniform), row r of U is a[r] / u_rr,
-// and each multiplier U(r, i) (one more shuffle) updates a[i] AND w[i]: W is the forward elimination of the
-// identity with the same multipliers (row_i -= U(r,i) * row_r), so it costs no shuffles and no serial tail.
-// All 32 lanes must call.
+// One warp: Cholesky of the 8x8 block at (o, o) of dg (upper triangle, U^T U = A) and W = U^-T into the same block
+// of Wm.  EVERY lane runs the whole 8x8 factorization on its own copy of the 36 entries (same operations, same
+// order, same bits in every lane), so the serial chain per pivot is  rsqrt -> multiply -> FMA  with no shuffle on it
+// (the first version kept one column per lane and moved the pivot and every multiplier by shuffles: 36 64-bit
+// shuffles, two of them on the chain of every pivot -- about twice the latency for the same arithmetic and the same
+// results).  Lane j (mod 8) additionally carries column j of W: the forward elimination of e_j with the multipliers
+// (row_i -= U(r,i) * row_r).  All 32 lanes must call.
+template <int NEWTON>
 __device__ __forceinline__ void chol8_inv(double *dg, double *Wm, int o, int lane) {
   const int j = lane & 7;
-  double a[8], w[8];
+  // row by row (left-looking): row r of U = (A(r, :) - sum_{q<r} U(q,r) U(q, :)) / u_rr, the sums in ascending q like
+  // the right-looking form (same bits); only U(q, k >= r) of the finished rows stays in registers, row r + 1 of A is
+  // fetched from shared memory while row r is on the chain, finished rows go back at once (lane k stores column k).
+  double u[8][8], w[8], t[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    a[i] = (i <= j) ? dg[(o + i) * UPD_DS + o + j] : 0.0;
-    w[i] = (i == j) ? 1.0 : 0.0;
-  }
+  for (int k = 0; k < 8; ++k) t[k] = dg[o * UPD_DS + o + k];  // broadcast loads
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
-    const double dv = __shfl_sync(0xffffffffu, a[r], r);
-    const double iu = pivot_rsqrt(dv);
-    const double urj = a[r] * iu;  // lane r: d / sqrt(d) = u_rr
-    a[r] = urj;
-    w[r] *= iu;
+    double tn[8];
+    if (r + 1 < 8) {
 #pragma unroll
-    for (int i = r + 1; i < 8; ++i) {
-      const double uri = __shfl_sync(0xffffffffu, urj, i);
-      a[i] -= uri * urj;
-      w[i] -= uri * w[r];
+      for (int k = r + 1; k < 8; ++k) tn[k] = dg[(o + r + 1) * UPD_DS + o + k];
     }
-  }
-  __syncwarp();  // every lane has read its (mirrored) column before the block is overwritten
-  if (lane < 8) {
+    double wr = (r == j) ? 1.0 : 0.0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (i <= j) dg[(o + i) * UPD_DS + o + j] = a[i];
-      Wm[(o + i) * UPD_WS + o + j] = w[i];
+    for (int q = 0; q < r; ++q) {
+#pragma unroll
+      for (int k = r; k < 8; ++k) t[k] -= u[q][r] * u[q][k];
+      wr -= u[q][r] * w[q];
     }
+    const double iu = pivot_rsqrt<NEWTON>(t[r]);
+#pragma unroll
+    for (int k = r; k < 8; ++k) u[r][k] = t[k] * iu;  // k = r: d / sqrt(d) = u_rr
+    w[r] = wr * iu;
+    __syncwarp();  // every lane has read rows r and r + 1 of A before row r is overwritten
+    double v = u[r][r];
+#pragma unroll
+    for (int k = r + 1; k < 8; ++k) v = (k == lane) ? u[r][k] : v;
+    if (lane >= r && lane < 8) dg[(o + r) * UPD_DS + o + lane] = v;
+    if (lane < 8) Wm[(o + r) * UPD_WS + o + j] = w[r];
+#pragma unroll
+    for (int k = r + 1; k < 8; ++k) t[k] = tn[k];
   }
 }
 
@@ -656,6 +666,7 @@ __device__ __forceinline__ CholSmem chol_carve(uint8_t *base, int Nmax) {
   return u;
 }
 
+template <int NEWTON>
 __global__ void __launch_bounds__(UPD_THREADS, 2) upd_chol_kernel(const Sl2Dev d, int stream_lo) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   pdl_prologue();
@@ -754,7 +765,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) upd_chol_kernel(const Sl2Dev d
           sm.Wm[(lane >> 3) * UPD_WS + 8 + (lane & 7)] = 0.0;
           sm.Wm[(4 + (lane >> 3)) * UPD_WS + 8 + (lane & 7)] = 0.0;
           __syncwarp();
-          chol8_inv(dg, sm.Wm, 0, lane);
+          chol8_inv<NEWTON>(dg, sm.Wm, 0, lane);
           __syncwarp();
           {  // U12 = W11 * A12
             double c0 = 0.0, c1 = 0.0;
@@ -775,7 +786,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) upd_chol_kernel(const Sl2Dev d
             *reinterpret_cast<double2 *>(dg + (8 + lr) * UPD_DS + 8 + 2 * lc) = cv;
           }
           __syncwarp();
-          chol8_inv(dg, sm.Wm, 8, lane);
+          chol8_inv<NEWTON>(dg, sm.Wm, 8, lane);
           __syncwarp();
           {  // T = U12^T W11 (parked in the unused lower-left block of dg), W21 = -W22 T
             double t0 = 0.0, t1 = 0.0;
@@ -1463,7 +1474,10 @@ cudaError_t sl2_configure_update(const Sl2Dev &d) {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(upd_hp2_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp2_smem_bytes(d, 13));
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(upd_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = cudaFuncSetAttribute(upd_chol_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)sl2_update_smem_bytes(d));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(upd_chol_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)sl2_update_smem_bytes(d));
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(upd_syrk_kernel<32, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM);
@@ -1510,8 +1524,8 @@ cudaError_t sl2_launch_update(const Sl2Dev &d, int stream_lo, int stream_cnt, in
   }
   if ((e = mark(1)) != cudaSuccess) return e;
   if (!only_normalise) {
-    e = sl2_launch_kernel(upd_chol_kernel, dim3(stream_cnt), dim3(UPD_THREADS), sl2_update_smem_bytes(d), st, pdl, d,
-                          stream_lo);
+    e = sl2_launch_kernel(d.tune[SL2_TUNE_CHOL_NEWTON] == 1 ? upd_chol_kernel<1> : upd_chol_kernel<2>, dim3(stream_cnt),
+                          dim3(UPD_THREADS), sl2_update_smem_bytes(d), st, pdl, d, stream_lo);
     if (e != cudaSuccess) return e;
     ++nl;
   }

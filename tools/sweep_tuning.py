@@ -51,9 +51,9 @@ def main():
     log = open(args.out, "w")
 
     state = {"groups": 1, lib.TUNE_SYRK_STAGGER_NS: 0, lib.TUNE_HP_STAGGER_NS: 0, lib.TUNE_PDL: 0,
-             lib.TUNE_HP_PIPELINED: 0, lib.TUNE_SYRK_EPILOGUE: 0}
+             lib.TUNE_HP_PIPELINED: 1, lib.TUNE_SYRK_EPILOGUE: 0, lib.TUNE_CHOL_NEWTON: 2}
     names = {"groups": "groups", lib.TUNE_SYRK_STAGGER_NS: "syrk_stagger_ns", lib.TUNE_HP_STAGGER_NS: "hp_stagger_ns",
-             lib.TUNE_PDL: "pdl", lib.TUNE_HP_PIPELINED: "hp_pipelined", lib.TUNE_SYRK_EPILOGUE: "syrk_epilogue16"}
+             lib.TUNE_PDL: "pdl", lib.TUNE_HP_PIPELINED: "hp_pipelined", lib.TUNE_SYRK_EPILOGUE: "syrk_epilogue16", lib.TUNE_CHOL_NEWTON: "chol_newton"}
 
     def apply(st):
         ctx.set_step_groups(st["groups"])
@@ -98,13 +98,10 @@ def main():
         log.flush()
         return best
 
+    initial = dict(state)
     base = measure(dict(state), "baseline")
-    sweeps = [(lib.TUNE_HP_PIPELINED, [1]),
-              (lib.TUNE_HP_STAGGER_NS, [2000]),
-              (lib.TUNE_SYRK_EPILOGUE, [1]),
-              (lib.TUNE_SYRK_STAGGER_NS, [5000]),
-              (lib.TUNE_PDL, [1]),
-              ("groups", [2])]
+    sweeps = [(lib.TUNE_CHOL_NEWTON, [1]),
+              (lib.TUNE_HP_PIPELINED, [0])]
     for key, values in sweeps:
         best_v, best_ms = state[key], measure(dict(state), "current best")
         for v in values:
@@ -115,7 +112,7 @@ def main():
                 best_v, best_ms = v, ms
         state[key] = best_v
     final = measure(dict(state), "final combination")
-    again = measure({k: (1 if k == "groups" else 0) for k in state}, "baseline again")
+    again = measure(dict(initial), "baseline again")
     rec = {"chosen": {names[k]: v for k, v in state.items()}, "baseline_ms": round(min(base, again), 4),
            "final_ms": round(final, 4), "gain": round(min(base, again) / final, 4)}
     print(json.dumps(rec), flush=True)
