@@ -1182,9 +1182,7 @@ __global__ void __launch_bounds__(64 * SOLVE_MAX_WARPS, 1) upd_solve_kernel(cons
 // 0.264 ms) with 2 x 32-row and with 4 x 16-row stages alike; 4 x 16 and 3 x 16 LDGSTS stages: 0.268-0.270 ms.
 // Warp w owns rows 16*(w%4).. and columns 32*(w/4).. of the tile:
 //   acc[i][j][e] = T(16*(w%4) + 8*i + lane/4, 32*(w/4) + 8*j + 2*(lane%4) + e).
-// EPI16: the epilogue loads the warp's 16 entries of P per thread at once (one L2 round trip, a few spills at the
-// 80-register limit of three CTAs per SM) instead of 8 + 8.
-template <int KC, int ST, bool EPI16>
+template <int KC, int ST>
 __global__ void __launch_bounds__(UPD_THREADS, 3) upd_syrk_kernel(const Sl2Dev d, int stream_lo) {
   constexpr int STAGE = 2 * KC * UPD_YS;  // doubles per stage (A slab, B slab)
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -1208,8 +1206,23 @@ __global__ void __launch_bounds__(UPD_THREADS, 3) upd_syrk_kernel(const Sl2Dev d
   double *__restrict__ x = d.x + (size_t)s * ld;
   const double *__restrict__ G = d.G + (size_t)s * d.mmax * ldg;
   const bool diag = ta == tb;
-  const bool skip = diag && wa >= wb + 32;      // sub-tile strictly below the diagonal: mirrored instead
-  const bool mirror = !diag || wa + 16 <= wb;   // sub-tile strictly above the diagonal
+  // 8x8 blocks of the warp's 16 x 32 sub-tile (bit 4 i + j = block (i, j)): an off-diagonal tile computes all of them
+  // and mirrors every one; a diagonal tile computes the blocks on / above the diagonal (36 of 64, not the 48 of the
+  // sub-tile granularity) and mirrors the ones strictly above.  The three shapes that occur are compiled as separate
+  // loop bodies chosen per warp (no predicate per DMMA: that variant measured 4 % slower).
+  const int bi0 = wa >> 3, bj0 = wb >> 3;
+  unsigned cmask = 0xFFu, mmask = 0xFFu;
+  if (diag) {
+    cmask = mmask = 0u;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (bi0 + i <= bj0 + j) cmask |= 1u << (4 * i + j);
+        if (bi0 + i < bj0 + j) mmask |= 1u << (4 * i + j);
+      }
+  }
+  const bool skip = cmask == 0u;  // sub-tile strictly below the diagonal: mirrored instead
   // the tile of P this warp updates: into L2 while the products run (the epilogue reads it once)
   if (!skip) {
 #pragma unroll
@@ -1279,56 +1292,58 @@ __global__ void __launch_bounds__(UPD_THREADS, 3) upd_syrk_kernel(const Sl2Dev d
     if (!skip) {
       const double *Ya = stage_buf + (size_t)(ch % ST) * STAGE;
       const double *Yb = diag ? Ya : Ya + KC * UPD_YS;
-      auto kstep = [&](int kk) {
-        double a[2], b[4];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) a[i] = Ya[(kk + lc) * UPD_YS + wa + i * 8 + lr];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = Yb[(kk + lc) * UPD_YS + wb + j * 8 + lr];
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-      };
       const int krem = kr - ch * KC;  // rows of this chunk that exist (the rest is zero fill)
-      if (krem >= KC) {
+      auto chunk = [&](auto mask_c) {
+        constexpr unsigned MASK = decltype(mask_c)::value;
+        auto kstep = [&](int kk) {
+          double a[2], b[4];
 #pragma unroll
-        for (int kk = 0; kk < KC; kk += 4) kstep(kk);
-      } else {
+          for (int i = 0; i < 2; ++i)
+            if ((MASK >> (4 * i)) & 0xFu) a[i] = Ya[(kk + lc) * UPD_YS + wa + i * 8 + lr];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if ((MASK >> j) & 0x11u) b[j] = Yb[(kk + lc) * UPD_YS + wb + j * 8 + lr];
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if ((MASK >> (4 * i + j)) & 1u) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        };
+        if (krem >= KC) {
+#pragma unroll
+          for (int kk = 0; kk < KC; kk += 4) kstep(kk);
+        } else {
 #pragma unroll 2
-        for (int kk = 0; kk < krem; kk += 4) kstep(kk);
-      }
+          for (int kk = 0; kk < krem; kk += 4) kstep(kk);
+        }
+      };
+      if (cmask == 0xFFu) chunk(std::integral_constant<unsigned, 0xFFu>{});
+      else if (cmask == 0xEFu) chunk(std::integral_constant<unsigned, 0xEFu>{});   // all but block (1, 0)
+      else chunk(std::integral_constant<unsigned, 0x8Cu>{});                       // blocks (0, 2), (0, 3), (1, 3)
     }
   }
   if (skip) return;
-  // the warp's 16 x 32 entries of P: the loads of a thread first (independent), then the subtraction and the stores
-  double pold[2][4][2];
-  auto load_old = [&](int i) {
+  // the warp's computed blocks of P: the loads of a row group first (independent), then the subtraction and the stores
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
     const int a = ta * 64 + wa + i * 8 + lr;
+    double pold[4][2];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int bq = tb * 64 + wb + j * 8 + 2 * lc + e;
-        pold[i][j][e] = (a < n && bq < n) ? P[a + (size_t)ld * bq] : 0.0;
+        pold[j][e] = (((cmask >> (4 * i + j)) & 1u) && a < n && bq < n) ? P[a + (size_t)ld * bq] : 0.0;
       }
-  };
-  if (EPI16) {
-    load_old(0);
-    load_old(1);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int a = ta * 64 + wa + i * 8 + lr;
-    if (!EPI16) load_old(i);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
+      if (!((cmask >> (4 * i + j)) & 1u)) continue;  // a block below the diagonal: written by the mirror of its twin
       const int bq = tb * 64 + wb + j * 8 + 2 * lc;
-      const double v0 = pold[i][j][0] - acc[i][j][0], v1 = pold[i][j][1] - acc[i][j][1];
+      const double v0 = pold[j][0] - acc[i][j][0], v1 = pold[j][1] - acc[i][j][1];
       if (a < n && bq < n) {
         P[a + (size_t)ld * bq] = v0;
         if (bq + 1 < n) P[a + (size_t)ld * (bq + 1)] = v1;
-        if (mirror) {  // lower counterpart: rows = b range (contiguous in P), column a
+        if ((mmask >> (4 * i + j)) & 1u) {  // lower counterpart: rows = b range (contiguous in P), column a
           double *dst = P + bq + (size_t)ld * a;
           if (bq + 1 < n) *reinterpret_cast<double2 *>(dst) = make_double2(v0, v1);
           else *dst = v0;
@@ -1480,9 +1495,7 @@ cudaError_t sl2_configure_update(const Sl2Dev &d) {
   e = cudaFuncSetAttribute(upd_chol_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)sl2_update_smem_bytes(d));
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(upd_syrk_kernel<32, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(upd_syrk_kernel<32, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM);
+  e = cudaFuncSetAttribute(upd_syrk_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM);
   if (e != cudaSuccess) return e;
   const int np = solve_np(d.Nmax);
   const int smem = (int)solve_smem(np);
@@ -1555,8 +1568,8 @@ cudaError_t sl2_launch_update(const Sl2Dev &d, int stream_lo, int stream_cnt, in
     // one 64x64 tile per CTA (measured: CTAs that walk several tiles with cross-tile prefetch were slower, 0.29-0.31
     // against 0.264 ms, because they cost the third resident CTA per SM)
     const int nt = (SL2_NXV + 3 * d.Nmax + 1 + 63) / 64;
-    e = sl2_launch_kernel(d.tune[SL2_TUNE_SYRK_EPILOGUE] ? upd_syrk_kernel<32, 2, true> : upd_syrk_kernel<32, 2, false>,
-                          dim3(nt * (nt + 1) / 2, stream_cnt), dim3(UPD_THREADS), SYRK_SMEM, st, pdl, d, stream_lo);
+    e = sl2_launch_kernel(upd_syrk_kernel<32, 2>, dim3(nt * (nt + 1) / 2, stream_cnt), dim3(UPD_THREADS), SYRK_SMEM,
+                          st, pdl, d, stream_lo);
     if (e != cudaSuccess) return e;
     ++nl;
   }

@@ -100,8 +100,7 @@ def main():
 
     initial = dict(state)
     base = measure(dict(state), "baseline")
-    sweeps = [(lib.TUNE_CHOL_NEWTON, [1]),
-              (lib.TUNE_HP_PIPELINED, [0])]
+    sweeps = [(lib.TUNE_HP_PIPELINED, [0])]
     for key, values in sweeps:
         best_v, best_ms = state[key], measure(dict(state), "current best")
         for v in values:
