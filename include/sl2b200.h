@@ -227,24 +227,14 @@ int sl2_wait_slot(sl2_ctx *ctx, int32_t slot);
 int sl2_set_step_groups(sl2_ctx *ctx, int32_t groups);
 int sl2_join(sl2_ctx *ctx);
 /* Scheduling knobs of the fused step (no reference counterpart: the reference runs one GoOneStep on one host
- * thread, monoslam.cpp:108-180).  None of them changes a result -- only when / where kernels and CTAs start --
- * and every value is valid at any time (takes effect with the next launch).  value >= 0.
- *   SL2_TUNE_SYRK_STAGGER_NS  the CTAs of the covariance-update tiles that start together on one SM start this
- *                             many ns apart, so their staging / write-back phases do not coincide (0 = off)
- *   SL2_TUNE_HP_STAGGER_NS    the same for the two H*P CTAs of an SM
- *   SL2_TUNE_PDL              the kernels of a step are launched with programmatic dependent launch (the next
- *                             kernel's CTAs are scheduled while the previous one drains): 0 never, 1 always,
- *                             2 (default) for launches that cover only a few camera streams (latency bound)
- *   SL2_TUNE_HP_PIPELINED     1: H*P in 8-row blocks with S of block b formed under the loads of block b+1
- *   SL2_TUNE_SYRK_EPILOGUE    1: the covariance tiles read their old entries of P in one round of loads
- *   SL2_TUNE_CHOL_NEWTON      Newton steps on the reciprocal-square-root seed of every Cholesky pivot: 2 (default,
- *                             ~1 ulp) or 1 (relative error ~1e-13 in the factor; this knob DOES change low-order bits) */
-#define SL2_TUNE_SYRK_STAGGER_NS 0
-#define SL2_TUNE_HP_STAGGER_NS 1
-#define SL2_TUNE_PDL 2
-#define SL2_TUNE_HP_PIPELINED 3
-#define SL2_TUNE_SYRK_EPILOGUE 4
-#define SL2_TUNE_CHOL_NEWTON 5
+ * thread, monoslam.cpp:108-180).  They never change a result -- only how the kernels are launched / pipelined --
+ * and every value is valid at any time (takes effect with the next launch).
+ *   SL2_TUNE_PDL           the kernels of a step are launched with programmatic dependent launch (the next kernel's
+ *                          CTAs are scheduled while the previous one drains): 0 never, 1 always, 2 (default) only for
+ *                          a single camera stream, where the step is bound by launch-to-launch latency
+ *   SL2_TUNE_HP_PIPELINED  1 (default): H*P in 8-row blocks with S of block b formed under the loads of block b+1 */
+#define SL2_TUNE_PDL 0
+#define SL2_TUNE_HP_PIPELINED 1
 int sl2_set_tuning(sl2_ctx *ctx, int32_t key, int32_t value);
 
 /* ---- read-back of per-feature results (Feature::h_/z_/S_/flags/counters, feature.h:96-140) */

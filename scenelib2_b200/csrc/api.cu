@@ -52,16 +52,12 @@ struct sl2_ctx {
   std::vector<cudaEvent_t> ev_cmp_b;  // per frame slot: group B is done with the slot
 };
 
-// Defaults of the scheduling knobs (measured on B200, C4 x 296 streams: profiles/r02_tuning_sweep.txt); the
+// Defaults of the scheduling knobs (measured on B200: profiles/r02_tuning_sweep.txt, r02_pdl_vs_batch.txt); the
 // environment variable SL2_TUNE="key=value,key=value" overrides them at context creation (experiments, and the
 // parity tests run once with everything switched on).
 static void tune_defaults(Sl2Dev &d) {
-  d.tune[SL2_TUNE_SYRK_STAGGER_NS] = 0;
-  d.tune[SL2_TUNE_HP_STAGGER_NS] = 0;
-  d.tune[SL2_TUNE_PDL] = 2;           // 2 = automatic: on for batches smaller than the GPU (launch-latency bound)
-  d.tune[SL2_TUNE_HP_PIPELINED] = 1;  // 0.107 -> 0.105 ms
-  d.tune[SL2_TUNE_SYRK_EPILOGUE] = 0;
-  d.tune[SL2_TUNE_CHOL_NEWTON] = 2;
+  d.tune[SL2_TUNE_PDL] = 2;           // automatic: on for a single camera stream (launch-latency bound), else off
+  d.tune[SL2_TUNE_HP_PIPELINED] = 1;  // 0.107 -> 0.105 ms at C4 x 296 streams
   const char *e = getenv("SL2_TUNE");
   while (e && *e) {
     char *end = nullptr;
@@ -305,7 +301,6 @@ int sl2_create(const sl2_config *cfg, sl2_ctx **out) {
   ALLOC(d.ncull, B);
   ALLOC(d.upd_m, B);
   ALLOC(d.Wp, B * SL2_MAX_PANELS * 256);
-  ALLOC(d.sm_ctr, SL2_TUNE_COUNT * 256);
   ALLOC(c->xv_stage, (size_t)d.slots * B * SL2_NXV);
 #undef ALLOC
   if (!ok) {

@@ -11,13 +11,9 @@
 #define SL2_MAX_FEAT_SMEM 128  // == SL2_MAX_FEATURES (include/sl2b200.h)
 
 // keys of sl2_set_tuning (include/sl2b200.h: SL2_TUNE_*)
-#define SL2_TUNE_SYRK_STAGGER_NS 0  // first-wave CTAs of upd_syrk on one SM start this far apart
-#define SL2_TUNE_HP_STAGGER_NS 1    // the second upd_hp CTA of an SM starts this much later
-#define SL2_TUNE_PDL 2              // programmatic dependent launch between the kernels of the fused step
-#define SL2_TUNE_HP_PIPELINED 3     // upd_hp: 8-row blocks, S phase of block b under the loads of block b+1
-#define SL2_TUNE_SYRK_EPILOGUE 4    // upd_syrk: 1 = the 16 old entries of P per thread in one round of loads
-#define SL2_TUNE_CHOL_NEWTON 5      // upd_chol: Newton steps on the rsqrt seed of a pivot (1 or 2)
-#define SL2_TUNE_COUNT 8
+#define SL2_TUNE_PDL 0           // programmatic dependent launch between the kernels of the fused step (0 / 1 / 2 = auto)
+#define SL2_TUNE_HP_PIPELINED 1  // upd_hp: 8-row blocks, S phase of block b under the loads of block b+1
+#define SL2_TUNE_COUNT 4
 
 // Device view of one context: everything the kernels need, passed by value.
 struct Sl2Dev {
@@ -70,7 +66,6 @@ struct Sl2Dev {
   // scheduling knobs (sl2_set_tuning; they never change a result, only when / where the work runs)
   int tune[SL2_TUNE_COUNT];
   int nsm;             // SMs of the device
-  unsigned *sm_ctr;    // [SL2_TUNE_COUNT][256] per-SM arrival counters of the staggered kernels
 };
 
 #define SL2_MAX_PANELS 16  // 16-row panels of S: m <= 2 * SL2_MAX_FEATURES = 256
@@ -104,29 +99,6 @@ __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
-__device__ __forceinline__ unsigned long long sl2_globaltimer() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-// Stagger the CTAs that start together on one SM: CTAs of one kernel that share an SM run in lockstep
-// (same length, same start), so their prologues / epilogues / barrier phases coincide and the pipe they are bound
-// by idles in those phases.  The k-th CTA to arrive on an SM (k < ways, first wave only) waits k * ns; later waves
-// inherit the offset because every CTA takes the same time.  `slot` selects a counter row.
-__device__ __forceinline__ void sl2_stagger(const Sl2Dev &d, int slot, int ns, int ways, unsigned linear_cta) {
-  if (ns <= 0 || linear_cta >= (unsigned)(ways * d.nsm)) return;  // uniform over the CTA
-  if (threadIdx.x == 0) {
-    unsigned smid;
-    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
-    const unsigned k = atomicAdd(d.sm_ctr + slot * 256 + (smid & 255), 1u) % (unsigned)ways;
-    if (k) {
-      const unsigned long long t0 = sl2_globaltimer(), dt = (unsigned long long)k * (unsigned)ns;
-      while (sl2_globaltimer() - t0 < dt) __nanosleep(256);
-    }
-  }
-  __syncthreads();
-}
-
 // SL2_TUNE_PDL: 0 never, 1 always, 2 (default) when the launch covers fewer camera streams than
 // SL2_PDL_AUTO_STREAMS.  Measured (profiles/r02_pdl_vs_batch.txt, C4): ONE stream 0.186 -> 0.183 ms per frame (the step
 // is a chain of 8 kernels of 7-70 us, bound by launch-to-launch latency: a step on an empty map goes 0.047 -> 0.032 ms),

@@ -108,64 +108,58 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint3
                : "memory");
 }
 
-// 1/sqrt(d) for a positive pivot: MUFU seed (about 22 bits) + Newton steps; a handful of FP64 instructions instead
-// of the library routine -- this sits on the serial path of every panel.  Two steps: about 1 ulp.  One step: relative
-// error ~1e-13, i.e. U^T U = S (1 + O(1e-13)) -- far inside the 1e-8 the parity tests hold the update to (north star
-// 1e-5) and consistent between U and W = U^-T, which are built from the same multipliers.
-template <int NEWTON>
+// 1/sqrt(d) for a positive pivot: MUFU seed + two Newton steps (about 1 ulp); a handful of FP64
+// instructions instead of the library routine -- this sits on the serial path of every panel.
 __device__ __forceinline__ double pivot_rsqrt(double dv) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(dv));
 #pragma unroll
-  for (int it = 0; it < NEWTON; ++it) {
+  for (int it = 0; it < 2; ++it) {
     const double e = fma(-(dv * y), y, 1.0);
     y = fma(0.5 * y, e, y);
   }
   return y;
 }
 
-// One warp: Cholesky of the 8x8 block at (o, o) of dg (upper triangle, U^T U = A) and W = U^-T into the same block
-// of Wm.  EVERY lane runs the whole 8x8 factorization on its own copy of the 36 entries (same operations, same
-// order, same bits in every lane), so the serial chain per pivot is  rsqrt -> multiply -> FMA  with no shuffle on it
-// (the first version kept one column per lane and moved the pivot and every multiplier by shuffles: 36 64-bit
-// shuffles, two of them on the chain of every pivot -- about twice the latency for the same arithmetic and the same
-// results).  Lane j (mod 8) additionally carries column j of W: the forward elimination of e_j with the multipliers
-// (row_i -= U(r,i) * row_r).  All 32 lanes must call.
-template <int NEWTON>
+// One warp: Cholesky of the 8x8 block at (o, o) of dg (upper triangle, U^T U = A) and W = U^-T into
+// the same block of Wm.  Lane j (mod 8) holds column j of A and column j of W in registers.  Per pivot r:
+// the pivot travels by one shuffle, 1/u_rr is computed by every lane (uniform), row r of U is a[r] / u_rr,
+// and each multiplier U(r, i) (one more shuffle) updates a[i] AND w[i]: W is the forward elimination of the
+// identity with the same multipliers (row_i -= U(r,i) * row_r), so it costs no shuffles and no serial tail.
+// All 32 lanes must call.  (Measured alternative, same bits: every lane factoring its own copy of the whole block
+// row by row with no shuffle at all -- 156 FP64 instructions per block instead of 136 + 36 shuffles -- left the
+// batched kernel at 0.116 ms and made the single-stream factor slower, 0.072 -> 0.076 ms; so did dropping the second
+// Newton step of the pivot's rsqrt: at 296 streams the panel's trailing update, fed from L2, is what the barrier
+// waits for, not the factor.)
 __device__ __forceinline__ void chol8_inv(double *dg, double *Wm, int o, int lane) {
   const int j = lane & 7;
-  // row by row (left-looking): row r of U = (A(r, :) - sum_{q<r} U(q,r) U(q, :)) / u_rr, the sums in ascending q like
-  // the right-looking form (same bits); only U(q, k >= r) of the finished rows stays in registers, row r + 1 of A is
-  // fetched from shared memory while row r is on the chain, finished rows go back at once (lane k stores column k).
-  double u[8][8], w[8], t[8];
+  double a[8], w[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) t[k] = dg[o * UPD_DS + o + k];  // broadcast loads
+  for (int i = 0; i < 8; ++i) {
+    a[i] = (i <= j) ? dg[(o + i) * UPD_DS + o + j] : 0.0;
+    w[i] = (i == j) ? 1.0 : 0.0;
+  }
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
-    double tn[8];
-    if (r + 1 < 8) {
+    const double dv = __shfl_sync(0xffffffffu, a[r], r);
+    const double iu = pivot_rsqrt(dv);
+    const double urj = a[r] * iu;  // lane r: d / sqrt(d) = u_rr
+    a[r] = urj;
+    w[r] *= iu;
 #pragma unroll
-      for (int k = r + 1; k < 8; ++k) tn[k] = dg[(o + r + 1) * UPD_DS + o + k];
+    for (int i = r + 1; i < 8; ++i) {
+      const double uri = __shfl_sync(0xffffffffu, urj, i);
+      a[i] -= uri * urj;
+      w[i] -= uri * w[r];
     }
-    double wr = (r == j) ? 1.0 : 0.0;
+  }
+  __syncwarp();  // every lane has read its (mirrored) column before the block is overwritten
+  if (lane < 8) {
 #pragma unroll
-    for (int q = 0; q < r; ++q) {
-#pragma unroll
-      for (int k = r; k < 8; ++k) t[k] -= u[q][r] * u[q][k];
-      wr -= u[q][r] * w[q];
+    for (int i = 0; i < 8; ++i) {
+      if (i <= j) dg[(o + i) * UPD_DS + o + j] = a[i];
+      Wm[(o + i) * UPD_WS + o + j] = w[i];
     }
-    const double iu = pivot_rsqrt<NEWTON>(t[r]);
-#pragma unroll
-    for (int k = r; k < 8; ++k) u[r][k] = t[k] * iu;  // k = r: d / sqrt(d) = u_rr
-    w[r] = wr * iu;
-    __syncwarp();  // every lane has read rows r and r + 1 of A before row r is overwritten
-    double v = u[r][r];
-#pragma unroll
-    for (int k = r + 1; k < 8; ++k) v = (k == lane) ? u[r][k] : v;
-    if (lane >= r && lane < 8) dg[(o + r) * UPD_DS + o + lane] = v;
-    if (lane < 8) Wm[(o + r) * UPD_WS + o + j] = w[r];
-#pragma unroll
-    for (int k = r + 1; k < 8; ++k) t[k] = tn[k];
   }
 }
 
@@ -300,7 +294,6 @@ __global__ void __launch_bounds__(HP_THREADS, 2) upd_hp_kernel(
     const double *st_Hy, const double *st_R, const double *st_nu) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   pdl_prologue();
-  sl2_stagger(d, SL2_TUNE_HP_STAGGER_NS, d.tune[SL2_TUNE_HP_STAGGER_NS], 2, blockIdx.y * gridDim.x + blockIdx.x);
   const int ld = d.ld, ldg = d.ldg;
   const HpSmem sm = hp_carve(smem_raw, d.Nmax, ld);
   const int s = stream_lo + blockIdx.y;
@@ -417,7 +410,6 @@ __global__ void __launch_bounds__(HP_THREADS, 2) upd_hp2_kernel(
     const double *st_Hy, const double *st_R, const double *st_nu) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   pdl_prologue();
-  sl2_stagger(d, SL2_TUNE_HP_STAGGER_NS, d.tune[SL2_TUNE_HP_STAGGER_NS], 2, blockIdx.y * gridDim.x + blockIdx.x);
   constexpr int R2 = 8, F2 = 4;  // rows / features per block
   const int ld = d.ld, ldg = d.ldg;
   const HpSmem sm = hp_carve(smem_raw, d.Nmax, ld);
@@ -666,7 +658,6 @@ __device__ __forceinline__ CholSmem chol_carve(uint8_t *base, int Nmax) {
   return u;
 }
 
-template <int NEWTON>
 __global__ void __launch_bounds__(UPD_THREADS, 2) upd_chol_kernel(const Sl2Dev d, int stream_lo) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   pdl_prologue();
@@ -765,7 +756,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) upd_chol_kernel(const Sl2Dev d
           sm.Wm[(lane >> 3) * UPD_WS + 8 + (lane & 7)] = 0.0;
           sm.Wm[(4 + (lane >> 3)) * UPD_WS + 8 + (lane & 7)] = 0.0;
           __syncwarp();
-          chol8_inv<NEWTON>(dg, sm.Wm, 0, lane);
+          chol8_inv(dg, sm.Wm, 0, lane);
           __syncwarp();
           {  // U12 = W11 * A12
             double c0 = 0.0, c1 = 0.0;
@@ -786,7 +777,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) upd_chol_kernel(const Sl2Dev d
             *reinterpret_cast<double2 *>(dg + (8 + lr) * UPD_DS + 8 + 2 * lc) = cv;
           }
           __syncwarp();
-          chol8_inv<NEWTON>(dg, sm.Wm, 8, lane);
+          chol8_inv(dg, sm.Wm, 8, lane);
           __syncwarp();
           {  // T = U12^T W11 (parked in the unused lower-left block of dg), W21 = -W22 T
             double t0 = 0.0, t1 = 0.0;
@@ -1198,7 +1189,6 @@ __global__ void __launch_bounds__(UPD_THREADS, 3) upd_syrk_kernel(const Sl2Dev d
   while ((tb + 1) * (tb + 2) / 2 <= t) ++tb;
   const int ta = t - tb * (tb + 1) / 2;
   if (tb * 64 >= n + 1) return;  // this stream's map is smaller than the capacity the grid was sized for
-  sl2_stagger(d, SL2_TUNE_SYRK_STAGGER_NS, d.tune[SL2_TUNE_SYRK_STAGGER_NS], 3, blockIdx.y * gridDim.x + blockIdx.x);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
   const int wa = (warp & 3) * 16, wb = (warp >> 2) * 32;
   const int ld = d.ld, ldg = d.ldg;
@@ -1489,10 +1479,7 @@ cudaError_t sl2_configure_update(const Sl2Dev &d) {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(upd_hp2_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp2_smem_bytes(d, 13));
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(upd_chol_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)sl2_update_smem_bytes(d));
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(upd_chol_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = cudaFuncSetAttribute(upd_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)sl2_update_smem_bytes(d));
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(upd_syrk_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM);
@@ -1537,8 +1524,8 @@ cudaError_t sl2_launch_update(const Sl2Dev &d, int stream_lo, int stream_cnt, in
   }
   if ((e = mark(1)) != cudaSuccess) return e;
   if (!only_normalise) {
-    e = sl2_launch_kernel(d.tune[SL2_TUNE_CHOL_NEWTON] == 1 ? upd_chol_kernel<1> : upd_chol_kernel<2>, dim3(stream_cnt),
-                          dim3(UPD_THREADS), sl2_update_smem_bytes(d), st, pdl, d, stream_lo);
+    e = sl2_launch_kernel(upd_chol_kernel, dim3(stream_cnt), dim3(UPD_THREADS), sl2_update_smem_bytes(d), st, pdl, d,
+                          stream_lo);
     if (e != cudaSuccess) return e;
     ++nl;
   }

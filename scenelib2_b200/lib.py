@@ -19,7 +19,7 @@ f32p = C.POINTER(C.c_float)
 
 SL2_MAX_FEATURES = 128
 # keys of Context.set_tuning (SL2_TUNE_* of include/sl2b200.h)
-TUNE_SYRK_STAGGER_NS, TUNE_HP_STAGGER_NS, TUNE_PDL, TUNE_HP_PIPELINED, TUNE_SYRK_EPILOGUE, TUNE_CHOL_NEWTON = 0, 1, 2, 3, 4, 5
+TUNE_PDL, TUNE_HP_PIPELINED = 0, 1
 
 
 class Sl2Config(C.Structure):

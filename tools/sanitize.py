@@ -61,6 +61,16 @@ cb = ctx_from_scenes(big, frame_slots=1)
 for t in range(2):
     cb.set_frames(0, np.stack([sc_.frames[t] for sc_ in big])); cb.step(0)
 cb.sync()
+# the BATCHED launch shapes (>= 296 streams): software-pipelined upd_hp, one solve CTA per stream walking the column
+# groups on its predicate-free path (m = 56 rows reach the last panel of the 4-panel instantiation), syrk with two
+# diagonal tiles per stream (block masks)
+uniq = [synth.make_scene("C2", stream_id=s, n_frames=1, n_features=28) for s in range(4)]
+many = [uniq[s % 4] for s in range(296)]
+cm = ctx_from_scenes(many, frame_slots=1)
+cm.set_frames(0, np.stack([sc_.frames[0] for sc_ in many])); cm.step(0); cm.sync()
+print("batched: matched", int((cm.features(295)["flags"] & 2).astype(bool).sum()), "of 28, state finite:",
+      bool(np.isfinite(cm.get_state(295)[1]).all()))
+cm.close()
 # device-side map growth
 n10 = 13 + 3 * 10
 ca = ctx_from_scenes([synth.make_scene("C2", n_frames=1, n_features=10)], max_features=12)

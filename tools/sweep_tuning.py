@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Sweep of the scheduling knobs of the fused step (sl2_set_tuning / sl2_set_step_groups) on ONE resident context:
+"""Sweep of the scheduling knobs of the fused step (sl2_set_tuning / sl2_set_step_groups) on ONE resident context
+(profiles/r02_tuning_sweep.txt also holds the knobs that were measured in round 2 and removed again: staggered CTA
+starts of upd_syrk / upd_hp, a one-round syrk epilogue, runs of 1-2-3 tiles per syrk CTA, 1 Newton step in upd_chol):
 C4 x 296 camera streams, frames resident in HBM.  Per setting: warm-up, `steps` timed steps back to back (CUDA
 events on the launching stream -> frames/s), then the per-kernel durations in timing mode.  Coordinate-wise: the
 best value of every knob is kept for the knobs that follow, and the final combination is re-measured against the
@@ -50,10 +52,8 @@ def main():
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     log = open(args.out, "w")
 
-    state = {"groups": 1, lib.TUNE_SYRK_STAGGER_NS: 0, lib.TUNE_HP_STAGGER_NS: 0, lib.TUNE_PDL: 0,
-             lib.TUNE_HP_PIPELINED: 1, lib.TUNE_SYRK_EPILOGUE: 0, lib.TUNE_CHOL_NEWTON: 2}
-    names = {"groups": "groups", lib.TUNE_SYRK_STAGGER_NS: "syrk_stagger_ns", lib.TUNE_HP_STAGGER_NS: "hp_stagger_ns",
-             lib.TUNE_PDL: "pdl", lib.TUNE_HP_PIPELINED: "hp_pipelined", lib.TUNE_SYRK_EPILOGUE: "syrk_epilogue16", lib.TUNE_CHOL_NEWTON: "chol_newton"}
+    state = {"groups": 1, lib.TUNE_PDL: 0, lib.TUNE_HP_PIPELINED: 1}
+    names = {"groups": "groups", lib.TUNE_PDL: "pdl", lib.TUNE_HP_PIPELINED: "hp_pipelined"}
 
     def apply(st):
         ctx.set_step_groups(st["groups"])
@@ -100,7 +100,7 @@ def main():
 
     initial = dict(state)
     base = measure(dict(state), "baseline")
-    sweeps = [(lib.TUNE_HP_PIPELINED, [0])]
+    sweeps = [(lib.TUNE_HP_PIPELINED, [0]), (lib.TUNE_PDL, [1]), ("groups", [2])]
     for key, values in sweeps:
         best_v, best_ms = state[key], measure(dict(state), "current best")
         for v in values:
