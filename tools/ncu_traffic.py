@@ -6,7 +6,7 @@ import json
 import subprocess
 import sys
 
-NAMES = {"upd_hp_kernel": "upd_hp", "upd_chol_kernel": "upd_chol", "upd_solve_kernel": "upd_solve",
+NAMES = {"upd_hp_kernel": "upd_hp", "upd_hp2_kernel": "upd_hp", "upd_chol_kernel": "upd_chol", "upd_solve_kernel": "upd_solve",
          "upd_syrk_kernel": "upd_syrk", "upd_finish_kernel": "upd_finish", "search_kernel": "search",
          "predict_kernel": "predict", "cull_kernel": "cull"}
 out = {}
