@@ -10,9 +10,10 @@
 // H is structurally sparse (7 + 3 non-zero columns per row) and is never formed.
 //
 //   kernel           grid                      work per CTA
-//   upd_hp           streams                   measurement list; G = [ S | H P | nu ] (m x (m+n+1), row-major scratch):
-//                                              a stream over P, thread = state column, 16 rows of H P per block,
-//                                              S = (H P) H^T + R from the block's rows in shared memory.
+//   upd_hp / upd_hp2 streams                   measurement list; G = [ S | H P | nu ] (m x (m+n+1), row-major scratch):
+//                                              a stream over P, thread = state column, 16 (upd_hp2: 8, double-buffered)
+//                                              rows of H P per block, S = (H P) H^T + R from the block's rows in shared
+//                                              memory (upd_hp2: under the loads of the next block).
 //   upd_chol         streams                   blocked Cholesky of the S part only (16-row panels, left-looking with
 //                                              a look-ahead for the next diagonal block) -> U in place, and
 //                                              W_pp = U_pp^-T of every panel.  The serial chain of the update
@@ -20,12 +21,16 @@
 //   upd_solve        streams (x column slabs)  Y = U^-T [H P | nu]: a warp pair owns 8 columns and keeps all m rows
 //                                              of them in REGISTERS (DMMA fragment layout); U and the W_pp arrive
 //                                              by bulk copies on mbarriers, once per CTA; the product runs on the
-//                                              FP64 tensor path.  Column groups are independent.
-//   upd_syrk         64x64 tiles x streams     P -= Y^T Y (upper tiles computed, lower mirrored; sub-tiles of a
-//                                              diagonal tile below the diagonal are skipped); the nu column rides
+//                                              FP64 tensor path, every tile of Y formed once, no per-tile guards
+//                                              when the rows reach the last panel.  Column groups are independent.
+//   upd_syrk         64x64 tiles x streams     P -= Y^T Y (upper tiles computed, lower mirrored; a diagonal tile
+//                                              computes its 8x8 blocks on / above the diagonal); the nu column rides
 //                                              along as column n of Y, so the tile row that holds it yields
 //                                              x += Y^T w in its epilogue.
 //   upd_finish       streams                   normalise_state, symmetrise, counters.
+//
+// Every kernel starts with pdl_prologue(): launched with the PDL attribute (sl2_use_pdl: a single camera stream) the
+// eight kernels of a step overlap their launch latencies; without it the two instructions do nothing.
 //
 // Every re-read of the round-1 single-kernel design (finished rows of G gathered from L2/HBM by every panel over
 // all 514 columns, Y slabs re-staged per tile by a CTA that owns the whole stream) is gone: G is written once and
