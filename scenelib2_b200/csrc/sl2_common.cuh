@@ -96,14 +96,16 @@ __device__ __forceinline__ rd rsqrt_(rd a) { return rd(__dsqrt_rn(a.v)); }
 // writes are visible (without the attribute both instructions do nothing).  Every kernel of the fused step
 // executes the pair FIRST, so completion is transitive along the chain of launches.
 __device__ __forceinline__ void pdl_prologue() {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // wait, THEN release the dependents: at most two kernels of the chain are resident at a time (triggering first
+  // lets the whole chain of a step pile up on the SMs: measured slower at every batch size, tools/run_pdl_order.sh)
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 // SL2_TUNE_PDL: 0 never, 1 always, 2 (default) when the launch covers fewer camera streams than
-// SL2_PDL_AUTO_STREAMS.  Measured (profiles/r02_pdl_vs_batch.txt, C4): ONE stream 0.186 -> 0.183 ms per frame (the step
+// SL2_PDL_AUTO_STREAMS.  Measured (profiles/r02_pdl_vs_batch.txt, C4): ONE stream 0.184 -> 0.178 ms per frame (the step
 // is a chain of 8 kernels of 7-70 us, bound by launch-to-launch latency: a step on an empty map goes 0.047 -> 0.032 ms),
-// but 4 streams 0.194 -> 0.212, 148 streams 0.633 -> 0.693, 296 streams 1.057 -> 1.115 ms: every kernel triggers its
-// dependents at its top, so the whole chain of the step becomes resident and waits on the SMs.
+// 16 streams neutral, 296 streams 1.049 -> 1.074 ms (with the trigger BEFORE the wait the whole chain of the step became
+// resident and waited on the SMs: 1.107 ms, and slower from 4 streams on).
 #define SL2_PDL_AUTO_STREAMS 2
 inline bool sl2_use_pdl(const Sl2Dev &d, int stream_cnt) {
   const int mode = d.tune[SL2_TUNE_PDL];
