@@ -5,7 +5,7 @@
 // decodes PGM (P5 / P2) and PNG itself: RFC 1950 / 1951 inflate (stored, fixed and dynamic Huffman blocks),
 // the five PNG scanline filters, colour types gray / gray+alpha / RGB / RGBA / palette at bit depths 1-16, and
 // the gray conversion OpenCV applies for IMREAD_GRAYSCALE (Y = (R*4899 + G*9617 + B*1868 + 8192) >> 14).
-// Interlaced (Adam7) files are rejected (empty result, like a failed imread).  JPEG is not decoded.
+// Interlaced (Adam7) files are rejected (empty result, like a failed imread).  JPEG: jpeg_decode.h.
 #pragma once
 #include <cstdint>
 #include <cstring>

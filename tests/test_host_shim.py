@@ -265,3 +265,64 @@ def test_png_and_pgm_frames_decode_like_imread(tmp_path):
     (tmp_path / "bad.png").write_bytes(cases[0][1][:60])
     (tmp_path / "text.txt").write_bytes(b"not an image")
     assert decode(tmp_path / "bad.png")[0] == -1 and decode(tmp_path / "text.txt")[0] == -1
+
+
+def test_jpeg_frames_decode_like_imread(tmp_path):
+    """FileGrabber::GetImageFile (filegrabber.cpp:106-109: cv::imread(path, 0)) on a JPEG: OpenCV asks libjpeg for
+    grayscale output = the luminance component through libjpeg's slow-integer IDCT.  The shim's own decoder
+    (host/jpeg_decode.h) must give the same bytes as cv2.imread(path, 0) -- the reference's very call -- for gray and
+    colour files, every chroma sampling, optimised Huffman tables, restart intervals, odd sizes, OpenCV's and PIL's
+    writers; progressive files are rejected like an unreadable image; truncated / corrupted files never crash."""
+    cv2 = pytest.importorskip("cv2")
+    Image = pytest.importorskip("PIL.Image")
+    import ctypes as C
+    import __graft_entry__ as g
+    g.build()
+    lib = C.CDLL(os.path.join(HOST, "libscenelib2_b200_host.so"))
+
+    def decode(path):
+        buf = np.zeros(1 << 20, np.uint8)
+        w, h = C.c_int(0), C.c_int(0)
+        rc = lib.sl2_host_decode_image(str(path).encode(), buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(w),
+                                       C.byref(h))
+        return rc, buf[:w.value * h.value].reshape(h.value, w.value) if rc == 0 else None
+
+    rng = np.random.default_rng(11)
+    checked = 0
+    for (H, W) in ((1, 1), (7, 9), (16, 16), (17, 33), (240, 320)):
+        yy, xx = np.mgrid[0:H, 0:W]
+        base = ((np.sin(xx / 5.0) + np.cos(yy / 4.0)) * 50 + 128 + rng.normal(0, 12, (H, W))).clip(0, 255).astype(np.uint8)
+        rgb = np.stack([base, np.roll(base, 1, 1), 255 - base], -1)
+        files = []
+        for sf in ("411", "420", "422", "440", "444"):
+            p = tmp_path / ("cv_%d_%d_%s.jpg" % (H, W, sf))
+            cv2.imwrite(str(p), rgb, [cv2.IMWRITE_JPEG_QUALITY, 80, cv2.IMWRITE_JPEG_SAMPLING_FACTOR,
+                                      getattr(cv2, "IMWRITE_JPEG_SAMPLING_FACTOR_" + sf)])
+            files.append(p)
+        for q, extra in ((10, []), (100, []), (75, [cv2.IMWRITE_JPEG_OPTIMIZE, 1]), (60, [cv2.IMWRITE_JPEG_RST_INTERVAL, 3])):
+            p = tmp_path / ("cvg_%d_%d_%d_%d.jpg" % (H, W, q, len(extra)))
+            cv2.imwrite(str(p), base, [cv2.IMWRITE_JPEG_QUALITY, q] + extra)
+            files.append(p)
+        for sub in (0, 1, 2):
+            p = tmp_path / ("pil_%d_%d_%d.jpg" % (H, W, sub))
+            Image.fromarray(rgb).save(str(p), quality=70, subsampling=sub, optimize=bool(sub & 1))
+            files.append(p)
+        for p in files:
+            want = cv2.imread(str(p), 0)
+            rc, got = decode(p)
+            assert rc == 0 and got.shape == want.shape and (got == want).all(), p.name
+            checked += 1
+        p = tmp_path / ("prog_%d_%d.jpg" % (H, W))
+        Image.fromarray(rgb).save(str(p), quality=70, progressive=True)
+        assert decode(p)[0] == -1
+    assert checked == 60
+    data = (tmp_path / "cv_240_320_420.jpg").read_bytes()
+    for cut in (3, 20, 200, len(data) // 2):
+        (tmp_path / "cut.jpg").write_bytes(data[:cut])
+        assert decode(tmp_path / "cut.jpg")[0] in (0, -1, -2)
+    for k in range(200):
+        b = bytearray(data)
+        for _ in range(1 + k % 6):
+            b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        (tmp_path / "mut.jpg").write_bytes(bytes(b))
+        assert decode(tmp_path / "mut.jpg")[0] in (0, -1, -2)    # -2: a mutated size field larger than the buffer
