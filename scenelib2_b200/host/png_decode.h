@@ -4,7 +4,7 @@
 // feature.cpp:119), i.e. any image format OpenCV knows, converted to one 8-bit gray channel.  The host shim
 // decodes PGM (P5 / P2) and PNG itself: RFC 1950 / 1951 inflate (stored, fixed and dynamic Huffman blocks),
 // the five PNG scanline filters, colour types gray / gray+alpha / RGB / RGBA / palette at bit depths 1-16, and
-// the gray conversion OpenCV applies for IMREAD_GRAYSCALE (Y = (R*4899 + G*9617 + B*1868 + 8192) >> 14).
+// the gray conversion cv::imread(path, 0) gets from libpng (Y = (R*9797 + G*19234 + B*3737) >> 15 on 8-bit samples).
 // Interlaced (Adam7) files are rejected (empty result, like a failed imread).  JPEG: jpeg_decode.h.
 #pragma once
 #include <cstdint>
@@ -240,7 +240,14 @@ inline bool decode_gray(const uint8_t *file, size_t n, std::vector<uint8_t> &gra
       const int per = 8 / depth, byte = cur[x / per], shift = 8 - depth * (x % per + 1);
       return (byte >> shift) & ((1 << depth) - 1);
     };
-    auto luma = [](int r, int gr, int b) { return (uint8_t)((r * 4899 + gr * 9617 + b * 1868 + 8192) >> 14); };
+    // cv::imread(path, 0) lets libpng do the conversion (png_set_rgb_to_gray(png, 1, 0.299, 0.587)): 15-bit
+    // coefficients 9797 / 19234 / 3737, truncated for 8-bit samples; 16-bit samples are converted at 16 bits WITH
+    // rounding and then stripped to their high byte (verified against OpenCV 4.13: tests/test_host_shim.py)
+    auto luma = [](int r, int gr, int b) { return (uint8_t)((r * 9797 + gr * 19234 + b * 3737) >> 15); };
+    auto sample16 = [&](int x, int ch) -> long {
+      const size_t o = ((size_t)x * channels + ch) * 2;
+      return ((long)cur[o] << 8) | cur[o + 1];
+    };
     for (int x = 0; x < width; ++x) {
       if (ctype == 0) {
         const int v = sample(x, 0);
@@ -250,6 +257,8 @@ inline bool decode_gray(const uint8_t *file, size_t n, std::vector<uint8_t> &gra
       } else if (ctype == 3) {
         const size_t i = (size_t)sample(x, 0) * 3;
         g[x] = i + 2 < plte.size() ? luma(plte[i], plte[i + 1], plte[i + 2]) : 0;
+      } else if (depth == 16) {
+        g[x] = (uint8_t)(((sample16(x, 0) * 9797 + sample16(x, 1) * 19234 + sample16(x, 2) * 3737 + 16384) >> 15) >> 8);
       } else {
         g[x] = luma(sample(x, 0), sample(x, 1), sample(x, 2));
       }

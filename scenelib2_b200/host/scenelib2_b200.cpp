@@ -53,9 +53,14 @@ double num(const std::map<std::string, std::string> &kv, const std::string &k, d
   return it == kv.end() ? def : std::atof(it->second.c_str());
 }
 
-// PGM decoder standing in for cv::imread(path, 0) (feature.cpp:119, filegrabber.cpp:106-109): binary P5
-// and ASCII P2, maxval <= 255, '#' comments in the header.  Returns an empty Mat for anything else
-// (cv::imread returns an empty Mat when it cannot decode).
+// PNM decoder standing in for cv::imread(path, 0) (feature.cpp:119, filegrabber.cpp:106-109): PBM / PGM / PPM, ASCII
+// (P1 P2 P3) and binary (P4 P5 P6), '#' comments in the header, with the conversions OpenCV's reader applies
+// (tests/test_host_shim.py compares every variant with cv2.imread(path, 0) where OpenCV is installed):
+//   bitmaps          1 -> 0, 0 -> 255
+//   maxval <= 255    binary samples as they are; ASCII samples scaled v * 255 / maxval when maxval < 255
+//   maxval  > 255    16-bit samples (binary: big-endian), high byte
+//   colour           Y = (R*4899 + G*9617 + B*1868 + 8192) >> 14 on the 8-bit samples
+// Returns an empty Mat for anything else (cv::imread returns an empty Mat when it cannot decode).
 cv::Mat decode_pgm_bytes(const std::vector<uint8_t> &b) {
   // hand-rolled header parser (no formatted stream extraction: the library is also loaded into foreign processes)
   size_t pos = 0;
@@ -77,30 +82,63 @@ cv::Mat decode_pgm_bytes(const std::vector<uint8_t> &b) {
     v = (int)t;
     return true;
   };
-  if (b.size() < 7 || b[0] != 'P' || (b[1] != '5' && b[1] != '2')) return cv::Mat();
-  const bool binary = b[1] == '5';
+  if (b.size() < 7 || b[0] != 'P' || b[1] < '1' || b[1] > '6') return cv::Mat();
+  const int kind = b[1] - '0';
+  const bool binary = kind >= 4, bitmap = kind == 1 || kind == 4, colour = kind == 3 || kind == 6;
   pos = 2;
-  int vals[3];
-  for (int k = 0; k < 3; ++k)
-    if (!number(vals[k])) return cv::Mat();
-  if (vals[0] <= 0 || vals[1] <= 0 || vals[2] <= 0 || vals[2] > 255 || vals[0] > 16384 || vals[1] > 16384) return cv::Mat();
-  cv::Mat m(vals[1], vals[0], CV_8UC1);
-  const size_t count = (size_t)vals[0] * vals[1];
+  int w = 0, h = 0, maxval = 1;
+  if (!number(w) || !number(h) || (!bitmap && !number(maxval))) return cv::Mat();
+  if (w <= 0 || h <= 0 || maxval <= 0 || maxval > 65535 || w > 16384 || h > 16384) return cv::Mat();
+  cv::Mat m(h, w, CV_8UC1);
+  const int ch = colour ? 3 : 1;
+  const bool wide = maxval > 255;
+  auto to8 = [&](int v, bool ascii) {  // one sample -> 8 bits
+    if (wide) return (v >> 8) & 255;
+    if (ascii && maxval < 255) return v * 255 / maxval;
+    return v & 255;
+  };
+  auto luma = [](int r, int g, int bl) { return (r * 4899 + g * 9617 + bl * 1868 + 8192) >> 14; };
+  if (binary) ++pos;  // the single whitespace byte after the header
+  if (bitmap) {
+    if (binary) {
+      const size_t rowb = ((size_t)w + 7) / 8;
+      if (pos + rowb * h > b.size()) return cv::Mat();
+      for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x)
+          m.data[(size_t)y * w + x] = ((b[pos + rowb * y + x / 8] >> (7 - x % 8)) & 1) ? 0 : 255;
+    } else {
+      for (size_t i = 0; i < (size_t)w * h; ++i) {  // digits may be packed without white space
+        skip();
+        if (pos >= b.size() || (b[pos] != '0' && b[pos] != '1')) return cv::Mat();
+        m.data[i] = b[pos++] == '1' ? 0 : 255;
+      }
+    }
+    return m;
+  }
+  const size_t count = (size_t)w * h;
   if (binary) {
-    ++pos;  // the single whitespace byte after maxval
-    if (pos + count > b.size()) return cv::Mat();
-    std::memcpy(m.data, b.data() + pos, count);
+    const size_t bps = wide ? 2 : 1;
+    if (pos + count * ch * bps > b.size()) return cv::Mat();
+    const uint8_t *q = b.data() + pos;
+    for (size_t i = 0; i < count; ++i) {
+      int v[3];
+      for (int c = 0; c < ch; ++c) v[c] = to8(wide ? (q[(i * ch + c) * 2] << 8) | q[(i * ch + c) * 2 + 1] : q[i * ch + c], false);
+      m.data[i] = (unsigned char)(colour ? luma(v[0], v[1], v[2]) : v[0]);
+    }
   } else {
     for (size_t i = 0; i < count; ++i) {
-      int v;
-      if (!number(v)) return cv::Mat();
-      m.data[i] = (unsigned char)v;
+      int v[3];
+      for (int c = 0; c < ch; ++c) {
+        if (!number(v[c])) return cv::Mat();
+        v[c] = to8(v[c], true);
+      }
+      m.data[i] = (unsigned char)(colour ? luma(v[0], v[1], v[2]) : v[0]);
     }
   }
   return m;
 }
 
-// cv::imread(path, 0) of the reference (filegrabber.cpp:106-109, feature.cpp:119): PGM, PNG or JPEG -> 8-bit gray; an
+// cv::imread(path, 0) of the reference (filegrabber.cpp:106-109, feature.cpp:119): PNM, PNG or JPEG -> 8-bit gray; an
 // unreadable / unsupported file gives an empty Mat like a failed imread
 cv::Mat decode_image(const std::string &path) {
   std::vector<uint8_t> bytes;

@@ -210,9 +210,10 @@ def _png_bytes(img, color_type=0, depth=8, filters=None, level=6, palette=None, 
 
 
 def test_png_and_pgm_frames_decode_like_imread(tmp_path):
-    """FileGrabber::GetImageFile (filegrabber.cpp:106-109: cv::imread(path, 0)) on the shim: PGM and PNG -> 8-bit gray.
+    """FileGrabber::GetImageFile (filegrabber.cpp:106-109: cv::imread(path, 0)) on the shim: PNM and PNG -> 8-bit gray.
     Every PNG filter type, stored / fixed / dynamic deflate blocks, split IDAT, gray 1-16 bit, RGB(A), gray+alpha and
-    palette images; the expected gray values are computed here with OpenCV's IMREAD_GRAYSCALE formula."""
+    palette images; the expected gray values are computed here with the formula cv::imread(path, 0) applies to a PNG
+    (libpng's rgb-to-gray) and, where OpenCV is installed, compared with cv2.imread(path, 0) itself."""
     import ctypes as C
     import __graft_entry__ as g
     g.build()
@@ -226,9 +227,9 @@ def test_png_and_pgm_frames_decode_like_imread(tmp_path):
                                        C.byref(h))
         return rc, buf[:w.value * h.value].reshape(h.value, w.value) if rc == 0 else None
 
-    def luma(rgb):
+    def luma(rgb):   # libpng's png_set_rgb_to_gray(0.299, 0.587), which is what cv::imread(path, 0) uses for a PNG
         r, gr, b = [rgb[..., k].astype(np.int64) for k in range(3)]
-        return ((r * 4899 + gr * 9617 + b * 1868 + 8192) >> 14).astype(np.uint8)
+        return ((r * 9797 + gr * 19234 + b * 3737) >> 15).astype(np.uint8)
 
     H, W = 37, 53
     smooth = (np.add.outer(np.arange(H) * 3, np.arange(W) * 2) % 256).astype(np.uint8)   # compressible: LZ77 matches
@@ -252,13 +253,59 @@ def test_png_and_pgm_frames_decode_like_imread(tmp_path):
     pal = rng.integers(0, 256, (16, 3), dtype=np.uint8)
     idx = rng.integers(0, 16, (H, W), dtype=np.uint8)
     cases.append(("palette4", _png_bytes(idx, color_type=3, depth=4, palette=pal), luma(pal[idx])))
+    rgb16 = rng.integers(0, 65536, (H, W, 3), dtype=np.uint16)   # converted at 16 bits with rounding, then stripped
+    r16, g16_, b16 = [rgb16[..., k].astype(np.int64) for k in range(3)]
+    cases.append(("rgb16", _png_bytes(rgb16, color_type=2, depth=16, filters=[1, 3]),
+                  (((r16 * 9797 + g16_ * 19234 + b16 * 3737 + 16384) >> 15) >> 8).astype(np.uint8)))
+    try:
+        import cv2   # the reference's own reader, when this image has it: the expected values above must be ITS values
+    except ImportError:
+        cv2 = None
     for name, data, want in cases:
         p = tmp_path / (name + ".png")
         p.write_bytes(data)
         rc, got = decode(p)
         assert rc == 0, name
         assert got.shape == want.shape and (got == want).all(), name
-    # PGM as before; garbage and truncated files give "no image" like a failed imread
+        if cv2 is not None:
+            ref = cv2.imread(str(p), 0)
+            assert ref is not None and ref.shape == got.shape and (ref == got).all(), name + " vs cv2.imread"
+    # the PNM family (PBM / PGM / PPM, ASCII and binary, 8 and 16 bit) with the conversions OpenCV's reader applies
+    def asc(v):
+        return b" ".join(b"%d" % x for x in np.asarray(v).ravel()) + b"\n"
+
+    def to8(v, mv, ascii_):
+        v = np.asarray(v, np.int64)
+        return v >> 8 if mv > 255 else (v * 255 // mv if (ascii_ and mv < 255) else v)
+
+    h2, w2 = 13, 19
+    for mv in (1, 15, 99, 255, 256, 1023, 65535):
+        a = rng.integers(0, mv + 1, (h2, w2)).astype(np.uint16)
+        c3 = rng.integers(0, mv + 1, (h2, w2, 3)).astype(np.uint16)
+        raw = (lambda v: v.astype(">u2").tobytes()) if mv > 255 else (lambda v: v.astype(np.uint8).tobytes())
+        pnm = [("p5", b"P5\n%d %d\n%d\n" % (w2, h2, mv) + raw(a), to8(a, mv, False)),
+               ("p2", b"P2\n# comment\n%d %d\n%d\n" % (w2, h2, mv) + asc(a), to8(a, mv, True)),
+               ("p6", b"P6\n%d %d\n%d\n" % (w2, h2, mv) + raw(c3), None), ("p3", b"P3\n%d %d\n%d\n" % (w2, h2, mv) + asc(c3), None)]
+        for kind, data, want in pnm:
+            if want is None:
+                v = to8(c3, mv, kind == "p3")
+                want = (v[..., 0] * 4899 + v[..., 1] * 9617 + v[..., 2] * 1868 + 8192) >> 14
+            p = tmp_path / ("%s_%d.pnm" % (kind, mv))
+            p.write_bytes(data)
+            rc, got = decode(p)
+            assert rc == 0 and (got == want).all(), p.name
+            if cv2 is not None:
+                assert (cv2.imread(str(p), 0) == got).all(), p.name + " vs cv2.imread"
+    bits = rng.integers(0, 2, (h2, w2), dtype=np.uint8)
+    for name, data in (("p1.pbm", b"P1\n%d %d\n" % (w2, h2) + asc(bits)),
+                       ("p1_packed.pbm", b"P1\n%d %d\n" % (w2, h2) + b"".join(b"%d" % x for x in bits.ravel()) + b"\n"),
+                       ("p4.pbm", b"P4\n%d %d\n" % (w2, h2) + np.packbits(bits, axis=1).tobytes())):
+        (tmp_path / name).write_bytes(data)
+        rc, got = decode(tmp_path / name)
+        assert rc == 0 and (got == np.where(bits == 1, 0, 255)).all(), name
+        if cv2 is not None:
+            assert (cv2.imread(str(tmp_path / name), 0) == got).all(), name + " vs cv2.imread"
+    # garbage and truncated files give "no image" like a failed imread
     (tmp_path / "a.pgm").write_bytes(b"P5\n%d %d\n255\n" % (W, H) + noise.tobytes())
     rc, got = decode(tmp_path / "a.pgm")
     assert rc == 0 and (got == noise).all()
