@@ -267,4 +267,61 @@ inline bool decode_gray(const uint8_t *file, size_t n, std::vector<uint8_t> &gra
   return true;
 }
 
+// 8-bit gray image -> PNG bytes (cv::imwrite("patch.png", patch) of MonoSLAM::SavePatch, monoslam.cpp:1569): filter 0 on
+// every scanline, one zlib stream of stored deflate blocks (the patches are 11 x 11 or 15 x 15 pixels; compression is
+// not the point, a file every PNG reader accepts is).
+inline void encode_gray(const uint8_t *img, int w, int h, size_t stride, std::vector<uint8_t> &out) {
+  auto crc32 = [](const uint8_t *p, size_t n) {
+    uint32_t c = 0xffffffffu;
+    for (size_t i = 0; i < n; ++i) {
+      c ^= p[i];
+      for (int k = 0; k < 8; ++k) c = (c >> 1) ^ (0xedb88320u & (0u - (c & 1u)));
+    }
+    return c ^ 0xffffffffu;
+  };
+  auto be32 = [](std::vector<uint8_t> &v, uint32_t x) {
+    for (int s = 24; s >= 0; s -= 8) v.push_back((uint8_t)(x >> s));
+  };
+  auto chunk = [&](const char *type, const std::vector<uint8_t> &body) {
+    be32(out, (uint32_t)body.size());
+    const size_t at = out.size();
+    out.insert(out.end(), type, type + 4);
+    out.insert(out.end(), body.begin(), body.end());
+    be32(out, crc32(out.data() + at, out.size() - at));
+  };
+  static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
+  out.assign(sig, sig + 8);
+  std::vector<uint8_t> ihdr;
+  be32(ihdr, (uint32_t)w);
+  be32(ihdr, (uint32_t)h);
+  const uint8_t tail[5] = {8, 0, 0, 0, 0};  // depth 8, gray, deflate, adaptive filtering, not interlaced
+  ihdr.insert(ihdr.end(), tail, tail + 5);
+  chunk("IHDR", ihdr);
+  std::vector<uint8_t> raw;  // filter byte 0 + the scanline
+  for (int y = 0; y < h; ++y) {
+    raw.push_back(0);
+    raw.insert(raw.end(), img + (size_t)y * stride, img + (size_t)y * stride + w);
+  }
+  std::vector<uint8_t> z = {0x78, 0x01};
+  uint32_t a1 = 1, a2 = 0;  // adler32
+  for (uint8_t b : raw) {
+    a1 = (a1 + b) % 65521u;
+    a2 = (a2 + a1) % 65521u;
+  }
+  size_t o = 0;
+  do {
+    const size_t nb = raw.size() - o < 65535 ? raw.size() - o : 65535;
+    z.push_back(o + nb == raw.size() ? 1 : 0);  // BFINAL, BTYPE = 00 (stored)
+    z.push_back((uint8_t)(nb & 255));
+    z.push_back((uint8_t)(nb >> 8));
+    z.push_back((uint8_t)(~nb & 255));
+    z.push_back((uint8_t)((~nb >> 8) & 255));
+    z.insert(z.end(), raw.begin() + o, raw.begin() + o + nb);
+    o += nb;
+  } while (o < raw.size());
+  be32(z, (a2 << 16) | a1);
+  chunk("IDAT", z);
+  chunk("IEND", {});
+}
+
 }  // namespace sl2png

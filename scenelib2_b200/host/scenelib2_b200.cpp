@@ -626,15 +626,16 @@ void MonoSLAM::InitialiseAutoFeature(cv::Mat frame) {  // monoslam.cpp:1535-1541
   if (set_image_selection_automatically(frame, us, vs, us + bw, vs + bh) > 0.0) InitialiseFeature(frame);
 }
 
-bool MonoSLAM::SavePatch() {  // monoslam.cpp:1551-1572 (patch.png through cv::imwrite there; PGM here)
+bool MonoSLAM::SavePatch() {  // monoslam.cpp:1551-1572: cv::imwrite("patch.png", patch) -- an 8-bit gray PNG here too
   if (marked_feature_label_ == -1) return false;
   for (Feature *f : feature_list_) {
     if (f->label_ != marked_feature_label_) continue;
-    std::ofstream o("patch.pgm", std::ios::binary);
+    std::vector<uint8_t> png;
+    sl2png::encode_gray(f->patch_.data, f->patch_.cols, f->patch_.rows, f->patch_.step, png);
+    std::ofstream o("patch.png", std::ios::binary);
     if (!o) return false;
-    o << "P5\n" << f->patch_.cols << " " << f->patch_.rows << "\n255\n";
-    for (int r = 0; r < f->patch_.rows; ++r) o.write((const char *)f->patch_.data + r * f->patch_.step, f->patch_.cols);
-    return true;
+    o.write((const char *)png.data(), (std::streamsize)png.size());
+    return (bool)o;
   }
   return false;
 }
@@ -725,6 +726,17 @@ bool FrameGrabber::Exhausted() {
 
 }  // namespace SceneLib2
 
+
+// test hook: the PNG writer behind MonoSLAM::SavePatch on a caller's 8-bit gray image; 0 on success
+extern "C" int sl2_host_write_png(const char *path, const unsigned char *gray, int w, int h) {
+  if (!path || !gray || w <= 0 || h <= 0) return -1;
+  std::vector<uint8_t> png;
+  sl2png::encode_gray(gray, w, h, (size_t)w, png);
+  std::ofstream o(path, std::ios::binary);
+  if (!o) return -1;
+  o.write((const char *)png.data(), (std::streamsize)png.size());
+  return o ? 0 : -1;
+}
 
 // test hook (tests/test_host_shim.py): decode one image file the way FileGrabber does; returns 0 and fills w / h /
 // out (cap bytes) on success, -1 when the file is not an image the shim reads, -2 when out is too small

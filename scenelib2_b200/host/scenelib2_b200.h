@@ -145,7 +145,7 @@ class MonoSLAM {  // monoslam.h:73-218 (hot-path subset + the calls of examples/
   // monoslam.h:79-81,142: caller-side surface of the example's buttons
   void InitialiseFeature(cv::Mat frame);      // template at the selected image location (uu_, vv_)
   void InitialiseAutoFeature(cv::Mat frame);  // Shi-Tomasi best patch of the central region, then the above
-  bool SavePatch();                           // template of the marked feature -> patch.pgm
+  bool SavePatch();                           // template of the marked feature -> patch.png
 
   int auto_select_n_features(int n);
   int make_measurements(cv::Mat image);

@@ -373,3 +373,36 @@ def test_jpeg_frames_decode_like_imread(tmp_path):
             b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
         (tmp_path / "mut.jpg").write_bytes(bytes(b))
         assert decode(tmp_path / "mut.jpg")[0] in (0, -1, -2)    # -2: a mutated size field larger than the buffer
+
+
+def test_save_patch_png_is_readable(tmp_path):
+    """MonoSLAM::SavePatch writes the marked feature's template with cv::imwrite("patch.png", ...) (monoslam.cpp:1569).
+    The shim's own PNG writer must produce a file any PNG reader accepts: read back with the shim's decoder and, where
+    installed, with OpenCV and PIL (which check the chunk CRCs and the zlib Adler-32)."""
+    import ctypes as C
+    import __graft_entry__ as g
+    g.build()
+    lib = C.CDLL(os.path.join(HOST, "libscenelib2_b200_host.so"))
+    rng = np.random.default_rng(2)
+    for (h, w) in ((11, 11), (15, 15), (1, 1), (300, 400)):    # 300 x 400: more than one stored deflate block
+        img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        p = tmp_path / ("patch_%d_%d.png" % (h, w))
+        assert lib.sl2_host_write_png(str(p).encode(), img.ctypes.data_as(C.c_void_p), w, h) == 0
+        buf = np.zeros(1 << 20, np.uint8)
+        cw, ch = C.c_int(0), C.c_int(0)
+        assert lib.sl2_host_decode_image(str(p).encode(), buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(cw),
+                                         C.byref(ch)) == 0
+        assert (buf[:w * h].reshape(h, w) == img).all()
+        try:
+            import cv2
+            back = cv2.imread(str(p), cv2.IMREAD_UNCHANGED)
+            assert back is not None and back.dtype == np.uint8 and (back == img).all()
+        except ImportError:
+            pass
+        try:
+            from PIL import Image
+            with Image.open(str(p)) as im:
+                im.load()
+                assert im.mode == "L" and (np.asarray(im) == img).all()
+        except ImportError:
+            pass
