@@ -16,6 +16,7 @@
 #include <stdexcept>
 
 #include "../../include/sl2b200.h"
+#include "bmp_decode.h"
 #include "jpeg_decode.h"
 #include "png_decode.h"
 
@@ -138,7 +139,7 @@ cv::Mat decode_pgm_bytes(const std::vector<uint8_t> &b) {
   return m;
 }
 
-// cv::imread(path, 0) of the reference (filegrabber.cpp:106-109, feature.cpp:119): PNM, PNG or JPEG -> 8-bit gray; an
+// cv::imread(path, 0) of the reference (filegrabber.cpp:106-109, feature.cpp:119): PNM, PNG, JPEG or BMP -> 8-bit gray; an
 // unreadable / unsupported file gives an empty Mat like a failed imread
 cv::Mat decode_image(const std::string &path) {
   std::vector<uint8_t> bytes;
@@ -156,6 +157,14 @@ cv::Mat decode_image(const std::string &path) {
     std::vector<uint8_t> gray;
     int w = 0, h = 0;
     if (!sl2png::decode_gray(bytes.data(), bytes.size(), gray, w, h)) return cv::Mat();
+    cv::Mat m(h, w, CV_8UC1);
+    std::memcpy(m.data, gray.data(), gray.size());
+    return m;
+  }
+  if (bytes.size() >= 2 && bytes[0] == 'B' && bytes[1] == 'M') {
+    std::vector<uint8_t> gray;
+    int w = 0, h = 0;
+    if (!sl2bmp::decode_gray(bytes.data(), bytes.size(), gray, w, h)) return cv::Mat();
     cv::Mat m(h, w, CV_8UC1);
     std::memcpy(m.data, gray.data(), gray.size());
     return m;

@@ -406,3 +406,56 @@ def test_save_patch_png_is_readable(tmp_path):
                 assert im.mode == "L" and (np.asarray(im) == img).all()
         except ImportError:
             pass
+
+
+def test_bmp_frames_decode_like_imread(tmp_path):
+    """cv::imread(path, 0) on Windows bitmaps (filegrabber.cpp:106-109): 1 / 4 / 8 bit with a palette, 24 and 32 bit,
+    bottom-up and top-down, from OpenCV's and PIL's writers.  The expected bytes are cv2.imread(path, 0)'s; the 32-bit
+    case pins the single-precision formula OpenCV uses there (checked over all 2^24 colours when the decoder was written)."""
+    cv2 = pytest.importorskip("cv2")
+    Image = pytest.importorskip("PIL.Image")
+    import ctypes as C
+    import struct
+    import __graft_entry__ as g
+    g.build()
+    lib = C.CDLL(os.path.join(HOST, "libscenelib2_b200_host.so"))
+
+    def decode(path):
+        buf = np.zeros(1 << 20, np.uint8)
+        w, h = C.c_int(0), C.c_int(0)
+        rc = lib.sl2_host_decode_image(str(path).encode(), buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(w),
+                                       C.byref(h))
+        return rc, buf[:w.value * h.value].reshape(h.value, w.value) if rc == 0 else None
+
+    rng = np.random.default_rng(3)
+    n = 0
+    for (h, w) in ((11, 11), (13, 17), (240, 320)):
+        gray = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        rgba = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        files = []
+        for name, arr in (("cv_g", gray), ("cv_c", rgb), ("cv_a", rgba)):
+            p = tmp_path / ("%s_%d.bmp" % (name, w))
+            cv2.imwrite(str(p), arr)
+            files.append(p)
+        for name, im in (("pil_L", Image.fromarray(gray)), ("pil_RGB", Image.fromarray(rgb)),
+                         ("pil_1", Image.fromarray(gray).convert("1")),
+                         ("pil_P", Image.fromarray(rgb).quantize(200)), ("pil_P4", Image.fromarray(rgb).quantize(16))):
+            p = tmp_path / ("%s_%d.bmp" % (name, w))
+            im.save(str(p), **({"bits": 4} if name == "pil_P4" else {}))
+            files.append(p)
+        rowb = (w * 3 + 3) // 4 * 4
+        body = b"".join(rgb[y, :, ::-1].tobytes() + b"\0" * (rowb - 3 * w) for y in range(h))
+        p = tmp_path / ("topdown_%d.bmp" % w)
+        p.write_bytes(b"BM" + struct.pack("<IHHI", 54 + len(body), 0, 0, 54) +
+                      struct.pack("<IiiHHIIiiII", 40, w, -h, 1, 24, 0, len(body), 2835, 2835, 0, 0) + body)
+        files.append(p)
+        for p in files:
+            want = cv2.imread(str(p), 0)
+            rc, got = decode(p)
+            assert rc == 0 and want is not None and got.shape == want.shape and (got == want).all(), p.name
+            n += 1
+    assert n == 27
+    data = (tmp_path / "cv_c_320.bmp").read_bytes()
+    (tmp_path / "cut.bmp").write_bytes(data[:1000])
+    assert decode(tmp_path / "cut.bmp")[0] == -1
